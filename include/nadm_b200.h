@@ -1,0 +1,134 @@
+/* nadm_b200.h — C ABI of the B200 (sm_100a) Neural ADMIXTURE hot-path library (libnadm_b200.so).
+ *
+ * Boundary.  The reference exposes its native code to Python as a pybind11 module JIT-built from
+ * neural_admixture/src/utils_c/pack2bit.cu (PYBIND11_MODULE at pack2bit.cu:144-147, loaded at model/train.py:122-125)
+ * and does everything else on the hot path through PyTorch eager ops inside
+ * neural_admixture/model/neural_admixture.py (Q_P.forward :157-177, NeuralAdmixture._run_epoch :394-417).
+ * This header is what a binding for that path binds instead: every entry point is `extern "C"`, takes plain device
+ * pointers + sizes + a CUDA stream, allocates nothing, retains no pointer, and is asynchronous on `stream`.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers owned by the caller unless marked [host];
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *   - return value: 0 on success, negative NADM_E* on failure; nadm_last_error() gives the message
+ *     (thread-local, valid until the next call on the same thread);
+ *   - genotype storage: sample-major 2-bit packed, SNP 4c+i in bits 2i..2i+1 of byte c of a row
+ *     (pack2bit.cu:26-31); codes 0,1,2 = genotype, 3 = missing (trained as 0: neural_admixture.py:169-170);
+ *     `pitch` = bytes between consecutive sample rows; the streaming kernels require pitch % 16 == 0, a 16-byte
+ *     aligned base and zero bits past SNP M-1 in every row (nadm_pack2bit produces that);
+ *   - a minibatch is B rows: row b is `row_idx[b]` when row_idx != NULL, else `row0 + b`
+ *     (replaces Dataset_admixture.__getitem__ + DataLoader collate, src/loaders.py:33,70-72);
+ *   - parameters use the reference's own layouts: V is M x C row-major (neural_admixture.py:129-130), each head's
+ *     P is M x k row-major (= decoders.decoders[i].weight, :73-74), W1 is H x C, W2 (all heads concatenated along
+ *     rows) is sumK x H;  Adam moments have the layout of their parameter.
+ */
+#ifndef NADM_B200_H
+#define NADM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NADM_OK 0
+#define NADM_EINVAL (-1)   /* bad argument (shape, alignment, unsupported C / k) */
+#define NADM_ECUDA (-2)    /* a CUDA runtime call or kernel launch failed */
+#define NADM_ENOSPC (-3)   /* workspace too small */
+
+#define NADM_MAX_C 16      /* n_components supported by the streaming kernels */
+#define NADM_MAX_K 16      /* populations per head */
+#define NADM_MAX_HEADS 32
+
+/* Adam hyper-parameters of one optimizer step (torch.optim.Adam, betas (0.9,0.95): neural_admixture.py:197-204).
+ * `step` is the 1-based step count AFTER increment (torch's state['step']). */
+typedef struct nadm_adam {
+    float lr;
+    float beta1;
+    float beta2;
+    float eps;
+    int32_t step;
+} nadm_adam_t;
+
+int nadm_version(void);
+const char* nadm_last_error(void);
+
+/* Number of kernels this library has launched from the calling process so far (bench.py's gpu_launches). */
+int64_t nadm_launch_count(void);
+
+/* ---- 2-bit pack / unpack: device -> device.  Replaces pack2bit_kernel (pack2bit.cu:10-36; the host wrapper
+ * pack2bit_cpu_to_gpu :65-117 stages <=1024 unpacked rows to the device and calls it) and unpack2bit_kernel /
+ * unpack2bit_gpu_to_gpu (pack2bit.cu:38-62, :120-142).  src: rows x M uint8 codes (pitch src_pitch bytes);
+ * dst: rows x ceil(M/4) bytes (pitch dst_pitch >= ceil(M/4)); bytes in [ceil(M/4), dst_pitch) are zeroed. */
+int nadm_pack2bit(const uint8_t* src, int64_t rows, int64_t M, int64_t src_pitch,
+                  uint8_t* dst, int64_t dst_pitch, void* stream);
+int nadm_unpack2bit(const uint8_t* src, int64_t rows, int64_t M, int64_t src_pitch,
+                    uint8_t* dst, int64_t dst_pitch, void* stream);
+
+/* Bytes of scratch the step functions below need for a batch of B rows, M SNPs (local slice), C components,
+ * hidden width H and sumK total populations over all heads. */
+size_t nadm_workspace_bytes(int32_t B, int64_t M, int32_t C, int32_t H, int32_t sumK);
+
+/* ---- encoder projection: Z[b, :] = X[b, :] @ V, X = genotype/2 with missing -> 0.
+ * Replaces `X.float()/2`, `where(X==1.5,0,X)`, `X @ self.V` (neural_admixture.py:169-172) and the per-step
+ * unpack (neural_admixture.py:404-406).  Also the whole of the inference / post-training Q pass's M-wide work
+ * (inference.py:71-77, neural_admixture.py:369-383).   Z: B x C. */
+int nadm_encoder_fwd(const uint8_t* packed, int64_t pitch, const int64_t* row_idx, int64_t row0, int32_t B,
+                     int64_t M, const float* V, int32_t C, float* Z, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- the small replicated network: RMSNorm(C, eps 1e-8) -> Linear(C,H)+ReLU -> per-head Linear(H,k) -> softmax
+ * (neural_admixture.py:135-144 construction, :173-176 forward).  ks [host]: nheads head sizes; Q: B x sumK
+ * (heads side by side); Hh: B x H post-ReLU activations and rinv: B (kept for the backward). */
+int nadm_mlp_fwd(const float* Z, int32_t B, int32_t C, int32_t H, const float* w_rms, const float* W1,
+                 const float* b1, const float* W2, const float* b2, const int32_t* ks, int32_t nheads,
+                 float* rinv, float* Hh, float* Q, void* stream);
+
+/* ---- fused decoder for ONE head: R = clamp(Q_k P_k^T, 0, 1); loss += BCE_sum(R, X); G = dLoss/dR through the
+ * clamp mask; dQ[:, q_off:q_off+k] = G P_k; dP = G^T Q_k; then Adam on P_k and clamp to [0,1].
+ * Replaces NeuralDecoder.forward (neural_admixture.py:83-98), BCELoss(sum) (:288,:431), their autograd backward
+ * (:410), the P part of optimizer.step() (:411) and restrict_P (:179-185,:412).  The B x M reconstruction, the
+ * float X and G never touch HBM.
+ *   Q, dQ : B x q_ld (q_ld = sumK), this head occupies columns [q_off, q_off+k)
+ *   P, Pm, Pv : M x k parameter and Adam moments, updated in place when adam != NULL
+ *   dP_out : optional M x k raw gradient output (tests); may be NULL
+ *   loss : 1 float, the head's loss is ADDED to it (zero it once per step). */
+int nadm_decoder_step(const uint8_t* packed, int64_t pitch, const int64_t* row_idx, int64_t row0, int32_t B,
+                      int64_t M, const float* Q, float* dQ, int32_t q_ld, int32_t q_off, int32_t k,
+                      float* P, float* Pm, float* Pv, const nadm_adam_t* adam /*[host], NULL = no update*/,
+                      float* dP_out, float* loss, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- backward of the small network + Adam on its parameters.  dQ: B x sumK (sum of the decoder's and, when
+ * labels != NULL, of supervised_loss_weight * CrossEntropyLoss(sum)(Q_0, labels) — neural_admixture.py:293,:473 —
+ * which this call adds itself, also adding that loss term to *loss).  Outputs dZ: B x C.  Updates w_rms, W1, b1,
+ * W2, b2 and their moments in place when adam != NULL; raw gradients go to the optional g_* buffers. */
+typedef struct nadm_mlp_params {
+    float* w_rms; float* W1; float* b1; float* W2; float* b2;          /* parameters             */
+    float* m_w_rms; float* m_W1; float* m_b1; float* m_W2; float* m_b2; /* Adam first moments     */
+    float* v_w_rms; float* v_W1; float* v_b1; float* v_W2; float* v_b2; /* Adam second moments    */
+    float* g_w_rms; float* g_W1; float* g_b1; float* g_W2; float* g_b2; /* optional raw gradients */
+} nadm_mlp_params_t;
+
+int nadm_mlp_bwd(const float* dQ, const float* Q, const float* Hh, const float* Z, const float* rinv,
+                 int32_t B, int32_t C, int32_t H, const int32_t* ks /*[host]*/, int32_t nheads,
+                 const int64_t* labels /*B, or NULL*/, float sup_weight,
+                 const nadm_mlp_params_t* params /*[host]*/, const nadm_adam_t* adam /*[host]*/,
+                 float* dZ, float* loss, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- encoder backward: dV = X^T dZ, then Adam on V.  Replaces the autograd of `X @ self.V`
+ * (neural_admixture.py:172,:410) and the V part of optimizer.step() (:411).  dV_out optional. */
+int nadm_encoder_bwd(const uint8_t* packed, int64_t pitch, const int64_t* row_idx, int64_t row0, int32_t B,
+                     int64_t M, const float* dZ, int32_t C, float* V, float* Vm, float* Vv,
+                     const nadm_adam_t* adam /*[host], NULL = no update*/, float* dV_out,
+                     void* ws, size_t ws_bytes, void* stream);
+
+/* ---- fp64 binomial log-likelihood of the packed matrix under (Q, P), missing skipped, eps-clamped
+ * (src/utils_c/utils.pyx:17-40, called at model/train.py:139,145).  Q: N x k, P: M x k (fp32); out: 1 double. */
+int nadm_loglikelihood(const uint8_t* packed, int64_t pitch, int64_t N, int64_t M, const float* Q,
+                       const float* P, int32_t k, double eps, double* out, void* ws, size_t ws_bytes,
+                       void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NADM_B200_H */

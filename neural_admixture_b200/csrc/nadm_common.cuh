@@ -1,0 +1,129 @@
+// Shared device/host helpers for libnadm_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/nadm_b200.h"
+
+namespace nadm {
+
+// ---- error plumbing -------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+void count_launch(int n = 1);
+int sm_count();
+
+#define NADM_REQUIRE(cond, ...)            \
+    do {                                   \
+        if (!(cond)) {                     \
+            nadm::set_error(__VA_ARGS__);  \
+            return NADM_EINVAL;            \
+        }                                  \
+    } while (0)
+
+#define NADM_CHECK_LAUNCH(what)                                  \
+    do {                                                         \
+        cudaError_t e__ = cudaGetLastError();                    \
+        if (e__ != cudaSuccess) return nadm::cuda_fail(e__, what); \
+        nadm::count_launch();                                    \
+    } while (0)
+
+// ---- tiling constants shared by kernels and the workspace query --------------------------------------------------
+constexpr int kMaxParts = 640;        // upper bound on per-CTA partial slabs (encoder slabs / decoder CTAs)
+constexpr int kStreamWarps = 8;       // warps per CTA in the lane<->byte streaming kernels
+constexpr int kTileSnps = 128;        // SNPs per CTA tile in those kernels: one byte (4 SNPs) per lane
+constexpr int kEncTileSnps = 256;     // SNPs per staged tile in the thread-per-row encoder forward
+
+struct AdamCoef {
+    float beta1, beta2, one_minus_beta1, one_minus_beta2, step_size, inv_bc2_sqrt, eps;
+    int enabled;
+};
+
+inline AdamCoef make_adam(const nadm_adam_t* a) {
+    AdamCoef c{};
+    if (!a) return c;
+    double bc1 = 1.0 - pow((double)a->beta1, (double)a->step);
+    double bc2 = 1.0 - pow((double)a->beta2, (double)a->step);
+    c.beta1 = a->beta1;
+    c.beta2 = a->beta2;
+    c.one_minus_beta1 = 1.0f - a->beta1;
+    c.one_minus_beta2 = 1.0f - a->beta2;
+    c.step_size = (float)((double)a->lr / bc1);
+    c.inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
+    c.eps = a->eps;
+    c.enabled = 1;
+    return c;
+}
+
+#ifdef __CUDACC__
+// torch.optim.Adam (no weight decay / amsgrad), same operation order as torch's fused kernel:
+//   m = lerp(m, g, 1-b1); v = b2*v + (1-b2)*g*g; p -= step_size * m / (sqrt(v)/sqrt(bc2) + eps)
+__device__ __forceinline__ float adam_apply(float p, float g, float& m, float& v, const AdamCoef& c) {
+    m = m + (g - m) * c.one_minus_beta1;
+    v = c.beta2 * v + c.one_minus_beta2 * g * g;
+    float denom = sqrtf(v) * c.inv_bc2_sqrt + c.eps;
+    return p - c.step_size * (m / denom);
+}
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem, int src_bytes) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+// 2-bit code -> 2*x as float (0,1,2; missing 3 -> 0).  x = code/2 with missing trained as 0
+// (neural_admixture.py:169-170); the factor 1/2 is applied once to the accumulated sums (exact: power of two).
+__device__ __forceinline__ float code_to_2x(unsigned c) {
+    c = (c == 3u) ? 0u : c;
+    return __uint_as_float(0x4B000000u | c) - 8388608.0f;
+}
+// clear every 2-bit field equal to 3 in a packed word
+__device__ __forceinline__ unsigned clear_missing(unsigned w) {
+    unsigned m3 = w & (w >> 1) & 0x55555555u;
+    return w ^ (m3 | (m3 << 1));
+}
+
+// Reduce N (power of two <= 32) per-lane values across the warp.  On return v[0] of lane l holds the warp-wide sum
+// of element (l / (32/N)); lanes with l % (32/N) == 0 are the canonical owners.  N-1 + log2(32/N) shuffles.
+template <int N>
+__device__ __forceinline__ float warp_reduce_vec(float (&v)[N], int lane) {
+    int width = 16;
+#pragma unroll
+    for (int n = N; n > 1; n >>= 1) {
+        const bool up = (lane & width) != 0;
+#pragma unroll
+        for (int j = 0; j < n / 2; ++j) {
+            float send = up ? v[j] : v[j + n / 2];
+            float keep = up ? v[j + n / 2] : v[j];
+            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, width);
+        }
+        width >>= 1;
+    }
+#pragma unroll
+    for (; width >= 1; width >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], width);
+    return v[0];
+}
+
+__device__ __forceinline__ float warp_sum(float x) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+__device__ __forceinline__ double warp_sum_d(double x) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+#endif  // __CUDACC__
+
+}  // namespace nadm

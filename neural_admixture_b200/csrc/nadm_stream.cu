@@ -1,0 +1,675 @@
+// Streaming kernels over the 2-bit packed genotype matrix (fp32 CUDA-core formulation).
+//
+//   pack2bit / unpack2bit     : bit layout of pack2bit.cu:26-31,53-60
+//   enc_fwd_kernel            : Z = X V            (neural_admixture.py:169-172)  thread-per-sample-row, tiles staged
+//                               through shared memory with cp.async, V tile broadcast from shared memory
+//   dec_kernel                : fused decoder + BCE loss + backward + Adam + clamp for one head
+//                               (neural_admixture.py:83-98, :288, :410-412)  lane<->genotype byte, warps split rows
+//   enc_bwd_kernel            : dV = X^T dZ + Adam (neural_admixture.py:172 backward, :411)
+//   reduce_parts_kernel       : deterministic sum of per-CTA partials (no atomics anywhere on the path)
+//   loglik_kernel             : fp64 log-likelihood (utils.pyx:17-40)
+#include "nadm_common.cuh"
+
+namespace nadm {
+
+// =================================================================================================================
+// pack / unpack
+// =================================================================================================================
+__global__ void pack2bit_kernel(const uint8_t* __restrict__ src, int64_t rows, int64_t M, int64_t src_pitch,
+                                uint8_t* __restrict__ dst, int64_t dst_pitch) {
+    // one thread packs 16 SNPs into one 32-bit word; grid.y strides over rows
+    const int64_t words = (dst_pitch + 3) / 4;
+    const int64_t pc = (M + 3) / 4;
+    for (int64_t row = blockIdx.y; row < rows; row += gridDim.y) {
+        const uint8_t* s = src + row * src_pitch;
+        uint8_t* d = dst + row * dst_pitch;
+        for (int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; w < words; w += (int64_t)gridDim.x * blockDim.x) {
+            const int64_t m0 = w * 16;
+            uint32_t out = 0;
+            if (m0 + 16 <= M && ((reinterpret_cast<uintptr_t>(s + m0) & 15) == 0)) {
+                uint4 v = *reinterpret_cast<const uint4*>(s + m0);
+                uint32_t q[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t x = q[j] & 0x03030303u;  // four codes, one per byte
+                    uint32_t b = (x | (x >> 6) | (x >> 12) | (x >> 18)) & 0xFFu;
+                    out |= b << (8 * j);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    int64_t m = m0 + i;
+                    uint32_t c = (m < M) ? (uint32_t)(s[m] & 3) : 0u;
+                    out |= c << (2 * i);
+                }
+            }
+            // store only the bytes that exist in this row (dst_pitch need not be a multiple of 4)
+            const int64_t b0 = w * 4;
+            if (b0 + 4 <= dst_pitch && ((reinterpret_cast<uintptr_t>(d + b0) & 3) == 0)) {
+                *reinterpret_cast<uint32_t*>(d + b0) = out;
+            } else {
+                for (int j = 0; j < 4; ++j)
+                    if (b0 + j < dst_pitch) d[b0 + j] = (uint8_t)(out >> (8 * j));
+            }
+            (void)pc;
+        }
+    }
+}
+
+__global__ void unpack2bit_kernel(const uint8_t* __restrict__ src, int64_t rows, int64_t M, int64_t src_pitch,
+                                  uint8_t* __restrict__ dst, int64_t dst_pitch) {
+    const int64_t pc = (M + 3) / 4;
+    for (int64_t row = blockIdx.y; row < rows; row += gridDim.y) {
+        const uint8_t* s = src + row * src_pitch;
+        uint8_t* d = dst + row * dst_pitch;
+        for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < pc; c += (int64_t)gridDim.x * blockDim.x) {
+            uint32_t b = s[c];
+            uint32_t four = (b & 3u) | ((b & 0xCu) << 6) | ((b & 0x30u) << 12) | ((b & 0xC0u) << 18);
+            const int64_t m0 = c * 4;
+            if (m0 + 4 <= M && ((reinterpret_cast<uintptr_t>(d + m0) & 3) == 0)) {
+                *reinterpret_cast<uint32_t*>(d + m0) = four;
+            } else {
+                for (int i = 0; i < 4; ++i)
+                    if (m0 + i < M) d[m0 + i] = (uint8_t)((four >> (8 * i)) & 3u);
+            }
+        }
+    }
+}
+
+// =================================================================================================================
+// deterministic partial reduction: out[i*out_ld_scale...] = sum_p part[p][i]
+// =================================================================================================================
+// part: nparts x (rows x cols_p) ; out: rows x out_ld, written at column offset out_off for cols < cols_out.
+__global__ void reduce_parts_kernel(const float* __restrict__ part, int nparts, int rows, int cols_p, int cols_out,
+                                    float* __restrict__ out, int out_ld, int out_off, float scale,
+                                    const float* __restrict__ loss_part, float* __restrict__ loss) {
+    const int64_t n = (int64_t)rows * cols_p;
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) {
+        const int r = (int)(i / cols_p), c = (int)(i % cols_p);
+        if (c < cols_out) {
+            float acc = 0.f;
+            const float* p = part + i;
+            int q = 0;
+            for (; q + 4 <= nparts; q += 4) {
+                float a0 = p[(int64_t)q * n], a1 = p[(int64_t)(q + 1) * n];
+                float a2 = p[(int64_t)(q + 2) * n], a3 = p[(int64_t)(q + 3) * n];
+                acc += (a0 + a1) + (a2 + a3);
+            }
+            for (; q < nparts; ++q) acc += p[(int64_t)q * n];
+            out[(int64_t)r * out_ld + out_off + c] = acc * scale;
+        }
+    }
+    if (loss_part != nullptr && blockIdx.x == 0 && threadIdx.x < 32) {
+        double acc = 0.0;
+        for (int q = threadIdx.x; q < nparts; q += 32) acc += (double)loss_part[q];
+        acc = warp_sum_d(acc);
+        if (threadIdx.x == 0) *loss = (float)((double)*loss + acc);
+    }
+}
+
+// =================================================================================================================
+// encoder forward: thread per sample row, genotype + V tiles staged through shared memory (2-stage cp.async)
+// =================================================================================================================
+constexpr int kEncRowBytes = kEncTileSnps / 4;      // 64 genotype bytes per row per tile
+constexpr int kEncRowStride = kEncRowBytes + 16;    // padded: conflict-free 16-byte reads across lanes
+
+template <int CP>
+__global__ void __launch_bounds__(256, 2)
+enc_fwd_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* __restrict__ row_idx, int64_t row0,
+               int B, int64_t M, const float* __restrict__ V, int C, float* __restrict__ Zpart, int ntiles,
+               int nslab) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int RB = blockDim.x;
+    const int tid = threadIdx.x;
+    const int slab = blockIdx.x;
+    const int bbase = blockIdx.y * RB;
+    int64_t* rowoff = reinterpret_cast<int64_t*>(smem);
+    const int stage_bytes = RB * kEncRowStride + kEncTileSnps * CP * 4;
+    uint8_t* stage0 = smem + ((RB * 8 + 15) / 16) * 16;
+
+    {
+        const int b = bbase + tid;
+        int64_t r = 0;
+        if (b < B) r = (row_idx != nullptr) ? row_idx[b] : (row0 + b);
+        rowoff[tid] = r * pitch;
+    }
+    __syncthreads();
+
+    const int t0 = (int)(((int64_t)ntiles * slab) / nslab);
+    const int t1 = (int)(((int64_t)ntiles * (slab + 1)) / nslab);
+    const bool v_vec = (C == CP) && ((reinterpret_cast<uintptr_t>(V) & 15) == 0);
+
+    auto issue = [&](int t, int s) {
+        uint8_t* gs = stage0 + s * stage_bytes;
+        float* vs = reinterpret_cast<float*>(gs + RB * kEncRowStride);
+        const int64_t byte0 = (int64_t)t * kEncRowBytes;
+        for (int i = tid; i < RB * 4; i += RB) {
+            const int rr = i >> 2, ch = i & 3;
+            const int64_t off = byte0 + ch * 16;
+            const bool ok = (bbase + rr < B) && (off + 16 <= pitch);
+            const uint8_t* src = ok ? (packed + rowoff[rr] + off) : packed;
+            cp_async16(gs + rr * kEncRowStride + ch * 16, src, ok ? 16 : 0);
+        }
+        const int64_t m0 = (int64_t)t * kEncTileSnps;
+        if (v_vec) {
+            constexpr int chunks = kEncTileSnps * CP / 4;
+            for (int i = tid; i < chunks; i += RB) {
+                const int64_t m = m0 + (i * 4) / CP;
+                const bool ok = m < M;
+                const float* src = ok ? (V + m0 * CP + (int64_t)i * 4) : V;
+                cp_async16(vs + i * 4, src, ok ? 16 : 0);
+            }
+        } else {
+            for (int i = tid; i < kEncTileSnps * CP; i += RB) {
+                const int s_ = i / CP, c = i % CP;
+                const int64_t m = m0 + s_;
+                const bool ok = (m < M) && (c < C);
+                const float* src = ok ? (V + m * C + c) : V;
+                cp_async4(vs + i, src, ok ? 4 : 0);
+            }
+        }
+        cp_async_commit();
+    };
+
+    float acc[CP];
+#pragma unroll
+    for (int c = 0; c < CP; ++c) acc[c] = 0.f;
+
+    if (t0 < t1) issue(t0, 0);
+    for (int t = t0; t < t1; ++t) {
+        const int s = (t - t0) & 1;
+        if (t + 1 < t1) {
+            issue(t + 1, s ^ 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        const uint8_t* gs = stage0 + s * stage_bytes;
+        const float* vs = reinterpret_cast<const float*>(gs + RB * kEncRowStride);
+        const uint4* grow = reinterpret_cast<const uint4*>(gs + tid * kEncRowStride);
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {
+            const uint4 w4 = grow[ch];
+            const uint32_t ws[4] = {clear_missing(w4.x), clear_missing(w4.y), clear_missing(w4.z), clear_missing(w4.w)};
+#pragma unroll
+            for (int wi = 0; wi < 4; ++wi) {
+                const uint32_t w = ws[wi];
+                if (w == 0u) continue;  // all-zero genotypes contribute nothing (per-thread skip, no sync inside)
+                const float* vrow = vs + (ch * 64 + wi * 16) * CP;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float x2 = __uint_as_float(0x4B000000u | ((w >> (2 * j)) & 3u)) - 8388608.0f;
+#pragma unroll
+                    for (int c4 = 0; c4 < CP / 4; ++c4) {
+                        const float4 v = *reinterpret_cast<const float4*>(vrow + j * CP + c4 * 4);
+                        acc[c4 * 4 + 0] = fmaf(x2, v.x, acc[c4 * 4 + 0]);
+                        acc[c4 * 4 + 1] = fmaf(x2, v.y, acc[c4 * 4 + 1]);
+                        acc[c4 * 4 + 2] = fmaf(x2, v.z, acc[c4 * 4 + 2]);
+                        acc[c4 * 4 + 3] = fmaf(x2, v.w, acc[c4 * 4 + 3]);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    const int b = bbase + tid;
+    if (b < B) {
+        float* out = Zpart + ((int64_t)slab * B + b) * CP;
+#pragma unroll
+        for (int c = 0; c < CP; ++c) out[c] = acc[c];
+    }
+}
+
+// =================================================================================================================
+// fused decoder (one head): lane <-> genotype byte (4 SNPs), the CTA's warps split the batch rows
+// =================================================================================================================
+template <int KP>
+__global__ void __launch_bounds__(kStreamWarps * 32)
+dec_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* __restrict__ row_idx, int64_t row0, int B,
+           int64_t M, const float* __restrict__ Q, int q_ld, int q_off, int k, float* __restrict__ P,
+           float* __restrict__ Pm, float* __restrict__ Pv, AdamCoef adam, float* __restrict__ dP_out,
+           float* __restrict__ dQpart, float* __restrict__ loss_part, int ntiles) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    constexpr int W = kStreamWarps;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int64_t* rowoff = reinterpret_cast<int64_t*>(smem);                       // B
+    float* Qs = reinterpret_cast<float*>(smem + (size_t)((B * 8 + 15) / 16) * 16);  // B x KP
+    float* dQs = Qs + (size_t)B * KP;                                           // B x KP
+    float* red = dQs + (size_t)B * KP;                                          // W x 128*KP
+
+    for (int b = tid; b < B; b += blockDim.x) {
+        const int64_t r = (row_idx != nullptr) ? row_idx[b] : (row0 + b);
+        rowoff[b] = r * pitch;
+    }
+    for (int i = tid; i < B * KP; i += blockDim.x) {
+        const int b = i / KP, kk = i % KP;
+        Qs[i] = (kk < k) ? Q[(int64_t)b * q_ld + q_off + kk] : 0.f;
+        dQs[i] = 0.f;
+    }
+    __syncthreads();
+
+    float lossacc = 0.f;
+    constexpr int OWN = 32 / KP;  // lanes per reduced element after warp_reduce_vec<KP>
+
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t m_lane = (int64_t)t * kTileSnps + lane * 4;
+        const int64_t byte_off = (int64_t)t * (kTileSnps / 4) + lane;
+        const bool byte_ok = byte_off < pitch;
+        float p[4][KP], dp[4][KP];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int kk = 0; kk < KP; ++kk) {
+                const int64_t m = m_lane + i;
+                p[i][kk] = (m < M && kk < k) ? P[m * k + kk] : 0.f;
+                dp[i][kk] = 0.f;
+            }
+
+        uint32_t g_next = 0;
+        if (warp < B && byte_ok) g_next = packed[rowoff[warp] + byte_off];
+        for (int b = warp; b < B; b += W) {
+            const uint32_t g = g_next;
+            if (b + W < B && byte_ok) g_next = packed[rowoff[b + W] + byte_off];
+            float q[KP], dq[KP];
+#pragma unroll
+            for (int c4 = 0; c4 < KP / 4; ++c4) {
+                const float4 v = *reinterpret_cast<const float4*>(Qs + (size_t)b * KP + c4 * 4);
+                q[c4 * 4 + 0] = v.x; q[c4 * 4 + 1] = v.y; q[c4 * 4 + 2] = v.z; q[c4 * 4 + 3] = v.w;
+            }
+#pragma unroll
+            for (int kk = 0; kk < KP; ++kk) dq[kk] = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t c = (g >> (2 * i)) & 3u;
+                const float x = (c == 1u) ? 0.5f : ((c == 2u) ? 1.0f : 0.0f);
+                float raw = 0.f;
+#pragma unroll
+                for (int kk = 0; kk < KP; ++kk) raw = fmaf(q[kk], p[i][kk], raw);
+                const float R = fminf(fmaxf(raw, 0.f), 1.f);
+                const float omr = 1.f - R;
+                const float den = fmaxf(omr * R, 1e-12f);
+                const bool inside = (raw >= 0.f) && (raw <= 1.f);
+                const float G = inside ? ((R - x) / den) : 0.f;
+                // BCE with torch's -100 log clamp; X in {0,.5,1} -> one log per element
+                const float arg = (c == 2u) ? R : ((c == 1u) ? (R * omr) : omr);
+                const float wgt = (c == 1u) ? 0.5f : 1.0f;
+                lossacc -= wgt * fmaxf(logf(arg), -100.f);
+#pragma unroll
+                for (int kk = 0; kk < KP; ++kk) {
+                    dp[i][kk] = fmaf(G, q[kk], dp[i][kk]);
+                    dq[kk] = fmaf(G, p[i][kk], dq[kk]);
+                }
+            }
+            const float tot = warp_reduce_vec<KP>(dq, lane);
+            if ((lane % OWN) == 0) dQs[(size_t)b * KP + lane / OWN] += tot;
+        }
+
+        // cross-warp reduction of dP, then Adam + clamp on this tile's P rows
+        float* myred = red + (size_t)warp * (kTileSnps * KP) + (size_t)lane * (4 * KP);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int c4 = 0; c4 < KP / 4; ++c4)
+                *reinterpret_cast<float4*>(myred + i * KP + c4 * 4) =
+                    make_float4(dp[i][c4 * 4], dp[i][c4 * 4 + 1], dp[i][c4 * 4 + 2], dp[i][c4 * 4 + 3]);
+        __syncthreads();
+        for (int o = tid; o < kTileSnps * KP; o += blockDim.x) {
+            float g = 0.f;
+#pragma unroll
+            for (int w = 0; w < W; ++w) g += red[(size_t)w * (kTileSnps * KP) + o];
+            const int sl = o / KP, kk = o % KP;
+            const int64_t m = (int64_t)t * kTileSnps + sl;
+            if (m < M && kk < k) {
+                const int64_t pi = m * k + kk;
+                if (dP_out != nullptr) dP_out[pi] = g;
+                if (adam.enabled) {
+                    float mm = Pm[pi], vv = Pv[pi];
+                    float pn = adam_apply(P[pi], g, mm, vv, adam);
+                    pn = fminf(fmaxf(pn, 0.f), 1.f);  // restrict_P (neural_admixture.py:179-185)
+                    P[pi] = pn; Pm[pi] = mm; Pv[pi] = vv;
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // per-CTA partials out
+    float* outp = dQpart + (size_t)blockIdx.x * B * KP;
+    for (int i = tid; i < B * KP; i += blockDim.x) outp[i] = dQs[i];
+    double l = warp_sum_d((double)lossacc);
+    __shared__ double lsh[W];
+    if (lane == 0) lsh[warp] = l;
+    __syncthreads();
+    if (tid == 0) {
+        double s = 0.0;
+        for (int w = 0; w < W; ++w) s += lsh[w];
+        loss_part[blockIdx.x] = (float)s;
+    }
+}
+
+// =================================================================================================================
+// encoder backward: dV = X^T dZ (+ Adam on V); same tiling as the decoder
+// =================================================================================================================
+template <int CP>
+__global__ void __launch_bounds__(kStreamWarps * 32)
+enc_bwd_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* __restrict__ row_idx, int64_t row0,
+               int B, int64_t M, const float* __restrict__ dZ, int C, float* __restrict__ V, float* __restrict__ Vm,
+               float* __restrict__ Vv, AdamCoef adam, float* __restrict__ dV_out, int ntiles) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    constexpr int W = kStreamWarps;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int64_t* rowoff = reinterpret_cast<int64_t*>(smem);
+    float* dZs = reinterpret_cast<float*>(smem + (size_t)((B * 8 + 15) / 16) * 16);  // B x CP
+    float* red = dZs + (size_t)B * CP;                                             // W x 128*CP
+
+    for (int b = tid; b < B; b += blockDim.x) {
+        const int64_t r = (row_idx != nullptr) ? row_idx[b] : (row0 + b);
+        rowoff[b] = r * pitch;
+    }
+    for (int i = tid; i < B * CP; i += blockDim.x) {
+        const int b = i / CP, c = i % CP;
+        dZs[i] = (c < C) ? dZ[(int64_t)b * C + c] : 0.f;
+    }
+    __syncthreads();
+
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t byte_off = (int64_t)t * (kTileSnps / 4) + lane;
+        const bool byte_ok = byte_off < pitch;
+        float dv[4][CP];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int c = 0; c < CP; ++c) dv[i][c] = 0.f;
+
+        uint32_t g_next = 0;
+        if (warp < B && byte_ok) g_next = packed[rowoff[warp] + byte_off];
+        for (int b = warp; b < B; b += W) {
+            const uint32_t g = g_next;
+            if (b + W < B && byte_ok) g_next = packed[rowoff[b + W] + byte_off];
+            if (__ballot_sync(0xffffffffu, g != 0u) == 0u) continue;
+            float dz[CP];
+#pragma unroll
+            for (int c4 = 0; c4 < CP / 4; ++c4) {
+                const float4 v = *reinterpret_cast<const float4*>(dZs + (size_t)b * CP + c4 * 4);
+                dz[c4 * 4 + 0] = v.x; dz[c4 * 4 + 1] = v.y; dz[c4 * 4 + 2] = v.z; dz[c4 * 4 + 3] = v.w;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float x2 = code_to_2x((g >> (2 * i)) & 3u);
+#pragma unroll
+                for (int c = 0; c < CP; ++c) dv[i][c] = fmaf(x2, dz[c], dv[i][c]);
+            }
+        }
+        float* myred = red + (size_t)warp * (kTileSnps * CP) + (size_t)lane * (4 * CP);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int c4 = 0; c4 < CP / 4; ++c4)
+                *reinterpret_cast<float4*>(myred + i * CP + c4 * 4) =
+                    make_float4(dv[i][c4 * 4], dv[i][c4 * 4 + 1], dv[i][c4 * 4 + 2], dv[i][c4 * 4 + 3]);
+        __syncthreads();
+        for (int o = tid; o < kTileSnps * CP; o += blockDim.x) {
+            float g = 0.f;
+#pragma unroll
+            for (int w = 0; w < W; ++w) g += red[(size_t)w * (kTileSnps * CP) + o];
+            g *= 0.5f;  // x = code/2
+            const int sl = o / CP, c = o % CP;
+            const int64_t m = (int64_t)t * kTileSnps + sl;
+            if (m < M && c < C) {
+                const int64_t vi = m * C + c;
+                if (dV_out != nullptr) dV_out[vi] = g;
+                if (adam.enabled) {
+                    float mm = Vm[vi], vv = Vv[vi];
+                    V[vi] = adam_apply(V[vi], g, mm, vv, adam);
+                    Vm[vi] = mm; Vv[vi] = vv;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// =================================================================================================================
+// fp64 log-likelihood (utils.pyx:17-40): lane <-> genotype byte, warps split rows, Q rows read through L1
+// =================================================================================================================
+__global__ void __launch_bounds__(256)
+loglik_kernel(const uint8_t* __restrict__ packed, int64_t pitch, int64_t N, int64_t M, const float* __restrict__ Q,
+              const float* __restrict__ P, int k, double eps, double* __restrict__ part, int ntiles) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int W = 8;
+    double acc = 0.0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t byte_off = (int64_t)t * 32 + lane;
+        const int64_t m_lane = (int64_t)t * 128 + lane * 4;
+        if (byte_off >= pitch) continue;
+        double p[4][NADM_MAX_K];
+        for (int i = 0; i < 4; ++i)
+            for (int kk = 0; kk < k; ++kk) p[i][kk] = (m_lane + i < M) ? (double)P[(m_lane + i) * k + kk] : 0.0;
+        for (int64_t n = warp; n < N; n += W) {
+            const uint32_t g = packed[n * pitch + byte_off];
+            const float* q = Q + n * k;
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t c = (g >> (2 * i)) & 3u;
+                if (c == 3u || m_lane + i >= M) continue;
+                double rec = 0.0;
+                for (int kk = 0; kk < k; ++kk) rec += (double)q[kk] * p[i][kk];
+                rec = fmax(eps, fmin(rec, 1.0 - eps));
+                double gd = fmax(eps, fmin((double)c, 2.0 - eps));
+                acc += gd * log(rec) + (2.0 - gd) * log1p(-rec);
+            }
+        }
+    }
+    acc = warp_sum_d(acc);
+    __shared__ double sh[W];
+    if (lane == 0) sh[warp] = acc;
+    __syncthreads();
+    if (tid == 0) {
+        double s = 0.0;
+        for (int w = 0; w < W; ++w) s += sh[w];
+        part[blockIdx.x] = s;
+    }
+}
+
+__global__ void sum_double_kernel(const double* __restrict__ part, int n, double* __restrict__ out) {
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += 32) acc += part[i];
+    acc = warp_sum_d(acc);
+    if (threadIdx.x == 0) *out = acc;
+}
+
+}  // namespace nadm
+
+// =================================================================================================================
+// C ABI
+// =================================================================================================================
+using namespace nadm;
+
+static int check_packed(const uint8_t* packed, int64_t pitch, int64_t M) {
+    NADM_REQUIRE(packed != nullptr, "packed is NULL");
+    NADM_REQUIRE(pitch >= (M + 3) / 4, "pitch %lld < ceil(M/4) = %lld", (long long)pitch, (long long)((M + 3) / 4));
+    NADM_REQUIRE(pitch % 16 == 0, "pitch %lld must be a multiple of 16 bytes", (long long)pitch);
+    NADM_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 15) == 0, "packed base must be 16-byte aligned");
+    return NADM_OK;
+}
+
+extern "C" int nadm_pack2bit(const uint8_t* src, int64_t rows, int64_t M, int64_t src_pitch, uint8_t* dst,
+                             int64_t dst_pitch, void* stream) {
+    NADM_REQUIRE(src && dst, "NULL pointer");
+    NADM_REQUIRE(rows >= 0 && M >= 0, "negative shape");
+    NADM_REQUIRE(src_pitch >= M && dst_pitch >= (M + 3) / 4, "pitch too small");
+    if (rows == 0 || dst_pitch == 0) return NADM_OK;
+    const int64_t words = (dst_pitch + 3) / 4;
+    dim3 grid((unsigned)std::min<int64_t>((words + 255) / 256, 4096), (unsigned)std::min<int64_t>(rows, 32768));
+    pack2bit_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, rows, M, src_pitch, dst, dst_pitch);
+    NADM_CHECK_LAUNCH("pack2bit_kernel");
+    return NADM_OK;
+}
+
+extern "C" int nadm_unpack2bit(const uint8_t* src, int64_t rows, int64_t M, int64_t src_pitch, uint8_t* dst,
+                               int64_t dst_pitch, void* stream) {
+    NADM_REQUIRE(src && dst, "NULL pointer");
+    NADM_REQUIRE(rows >= 0 && M >= 0, "negative shape");
+    NADM_REQUIRE(src_pitch >= (M + 3) / 4 && dst_pitch >= M, "pitch too small");
+    if (rows == 0 || M == 0) return NADM_OK;
+    const int64_t pc = (M + 3) / 4;
+    dim3 grid((unsigned)std::min<int64_t>((pc + 255) / 256, 4096), (unsigned)std::min<int64_t>(rows, 32768));
+    unpack2bit_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, rows, M, src_pitch, dst, dst_pitch);
+    NADM_CHECK_LAUNCH("unpack2bit_kernel");
+    return NADM_OK;
+}
+
+static inline int pad_c(int C) { return C <= 8 ? 8 : 16; }
+static inline int pad_k(int k) { return k <= 4 ? 4 : (k <= 8 ? 8 : 16); }
+
+extern "C" size_t nadm_workspace_bytes(int32_t B, int64_t M, int32_t C, int32_t H, int32_t sumK) {
+    (void)M;
+    size_t enc = (size_t)kMaxParts * (size_t)B * 16 * sizeof(float);
+    size_t dec = (size_t)kMaxParts * ((size_t)B * 16 + 1) * sizeof(float);
+    size_t mlp = ((size_t)B * ((size_t)sumK + (size_t)H + (size_t)C + 2) + 64) * sizeof(float) + 4096;
+    size_t ll = (size_t)kMaxParts * sizeof(double) * 2;
+    size_t m = enc > dec ? enc : dec;
+    m = m > mlp ? m : mlp;
+    m = m > ll ? m : ll;
+    return m + 256;
+}
+
+template <int CP>
+static int launch_enc_fwd(const uint8_t* packed, int64_t pitch, const int64_t* row_idx, int64_t row0, int B, int64_t M,
+                          const float* V, int C, float* Z, float* ws, size_t ws_bytes, cudaStream_t st) {
+    const int ngroups = (B + 255) / 256;
+    int RB = (B + ngroups - 1) / ngroups;
+    RB = ((RB + 31) / 32) * 32;
+    const int ntiles = (int)((M + kEncTileSnps - 1) / kEncTileSnps);
+    int nslab = std::max(1, (2 * sm_count()) / ngroups);
+    nslab = std::min(std::min(nslab, ntiles), kMaxParts);
+    NADM_REQUIRE((size_t)nslab * B * CP * sizeof(float) <= ws_bytes, "workspace too small for encoder_fwd");
+    const size_t smem = ((RB * 8 + 15) / 16) * 16 + 2 * ((size_t)RB * kEncRowStride + kEncTileSnps * CP * 4);
+    static bool attr_done[2] = {false, false};
+    if (!attr_done[CP == 16]) {
+        cudaError_t e = cudaFuncSetAttribute(enc_fwd_kernel<CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(enc_fwd)");
+        attr_done[CP == 16] = true;
+    }
+    enc_fwd_kernel<CP><<<dim3(nslab, ngroups), RB, smem, st>>>(packed, pitch, row_idx, row0, B, M, V, C, ws, ntiles, nslab);
+    NADM_CHECK_LAUNCH("enc_fwd_kernel");
+    const int64_t n = (int64_t)B * CP;
+    reduce_parts_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ws, nslab, B, CP, C, Z, C, 0, 0.5f, nullptr, nullptr);
+    NADM_CHECK_LAUNCH("reduce_parts_kernel");
+    return NADM_OK;
+}
+
+extern "C" int nadm_encoder_fwd(const uint8_t* packed, int64_t pitch, const int64_t* row_idx, int64_t row0, int32_t B,
+                                int64_t M, const float* V, int32_t C, float* Z, void* ws, size_t ws_bytes,
+                                void* stream) {
+    if (int rc = check_packed(packed, pitch, M)) return rc;
+    NADM_REQUIRE(B > 0 && M > 0, "empty batch or no SNPs (B=%d, M=%lld)", B, (long long)M);
+    NADM_REQUIRE(C >= 1 && C <= NADM_MAX_C, "n_components C=%d unsupported (1..%d)", C, NADM_MAX_C);
+    NADM_REQUIRE(V && Z && ws, "NULL pointer");
+    if (pad_c(C) == 8)
+        return launch_enc_fwd<8>(packed, pitch, row_idx, row0, B, M, V, C, Z, (float*)ws, ws_bytes, (cudaStream_t)stream);
+    return launch_enc_fwd<16>(packed, pitch, row_idx, row0, B, M, V, C, Z, (float*)ws, ws_bytes, (cudaStream_t)stream);
+}
+
+template <int KP>
+static int launch_dec(const uint8_t* packed, int64_t pitch, const int64_t* row_idx, int64_t row0, int B, int64_t M,
+                      const float* Q, float* dQ, int q_ld, int q_off, int k, float* P, float* Pm, float* Pv,
+                      const nadm_adam_t* adam, float* dP_out, float* loss, float* ws, size_t ws_bytes,
+                      cudaStream_t st) {
+    const int ntiles = (int)((M + kTileSnps - 1) / kTileSnps);
+    const size_t smem = ((size_t)(B * 8 + 15) / 16) * 16 + (size_t)2 * B * KP * 4 + (size_t)kStreamWarps * kTileSnps * KP * 4;
+    NADM_REQUIRE(smem <= 227 * 1024, "batch B=%d too large for the fused decoder (needs %zu bytes of shared memory)", B, smem);
+    const int per_sm = std::max(1, (int)((227 * 1024) / (smem + 1024)));
+    int ncta = std::min(std::min(ntiles, sm_count() * std::min(per_sm, 3)), kMaxParts);
+    NADM_REQUIRE((size_t)ncta * ((size_t)B * KP + 1) * sizeof(float) <= ws_bytes, "workspace too small for decoder_step");
+    static bool attr_done[3] = {false, false, false};
+    const int ai = KP == 4 ? 0 : (KP == 8 ? 1 : 2);
+    if (!attr_done[ai]) {
+        cudaError_t e = cudaFuncSetAttribute(dec_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(dec)");
+        attr_done[ai] = true;
+    }
+    float* dQpart = ws;
+    float* loss_part = ws + (size_t)ncta * B * KP;
+    dec_kernel<KP><<<ncta, kStreamWarps * 32, smem, st>>>(packed, pitch, row_idx, row0, B, M, Q, q_ld, q_off, k, P, Pm, Pv,
+                                                         make_adam(adam), dP_out, dQpart, loss_part, ntiles);
+    NADM_CHECK_LAUNCH("dec_kernel");
+    const int64_t n = (int64_t)B * KP;
+    reduce_parts_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dQpart, ncta, B, KP, k, dQ, q_ld, q_off, 1.0f, loss_part, loss);
+    NADM_CHECK_LAUNCH("reduce_parts_kernel");
+    return NADM_OK;
+}
+
+extern "C" int nadm_decoder_step(const uint8_t* packed, int64_t pitch, const int64_t* row_idx, int64_t row0, int32_t B,
+                                 int64_t M, const float* Q, float* dQ, int32_t q_ld, int32_t q_off, int32_t k, float* P,
+                                 float* Pm, float* Pv, const nadm_adam_t* adam, float* dP_out, float* loss, void* ws,
+                                 size_t ws_bytes, void* stream) {
+    if (int rc = check_packed(packed, pitch, M)) return rc;
+    NADM_REQUIRE(B > 0 && M > 0, "empty batch or no SNPs (B=%d, M=%lld)", B, (long long)M);
+    NADM_REQUIRE(k >= 1 && k <= NADM_MAX_K, "k=%d unsupported (1..%d)", k, NADM_MAX_K);
+    NADM_REQUIRE(q_off >= 0 && q_off + k <= q_ld, "head columns [%d,%d) outside q_ld=%d", q_off, q_off + k, q_ld);
+    NADM_REQUIRE(Q && dQ && P && loss && ws, "NULL pointer");
+    NADM_REQUIRE(adam == nullptr || (Pm && Pv), "Adam moments are NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    float* w = (float*)ws;
+    switch (pad_k(k)) {
+        case 4: return launch_dec<4>(packed, pitch, row_idx, row0, B, M, Q, dQ, q_ld, q_off, k, P, Pm, Pv, adam, dP_out, loss, w, ws_bytes, st);
+        case 8: return launch_dec<8>(packed, pitch, row_idx, row0, B, M, Q, dQ, q_ld, q_off, k, P, Pm, Pv, adam, dP_out, loss, w, ws_bytes, st);
+        default: return launch_dec<16>(packed, pitch, row_idx, row0, B, M, Q, dQ, q_ld, q_off, k, P, Pm, Pv, adam, dP_out, loss, w, ws_bytes, st);
+    }
+}
+
+template <int CP>
+static int launch_enc_bwd(const uint8_t* packed, int64_t pitch, const int64_t* row_idx, int64_t row0, int B, int64_t M,
+                          const float* dZ, int C, float* V, float* Vm, float* Vv, const nadm_adam_t* adam, float* dV_out,
+                          cudaStream_t st) {
+    const int ntiles = (int)((M + kTileSnps - 1) / kTileSnps);
+    const size_t smem = ((size_t)(B * 8 + 15) / 16) * 16 + (size_t)B * CP * 4 + (size_t)kStreamWarps * kTileSnps * CP * 4;
+    NADM_REQUIRE(smem <= 227 * 1024, "batch B=%d too large for encoder_bwd (needs %zu bytes of shared memory)", B, smem);
+    const int per_sm = std::max(1, (int)((227 * 1024) / (smem + 1024)));
+    const int ncta = std::min(ntiles, sm_count() * std::min(per_sm, 3));
+    static bool attr_done[2] = {false, false};
+    if (!attr_done[CP == 16]) {
+        cudaError_t e = cudaFuncSetAttribute(enc_bwd_kernel<CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(enc_bwd)");
+        attr_done[CP == 16] = true;
+    }
+    enc_bwd_kernel<CP><<<ncta, kStreamWarps * 32, smem, st>>>(packed, pitch, row_idx, row0, B, M, dZ, C, V, Vm, Vv,
+                                                             make_adam(adam), dV_out, ntiles);
+    NADM_CHECK_LAUNCH("enc_bwd_kernel");
+    return NADM_OK;
+}
+
+extern "C" int nadm_encoder_bwd(const uint8_t* packed, int64_t pitch, const int64_t* row_idx, int64_t row0, int32_t B,
+                                int64_t M, const float* dZ, int32_t C, float* V, float* Vm, float* Vv,
+                                const nadm_adam_t* adam, float* dV_out, void* ws, size_t ws_bytes, void* stream) {
+    (void)ws; (void)ws_bytes;
+    if (int rc = check_packed(packed, pitch, M)) return rc;
+    NADM_REQUIRE(B > 0 && M > 0, "empty batch or no SNPs (B=%d, M=%lld)", B, (long long)M);
+    NADM_REQUIRE(C >= 1 && C <= NADM_MAX_C, "n_components C=%d unsupported (1..%d)", C, NADM_MAX_C);
+    NADM_REQUIRE(dZ && V, "NULL pointer");
+    NADM_REQUIRE(adam == nullptr || (Vm && Vv), "Adam moments are NULL");
+    NADM_REQUIRE(adam != nullptr || dV_out != nullptr, "nothing to do: neither Adam nor dV_out requested");
+    if (pad_c(C) == 8)
+        return launch_enc_bwd<8>(packed, pitch, row_idx, row0, B, M, dZ, C, V, Vm, Vv, adam, dV_out, (cudaStream_t)stream);
+    return launch_enc_bwd<16>(packed, pitch, row_idx, row0, B, M, dZ, C, V, Vm, Vv, adam, dV_out, (cudaStream_t)stream);
+}
+
+extern "C" int nadm_loglikelihood(const uint8_t* packed, int64_t pitch, int64_t N, int64_t M, const float* Q,
+                                  const float* P, int32_t k, double eps, double* out, void* ws, size_t ws_bytes,
+                                  void* stream) {
+    NADM_REQUIRE(packed && Q && P && out && ws, "NULL pointer");
+    NADM_REQUIRE(pitch >= (M + 3) / 4, "pitch too small");
+    NADM_REQUIRE(k >= 1 && k <= NADM_MAX_K, "k=%d unsupported (1..%d)", k, NADM_MAX_K);
+    NADM_REQUIRE(N > 0 && M > 0, "empty matrix");
+    const int ntiles = (int)((M + 127) / 128);
+    const int ncta = std::min(std::min(ntiles, 4 * sm_count()), kMaxParts);
+    NADM_REQUIRE((size_t)ncta * sizeof(double) <= ws_bytes, "workspace too small for loglikelihood");
+    double* part = (double*)ws;
+    loglik_kernel<<<ncta, 256, 0, (cudaStream_t)stream>>>(packed, pitch, N, M, Q, P, k, eps, part, ntiles);
+    NADM_CHECK_LAUNCH("loglik_kernel");
+    sum_double_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(part, ncta, out);
+    NADM_CHECK_LAUNCH("sum_double_kernel");
+    return NADM_OK;
+}

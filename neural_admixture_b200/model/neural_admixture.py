@@ -1,0 +1,419 @@
+"""B200 mirror of the reference's ``neural_admixture/model/neural_admixture.py`` for the per-minibatch hot path.
+
+Same public names and argument meaning as the reference (``Q_P``, ``NeuralAdmixture`` with ``launch_training`` /
+``process_results`` / ``display_divergences``; reference file cited per method), but none of its arithmetic runs in
+PyTorch: every step is a fixed sequence of calls into ``libnadm_b200.so`` (``include/nadm_b200.h``) operating directly
+on the 2-bit packed genotype matrix.  torch provides device memory, streams and ``torch.distributed`` only.
+
+Differences a caller can see (all deliberate):
+  * CUDA only.  There is no CPU / MPS path and no PyTorch fallback: a missing library or a non-CUDA device raises.
+  * ``torch.set_float32_matmul_precision('medium')`` (reference :349) is not applied: all contractions are fp32.
+  * multi-GPU is SNP-axis sharding with the single-process sampler and batch size (reference :287,:315-319 uses
+    sample-axis DDP, which changes the gradient scale and the sampler); every rank passes its own column slice.
+  * ``Q_P.forward`` in training mode is not materialised (the B x M reconstruction never exists); the training step
+    is ``NeuralAdmixture``'s fused path.  In inference mode ``forward`` takes the reference's uint8 B x M input.
+"""
+from __future__ import annotations
+
+import json
+import logging
+import sys
+from pathlib import Path
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from .. import ops
+from .._lib import MlpParams, NadmError
+
+logging.basicConfig(stream=sys.stdout, level=logging.INFO, format="%(message)s")
+log = logging.getLogger(__name__)
+
+
+class NeuralEncoder(torch.nn.Module):
+    """Holder of the per-K heads ``Linear(H, k)`` (reference :15-49); state_dict keys ``heads.{i}.weight|bias``."""
+
+    def __init__(self, input_size: int, ks: List[int]):
+        super().__init__()
+        self.ks = sorted(ks)
+        self.min_k_val = min(self.ks)
+        self.heads = torch.nn.ModuleList(torch.nn.Linear(input_size, k, bias=True) for k in self.ks)
+
+
+class _DecoderWeight(torch.nn.Module):
+    def __init__(self, w: torch.Tensor):
+        super().__init__()
+        self.weight = torch.nn.Parameter(w, requires_grad=False)
+
+
+class NeuralDecoder(torch.nn.Module):
+    """Holder of the per-K allele-frequency matrices: ``decoders[i].weight`` is P_k, M x k (reference :51-98 keeps it
+    as the weight of ``Linear(k, M, bias=False)``).  ``inits`` is the (sum K) x M initial P, sliced per head as in
+    reference :69-76; here each slice is stored contiguous M x k, the layout the kernels stream."""
+
+    def __init__(self, inits: torch.Tensor, ks: List[int]):
+        super().__init__()
+        self.ks = sorted(ks)
+        self.min_k_val = min(self.ks)
+        mods, ini = [], 0
+        for k in self.ks:
+            mods.append(_DecoderWeight(inits[ini:ini + k].T.contiguous().clone()))
+            ini += k
+        self.decoders = torch.nn.ModuleList(mods)
+
+
+class FusedAdamState:
+    """What ``create_custom_adam`` returns: Adam(betas=(0.9, 0.95), eps=1e-8) state for every parameter of a
+    ``Q_P`` (reference :187-204).  The update itself is fused into the kernels that produce each gradient."""
+
+    def __init__(self, model: "Q_P", lr: float, betas=(0.9, 0.95), eps: float = 1e-8):
+        self.lr, self.betas, self.eps, self.step_count = float(lr), (float(betas[0]), float(betas[1])), float(eps), 0
+        model.bind()
+        z = torch.zeros_like
+        self.m = {"V": z(model.V), "w_rms": z(model.batch_norm.weight), "W1": z(model.common_encoder[0].weight),
+                  "b1": z(model.common_encoder[0].bias), "W2": z(model.W2cat), "b2": z(model.b2cat),
+                  "P": [z(d.weight) for d in model.decoders.decoders]}
+        self.v = {k: ([z(t) for t in val] if isinstance(val, list) else z(val)) for k, val in self.m.items()}
+
+    def hyper(self):
+        return ops.adam_hyper(self.lr, self.step_count, self.betas[0], self.betas[1], self.eps)
+
+
+class Q_P(torch.nn.Module):
+    """Same constructor, attributes and state_dict keys as the reference ``Q_P`` (:100-230):
+    ``V`` (M x C), ``batch_norm.weight`` (C), ``common_encoder.0.{weight,bias}``,
+    ``multihead_encoder.heads.{i}.{weight,bias}``, ``decoders.decoders.{i}.weight`` (M x k)."""
+
+    def __init__(self, hidden_size: int, num_features: int, V: Optional[torch.Tensor] = None,
+                 P: Optional[torch.Tensor] = None, ks_list: List[int] = [], is_train: bool = True) -> None:
+        super().__init__()
+        self.ks_list = list(ks_list)
+        self.V = torch.nn.Parameter(V.contiguous(), requires_grad=False) if V is not None else None
+        self.num_features = num_features
+        self.hidden_size = hidden_size
+        # construction order = the reference's (:135-143), so the same torch seed gives the same initial weights
+        self.batch_norm = torch.nn.RMSNorm(self.num_features, eps=1e-8)
+        self.encoder_activation = torch.nn.ReLU(inplace=True)
+        self.common_encoder = torch.nn.Sequential(
+            torch.nn.Linear(self.num_features, self.hidden_size, bias=True), self.encoder_activation)
+        self.multihead_encoder = NeuralEncoder(self.hidden_size, ks=self.ks_list)
+        if P is not None:
+            self.decoders = NeuralDecoder(P, ks=self.ks_list)
+        for p in self.parameters():
+            p.requires_grad_(False)
+        self.is_train = is_train
+        self.return_func = self._return_training if is_train else self._return_infer
+        self.W2cat = None
+        self.b2cat = None
+        self._bufs: Dict[int, dict] = {}
+
+    # ---- binding: flat device buffers the kernels read; the per-head nn.Parameters become views of them ----------
+    def bind(self) -> None:
+        dev = self.batch_norm.weight.device
+        if dev.type != "cuda":
+            raise NadmError("Q_P runs on CUDA only (no CPU/MPS path): move the module to a cuda device first")
+        heads = self.multihead_encoder.heads
+        if self.W2cat is not None and self.W2cat.device == dev and heads[0].weight.data_ptr() == self.W2cat.data_ptr():
+            return
+        ks = self.multihead_encoder.ks
+        self.W2cat = torch.cat([h.weight.data for h in heads], dim=0).contiguous()
+        self.b2cat = torch.cat([h.bias.data for h in heads], dim=0).contiguous()
+        off = 0
+        for h, k in zip(heads, ks):
+            h.weight.data = self.W2cat[off:off + k]
+            h.bias.data = self.b2cat[off:off + k]
+            off += k
+        for t in (self.batch_norm.weight, self.common_encoder[0].weight, self.common_encoder[0].bias):
+            t.data = t.data.contiguous()
+        if self.V is not None:
+            self.V.data = self.V.data.contiguous()
+        self._bufs = {}
+
+    def _fwd_buffers(self, B: int) -> dict:
+        buf = self._bufs.get(B)
+        if buf is None:
+            dev, H, C = self.W2cat.device, self.hidden_size, self.num_features
+            sumK = self.W2cat.shape[0]
+            f = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+            M = self.V.shape[0]
+            buf = {"Z": f(B, C), "rinv": f(B), "Hh": f(B, H), "Q": f(B, sumK),
+                   "ws": torch.empty(ops.workspace_bytes(B, M, C, H, sumK), dtype=torch.uint8, device=dev)}
+            self._bufs[B] = buf
+        return buf
+
+    def encode_packed(self, pg: ops.PackedGenotypes, *, row_idx: Optional[torch.Tensor] = None, row0: int = 0,
+                      B: Optional[int] = None, allreduce=None) -> Tuple[List[torch.Tensor], dict]:
+        """Forward of the encoder on rows of a packed matrix: Z = X V -> RMSNorm -> MLP -> per-head softmax
+        (reference :169-176).  ``allreduce`` (callable on a tensor) sums the partial projection over SNP shards."""
+        self.bind()
+        B = row_idx.numel() if row_idx is not None else B
+        buf = self._fwd_buffers(B)
+        ops.encoder_fwd(pg, self.V.data, buf["Z"], buf["ws"], row_idx=row_idx, row0=row0, B=B)
+        if allreduce is not None:
+            allreduce(buf["Z"])
+        ks = self.multihead_encoder.ks
+        ops.mlp_fwd(buf["Z"], self.batch_norm.weight.data, self.common_encoder[0].weight.data,
+                    self.common_encoder[0].bias.data, self.W2cat, self.b2cat, ks, buf["rinv"], buf["Hh"], buf["Q"])
+        probs, off = [], 0
+        for k in ks:
+            probs.append(buf["Q"][:, off:off + k])
+            off += k
+        return probs, buf
+
+    def _return_training(self, probs):
+        raise NadmError("Q_P.forward in training mode is not materialised by the B200 engine (the B x M reconstruction "
+                        "never exists in memory); train through NeuralAdmixture.launch_training")
+
+    def _return_infer(self, probs):
+        return probs
+
+    def forward(self, X: torch.Tensor):
+        """Inference-mode forward with the reference's signature (:157-177): ``X`` is a uint8 B x M tensor of
+        genotype codes on the device; returns ``(probs_list, X)``."""
+        if self.return_func != self._return_infer:
+            return self._return_training(None), X
+        if X.dtype != torch.uint8 or X.dim() != 2 or not X.is_cuda:
+            raise NadmError("Q_P.forward expects a uint8 B x M CUDA tensor of genotype codes")
+        B, M = X.shape
+        pg = ops.PackedGenotypes.empty(B, M, X.device)
+        ops.pack2bit(X.contiguous(), pg.storage, M)
+        probs, _ = self.encode_packed(pg, row0=0, B=B)
+        return self.return_func([p.clone() for p in probs]), X
+
+    @torch.no_grad()
+    def restrict_P(self):
+        """P in [0,1] (reference :179-185).  The fused decoder step already clamps; kept for API parity."""
+        for dec in self.decoders.decoders:
+            dec.weight.data.clamp_(0., 1.)
+
+    def create_custom_adam(self, device: torch.device, lr: float = 1e-5) -> FusedAdamState:
+        """Reference :187-204: one Adam, betas (0.9, 0.95), same lr for every group."""
+        return FusedAdamState(self, lr)
+
+    def save_config(self, name: str, save_dir: str) -> None:
+        """``{name}_config.json`` with the reference's keys (:206-230)."""
+        cfg = {"ks": self.ks_list, "num_features": self.num_features, "hidden_size": self.hidden_size,
+               "activation": "relu"}
+        with open(Path(save_dir) / f"{name}_config.json", "w") as fb:
+            json.dump(cfg, fb)
+        log.info("    Configuration file saved.")
+
+
+class NeuralAdmixture:
+    """Reference ``NeuralAdmixture`` (:232-553) on the fused B200 path.  Constructor arguments are the reference's
+    (:248-249)."""
+
+    def __init__(self, k: int, epochs: int, batch_size: int, learning_rate: float, device: torch.device, seed: int,
+                 num_gpus: int, master: bool, pack2bit, min_k: int, max_k: int,
+                 supervised_loss_weight: Optional[float] = 100):
+        self.k, self.min_k, self.max_k = k, min_k, max_k
+        self.ks_list = [k] if k is not None else list(range(min_k, max_k + 1))
+        self.num_gpus = num_gpus
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise NadmError("the B200 engine runs on CUDA devices only (no CPU path)")
+        self.master = master
+        self.seed = seed
+        self.generator = torch.Generator().manual_seed(self.seed)   # reference :283
+        self.epochs = epochs
+        # SNP-axis sharding keeps the global batch on every rank (the reference's sample-axis DDP divides it, :287)
+        self.batch_size = batch_size
+        self.lr = learning_rate
+        self.supervised_loss_weight = supervised_loss_weight
+        self.pack2bit = pack2bit
+        self.sharded = bool(num_gpus > 1 and torch.distributed.is_available() and torch.distributed.is_initialized())
+        self.loss_history: List[float] = []
+
+    # ---- model ---------------------------------------------------------------------------------------------------
+    def initialize_model(self, P: torch.Tensor, hidden_size: int, num_features: int, V: torch.Tensor,
+                         ks_list: List[int]) -> None:
+        """Reference :298-322 (no DDP wrapper: the only exchange is two small all-reduces per step)."""
+        self.base_model = Q_P(hidden_size, num_features, V, P, ks_list).to(self.device)
+        self.base_model.bind()
+        if self.sharded:
+            # identical replicated parameters on every rank (DDP's constructor broadcast, reference :317)
+            for t in (self.base_model.batch_norm.weight, self.base_model.common_encoder[0].weight,
+                      self.base_model.common_encoder[0].bias, self.base_model.W2cat, self.base_model.b2cat):
+                torch.distributed.broadcast(t.data, src=0)
+        self.model = self.base_model
+        self.raw_model = self.base_model
+
+    def _allreduce(self, t: torch.Tensor) -> None:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM)
+
+    def _step_buffers(self, B: int) -> dict:
+        buf = self._train_bufs.get(B)
+        if buf is None:
+            sumK = sum(self.ks_list)
+            dev = self.device
+            dq_loss = torch.zeros(B * sumK + 1, dtype=torch.float32, device=dev)
+            buf = {"dq_loss": dq_loss, "dQ": dq_loss[:B * sumK].view(B, sumK), "loss": dq_loss[B * sumK:],
+                   "dZ": torch.empty((B, self.raw_model.num_features), dtype=torch.float32, device=dev)}
+            self._train_bufs[B] = buf
+        return buf
+
+    def _mlp_params(self) -> MlpParams:
+        m, o = self.raw_model, self.optimizer
+        p = MlpParams()
+        tensors = {"w_rms": m.batch_norm.weight.data, "W1": m.common_encoder[0].weight.data,
+                   "b1": m.common_encoder[0].bias.data, "W2": m.W2cat, "b2": m.b2cat}
+        for n, t in tensors.items():
+            setattr(p, n, t.data_ptr())
+            setattr(p, "m_" + n, o.m[n].data_ptr())
+            setattr(p, "v_" + n, o.v[n].data_ptr())
+            setattr(p, "g_" + n, None)
+        return p
+
+    def _train_step(self, row_idx: torch.Tensor, labels: Optional[torch.Tensor], loss_out: torch.Tensor) -> None:
+        """One minibatch: the body of the reference's ``_run_epoch`` loop (:403-414) — forward, loss, backward,
+        Adam on every parameter, P clamp — as 5 library calls.  ``loss_out`` (1 float on device) receives the step's
+        loss; nothing is synchronised with the host."""
+        m, o, pg = self.raw_model, self.optimizer, self.packed
+        B = row_idx.numel()
+        probs, fb = m.encode_packed(pg, row_idx=row_idx, allreduce=self._allreduce if self.sharded else None)
+        sb = self._step_buffers(B)
+        sb["loss"].zero_()
+        o.step_count += 1
+        hyper = o.hyper()
+        off = 0
+        for i, k in enumerate(m.multihead_encoder.ks):
+            ops.decoder_step(pg, fb["Q"], sb["dQ"], off, k, m.decoders.decoders[i].weight.data, o.m["P"][i], o.v["P"][i],
+                             hyper, sb["loss"], fb["ws"], row_idx=row_idx)
+            off += k
+        if self.sharded:
+            self._allreduce(sb["dq_loss"])
+        ops.mlp_bwd(sb["dQ"], fb["Q"], fb["Hh"], fb["Z"], fb["rinv"], m.multihead_encoder.ks, self._mlp_params(), hyper,
+                    sb["dZ"], sb["loss"], fb["ws"], labels=labels,
+                    sup_weight=float(self.supervised_loss_weight) if labels is not None else 0.0)
+        ops.encoder_bwd(pg, sb["dZ"], m.V.data, o.m["V"], o.v["V"], hyper, fb["ws"], row_idx=row_idx)
+        loss_out.copy_(sb["loss"])
+
+    def epoch_order(self, N: int) -> torch.Tensor:
+        """Row order of one epoch: exactly what the reference's ``RandomSampler(dataset, generator=self.generator)``
+        yields (src/loaders.py:29-30, generator from :283)."""
+        sampler = torch.utils.data.RandomSampler(range(N), generator=self.generator)
+        return torch.tensor(list(sampler), dtype=torch.int64)
+
+    def _run_epoch(self, epoch: int, order_dev: torch.Tensor, pops: Optional[torch.Tensor]) -> None:
+        """Reference :394-417 / :434-458.  The per-step ``loss.item()`` host sync of the reference is replaced by one
+        device->host read per epoch of the per-step losses, summed in the same order."""
+        N = order_dev.numel()
+        nsteps = (N + self.batch_size - 1) // self.batch_size
+        losses = torch.zeros(nsteps, dtype=torch.float32, device=self.device)
+        for s in range(nsteps):
+            idx = order_dev[s * self.batch_size:(s + 1) * self.batch_size]
+            labels = pops[idx].contiguous() if pops is not None else None
+            self._train_step(idx, labels, losses[s:s + 1])
+        every = 2 if pops is not None else 5
+        loss_acc = float(losses.double().sum().item()) if (epoch % every == 0 or self.keep_loss_history) else None
+        if loss_acc is not None:
+            self.loss_history.append(loss_acc)
+        if epoch % every == 0 and self.master:
+            log.info(f"            Loss in epoch {epoch:3d} on device {self.device} is {loss_acc:,.0f}")
+
+    keep_loss_history = False
+
+    def launch_training(self, P: torch.Tensor, data, hidden_size: int, num_features: int, V: torch.Tensor, M: int,
+                        N: int, pops: Optional[torch.Tensor] = None):
+        """Reference :324-392.  ``data`` is the device-resident 2-bit packed matrix: either a
+        ``ops.PackedGenotypes`` or an N x ceil(M/4) uint8 CUDA tensor in the reference's layout (model/train.py:121).
+        ``P`` is (sum K) x M, ``V`` is M x C.  In sharded mode M / P / V / data are this rank's SNP slice.
+        Returns ``(Qs, Ps, raw_model)`` like the reference (numpy lists on the master rank)."""
+        self.M, self.N = M, N
+        if isinstance(data, ops.PackedGenotypes):
+            self.packed = data
+        else:
+            if not (torch.is_tensor(data) and data.is_cuda and data.dtype == torch.uint8):
+                raise NadmError("launch_training needs the 2-bit packed genotype matrix on the CUDA device")
+            self.packed = ops.PackedGenotypes.from_reference_layout(data, M)
+        if self.packed.N != N or self.packed.M != M:
+            raise NadmError(f"packed matrix is {self.packed.N} x {self.packed.M}, expected {N} x {M}")
+        self._train_bufs: Dict[int, dict] = {}
+        self.initialize_model(P.to(self.device, torch.float32), hidden_size, num_features,
+                              V.to(self.device, torch.float32), self.ks_list)
+        if pops is not None:
+            pops = pops.to(self.device, torch.int64)
+
+        if self.master:
+            log.info("")
+            log.info("    Starting training...")
+            log.info("")
+        self.optimizer = self.raw_model.create_custom_adam(device=self.device, lr=self.lr)
+        for epoch in range(self.epochs):
+            order = self.epoch_order(N).to(self.device, non_blocking=True)
+            self._run_epoch(epoch, order, pops)
+
+        # inference of Q for every sample, sequential batches of min(N, 1024) (reference :368-383)
+        Qs = self.infer_Q(min(N, 1024))
+        if self.master:
+            log.info("")
+            log.info("    Training finished!")
+            log.info("")
+        self.display_divergences(self.k)
+        return self.process_results(Qs)
+
+    def infer_Q(self, batch: int) -> List[torch.Tensor]:
+        ks = self.raw_model.multihead_encoder.ks
+        outs = [torch.empty((self.N, k), dtype=torch.float32, device=self.device) for k in ks]
+        for r0 in range(0, self.N, batch):
+            B = min(batch, self.N - r0)
+            probs, _ = self.raw_model.encode_packed(self.packed, row0=r0, B=B,
+                                                    allreduce=self._allreduce if self.sharded else None)
+            for o, p in zip(outs, probs):
+                o[r0:r0 + B].copy_(p)
+        return outs
+
+    def gather_P(self) -> List[torch.Tensor]:
+        """Full M x k P per head on every rank (concatenating the SNP shards in rank order)."""
+        Ps = [d.weight.data for d in self.raw_model.decoders.decoders]
+        if not self.sharded:
+            return Ps
+        world = torch.distributed.get_world_size()
+        out = []
+        for P in Ps:
+            sizes = [torch.zeros(1, dtype=torch.int64, device=self.device) for _ in range(world)]
+            torch.distributed.all_gather(sizes, torch.tensor([P.shape[0]], dtype=torch.int64, device=self.device))
+            mx = int(max(s.item() for s in sizes))
+            pad = torch.zeros((mx, P.shape[1]), dtype=P.dtype, device=self.device)
+            pad[:P.shape[0]] = P
+            parts = [torch.empty_like(pad) for _ in range(world)]
+            torch.distributed.all_gather(parts, pad)
+            out.append(torch.cat([p[:int(s.item())] for p, s in zip(parts, sizes)], dim=0))
+        return out
+
+    def display_divergences(self, k) -> None:
+        """Hudson's Fst between estimated populations (reference :476-509)."""
+        Ps = self.gather_P()
+        if not self.master:
+            return
+        for P, k in zip(Ps, self.ks_list):
+            header = "\t".join(f"Pop{p}" for p in range(k - 1))
+            log.info("    Results:")
+            log.info(f"\n            Fst divergences between estimated populations: (K = {k})")
+            log.info("")
+            log.info(f"                \t{header}")
+            log.info("            Pop0")
+            for j in range(1, k):
+                out = f"            Pop{j}"
+                for l in range(j):
+                    out += f"\t{self._hudsons_fst(P[:, l], P[:, j]):0.3f}"
+                log.info(out)
+            log.info("\n")
+
+    def process_results(self, Qs: List[torch.Tensor]):
+        """Reference :511-530."""
+        Ps = self.gather_P()
+        if self.master:
+            return [Q.cpu().numpy() for Q in Qs], [P.detach().cpu().numpy() for P in Ps], self.raw_model
+        return [], [], self.raw_model
+
+    @staticmethod
+    def _hudsons_fst(pop1: torch.Tensor, pop2: torch.Tensor) -> float:
+        """mean((p1-p2)^2) / (mean(p1(1-p2) + p2(1-p1)) + 1e-7)  (reference :532-553)."""
+        try:
+            num = torch.mean((pop1 - pop2) ** 2)
+            den = torch.mean(pop1 * (1 - pop2) + pop2 * (1 - pop1)) + 1e-7
+            return (num / den).item()
+        except Exception as e:  # pragma: no cover
+            log.info(f"            Error computing Hudson's Fst: {e}")
+            return float("nan")

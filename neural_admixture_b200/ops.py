@@ -1,0 +1,187 @@
+"""Tensor-level wrappers over the C ABI (include/nadm_b200.h).  torch is used for device memory and streams only;
+every computation below is a call into libnadm_b200.so on the current CUDA stream."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import AdamHyper, MlpParams, NadmError, check
+
+PITCH_ALIGN = 128  # bytes; rows of the packed matrix start on 128-byte lines
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise NadmError("libnadm_b200 operates on CUDA tensors only (there is no CPU path)")
+
+
+def padded_pitch(M: int) -> int:
+    pc = (M + 3) // 4
+    return ((pc + PITCH_ALIGN - 1) // PITCH_ALIGN) * PITCH_ALIGN
+
+
+def launch_count() -> int:
+    return int(_lib.load().nadm_launch_count())
+
+
+def pack2bit(src: torch.Tensor, dst: torch.Tensor, M: Optional[int] = None) -> None:
+    """src: rows x M uint8 codes (cuda), dst: rows x >=ceil(M/4) uint8 (cuda); row strides are honoured."""
+    _need_cuda(src, dst)
+    assert src.dtype == torch.uint8 and dst.dtype == torch.uint8 and src.dim() == 2 and dst.dim() == 2
+    assert src.stride(1) == 1 and dst.stride(1) == 1
+    rows = src.shape[0]
+    M = src.shape[1] if M is None else M
+    assert dst.shape[0] == rows
+    src_pitch = src.stride(0) if rows > 1 else max(src.shape[1], 1)
+    if rows > 1 and dst.stride(0) != dst.shape[1]:
+        raise NadmError("pack2bit: destination rows must be contiguous (the kernel zero-fills each row's tail)")
+    check(_lib.load().nadm_pack2bit(_ptr(src), rows, M, src_pitch, _ptr(dst), dst.shape[1], _stream()))
+
+
+def unpack2bit(src: torch.Tensor, dst: torch.Tensor) -> None:
+    """src: rows x >=ceil(M/4) packed (cuda), dst: rows x M uint8 (cuda)."""
+    _need_cuda(src, dst)
+    assert src.dtype == torch.uint8 and dst.dtype == torch.uint8 and src.dim() == 2 and dst.dim() == 2
+    assert src.stride(1) == 1 and dst.stride(1) == 1
+    rows, M = dst.shape
+    assert src.shape[0] == rows
+    src_pitch = src.stride(0) if rows > 1 else src.shape[1]
+    dst_pitch = dst.stride(0) if rows > 1 else max(M, 1)
+    check(_lib.load().nadm_unpack2bit(_ptr(src), rows, M, src_pitch, _ptr(dst), dst_pitch, _stream()))
+
+
+def workspace_bytes(B: int, M: int, C_: int, H: int, sumK: int) -> int:
+    return int(_lib.load().nadm_workspace_bytes(B, M, C_, H, sumK))
+
+
+def _ks_array(ks: Sequence[int]):
+    return (C.c_int32 * len(ks))(*[int(k) for k in ks])
+
+
+def adam_hyper(lr: float, step: int, beta1: float = 0.9, beta2: float = 0.95, eps: float = 1e-8) -> AdamHyper:
+    return AdamHyper(lr, beta1, beta2, eps, step)
+
+
+class PackedGenotypes:
+    """Sample-major 2-bit genotype matrix on the device, rows padded to PITCH_ALIGN bytes with zero tails."""
+
+    def __init__(self, storage: torch.Tensor, N: int, M: int):
+        assert storage.dtype == torch.uint8 and storage.dim() == 2 and storage.is_cuda and storage.is_contiguous()
+        assert storage.shape[0] == N and storage.shape[1] % 16 == 0 and storage.shape[1] >= (M + 3) // 4
+        self.storage, self.N, self.M = storage, N, M
+
+    @property
+    def pitch(self) -> int:
+        return self.storage.shape[1]
+
+    @classmethod
+    def empty(cls, N: int, M: int, device) -> "PackedGenotypes":
+        return cls(torch.zeros((N, padded_pitch(M)), dtype=torch.uint8, device=device), N, M)
+
+    @classmethod
+    def from_reference_layout(cls, packed: torch.Tensor, M: int) -> "PackedGenotypes":
+        """Adopt an N x ceil(M/4) tensor in the reference's layout (model/train.py:121).  Zero-copy when the row
+        pitch already satisfies the kernels' 16-byte rule, otherwise one device-side re-pitch copy."""
+        N, pc = packed.shape
+        assert pc >= (M + 3) // 4
+        if packed.is_contiguous() and pc % 16 == 0 and packed.data_ptr() % 16 == 0:
+            return cls(packed, N, M)
+        out = cls.empty(N, M, packed.device)
+        out.storage[:, :pc].copy_(packed)
+        return out
+
+    @classmethod
+    def from_unpacked_host(cls, G: torch.Tensor, device, col0: int = 0, col1: Optional[int] = None,
+                           chunk_rows: int = 1024) -> "PackedGenotypes":
+        """Host uint8 N x M codes -> device packed, columns [col0, col1) only (a rank's SNP slice).  Staged through
+        pinned memory in chunks of rows, packed on the device (role of pack2bit_cpu_to_gpu, pack2bit.cu:65-117)."""
+        assert G.dtype == torch.uint8 and G.dim() == 2 and not G.is_cuda
+        N = G.shape[0]
+        col1 = G.shape[1] if col1 is None else col1
+        Mloc = col1 - col0
+        out = cls.empty(N, Mloc, device)
+        stage = torch.empty((min(chunk_rows, max(N, 1)), Mloc), dtype=torch.uint8, device=device)
+        for r0 in range(0, N, chunk_rows):
+            r1 = min(N, r0 + chunk_rows)
+            stage[: r1 - r0].copy_(G[r0:r1, col0:col1], non_blocking=False)
+            pack2bit(stage[: r1 - r0], out.storage[r0:r1], Mloc)
+        return out
+
+
+def encoder_fwd(pg: PackedGenotypes, V: torch.Tensor, Z: torch.Tensor, ws: torch.Tensor, *,
+                row_idx: Optional[torch.Tensor] = None, row0: int = 0, B: Optional[int] = None) -> None:
+    _need_cuda(V, Z, ws, row_idx)
+    B = (row_idx.numel() if row_idx is not None else B)
+    assert V.dtype == torch.float32 and V.is_contiguous() and V.shape[0] == pg.M
+    assert Z.dtype == torch.float32 and Z.is_contiguous() and Z.shape == (B, V.shape[1])
+    assert row_idx is None or (row_idx.dtype == torch.int64 and row_idx.is_contiguous())
+    check(_lib.load().nadm_encoder_fwd(_ptr(pg.storage), pg.pitch, _ptr(row_idx), row0, B, pg.M, _ptr(V), V.shape[1],
+                                       _ptr(Z), _ptr(ws), ws.numel() * ws.element_size(), _stream()))
+
+
+def mlp_fwd(Z, w_rms, W1, b1, W2, b2, ks, rinv, Hh, Q) -> None:
+    _need_cuda(Z, w_rms, W1, b1, W2, b2, rinv, Hh, Q)
+    B, C_ = Z.shape
+    H = W1.shape[0]
+    for t in (Z, w_rms, W1, b1, W2, b2, rinv, Hh, Q):
+        assert t.dtype == torch.float32 and t.is_contiguous()
+    assert W2.shape == (sum(ks), H) and Q.shape == (B, sum(ks)) and Hh.shape == (B, H)
+    check(_lib.load().nadm_mlp_fwd(_ptr(Z), B, C_, H, _ptr(w_rms), _ptr(W1), _ptr(b1), _ptr(W2), _ptr(b2),
+                                   _ks_array(ks), len(ks), _ptr(rinv), _ptr(Hh), _ptr(Q), _stream()))
+
+
+def decoder_step(pg: PackedGenotypes, Q, dQ, q_off: int, k: int, P, Pm, Pv, adam: Optional[AdamHyper], loss, ws, *,
+                 row_idx=None, row0: int = 0, dP_out=None) -> None:
+    _need_cuda(Q, dQ, P, Pm, Pv, loss, ws, row_idx, dP_out)
+    B, q_ld = Q.shape
+    assert P.shape == (pg.M, k) and P.is_contiguous() and P.dtype == torch.float32
+    assert Q.is_contiguous() and dQ.is_contiguous() and dQ.shape == Q.shape
+    assert row_idx is None or (row_idx.dtype == torch.int64 and row_idx.is_contiguous() and row_idx.numel() == B)
+    check(_lib.load().nadm_decoder_step(_ptr(pg.storage), pg.pitch, _ptr(row_idx), row0, B, pg.M, _ptr(Q), _ptr(dQ),
+                                        q_ld, q_off, k, _ptr(P), _ptr(Pm), _ptr(Pv),
+                                        None if adam is None else C.byref(adam), _ptr(dP_out), _ptr(loss), _ptr(ws),
+                                        ws.numel() * ws.element_size(), _stream()))
+
+
+def mlp_bwd(dQ, Q, Hh, Z, rinv, ks, params: MlpParams, adam: Optional[AdamHyper], dZ, loss, ws, *, labels=None,
+            sup_weight: float = 0.0) -> None:
+    _need_cuda(dQ, Q, Hh, Z, rinv, dZ, loss, ws, labels)
+    B, C_ = Z.shape
+    H = Hh.shape[1]
+    assert labels is None or (labels.dtype == torch.int64 and labels.is_contiguous() and labels.numel() == B)
+    check(_lib.load().nadm_mlp_bwd(_ptr(dQ), _ptr(Q), _ptr(Hh), _ptr(Z), _ptr(rinv), B, C_, H, _ks_array(ks), len(ks),
+                                   _ptr(labels), float(sup_weight), C.byref(params),
+                                   None if adam is None else C.byref(adam), _ptr(dZ), _ptr(loss), _ptr(ws),
+                                   ws.numel() * ws.element_size(), _stream()))
+
+
+def encoder_bwd(pg: PackedGenotypes, dZ, V, Vm, Vv, adam: Optional[AdamHyper], ws, *, row_idx=None, row0: int = 0,
+                dV_out=None) -> None:
+    _need_cuda(dZ, V, Vm, Vv, ws, row_idx, dV_out)
+    B, C_ = dZ.shape
+    assert V.shape == (pg.M, C_) and V.is_contiguous() and dZ.is_contiguous()
+    check(_lib.load().nadm_encoder_bwd(_ptr(pg.storage), pg.pitch, _ptr(row_idx), row0, B, pg.M, _ptr(dZ), C_, _ptr(V),
+                                       _ptr(Vm), _ptr(Vv), None if adam is None else C.byref(adam), _ptr(dV_out),
+                                       _ptr(ws), ws.numel() * ws.element_size(), _stream()))
+
+
+def loglikelihood(pg: PackedGenotypes, Q: torch.Tensor, P: torch.Tensor, ws: torch.Tensor, eps: float = 1e-6) -> float:
+    _need_cuda(Q, P, ws)
+    k = P.shape[1]
+    assert Q.shape == (pg.N, k) and P.shape == (pg.M, k) and Q.is_contiguous() and P.is_contiguous()
+    out = torch.zeros(1, dtype=torch.float64, device=Q.device)
+    check(_lib.load().nadm_loglikelihood(_ptr(pg.storage), pg.pitch, pg.N, pg.M, _ptr(Q), _ptr(P), k, eps, _ptr(out),
+                                         _ptr(ws), ws.numel() * ws.element_size(), _stream()))
+    return float(out.item())
