@@ -34,7 +34,8 @@ int sm_count();
 constexpr int kMaxParts = 640;        // upper bound on per-CTA partial slabs (encoder slabs / decoder CTAs)
 constexpr int kStreamWarps = 8;       // warps per CTA in the lane<->byte streaming kernels
 constexpr int kTileSnps = 128;        // SNPs per CTA tile in those kernels: one byte (4 SNPs) per lane
-constexpr int kEncTileSnps = 256;     // SNPs per staged tile in the thread-per-row encoder forward
+constexpr int kEncTileSnps = 256;
+constexpr int kMaxDynSmem = 220 * 1024;  // dynamic shared memory opt-in (227 KB per CTA minus static + reserve)
 
 struct AdamCoef {
     float beta1, beta2, one_minus_beta1, one_minus_beta2, step_size, inv_bc2_sqrt, eps;

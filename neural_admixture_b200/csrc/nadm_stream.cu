@@ -579,14 +579,14 @@ static int launch_dec(const uint8_t* packed, int64_t pitch, const int64_t* row_i
                       cudaStream_t st) {
     const int ntiles = (int)((M + kTileSnps - 1) / kTileSnps);
     const size_t smem = ((size_t)(B * 8 + 15) / 16) * 16 + (size_t)2 * B * KP * 4 + (size_t)kStreamWarps * kTileSnps * KP * 4;
-    NADM_REQUIRE(smem <= 227 * 1024, "batch B=%d too large for the fused decoder (needs %zu bytes of shared memory)", B, smem);
-    const int per_sm = std::max(1, (int)((227 * 1024) / (smem + 1024)));
+    NADM_REQUIRE(smem <= (size_t)kMaxDynSmem, "batch B=%d too large for the fused decoder (needs %zu bytes of shared memory)", B, smem);
+    const int per_sm = std::max(1, (int)((227 * 1024) / (smem + 2048)));
     int ncta = std::min(std::min(ntiles, sm_count() * std::min(per_sm, 3)), kMaxParts);
     NADM_REQUIRE((size_t)ncta * ((size_t)B * KP + 1) * sizeof(float) <= ws_bytes, "workspace too small for decoder_step");
     static bool attr_done[3] = {false, false, false};
     const int ai = KP == 4 ? 0 : (KP == 8 ? 1 : 2);
     if (!attr_done[ai]) {
-        cudaError_t e = cudaFuncSetAttribute(dec_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(dec_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(dec)");
         attr_done[ai] = true;
     }
@@ -626,12 +626,12 @@ static int launch_enc_bwd(const uint8_t* packed, int64_t pitch, const int64_t* r
                           cudaStream_t st) {
     const int ntiles = (int)((M + kTileSnps - 1) / kTileSnps);
     const size_t smem = ((size_t)(B * 8 + 15) / 16) * 16 + (size_t)B * CP * 4 + (size_t)kStreamWarps * kTileSnps * CP * 4;
-    NADM_REQUIRE(smem <= 227 * 1024, "batch B=%d too large for encoder_bwd (needs %zu bytes of shared memory)", B, smem);
-    const int per_sm = std::max(1, (int)((227 * 1024) / (smem + 1024)));
+    NADM_REQUIRE(smem <= (size_t)kMaxDynSmem, "batch B=%d too large for encoder_bwd (needs %zu bytes of shared memory)", B, smem);
+    const int per_sm = std::max(1, (int)((227 * 1024) / (smem + 2048)));
     const int ncta = std::min(ntiles, sm_count() * std::min(per_sm, 3));
     static bool attr_done[2] = {false, false};
     if (!attr_done[CP == 16]) {
-        cudaError_t e = cudaFuncSetAttribute(enc_bwd_kernel<CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(enc_bwd_kernel<CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(enc_bwd)");
         attr_done[CP == 16] = true;
     }

@@ -1,0 +1,433 @@
+"""Parity of the CUDA path (through the C ABI, via neural_admixture_b200.ops) with the CPU oracle and with the golden
+fixtures generated from the reference.  Needs a B200: run with ``-m gpu``.
+
+Tolerances (floating point; fp32 kernels vs the fp64 oracle):
+  KERNEL_TOL = 2e-5   relative Frobenius error of one kernel's output (fp32 rounding of M-long sums)
+  STEP_TOL   = 5e-5   parameters after one/two full optimisation steps (Adam normalises gradients: |dp| = lr)
+  QP_TOL     = 1e-4   north-star bar: ||Q - Q_ref||_F / ||Q_ref||_F (and P) after short trainings
+Integer work (pack / unpack) is bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+import nadm_oracle as orc
+from helpers import load_golden, sub, state_from_sd, sd_name, relF
+
+pytestmark = pytest.mark.gpu
+
+KERNEL_TOL = 2e-5
+STEP_TOL = 5e-5
+QP_TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "the -m gpu tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from neural_admixture_b200 import ops as _ops
+    return _ops
+
+
+def t(a, dev, dtype=torch.float32):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype, device=dev).contiguous()
+
+
+def rand_genotypes(rng, N, M, miss=0.02):
+    G = rng.integers(0, 3, size=(N, M), dtype=np.uint8)
+    G[rng.random((N, M)) < miss] = 3
+    return G
+
+
+def packed_from(ops, G, dev):
+    return ops.PackedGenotypes.from_unpacked_host(torch.as_tensor(G), dev)
+
+
+def ws_for(ops, B, M, C, H, sumK, dev):
+    return torch.empty(ops.workspace_bytes(B, M, C, H, sumK), dtype=torch.uint8, device=dev)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# integer work: bit-exact
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,M", [(1, 1), (3, 4), (5, 7), (16, 203), (2, 1025), (33, 4096), (7, 65537)])
+def test_pack_unpack_bit_exact(ops, dev, N, M):
+    rng = np.random.default_rng(N * 1000 + M)
+    G = rng.integers(0, 256, size=(N, M), dtype=np.uint8)          # high bits must be dropped (pack2bit.cu:29)
+    src = torch.as_tensor(G, device=dev)
+    pc = (M + 3) // 4
+    dst = torch.full((N, pc), 0xAA, dtype=torch.uint8, device=dev)
+    ops.pack2bit(src, dst)
+    assert np.array_equal(dst.cpu().numpy(), orc.pack2bit(G))
+    back = torch.full((N, M), 9, dtype=torch.uint8, device=dev)
+    ops.unpack2bit(dst, back)
+    assert np.array_equal(back.cpu().numpy(), G & 3)
+    # padded-pitch container: tail bytes are zero
+    pg = packed_from(ops, G & 3, dev)
+    st = pg.storage.cpu().numpy()
+    assert np.array_equal(st[:, :pc], orc.pack2bit(G)) and not st[:, pc:].any()
+
+
+def test_reference_pack2bit_module_surface(ops, dev):
+    """Same two functions, argument meaning and error behaviour as the reference's pybind module
+    (pack2bit.cu:65-76,120-130,144-147)."""
+    from neural_admixture_b200.src import pack2bit
+    from neural_admixture_b200._lib import NadmError
+    rng = np.random.default_rng(5)
+    G = rand_genotypes(rng, 1500, 777)                              # > 1024 rows: two staging chunks
+    out = torch.empty((1500, (777 + 3) // 4), dtype=torch.uint8, device=dev)
+    pack2bit.pack2bit_cpu_to_gpu(torch.as_tensor(G), out)
+    assert np.array_equal(out.cpu().numpy(), orc.pack2bit(G))
+    un = torch.empty((800, 777), dtype=torch.uint8, device=dev)
+    pack2bit.unpack2bit_gpu_to_gpu(out[:800].contiguous(), un)
+    assert np.array_equal(un.cpu().numpy(), G[:800])
+    with pytest.raises(NadmError):
+        pack2bit.pack2bit_cpu_to_gpu(torch.as_tensor(G).to(dev), out)
+    with pytest.raises(NadmError):
+        pack2bit.pack2bit_cpu_to_gpu(torch.as_tensor(G), out[:, :-1])
+    with pytest.raises(NadmError):
+        pack2bit.unpack2bit_gpu_to_gpu(out.cpu(), un)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# kernels vs oracle
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,M,C,B,gather", [(64, 203, 8, 48, True), (300, 4099, 8, 300, True), (40, 1024, 8, 40, False),
+                                            (1000, 20000, 8, 800, True), (17, 5, 3, 17, True), (520, 777, 16, 513, True)])
+def test_encoder_fwd(ops, dev, N, M, C, B, gather):
+    rng = np.random.default_rng(M)
+    G = rand_genotypes(rng, N, M)
+    V = (rng.standard_normal((M, C)) / np.sqrt(M)).astype(np.float32)
+    idx = rng.permutation(N)[:B] if gather else np.arange(3 if N > B + 3 else 0, (3 if N > B + 3 else 0) + B)
+    pg = packed_from(ops, G, dev)
+    Z = torch.empty((B, C), dtype=torch.float32, device=dev)
+    ws = ws_for(ops, B, M, C, 64, 8, dev)
+    if gather:
+        ops.encoder_fwd(pg, t(V, dev), Z, ws, row_idx=t(idx, dev, torch.int64))
+    else:
+        ops.encoder_fwd(pg, t(V, dev), Z, ws, row0=int(idx[0]), B=B)
+    ref = orc.encoder_fwd(orc.genotype_to_x(G[idx]), V.astype(np.float64))
+    assert relF(Z.cpu().numpy(), ref) < KERNEL_TOL
+
+
+@pytest.mark.parametrize("ks,H,B", [([5], 64, 48), ([8], 1024, 800), ([3, 4, 5], 32, 150), (list(range(4, 13)), 1024, 77)])
+def test_mlp_fwd_bwd(ops, dev, ks, H, B):
+    from neural_admixture_b200._lib import MlpParams
+    rng = np.random.default_rng(B)
+    C, sumK = 8, sum(ks)
+    Z = rng.standard_normal((B, C)) * 0.3
+    w_rms = 1 + 0.1 * rng.standard_normal(C)
+    W1 = rng.standard_normal((H, C)) / np.sqrt(C)
+    b1 = 0.1 * rng.standard_normal(H)
+    W2 = [rng.standard_normal((k, H)) / np.sqrt(H) for k in ks]
+    b2 = [0.1 * rng.standard_normal(k) for k in ks]
+    Zn, rinv, Hh, Qs = orc.mlp_fwd(Z, w_rms, W1, b1, W2, b2)
+    d = {"Z": t(Z, dev), "w_rms": t(w_rms, dev), "W1": t(W1, dev), "b1": t(b1, dev),
+         "W2": t(np.concatenate(W2, 0), dev), "b2": t(np.concatenate(b2, 0), dev)}
+    rinv_d = torch.empty(B, device=dev)
+    Hh_d = torch.empty((B, H), device=dev)
+    Q_d = torch.empty((B, sumK), device=dev)
+    ops.mlp_fwd(d["Z"], d["w_rms"], d["W1"], d["b1"], d["W2"], d["b2"], ks, rinv_d, Hh_d, Q_d)
+    assert relF(Q_d.cpu().numpy(), np.concatenate(Qs, 1)) < KERNEL_TOL
+    assert relF(Hh_d.cpu().numpy(), Hh) < KERNEL_TOL
+    # backward with raw gradients out (no Adam), supervised term on when single head
+    dQs = [rng.standard_normal(q.shape) * 10 for q in Qs]
+    y = rng.integers(0, ks[0], size=B) if len(ks) == 1 else None
+    dQs_ref = [g.copy() for g in dQs]
+    sup_loss = 0.0
+    if y is not None:
+        sup_loss, dsup = orc.supervised_loss_grads(Qs[0], y, 100.0)
+        dQs_ref[0] = dQs_ref[0] + dsup
+    dZ, dw, dW1, db1, dW2, db2 = orc.mlp_bwd(dQs_ref, Qs, Hh, Zn, rinv, Z, w_rms, W1, W2)
+    g = {n: torch.zeros_like(d[n]) for n in ["w_rms", "W1", "b1", "W2", "b2"]}
+    p = MlpParams()
+    for n in g:
+        setattr(p, n, d[n].data_ptr())
+        setattr(p, "g_" + n, g[n].data_ptr())
+    dZ_d = torch.empty((B, C), device=dev)
+    loss = torch.zeros(1, device=dev)
+    ws = ws_for(ops, B, 1000, C, H, sumK, dev)
+    ops.mlp_bwd(t(np.concatenate(dQs, 1), dev), Q_d, Hh_d, d["Z"], rinv_d, ks, p, None, dZ_d, loss, ws,
+                labels=None if y is None else t(y, dev, torch.int64), sup_weight=100.0 if y is not None else 0.0)
+    tol = 5e-5
+    assert relF(dZ_d.cpu().numpy(), dZ) < tol
+    assert relF(g["W1"].cpu().numpy(), dW1) < tol
+    assert relF(g["b1"].cpu().numpy(), db1) < tol
+    assert relF(g["W2"].cpu().numpy(), np.concatenate(dW2, 0)) < tol
+    assert relF(g["b2"].cpu().numpy(), np.concatenate(db2, 0)) < tol
+    assert relF(g["w_rms"].cpu().numpy(), dw) < tol
+    if y is not None:
+        assert abs(loss.item() - sup_loss) < 1e-5 * abs(sup_loss)
+
+
+@pytest.mark.parametrize("N,M,k,B,edge", [(64, 203, 5, 48, True), (300, 4099, 8, 300, False), (1000, 20000, 8, 800, True),
+                                          (40, 1024, 3, 40, True), (90, 515, 12, 77, False), (20, 9, 2, 20, True)])
+def test_decoder_step_grads(ops, dev, N, M, k, B, edge):
+    rng = np.random.default_rng(M + k)
+    G = rand_genotypes(rng, N, M)
+    P = rng.uniform(0.02, 0.98, size=(M, k)).astype(np.float32)
+    if edge:  # exact 0 / 1 entries: the 1e-12 floor (+-1e12 gradients) and the inclusive clamp mask
+        P[5 % M, :] = 0.0
+        P[min(17, M - 1), 0] = 0.0
+        P[min(23, M - 1), k - 1] = 1.0
+    Q = rng.dirichlet(0.3 * np.ones(k), size=B).astype(np.float32)
+    idx = rng.permutation(N)[:B]
+    pg = packed_from(ops, G, dev)
+    sumK, q_off = k + 3, 2                                       # the head sits inside a wider Q / dQ
+    Qw = np.zeros((B, sumK), dtype=np.float32)
+    Qw[:, q_off:q_off + k] = Q
+    dQ = torch.full((B, sumK), 7.0, device=dev)
+    dP = torch.empty((M, k), device=dev)
+    loss = torch.zeros(1, device=dev)
+    P_d = t(P, dev)
+    ws = ws_for(ops, B, M, 8, 64, sumK, dev)
+    ops.decoder_step(pg, t(Qw, dev), dQ, q_off, k, P_d, None, None, None, loss, ws, row_idx=t(idx, dev, torch.int64),
+                     dP_out=dP)
+    l_ref, dQ_ref, dP_ref = orc.decoder_loss_grads(orc.genotype_to_x(G[idx]), Q.astype(np.float64), P.astype(np.float64))
+    assert abs(loss.item() - l_ref) < 1e-5 * abs(l_ref)
+    assert relF(dQ[:, q_off:q_off + k].cpu().numpy(), dQ_ref) < KERNEL_TOL
+    assert relF(dP.cpu().numpy(), dP_ref) < KERNEL_TOL
+    assert torch.all(dQ[:, :q_off] == 7.0) and torch.all(dQ[:, q_off + k:] == 7.0)   # other heads' columns untouched
+    assert np.array_equal(P_d.cpu().numpy(), P)                   # no Adam requested: P unchanged
+    if edge:
+        assert np.abs(dP_ref).max() > 1e10
+
+
+@pytest.mark.parametrize("N,M,C,B", [(64, 203, 8, 48), (300, 4099, 8, 300), (1000, 20000, 8, 800), (30, 6, 5, 30)])
+def test_encoder_bwd(ops, dev, N, M, C, B):
+    rng = np.random.default_rng(M + 1)
+    G = rand_genotypes(rng, N, M)
+    dZ = rng.standard_normal((B, C)).astype(np.float32)
+    idx = rng.permutation(N)[:B]
+    pg = packed_from(ops, G, dev)
+    V = torch.zeros((M, C), device=dev)
+    dV = torch.empty((M, C), device=dev)
+    ops.encoder_bwd(pg, t(dZ, dev), V, None, None, None, ws_for(ops, B, M, C, 64, 8, dev),
+                    row_idx=t(idx, dev, torch.int64), dV_out=dV)
+    ref = orc.encoder_bwd(orc.genotype_to_x(G[idx]), dZ.astype(np.float64))
+    assert relF(dV.cpu().numpy(), ref) < KERNEL_TOL
+
+
+def test_adam_fused_matches_oracle(ops, dev):
+    """Adam + restrict_P fused into the decoder / encoder-backward kernels, three consecutive steps."""
+    rng = np.random.default_rng(3)
+    N, M, k, C, B = 80, 1029, 6, 8, 64
+    G = rand_genotypes(rng, N, M)
+    pg = packed_from(ops, G, dev)
+    P = rng.uniform(0.0, 1.0, size=(M, k))
+    V = rng.standard_normal((M, C)) / np.sqrt(M)
+    P_d, Pm, Pv = t(P, dev), torch.zeros((M, k), device=dev), torch.zeros((M, k), device=dev)
+    V_d, Vm, Vv = t(V, dev), torch.zeros((M, C), device=dev), torch.zeros((M, C), device=dev)
+    P_o, V_o = P_d.cpu().numpy().astype(np.float64), V_d.cpu().numpy().astype(np.float64)
+    mo = {n: np.zeros_like(a) for n, a in (("P", P_o), ("V", V_o))}
+    vo = {n: np.zeros_like(a) for n, a in (("P", P_o), ("V", V_o))}
+    ws = ws_for(ops, B, M, C, 64, k, dev)
+    for step in range(1, 4):
+        idx = rng.permutation(N)[:B]
+        Q = rng.dirichlet(0.3 * np.ones(k), size=B).astype(np.float32)
+        dZ = rng.standard_normal((B, C)).astype(np.float32)
+        x = orc.genotype_to_x(G[idx])
+        _, _, dP_ref = orc.decoder_loss_grads(x, Q.astype(np.float64), P_o)
+        orc.adam_update(P_o, dP_ref, mo["P"], vo["P"], step, 2e-3)
+        np.clip(P_o, 0, 1, out=P_o)
+        orc.adam_update(V_o, orc.encoder_bwd(x, dZ.astype(np.float64)), mo["V"], vo["V"], step, 2e-3)
+        hyper = ops.adam_hyper(2e-3, step)
+        dQ = torch.zeros((B, k), device=dev)
+        loss = torch.zeros(1, device=dev)
+        ops.decoder_step(pg, t(Q, dev), dQ, 0, k, P_d, Pm, Pv, hyper, loss, ws, row_idx=t(idx, dev, torch.int64))
+        ops.encoder_bwd(pg, t(dZ, dev), V_d, Vm, Vv, hyper, ws, row_idx=t(idx, dev, torch.int64))
+        assert relF(P_d.cpu().numpy(), P_o) < STEP_TOL, step
+        assert relF(V_d.cpu().numpy(), V_o) < STEP_TOL, step
+        assert P_d.min().item() >= 0.0 and P_d.max().item() <= 1.0
+
+
+def test_loglikelihood(ops, dev):
+    rng = np.random.default_rng(9)
+    N, M, k = 210, 1333, 5
+    G = rand_genotypes(rng, N, M, miss=0.05)
+    P = rng.uniform(0, 1, size=(M, k)).astype(np.float32)
+    Q = rng.dirichlet(np.ones(k), size=N).astype(np.float32)
+    pg = packed_from(ops, G, dev)
+    ll = ops.loglikelihood(pg, t(Q, dev), t(P, dev), ws_for(ops, 64, M, 8, 64, k, dev))
+    ref = orc.loglikelihood(G, P, Q)
+    assert abs(ll - ref) < 1e-9 * abs(ref)
+
+
+def test_error_behaviour(ops, dev):
+    from neural_admixture_b200._lib import NadmError
+    pg = ops.PackedGenotypes.empty(8, 64, dev)
+    Z = torch.empty((8, 8), device=dev)
+    with pytest.raises(NadmError, match="unsupported"):
+        ops.encoder_fwd(pg, torch.zeros((64, 40), device=dev), torch.empty((8, 40), device=dev),
+                        torch.empty(1 << 20, dtype=torch.uint8, device=dev), row0=0, B=8)
+    with pytest.raises(NadmError, match="workspace"):
+        ops.encoder_fwd(pg, torch.zeros((64, 8), device=dev), Z, torch.empty(16, dtype=torch.uint8, device=dev),
+                        row0=0, B=8)
+    with pytest.raises(NadmError, match="CUDA tensors only"):
+        ops.encoder_fwd(pg, torch.zeros((64, 8)), Z, torch.empty(1 << 20, dtype=torch.uint8, device=dev), row0=0, B=8)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# golden fixtures produced by the reference itself
+# ---------------------------------------------------------------------------------------------------------------
+def _engine_from_fixture(g, dev, epochs=None, G=None):
+    """NeuralAdmixture on the fixture's data, starting from the fixture's initial parameters (the reference's MLP
+    initialisation depends on torch's global RNG state at construction, so parameters are loaded, not re-drawn)."""
+    from neural_admixture_b200 import ops as _ops
+    from neural_admixture_b200.model.neural_admixture import NeuralAdmixture
+    ks = [int(k) for k in g["ks"]]
+    init = sub(g, "init/")
+    G = g["G"] if G is None else G
+    N, M = G.shape
+    k = ks[0] if len(ks) == 1 else None
+    na = NeuralAdmixture(k, int(g["epochs"]) if epochs is None else epochs, int(g["batch"]), float(g["lr"]), dev,
+                         int(g["seed"]), 0, True, "nadm_b200", None if k else min(ks), None if k else max(ks))
+    na.keep_loss_history = True
+    orig = na.initialize_model
+
+    def init_and_load(P, hidden_size, num_features, V, ks_list):
+        orig(P, hidden_size, num_features, V, ks_list)
+        na.raw_model.load_state_dict({n: torch.as_tensor(a) for n, a in init.items()})
+        na.raw_model.bind()
+
+    na.initialize_model = init_and_load
+    P_init = np.concatenate([init[f"decoders.decoders.{i}.weight"].T for i in range(len(ks))], axis=0)
+    packed = _ops.PackedGenotypes.from_unpacked_host(torch.as_tensor(G), dev)
+    H = init["common_encoder.0.weight"].shape[0]
+    pops = torch.as_tensor(g["pops"], dtype=torch.int64) if "pops" in g else None
+    Qs, Ps, raw = na.launch_training(t(P_init, dev), packed, H, init["V"].shape[1], t(init["V"], dev), M, N, pops)
+    return na, Qs, Ps, raw
+
+
+def test_step_fixture_two_steps(ops, dev):
+    """tests/golden/step_k5.npz: two steps of the reference's Q_P + fused Adam + restrict_P on one batch, with missing
+    codes and exact 0/1 entries of P."""
+    from neural_admixture_b200.model.neural_admixture import NeuralAdmixture
+    g = load_golden("step_k5.npz")
+    G, init = g["G"], sub(g, "init/")
+    B, M = G.shape
+    na = NeuralAdmixture(5, 0, B, float(g["lr"]), dev, 0, 0, True, "nadm_b200", None, None)
+    na.M, na.N = M, B
+    na.packed = packed_from(ops, G, dev)
+    na._train_bufs = {}
+    P_init = init["decoders.decoders.0.weight"].T
+    na.initialize_model(t(P_init, dev), init["common_encoder.0.weight"].shape[0], 8, t(init["V"], dev), [5])
+    na.raw_model.load_state_dict({n: torch.as_tensor(a) for n, a in init.items()})
+    na.raw_model.bind()
+    na.optimizer = na.raw_model.create_custom_adam(device=dev, lr=float(g["lr"]))
+    idx = torch.arange(B, device=dev)
+    loss = torch.zeros(1, device=dev)
+    for step, key in enumerate(["after1/", "after2/"]):
+        na._train_step(idx, None, loss)
+        assert abs(loss.item() - g["losses"][step]) < 2e-5 * abs(g["losses"][step])
+        ref = sub(g, key)
+        sd = {n: a.detach().cpu().numpy() for n, a in na.raw_model.state_dict().items()}
+        for name, a in ref.items():
+            assert relF(sd[name], a) < STEP_TOL, (key, name)
+
+
+@pytest.mark.parametrize("fixture", ["train_k3.npz", "train_k3to5.npz", "train_sup_k3.npz"])
+def test_training_fixtures(dev, fixture):
+    g = load_golden(fixture)
+    na, Qs, Ps, raw = _engine_from_fixture(g, dev)
+    np.testing.assert_allclose(na.loss_history, g["epoch_losses"], rtol=5e-5)
+    for i in range(len(g["ks"])):
+        assert relF(Qs[i], g[f"Q/{i}"]) < QP_TOL, i
+        assert relF(Ps[i], g[f"P/{i}"]) < QP_TOL, i
+    final = sub(g, "final/")
+    assert relF(raw.V.detach().cpu().numpy(), final["V"]) < QP_TOL
+    # the sampler stream is the reference's (loaders.py:29-30)
+    from neural_admixture_b200.model.neural_admixture import NeuralAdmixture
+    fresh = NeuralAdmixture(3, 1, 8, 1e-3, dev, int(g["seed"]), 0, True, None, 3, 5)
+    for e in range(g["orders"].shape[0]):
+        assert np.array_equal(fresh.epoch_order(g["G"].shape[0]).numpy(), g["orders"][e])
+
+
+def test_demo_fixture(dev):
+    """The reference's only integration test (demo/run_demo.sh + run_diagnostics.py): K=7, 5 epochs, seed 42 on the
+    shipped BED (105 x 8451), from the reference's own RSVD/GMM initialisation."""
+    g = load_golden("demo_k7.npz")
+    G = orc.unpack2bit(g["G_packed"], int(g["M"]))
+    na, Qs, Ps, raw = _engine_from_fixture(g, dev, G=G)
+    np.testing.assert_allclose(na.loss_history, g["epoch_losses"], rtol=5e-5)
+    assert relF(Qs[0], g["Q/0"]) < QP_TOL
+    assert relF(Ps[0], g["P/0"]) < QP_TOL
+    assert relF(Qs[0], g["expected_Q"]) < 5e-3      # the shipped .expected file, at the level the reference itself reaches
+    assert (Ps[0] == 0.0).mean() > 0.2               # the clamp / 1e-12-floor branch is hit constantly here
+
+
+def test_infer_forward_surface(ops, dev):
+    """Q_P in inference mode: reference signature forward(uint8 B x M) -> (probs_list, X) (inference.py:56-58,75)."""
+    from neural_admixture_b200.model.neural_admixture import Q_P
+    g = load_golden("train_k3to5.npz")
+    ks = [int(k) for k in g["ks"]]
+    final = {n: a for n, a in sub(g, "final/").items() if not n.startswith("decoders")}   # what main.py:41-42 saves
+    H, C = final["common_encoder.0.weight"].shape
+    model = Q_P(H, C, ks_list=ks, V=torch.as_tensor(final["V"]), is_train=False)
+    model.load_state_dict({n: torch.as_tensor(a) for n, a in final.items()})
+    model.to(dev)
+    X = torch.as_tensor(g["G"][:100], device=dev)
+    probs, Xo = model(X)
+    assert Xo is X and len(probs) == len(ks)
+    for i in range(len(ks)):
+        assert relF(probs[i].cpu().numpy(), g[f"Q/{i}"][:100]) < QP_TOL
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# full-size properties (config 2: 10k x 100k, K = 8; B = 800) — no oracle needed
+# ---------------------------------------------------------------------------------------------------------------
+def test_fullsize_properties(ops, dev):
+    N, M, C, k, B = 10000, 100000, 8, 8, 800
+    gen = torch.Generator(device=dev).manual_seed(42)
+    pg = ops.PackedGenotypes.empty(N, M, dev)
+    for r0 in range(0, N, 1000):
+        codes = torch.randint(0, 4, (1000, M), dtype=torch.uint8, device=dev, generator=gen)
+        ops.pack2bit(codes, pg.storage[r0:r0 + 1000], M)
+    idx = torch.randperm(N, device=dev, generator=gen)[:B].contiguous()
+    ws = ws_for(ops, B, M, C, 1024, k, dev)
+    V1 = torch.randn((M, C), device=dev, generator=gen) / M ** 0.5
+    V2 = torch.randn((M, C), device=dev, generator=gen) / M ** 0.5
+    Z1, Z2, Z12 = (torch.empty((B, C), device=dev) for _ in range(3))
+    ops.encoder_fwd(pg, V1, Z1, ws, row_idx=idx)
+    ops.encoder_fwd(pg, V2, Z2, ws, row_idx=idx)
+    ops.encoder_fwd(pg, (V1 + V2).contiguous(), Z12, ws, row_idx=idx)
+    assert relF((Z1 + Z2).cpu().numpy(), Z12.cpu().numpy()) < KERNEL_TOL          # linearity in V
+    # V = 1: Z[b, c] = sum_m x[b, m]  -> exact dosage count / 2 per row (integers < 2^24: exact in fp32 partials)
+    ones = torch.ones((M, C), device=dev)
+    ops.encoder_fwd(pg, ones, Z1, ws, row_idx=idx)
+    un = torch.empty((B, M), dtype=torch.uint8, device=dev)
+    ops.unpack2bit(pg.storage[idx].contiguous()[:, :(M + 3) // 4].contiguous(), un)
+    dosage = torch.where(un == 3, torch.zeros_like(un), un).sum(dim=1, dtype=torch.int64).double() / 2
+    assert torch.equal(Z1[:, 0].double(), dosage) and torch.equal(Z1[:, 0], Z1[:, C - 1])
+    # adjoint identity: <dZ, X V> == <X^T dZ, V>
+    dZ = torch.randn((B, C), device=dev, generator=gen)
+    dV = torch.empty((M, C), device=dev)
+    ops.encoder_bwd(pg, dZ, torch.zeros((M, C), device=dev), None, None, None, ws, row_idx=idx, dV_out=dV)
+    ops.encoder_fwd(pg, V1, Z1, ws, row_idx=idx)
+    lhs = (dZ.double() * Z1.double()).sum().item()
+    rhs = (dV.double() * V1.double()).sum().item()
+    assert abs(lhs - rhs) < 1e-4 * max(abs(lhs), (dZ.double().norm() * Z1.double().norm()).item() * 1e-2)
+    # decoder: with Q = one-hot(0) for every row, R[b, m] = P[m, 0]: dP[:, 1:] == 0 and dQ[b, j] = sum_m G[b,m] P[m,j];
+    # also <dQ, Q> == <dP, P> (both equal sum G * R).
+    Q = torch.zeros((B, k), device=dev)
+    Q[:, 0] = 1.0
+    P = torch.rand((M, k), device=dev, generator=gen) * 0.9 + 0.05
+    dQ = torch.zeros((B, k), device=dev)
+    dP = torch.empty((M, k), device=dev)
+    loss = torch.zeros(1, device=dev)
+    ops.decoder_step(pg, Q, dQ, 0, k, P, None, None, None, loss, ws, row_idx=idx, dP_out=dP)
+    assert torch.count_nonzero(dP[:, 1:]).item() == 0
+    a = (dQ.double() * Q.double()).sum().item()
+    b = (dP.double() * P.double()).sum().item()
+    assert abs(a - b) < 1e-4 * abs(a)
+    # closed form of the loss for this Q: counts of each code per SNP column
+    codes = torch.where(un == 3, torch.zeros_like(un), un)
+    p0 = P[:, 0].double()
+    n1 = (codes == 1).sum(0).double()
+    n2 = (codes == 2).sum(0).double()
+    n0 = B - n1 - n2
+    closed = -(n2 * p0.log() + n0 * (1 - p0).log() + 0.5 * n1 * (p0.log() + (1 - p0).log())).sum().item()
+    assert abs(loss.item() - closed) < 2e-5 * abs(closed)
