@@ -264,13 +264,20 @@ class NeuralAdmixture:
             setattr(p, "g_" + n, None)
         return p
 
-    def _train_step(self, row_idx: torch.Tensor, labels: Optional[torch.Tensor], loss_out: torch.Tensor) -> None:
+    def _train_step(self, row_idx: Optional[torch.Tensor], labels: Optional[torch.Tensor], loss_out: torch.Tensor,
+                    pg: Optional[ops.PackedGenotypes] = None) -> None:
         """One minibatch: the body of the reference's ``_run_epoch`` loop (:403-414) — forward, loss, backward,
         Adam on every parameter, P clamp — as 5 library calls.  ``loss_out`` (1 float on device) receives the step's
-        loss; nothing is synchronised with the host."""
-        m, o, pg = self.raw_model, self.optimizer, self.packed
-        B = row_idx.numel()
-        probs, fb = m.encode_packed(pg, row_idx=row_idx, allreduce=self._allreduce if self.sharded else None)
+        loss; nothing is synchronised with the host.  The batch is rows ``row_idx`` of the resident matrix, or all
+        rows of ``pg`` (a staged batch, see ``train_from_host``)."""
+        m, o = self.raw_model, self.optimizer
+        if pg is None:
+            pg = self.packed
+            B = row_idx.numel()
+        else:
+            row_idx, B = None, pg.N
+        probs, fb = m.encode_packed(pg, row_idx=row_idx, row0=0, B=B,
+                                    allreduce=self._allreduce if self.sharded else None)
         sb = self._step_buffers(B)
         sb["loss"].zero_()
         o.step_count += 1
@@ -313,24 +320,32 @@ class NeuralAdmixture:
 
     keep_loss_history = False
 
+    def prepare(self, P: torch.Tensor, data, hidden_size: int, num_features: int, V: torch.Tensor, M: int, N: int):
+        """Everything ``launch_training`` does before its epoch loop (reference :343-364): adopt the packed matrix,
+        build the model on the device, create the optimizer state."""
+        self.M, self.N = M, N
+        if isinstance(data, ops.PackedGenotypes) or data is None:
+            self.packed = data
+        else:
+            if not (torch.is_tensor(data) and data.is_cuda and data.dtype == torch.uint8):
+                raise NadmError("launch_training needs the 2-bit packed genotype matrix on the CUDA device")
+            self.packed = ops.PackedGenotypes.from_reference_layout(data, M)
+        if self.packed is not None and (self.packed.N != N or self.packed.M != M):
+            raise NadmError(f"packed matrix is {self.packed.N} x {self.packed.M}, expected {N} x {M}")
+        self._train_bufs: Dict[int, dict] = {}
+        self.initialize_model(P.to(self.device, torch.float32), hidden_size, num_features,
+                              V.to(self.device, torch.float32), self.ks_list)
+        self.optimizer = self.raw_model.create_custom_adam(device=self.device, lr=self.lr)
+
     def launch_training(self, P: torch.Tensor, data, hidden_size: int, num_features: int, V: torch.Tensor, M: int,
                         N: int, pops: Optional[torch.Tensor] = None):
         """Reference :324-392.  ``data`` is the device-resident 2-bit packed matrix: either a
         ``ops.PackedGenotypes`` or an N x ceil(M/4) uint8 CUDA tensor in the reference's layout (model/train.py:121).
         ``P`` is (sum K) x M, ``V`` is M x C.  In sharded mode M / P / V / data are this rank's SNP slice.
         Returns ``(Qs, Ps, raw_model)`` like the reference (numpy lists on the master rank)."""
-        self.M, self.N = M, N
-        if isinstance(data, ops.PackedGenotypes):
-            self.packed = data
-        else:
-            if not (torch.is_tensor(data) and data.is_cuda and data.dtype == torch.uint8):
-                raise NadmError("launch_training needs the 2-bit packed genotype matrix on the CUDA device")
-            self.packed = ops.PackedGenotypes.from_reference_layout(data, M)
-        if self.packed.N != N or self.packed.M != M:
-            raise NadmError(f"packed matrix is {self.packed.N} x {self.packed.M}, expected {N} x {M}")
-        self._train_bufs: Dict[int, dict] = {}
-        self.initialize_model(P.to(self.device, torch.float32), hidden_size, num_features,
-                              V.to(self.device, torch.float32), self.ks_list)
+        if data is None:
+            raise NadmError("launch_training needs the 2-bit packed genotype matrix on the CUDA device")
+        self.prepare(P, data, hidden_size, num_features, V, M, N)
         if pops is not None:
             pops = pops.to(self.device, torch.int64)
 
@@ -338,7 +353,6 @@ class NeuralAdmixture:
             log.info("")
             log.info("    Starting training...")
             log.info("")
-        self.optimizer = self.raw_model.create_custom_adam(device=self.device, lr=self.lr)
         for epoch in range(self.epochs):
             order = self.epoch_order(N).to(self.device, non_blocking=True)
             self._run_epoch(epoch, order, pops)
@@ -351,6 +365,49 @@ class NeuralAdmixture:
             log.info("")
         self.display_divergences(self.k)
         return self.process_results(Qs)
+
+    def train_from_host(self, host_batches, labels=None) -> List[float]:
+        """Out-of-core feed: train on minibatches whose 2-bit packed rows live in (pinned) HOST memory — each element
+        of ``host_batches`` is a uint8 B x pitch tensor in the ``PackedGenotypes`` row layout.  Per step: the batch is
+        copied host->device on a side stream into one of two staging buffers (overlapping the previous step's
+        kernels), the fused step runs on it, and the step's loss is read back to the host (the reference's
+        ``loss.item()``, :414).  Returns the per-step losses.  Requires ``prepare`` (or ``launch_training``) first."""
+        main = torch.cuda.current_stream(self.device)
+        copy = getattr(self, "_copy_stream", None)
+        if copy is None:
+            copy = self._copy_stream = torch.cuda.Stream(self.device)
+        stage, ready, free = [None, None], [torch.cuda.Event(), torch.cuda.Event()], [None, None]
+        loss_dev = torch.zeros(1, dtype=torch.float32, device=self.device)
+        loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+        out: List[float] = []
+
+        def prefetch(i):
+            hb = host_batches[i]
+            s = i & 1
+            if stage[s] is None or stage[s].storage.shape != hb.shape:
+                stage[s] = ops.PackedGenotypes(torch.empty(hb.shape, dtype=torch.uint8, device=self.device),
+                                               hb.shape[0], self.M)
+            with torch.cuda.stream(copy):
+                if free[s] is not None:
+                    copy.wait_event(free[s])
+                stage[s].storage.copy_(hb, non_blocking=True)
+                ready[s].record(copy)
+
+        n = len(host_batches)
+        if n:
+            prefetch(0)
+        for i in range(n):
+            s = i & 1
+            if i + 1 < n:
+                prefetch(i + 1)
+            main.wait_event(ready[s])
+            self._train_step(None, None if labels is None else labels[i], loss_dev, pg=stage[s])
+            free[s] = torch.cuda.Event()
+            free[s].record(main)
+            loss_host.copy_(loss_dev, non_blocking=True)
+            main.synchronize()
+            out.append(float(loss_host[0]))
+        return out
 
     def infer_Q(self, batch: int) -> List[torch.Tensor]:
         ks = self.raw_model.multihead_encoder.ks
