@@ -4,6 +4,9 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <stdlib.h>
+#include <math.h>
+#include <algorithm>
 
 #include "../../include/nadm_b200.h"
 
@@ -57,6 +60,15 @@ inline AdamCoef make_adam(const nadm_adam_t* a) {
     c.enabled = 1;
     return c;
 }
+
+// tensor-core (tcgen05) encoder kernels, nadm_tc_enc.cu
+int launch_enc_fwd_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_idx, int64_t row0, int B, int64_t M,
+                      const float* V, int C, float* Z, void* ws, size_t ws_bytes, cudaStream_t st);
+int launch_enc_bwd_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_idx, int64_t row0, int B, int64_t M,
+                      const float* dZ, int C, float* V, float* Vm, float* Vv, const nadm_adam_t* adam, float* dV_out,
+                      cudaStream_t st);
+size_t enc_tc_workspace_bytes(int B);
+bool use_generic_kernels();   // NADM_GENERIC=1: force the CUDA-core formulation (A/B testing only)
 
 #ifdef __CUDACC__
 // torch.optim.Adam (no weight decay / amsgrad), same operation order as torch's fused kernel:

@@ -40,6 +40,15 @@ int sm_count() {
     return cached[dev];
 }
 
+bool use_generic_kernels() {
+    static int cached = -1;
+    if (cached < 0) {
+        const char* e = getenv("NADM_GENERIC");
+        cached = (e != nullptr && e[0] == '1') ? 1 : 0;
+    }
+    return cached == 1;
+}
+
 constexpr int kMlpRows = 4;       // batch rows per CTA in the per-row kernels
 constexpr int kMlpThreads = 256;
 constexpr int kMaxSumK = NADM_MAX_K * NADM_MAX_HEADS;

@@ -529,6 +529,8 @@ extern "C" size_t nadm_workspace_bytes(int32_t B, int64_t M, int32_t C, int32_t 
     size_t dec = (size_t)kMaxParts * ((size_t)B * 16 + 1) * sizeof(float);
     size_t mlp = ((size_t)B * ((size_t)sumK + (size_t)H + (size_t)C + 2) + 64) * sizeof(float) + 4096;
     size_t ll = (size_t)kMaxParts * sizeof(double) * 2;
+    size_t enc_tc = enc_tc_workspace_bytes(B);
+    enc = enc > enc_tc ? enc : enc_tc;
     size_t m = enc > dec ? enc : dec;
     m = m > mlp ? m : mlp;
     m = m > ll ? m : ll;
@@ -567,6 +569,16 @@ extern "C" int nadm_encoder_fwd(const uint8_t* packed, int64_t pitch, const int6
     NADM_REQUIRE(B > 0 && M > 0, "empty batch or no SNPs (B=%d, M=%lld)", B, (long long)M);
     NADM_REQUIRE(C >= 1 && C <= NADM_MAX_C, "n_components C=%d unsupported (1..%d)", C, NADM_MAX_C);
     NADM_REQUIRE(V && Z && ws, "NULL pointer");
+    if (C <= 8 && !use_generic_kernels() && (reinterpret_cast<uintptr_t>(V) & 15) == 0) {
+        // tensor-core path: at most 2048 rows (16 blocks of 128) per launch
+        for (int r0 = 0; r0 < B; r0 += 2048) {
+            const int nb = std::min(2048, B - r0);
+            if (int rc = launch_enc_fwd_tc(packed, pitch, row_idx ? row_idx + r0 : nullptr, row0 + r0, nb, M, V, C,
+                                           Z + (int64_t)r0 * C, ws, ws_bytes, (cudaStream_t)stream))
+                return rc;
+        }
+        return NADM_OK;
+    }
     if (pad_c(C) == 8)
         return launch_enc_fwd<8>(packed, pitch, row_idx, row0, B, M, V, C, Z, (float*)ws, ws_bytes, (cudaStream_t)stream);
     return launch_enc_fwd<16>(packed, pitch, row_idx, row0, B, M, V, C, Z, (float*)ws, ws_bytes, (cudaStream_t)stream);
@@ -651,6 +663,9 @@ extern "C" int nadm_encoder_bwd(const uint8_t* packed, int64_t pitch, const int6
     NADM_REQUIRE(dZ && V, "NULL pointer");
     NADM_REQUIRE(adam == nullptr || (Vm && Vv), "Adam moments are NULL");
     NADM_REQUIRE(adam != nullptr || dV_out != nullptr, "nothing to do: neither Adam nor dV_out requested");
+    if (C <= 8 && B <= 2048 && !use_generic_kernels() && (reinterpret_cast<uintptr_t>(V) & 15) == 0 &&
+        (dV_out == nullptr || (reinterpret_cast<uintptr_t>(dV_out) & 15) == 0))
+        return launch_enc_bwd_tc(packed, pitch, row_idx, row0, B, M, dZ, C, V, Vm, Vv, adam, dV_out, (cudaStream_t)stream);
     if (pad_c(C) == 8)
         return launch_enc_bwd<8>(packed, pitch, row_idx, row0, B, M, dZ, C, V, Vm, Vv, adam, dV_out, (cudaStream_t)stream);
     return launch_enc_bwd<16>(packed, pitch, row_idx, row0, B, M, dZ, C, V, Vm, Vv, adam, dV_out, (cudaStream_t)stream);

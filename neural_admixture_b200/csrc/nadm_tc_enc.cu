@@ -1,0 +1,480 @@
+// Encoder projection and its backward on the 5th-generation tensor cores (tcgen05, kind::i8), sm_100a.
+//
+//   forward   Z[b, c]  = sum_m x[b, m] V[m, c]              (neural_admixture.py:169-172)
+//   backward  dV[m, c] = sum_b x[b, m] dZ[b, c] ; Adam(V)     (autograd of :172, optimizer.step :411)
+//
+// x = code / 2 with code in {0, 1, 2} (missing 3 -> 0) is an exact small integer, so both contractions are done in
+// EXACT integer arithmetic: the fp32 factor (V, resp. dZ) is written as a 32-bit fixed-point number relative to a
+// power-of-two scale >= max|.| and split into four signed base-256 digits; the tensor core multiplies the unsigned
+// genotype bytes with the int8 digit planes (N = 4 planes x 8 components = 32 columns) into int32 accumulators in
+// tensor memory, and the epilogue recombines the planes in int64.  The result is independent of summation order
+// (bit-reproducible for any grid / sharding) and carries only the fixed-point quantisation of the fp32 factor
+// (<= 2^-31 of its largest entry), i.e. it is more accurate than an fp32 FMA chain.
+//
+// Data movement: the B gathered rows of the 2-bit packed matrix are streamed once per kernel with 128-bit loads (each
+// row's 64 bytes = 256 SNPs per tile, 4 tiles prefetched in registers), widened to one byte per genotype with four
+// shift/mask operations per 16 SNPs and stored straight into the UMMA shared-memory layout; the same tile is the
+// K-major operand X of the forward and the MN-major operand X^T of the backward (nadm_tc.cuh).  Inside a group of 16
+// SNPs the byte position p holds SNP sigma(p) = 4 (p % 4) + p / 4; the digit operand / epilogue use the same map.
+#include "nadm_common.cuh"
+#include "nadm_tc.cuh"
+
+namespace nadm {
+using namespace tc;
+
+constexpr int kSub = 256;                  // SNPs per genotype tile: 64 packed bytes of every row
+constexpr int kATile = 128 * kSub;         // bytes of one widened tile (128 rows x 256 SNPs)
+constexpr int kAStages = 4;                // ring of widened tiles
+constexpr int kDigTile = kSub * 32;        // digit bytes per 256 K positions (4 planes x 8 components each)
+constexpr int kProdWarps = 8;
+constexpr int kProdThreads = kProdWarps * 32;
+constexpr int kPrefetch = 4;               // genotype tiles prefetched in registers per producer thread
+constexpr int kMaxBlkTc = 16;              // 16 blocks of 128 rows per launch (16 x 32 tensor-memory columns)
+constexpr uint32_t kIdescFwd = instr_desc(kAccS32, kFmtU8, kFmtS8, /*A MN*/ false, /*B MN*/ true, 128, 32);
+constexpr uint32_t kIdescBwd = instr_desc(kAccS32, kFmtU8, kFmtS8, /*A MN*/ true, /*B MN*/ true, 128, 32);
+
+__device__ __forceinline__ int sigma16(int p) { return 4 * (p & 3) + (p >> 2); }
+
+__device__ __forceinline__ uint4 ldg_nc(const uint8_t* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+// 16 packed SNPs -> 16 bytes (codes 0,1,2; missing cleared), byte position p <-> SNP sigma16(p)
+__device__ __forceinline__ void widen_store(uint8_t* dst, uint32_t w) {
+    const uint32_t c = clear_missing(w);
+    uint4 o;
+    o.x = c & 0x03030303u;
+    o.y = (c >> 2) & 0x03030303u;
+    o.z = (c >> 4) & 0x03030303u;
+    o.w = (c >> 6) & 0x03030303u;
+    *reinterpret_cast<uint4*>(dst) = o;
+}
+
+// power-of-two fixed-point scale for values with absolute maximum `mx`: q = rint(v * inv) fits in [-2^30, 2^30]
+struct FixScale {
+    float inv;      // 2^(30 - e)
+    double back;    // 2^(e - 30)
+};
+__device__ __forceinline__ FixScale fix_scale(float mx) {
+    FixScale s;
+    const int E = (int)((__float_as_uint(mx) >> 23) & 0xFF);       // biased exponent: mx < 2^(E - 126)
+    if (mx == 0.f || E == 0) { s.inv = 0.f; s.back = 0.0; return s; }
+    const int e = max(E - 126, -96);                                // keep 2^(30-e) a finite float
+    s.inv = __uint_as_float((uint32_t)(127 + 30 - e) << 23);
+    s.back = __longlong_as_double((long long)(1023 + e - 30) << 52);
+    return s;
+}
+// four signed base-256 digits of q, most significant first: q = ((d0*256 + d1)*256 + d2)*256 + d3
+__device__ __forceinline__ void digits4(int q, int (&d)[4]) {
+#pragma unroll
+    for (int i = 3; i > 0; --i) {
+        const int low = (q << 24) >> 24;
+        d[i] = low;
+        q = (q - low) >> 8;
+    }
+    d[0] = q;
+}
+__device__ __forceinline__ long long combine4(const uint32_t* v, int c) {
+    long long z = (int)v[c];
+    z = z * 256 + (int)v[8 + c];
+    z = z * 256 + (int)v[16 + c];
+    z = z * 256 + (int)v[24 + c];
+    return z;
+}
+// write the digits of 8 components (one K position) into an MN-major digit tile: 2 chunks of 16 bytes, 128 B apart
+__device__ __forceinline__ void store_digits(uint8_t* tile_pos, const float (&v)[8], float inv) {
+    uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // w[2*p + h]: plane p, components 4h..4h+3
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        int d[4];
+        digits4(__float2int_rn(v[c] * inv), d);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) w[2 * p + (c >> 2)] |= (uint32_t)(d[p] & 0xFF) << (8 * (c & 3));
+    }
+    *reinterpret_cast<uint4*>(tile_pos) = make_uint4(w[0], w[1], w[2], w[3]);
+    *reinterpret_cast<uint4*>(tile_pos + 128) = make_uint4(w[4], w[5], w[6], w[7]);
+}
+
+struct TileLoad {
+    uint4 w[2];
+};
+
+// rows [blk*128, blk*128 + 128) x SNPs [t*256, t*256 + 256): thread (r = lane % 8, q = lane / 8) of producer warp pw
+// reads bytes [16 q, 16 q + 16) of the tile's 64 bytes of rows 8 (pw + 8 it) + r.
+__device__ __forceinline__ void load_tile(TileLoad& L, const uint8_t* __restrict__ packed, int64_t pitch,
+                                          const int64_t* rowoff, int B, int blk, int64_t t, int pw, int lane) {
+    const int r = lane & 7, q = lane >> 3;
+    const int64_t off = t * (kSub / 4) + q * 16;
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const int b = blk * 128 + (pw + it * kProdWarps) * 8 + r;
+        L.w[it] = make_uint4(0u, 0u, 0u, 0u);
+        if (b < B && off + 16 <= pitch) L.w[it] = ldg_nc(packed + rowoff[b] + off);
+    }
+}
+__device__ __forceinline__ void widen_tile(uint8_t* tile, const TileLoad& L, int B, int blk, int pw, int lane) {
+    const int r = lane & 7, q = lane >> 3;
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const int g = pw + it * kProdWarps;                      // 8-row group inside the block
+        if (blk * 128 + g * 8 >= B) continue;                    // whole group past the batch: nothing reads it
+        uint8_t* dst = tile + r * 16 + g * 2048 + (q * 4) * 128;
+        widen_store(dst, L.w[it].x);
+        widen_store(dst + 128, L.w[it].y);
+        widen_store(dst + 256, L.w[it].z);
+        widen_store(dst + 384, L.w[it].w);
+    }
+}
+
+// =================================================================================================================
+// |max| of a float array (scale of the fixed-point split), result as float bits via atomicMax
+// =================================================================================================================
+__global__ void absmax_kernel(const float* __restrict__ x, int64_t n, uint32_t* __restrict__ out) {
+    float m = 0.f;
+    const int64_t n4 = n / 4;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = reinterpret_cast<const float4*>(x)[i];
+        m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (int)(n - n4 * 4)) m = fmaxf(m, fabsf(x[n4 * 4 + threadIdx.x]));
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));
+}
+
+// =================================================================================================================
+// forward
+// =================================================================================================================
+struct EncSmem {
+    uint64_t fullA[kAStages], emptyA[kAStages], fullV[2], emptyV[2], done;
+    uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kProdThreads + 32, 1)
+enc_fwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* __restrict__ row_idx, int64_t row0,
+                  int B, int64_t M, const float* __restrict__ V, int C, const uint32_t* __restrict__ vmax_bits,
+                  long long* __restrict__ part, int T) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* tilesA = smem;                                         // kAStages x 32 KB
+    uint8_t* tilesV = tilesA + kAStages * kATile;                   // 2 x 8 KB
+    int64_t* rowoff = reinterpret_cast<int64_t*>(tilesV + 2 * kDigTile);
+    EncSmem* S = reinterpret_cast<EncSmem*>(rowoff + ((B + 1) & ~1));
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nblk = (B + 127) / 128;
+    const int t0 = (int)(((int64_t)T * blockIdx.x) / gridDim.x), t1 = (int)(((int64_t)T * (blockIdx.x + 1)) / gridDim.x);
+    const int ntile = (t1 - t0) * nblk;
+
+    for (int b = tid; b < B; b += blockDim.x) rowoff[b] = ((row_idx != nullptr) ? row_idx[b] : (row0 + b)) * pitch;
+    if (tid == 0) {
+        for (int s = 0; s < kAStages; ++s) { mbar_init(&S->fullA[s], kProdThreads); mbar_init(&S->emptyA[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&S->fullV[s], kProdThreads); mbar_init(&S->emptyV[s], 1); }
+        mbar_init(&S->done, 1);
+        mbar_init_fence();
+    }
+    if (warp == kProdWarps) tmem_alloc<512>(&S->tmem_base);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tbase = S->tmem_base;
+
+    if (warp < kProdWarps) {
+        // ---------------- producers: digit tiles of V and widened genotype tiles ----------------
+        const FixScale fs = fix_scale(__uint_as_float(*vmax_bits));
+        TileLoad L[kPrefetch];
+#pragma unroll
+        for (int p = 0; p < kPrefetch; ++p)
+            if (p < ntile) load_tile(L[p], packed, pitch, rowoff, B, p % nblk, t0 + p / nblk, warp, lane);
+        for (int i0 = 0; i0 < ntile; i0 += kPrefetch) {
+#pragma unroll
+            for (int p = 0; p < kPrefetch; ++p) {
+                const int i = i0 + p;
+                if (i >= ntile) break;
+                const int blk = i % nblk, tt = i / nblk;
+                if (blk == 0) {
+                    // digits of V for K positions of sub-tile t0 + tt: thread tid <-> position tid
+                    const int vs = tt & 1;
+                    const int64_t m = (int64_t)(t0 + tt) * kSub + (tid & ~15) + sigma16(tid & 15);
+                    float v[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) v[c] = (m < M && c < C) ? V[m * C + c] : 0.f;
+                    mbar_wait(&S->emptyV[vs], ((tt >> 1) & 1) ^ 1);
+                    store_digits(tilesV + vs * kDigTile + (tid & 7) * 16 + (tid >> 3) * 256, v, fs.inv);
+                    fence_async_smem();
+                    mbar_arrive(&S->fullV[vs]);
+                }
+                const int s = i % kAStages;
+                mbar_wait(&S->emptyA[s], ((i / kAStages) & 1) ^ 1);
+                widen_tile(tilesA + s * kATile, L[p], B, blk, warp, lane);
+                fence_async_smem();
+                mbar_arrive(&S->fullA[s]);
+                const int nx = i + kPrefetch;
+                if (nx < ntile) load_tile(L[p], packed, pitch, rowoff, B, nx % nblk, t0 + nx / nblk, warp, lane);
+            }
+        }
+        // ---------------- epilogue: recombine the digit planes, write this CTA's exact partial sums ----------------
+        mbar_wait(&S->done, 0);
+        tc_fence_after_sync();
+        const int q = warp & 3;
+        for (int blk = warp >> 2; blk < nblk; blk += 2) {
+            uint32_t v[32];
+            tmem_ld32(tbase + ((uint32_t)(q * 32) << 16) + blk * 32, v);
+            tmem_wait_ld();
+            const int b = blk * 128 + q * 32 + lane;
+            if (b < B) {
+                long long* out = part + ((int64_t)blockIdx.x * B + b) * 8;
+#pragma unroll
+                for (int c = 0; c < 8; c += 2) {
+                    longlong2 z;
+                    z.x = (ntile > 0) ? combine4(v, c) : 0;
+                    z.y = (ntile > 0) ? combine4(v, c + 1) : 0;
+                    *reinterpret_cast<longlong2*>(out + c) = z;
+                }
+            }
+        }
+    } else if (lane == 0) {
+        // ---------------- MMA issuer ----------------
+        for (int i = 0; i < ntile; ++i) {
+            const int blk = i % nblk, tt = i / nblk, vs = tt & 1, s = i % kAStages;
+            if (blk == 0) mbar_wait(&S->fullV[vs], (tt >> 1) & 1);
+            mbar_wait(&S->fullA[s], (i / kAStages) & 1);
+            tc_fence_after_sync();
+            const uint32_t a0 = smem_u32(tilesA + s * kATile), b0 = smem_u32(tilesV + vs * kDigTile);
+#pragma unroll
+            for (int ks = 0; ks < kSub / 32; ++ks)
+                mma_i8_ss(tbase + blk * 32, smem_desc(a0 + ks * 256, 128, 2048), smem_desc(b0 + ks * 1024, 256, 128),
+                          kIdescFwd, (tt > 0 || ks > 0) ? 1u : 0u);
+            mma_commit(&S->emptyA[s]);
+            if (blk == nblk - 1) mma_commit(&S->emptyV[vs]);
+        }
+        mma_commit(&S->done);
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == kProdWarps) tmem_dealloc<512>(tbase);
+}
+
+// Z[b, c] = 0.5 * 2^(e-30) * sum over CTAs of the exact int64 partials
+__global__ void enc_fwd_reduce_kernel(const long long* __restrict__ part, int nparts, int B, int C,
+                                      const uint32_t* __restrict__ vmax_bits, float* __restrict__ Z) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * 8) return;
+    const int b = i >> 3, c = i & 7;
+    if (c >= C) return;
+    long long acc = 0;
+    for (int p = 0; p < nparts; ++p) acc += part[(int64_t)p * B * 8 + i];
+    const FixScale fs = fix_scale(__uint_as_float(*vmax_bits));
+    Z[(int64_t)b * C + c] = (float)((double)acc * fs.back * 0.5);
+}
+
+// =================================================================================================================
+// backward: dV = X^T dZ, Adam on V
+// =================================================================================================================
+struct EncBwdSmem {
+    uint64_t fullA[kAStages], emptyA[kAStages], dfull[2], dempty[2];
+    uint32_t tmem_base;
+    float red[32];
+};
+
+__global__ void __launch_bounds__(kProdThreads + 32 + 128, 1)
+enc_bwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* __restrict__ row_idx, int64_t row0,
+                  int B, int64_t M, const float* __restrict__ dZ, int C, float* __restrict__ V, float* __restrict__ Vm,
+                  float* __restrict__ Vv, AdamCoef adam, float* __restrict__ dV_out, int T) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int nblk = (B + 127) / 128;
+    uint8_t* tilesA = smem;                                         // kAStages x 32 KB
+    uint8_t* digZ = tilesA + kAStages * kATile;                     // nblk x 4 KB: dZ digits, K position = batch row
+    int64_t* rowoff = reinterpret_cast<int64_t*>(digZ + nblk * 4096);
+    EncBwdSmem* S = reinterpret_cast<EncBwdSmem*>(rowoff + ((B + 1) & ~1));
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int t0 = (int)(((int64_t)T * blockIdx.x) / gridDim.x), t1 = (int)(((int64_t)T * (blockIdx.x + 1)) / gridDim.x);
+    const int ntile = (t1 - t0) * nblk;
+
+    for (int b = tid; b < B; b += blockDim.x) rowoff[b] = ((row_idx != nullptr) ? row_idx[b] : (row0 + b)) * pitch;
+    if (tid == 0) {
+        for (int s = 0; s < kAStages; ++s) { mbar_init(&S->fullA[s], kProdThreads); mbar_init(&S->emptyA[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&S->dfull[s], 1); mbar_init(&S->dempty[s], 128); }
+        mbar_init_fence();
+    }
+    if (warp == kProdWarps) tmem_alloc<128>(&S->tmem_base);
+    // |max| of dZ over the batch (every CTA computes the same value)
+    float mx = 0.f;
+    for (int i = tid; i < B * C; i += blockDim.x) mx = fmaxf(mx, fabsf(dZ[i]));
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) S->red[warp] = mx;
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    mx = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) mx = fmaxf(mx, S->red[w]);
+    const FixScale fs = fix_scale(mx);
+    for (int b = tid; b < nblk * 128; b += blockDim.x) {
+        float v[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[c] = (b < B && c < C) ? dZ[(int64_t)b * C + c] : 0.f;
+        store_digits(digZ + (b & 7) * 16 + (b >> 3) * 256, v, fs.inv);
+    }
+    fence_async_smem();
+    __syncthreads();
+    const uint32_t tbase = S->tmem_base;
+
+    if (warp < kProdWarps) {
+        // ---------------- producers: widened genotype tiles, order (sub-tile, block) ----------------
+        TileLoad L[kPrefetch];
+#pragma unroll
+        for (int p = 0; p < kPrefetch; ++p)
+            if (p < ntile) load_tile(L[p], packed, pitch, rowoff, B, p % nblk, t0 + p / nblk, warp, lane);
+        for (int i0 = 0; i0 < ntile; i0 += kPrefetch) {
+#pragma unroll
+            for (int p = 0; p < kPrefetch; ++p) {
+                const int i = i0 + p;
+                if (i >= ntile) break;
+                const int s = i % kAStages;
+                mbar_wait(&S->emptyA[s], ((i / kAStages) & 1) ^ 1);
+                widen_tile(tilesA + s * kATile, L[p], B, i % nblk, warp, lane);
+                fence_async_smem();
+                mbar_arrive(&S->fullA[s]);
+                const int nx = i + kPrefetch;
+                if (nx < ntile) load_tile(L[p], packed, pitch, rowoff, B, nx % nblk, t0 + nx / nblk, warp, lane);
+            }
+        }
+    } else if (warp == kProdWarps) {
+        // ---------------- MMA issuer ----------------
+        if (lane == 0) {
+            for (int i = 0; i < ntile; ++i) {
+                const int blk = i % nblk, tt = i / nblk, buf = tt & 1, s = i % kAStages;
+                if (blk == 0) {
+                    mbar_wait(&S->dempty[buf], ((tt >> 1) & 1) ^ 1);
+                }
+                mbar_wait(&S->fullA[s], (i / kAStages) & 1);
+                tc_fence_after_sync();
+                const uint32_t a0 = smem_u32(tilesA + s * kATile), b0 = smem_u32(digZ + blk * 4096);
+                const int nks = min(4, (B - blk * 128 + 31) / 32);          // K steps holding real batch rows
+                for (int h = 0; h < 2; ++h)
+                    for (int ks = 0; ks < nks; ++ks)
+                        mma_i8_ss(tbase + buf * 64 + h * 32, smem_desc(a0 + h * 1024 + ks * 8192, 2048, 128),
+                                  smem_desc(b0 + ks * 1024, 256, 128), kIdescBwd, (blk > 0 || ks > 0) ? 1u : 0u);
+                mma_commit(&S->emptyA[s]);
+                if (blk == nblk - 1) mma_commit(&S->dfull[buf]);
+            }
+        }
+    } else {
+        // ---------------- epilogue: digit planes -> dV -> Adam on V, one SNP per thread ----------------
+        const int q = warp & 3;             // tensor-memory lane quadrant this warp may access (warp id % 4)
+        for (int tt = 0; tt < t1 - t0; ++tt) {
+            const int buf = tt & 1;
+            mbar_wait(&S->dfull[buf], (tt >> 1) & 1);
+            tc_fence_after_sync();
+            uint32_t v[2][32];
+            tmem_ld32(tbase + ((uint32_t)(q * 32) << 16) + buf * 64, v[0]);
+            tmem_ld32(tbase + ((uint32_t)(q * 32) << 16) + buf * 64 + 32, v[1]);
+            tmem_wait_ld();
+            tc_fence_before_sync();
+            mbar_arrive(&S->dempty[buf]);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int pos = q * 32 + lane;
+                const int64_t m = (int64_t)(t0 + tt) * kSub + h * 128 + (pos & ~15) + sigma16(pos & 15);
+                if (m >= M) continue;
+                float g[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) g[c] = (float)((double)combine4(v[h], c) * fs.back * 0.5);
+                if (C == 8) {
+                    float4* gv = reinterpret_cast<float4*>(g);
+                    if (dV_out != nullptr) {
+                        reinterpret_cast<float4*>(dV_out + m * 8)[0] = gv[0];
+                        reinterpret_cast<float4*>(dV_out + m * 8)[1] = gv[1];
+                    }
+                    if (adam.enabled) {
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) {
+                            float4 p4 = reinterpret_cast<float4*>(V + m * 8)[hh];
+                            float4 m4 = reinterpret_cast<float4*>(Vm + m * 8)[hh];
+                            float4 v4 = reinterpret_cast<float4*>(Vv + m * 8)[hh];
+                            p4.x = adam_apply(p4.x, g[hh * 4 + 0], m4.x, v4.x, adam);
+                            p4.y = adam_apply(p4.y, g[hh * 4 + 1], m4.y, v4.y, adam);
+                            p4.z = adam_apply(p4.z, g[hh * 4 + 2], m4.z, v4.z, adam);
+                            p4.w = adam_apply(p4.w, g[hh * 4 + 3], m4.w, v4.w, adam);
+                            reinterpret_cast<float4*>(V + m * 8)[hh] = p4;
+                            reinterpret_cast<float4*>(Vm + m * 8)[hh] = m4;
+                            reinterpret_cast<float4*>(Vv + m * 8)[hh] = v4;
+                        }
+                    }
+                } else {
+                    for (int c = 0; c < C; ++c) {
+                        const int64_t vi = m * C + c;
+                        if (dV_out != nullptr) dV_out[vi] = g[c];
+                        if (adam.enabled) {
+                            float mm = Vm[vi], vv = Vv[vi];
+                            V[vi] = adam_apply(V[vi], g[c], mm, vv, adam);
+                            Vm[vi] = mm;
+                            Vv[vi] = vv;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == kProdWarps) tmem_dealloc<128>(tbase);
+}
+
+// =================================================================================================================
+// host launchers (called from the C ABI in nadm_stream.cu)
+// =================================================================================================================
+size_t enc_tc_workspace_bytes(int B) { return (size_t)sm_count() * (size_t)B * 8 * sizeof(long long) + 256; }
+
+int launch_enc_fwd_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_idx, int64_t row0, int B, int64_t M,
+                      const float* V, int C, float* Z, void* ws, size_t ws_bytes, cudaStream_t st) {
+    const int T = (int)((M + kSub - 1) / kSub);
+    const int ncta = std::min(T, sm_count());
+    const size_t need = (size_t)ncta * B * 8 * sizeof(long long) + 256;
+    NADM_REQUIRE(need <= ws_bytes, "workspace too small for encoder_fwd (%zu > %zu)", need, ws_bytes);
+    uint32_t* vmax = reinterpret_cast<uint32_t*>(ws);
+    long long* part = reinterpret_cast<long long*>(reinterpret_cast<uint8_t*>(ws) + 256);
+    cudaError_t e = cudaMemsetAsync(vmax, 0, 4, st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(vmax)");
+    const int64_t n = M * C;
+    absmax_kernel<<<(unsigned)std::min<int64_t>((n / 4 + 255) / 256 + 1, 4 * sm_count()), 256, 0, st>>>(V, n, vmax);
+    NADM_CHECK_LAUNCH("absmax_kernel");
+    const size_t smem = (size_t)kAStages * kATile + 2 * kDigTile + (size_t)((B + 1) & ~1) * 8 + sizeof(EncSmem) + 64;
+    static bool attr = false;
+    if (!attr) {
+        e = cudaFuncSetAttribute(enc_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(enc_fwd_tc)");
+        attr = true;
+    }
+    enc_fwd_tc_kernel<<<ncta, kProdThreads + 32, smem, st>>>(packed, pitch, row_idx, row0, B, M, V, C, vmax, part, T);
+    NADM_CHECK_LAUNCH("enc_fwd_tc_kernel");
+    enc_fwd_reduce_kernel<<<(B * 8 + 255) / 256, 256, 0, st>>>(part, ncta, B, C, vmax, Z);
+    NADM_CHECK_LAUNCH("enc_fwd_reduce_kernel");
+    return NADM_OK;
+}
+
+int launch_enc_bwd_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_idx, int64_t row0, int B, int64_t M,
+                      const float* dZ, int C, float* V, float* Vm, float* Vv, const nadm_adam_t* adam, float* dV_out,
+                      cudaStream_t st) {
+    const int T = (int)((M + kSub - 1) / kSub);
+    const int ncta = std::min(T, sm_count());
+    const int nblk = (B + 127) / 128;
+    const size_t smem = (size_t)kAStages * kATile + (size_t)nblk * 4096 + (size_t)((B + 1) & ~1) * 8 +
+                        sizeof(EncBwdSmem) + 64;
+    NADM_REQUIRE(smem <= (size_t)kMaxDynSmem, "batch B=%d too large for encoder_bwd", B);
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(enc_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(enc_bwd_tc)");
+        attr = true;
+    }
+    enc_bwd_tc_kernel<<<ncta, kProdThreads + 32 + 128, smem, st>>>(packed, pitch, row_idx, row0, B, M, dZ, C, V, Vm, Vv,
+                                                                  make_adam(adam), dV_out, T);
+    NADM_CHECK_LAUNCH("enc_bwd_tc_kernel");
+    return NADM_OK;
+}
+
+}  // namespace nadm
