@@ -68,6 +68,14 @@ int launch_enc_bwd_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_i
                       const float* dZ, int C, float* V, float* Vm, float* Vv, const nadm_adam_t* adam, float* dV_out,
                       cudaStream_t st);
 size_t enc_tc_workspace_bytes(int B);
+// tensor-core fused decoder, nadm_tc_dec.cu
+bool dec_tc_supported(int B, int k);
+int launch_dec_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_idx, int64_t row0, int B, int64_t M,
+                  const float* Q, float* dQ, int q_ld, int q_off, int k, float* P, float* Pm, float* Pv,
+                  const nadm_adam_t* adam, float* dP_out, float* loss, float* ws, size_t ws_bytes, cudaStream_t st);
+// deterministic sum of per-CTA partials (nadm_stream.cu)
+int launch_reduce_parts(const float* part, int nparts, int rows, int cols_p, int cols_out, float* out, int out_ld,
+                        int out_off, float scale, const float* loss_part, float* loss, cudaStream_t st);
 bool use_generic_kernels();   // NADM_GENERIC=1: force the CUDA-core formulation (A/B testing only)
 
 #ifdef __CUDACC__

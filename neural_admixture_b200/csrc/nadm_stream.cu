@@ -520,6 +520,17 @@ extern "C" int nadm_unpack2bit(const uint8_t* src, int64_t rows, int64_t M, int6
     return NADM_OK;
 }
 
+namespace nadm {
+int launch_reduce_parts(const float* part, int nparts, int rows, int cols_p, int cols_out, float* out, int out_ld,
+                        int out_off, float scale, const float* loss_part, float* loss, cudaStream_t st) {
+    const int64_t n = (int64_t)rows * cols_p;
+    reduce_parts_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(part, nparts, rows, cols_p, cols_out, out, out_ld,
+                                                                    out_off, scale, loss_part, loss);
+    NADM_CHECK_LAUNCH("reduce_parts_kernel");
+    return NADM_OK;
+}
+}  // namespace nadm
+
 static inline int pad_c(int C) { return C <= 8 ? 8 : 16; }
 static inline int pad_k(int k) { return k <= 4 ? 4 : (k <= 8 ? 8 : 16); }
 
@@ -625,6 +636,12 @@ extern "C" int nadm_decoder_step(const uint8_t* packed, int64_t pitch, const int
     NADM_REQUIRE(adam == nullptr || (Pm && Pv), "Adam moments are NULL");
     cudaStream_t st = (cudaStream_t)stream;
     float* w = (float*)ws;
+    if (!use_generic_kernels() && dec_tc_supported(B, k) && (reinterpret_cast<uintptr_t>(P) & 15) == 0 &&
+        (Pm == nullptr || (reinterpret_cast<uintptr_t>(Pm) & 15) == 0) &&
+        (Pv == nullptr || (reinterpret_cast<uintptr_t>(Pv) & 15) == 0) &&
+        (dP_out == nullptr || (reinterpret_cast<uintptr_t>(dP_out) & 15) == 0))
+        return launch_dec_tc(packed, pitch, row_idx, row0, B, M, Q, dQ, q_ld, q_off, k, P, Pm, Pv, adam, dP_out, loss, w,
+                             ws_bytes, st);
     switch (pad_k(k)) {
         case 4: return launch_dec<4>(packed, pitch, row_idx, row0, B, M, Q, dQ, q_ld, q_off, k, P, Pm, Pv, adam, dP_out, loss, w, ws_bytes, st);
         case 8: return launch_dec<8>(packed, pitch, row_idx, row0, B, M, Q, dQ, q_ld, q_off, k, P, Pm, Pv, adam, dP_out, loss, w, ws_bytes, st);

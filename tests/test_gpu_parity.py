@@ -46,6 +46,16 @@ def packed_from(ops, G, dev):
     return ops.PackedGenotypes.from_unpacked_host(torch.as_tensor(G), dev)
 
 
+def decoder_grads_with_fp32_raw(x, Q, P):
+    """orc.decoder_loss_grads with raw = Q P^T rounded once to fp32 (everything else fp64): the error floor of ANY
+    fp32 implementation of the decoder, the reference's own included."""
+    raw = (Q @ P.T).astype(np.float32).astype(np.float64)
+    R = np.clip(raw, 0.0, 1.0)
+    Gm = (R - x) / np.maximum((1.0 - R) * R, 1e-12)
+    Gm = np.where((raw >= 0.0) & (raw <= 1.0), Gm, 0.0)
+    return None, Gm @ P, Gm.T @ Q
+
+
 def ws_for(ops, B, M, C, H, sumK, dev):
     return torch.empty(ops.workspace_bytes(B, M, C, H, sumK), dtype=torch.uint8, device=dev)
 
@@ -186,10 +196,14 @@ def test_decoder_step_grads(ops, dev, N, M, k, B, edge):
     ws = ws_for(ops, B, M, 8, 64, sumK, dev)
     ops.decoder_step(pg, t(Qw, dev), dQ, q_off, k, P_d, None, None, None, loss, ws, row_idx=t(idx, dev, torch.int64),
                      dP_out=dP)
-    l_ref, dQ_ref, dP_ref = orc.decoder_loss_grads(orc.genotype_to_x(G[idx]), Q.astype(np.float64), P.astype(np.float64))
+    x = orc.genotype_to_x(G[idx])
+    l_ref, dQ_ref, dP_ref = orc.decoder_loss_grads(x, Q.astype(np.float64), P.astype(np.float64))
+    # conditioning: G = (R - x) / (R (1 - R)) amplifies the rounding of raw = Q P^T when R is within ~1e-4 of 0 or 1.
+    # The bar is "raw good to 4 fp32 ulps": tolerance = KERNEL_TOL + 8 x the effect of rounding raw to fp32 once.
+    _, dQ_r32, dP_r32 = decoder_grads_with_fp32_raw(x, Q.astype(np.float64), P.astype(np.float64))
     assert abs(loss.item() - l_ref) < 1e-5 * abs(l_ref)
-    assert relF(dQ[:, q_off:q_off + k].cpu().numpy(), dQ_ref) < KERNEL_TOL
-    assert relF(dP.cpu().numpy(), dP_ref) < KERNEL_TOL
+    assert relF(dQ[:, q_off:q_off + k].cpu().numpy(), dQ_ref) < KERNEL_TOL + 8 * relF(dQ_r32, dQ_ref)
+    assert relF(dP.cpu().numpy(), dP_ref) < KERNEL_TOL + 8 * relF(dP_r32, dP_ref)
     assert torch.all(dQ[:, :q_off] == 7.0) and torch.all(dQ[:, q_off + k:] == 7.0)   # other heads' columns untouched
     assert np.array_equal(P_d.cpu().numpy(), P)                   # no Adam requested: P unchanged
     if edge:
