@@ -240,61 +240,77 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
         }
     } else if (warp == 8) {
         // =============================== MMA issuer ===============================
-        if (lane == 0) {
-            const uint32_t qa = smem_u32(QA), pt = smem_u32(PT), gtb = smem_u32(GT);
-            int p_waited = -1;                                          // last sub-tile whose P tile we waited for
-            auto issue_mma1 = [&](int u) {
-                const int sub = u / nblk, blk = u % nblk, slot = u % kSlots;
-                if (sub > p_waited) {
-                    mbar_wait(&S->pfull[sub % kPStages], (sub / kPStages) & 1);
-                    tc_fence_after_sync();
-                    p_waited = sub;
-                }
-                // Q chunks [h m l] (stride 128, 8-row groups 384 apart); P chunks [h l m h] (8-row groups 512 apart).
-                // A K=16 instruction multiplies two chunk pairs: start address = first chunk, LBO = distance to the second.
-                const uint32_t a = qa + blk * kQBlkBytes, b = pt + (sub % kPStages) * kPTileBytes, d = tbase + slot * 64;
-                mma_f16_ss(d, smem_desc(a, 128, 384), smem_desc(b, 256, 512), kIdesc1, 0u);              // h.h + m.m
-                mma_f16_ss(d, smem_desc(a, 128, 384), smem_desc(b + 256, 128, 512), kIdesc1, 1u);        // h.m + m.h
-                mma_f16_ss(d, smem_desc(a, 256, 384), smem_desc(b + 128, 256, 512), kIdesc1, 1u);        // h.l + l.h
-                mma_f16_ss(d, smem_desc(a + 128, 128, 384), smem_desc(b + 128, 128, 512), kIdesc1, 1u);  // m.l + l.m
-                mma_commit(&S->d1full[slot]);
-            };
-            for (int u = 0; u < min(kSlots, U); ++u) issue_mma1(u);
-            for (int u = 0; u < U; ++u) {
-                const int sub = u / nblk, blk = u % nblk, slot = u % kSlots, g = u % ngt, dbuf = sub & 1;
-                mbar_wait(&S->gready[slot], (u / kSlots) & 1);
+        // The whole warp walks the unit sequence and waits on the barriers; one elected lane issues.  Descriptors are
+        // built once; per instruction only the 14-bit start-address field (16-byte units) is advanced.
+        const uint32_t qa = smem_u32(QA), pt = smem_u32(PT), gtb = smem_u32(GT);
+        // Q chunks [h m l] (128 B apart, 8-row groups 384 B apart); P chunks [h l m h] (8-row groups 512 B apart).
+        // A K=16 instruction multiplies two chunk pairs: start address = first chunk, LBO = distance to the second.
+        const uint64_t A_hm = smem_desc(qa, 128, 384), A_hl = smem_desc(qa, 256, 384), A_ml = smem_desc(qa + 128, 128, 384);
+        const uint64_t B_hm = smem_desc(pt, 256, 512), B_mh = smem_desc(pt + 256, 128, 512);
+        const uint64_t B_lh = smem_desc(pt + 128, 256, 512), B_lm = smem_desc(pt + 128, 128, 512);
+        const uint64_t B2 = smem_desc(pt, 512, 128);                       // P tile as MN-major [32 x K] operand
+        const uint64_t A3 = smem_desc(gtb, 1024, 128), B3 = smem_desc(qa, 384, 128);
+        int p_waited = -1;                                              // last sub-tile whose P tile we waited for
+        auto issue_mma1 = [&](int u) {
+            const int sub = u / nblk, blk = u - sub * nblk, slot = u % kSlots;
+            if (sub > p_waited) {
+                mbar_wait(&S->pfull[sub % kPStages], (sub / kPStages) & 1);
                 tc_fence_after_sync();
-                if (blk == 0) {
-                    mbar_wait(&S->d3empty[dbuf], ((sub >> 1) & 1) ^ 1);
-                    tc_fence_after_sync();
-                }
+                p_waited = sub;
+            }
+            if (elect_one()) {
+                const uint64_t ao = (uint64_t)(blk * (kQBlkBytes >> 4)), bo = (uint64_t)((sub % kPStages) * (kPTileBytes >> 4));
+                const uint32_t d = tbase + slot * 64;
+                mma_f16_ss(d, A_hm + ao, B_hm + bo, kIdesc1, 0u);       // h.h + m.m
+                mma_f16_ss(d, A_hm + ao, B_mh + bo, kIdesc1, 1u);       // h.m + m.h
+                mma_f16_ss(d, A_hl + ao, B_lh + bo, kIdesc1, 1u);       // h.l + l.h
+                mma_f16_ss(d, A_ml + ao, B_lm + bo, kIdesc1, 1u);       // m.l + l.m
+                mma_commit(&S->d1full[slot]);
+            }
+            __syncwarp();
+        };
+        for (int u = 0; u < min(kSlots, U); ++u) issue_mma1(u);
+        for (int u = 0; u < U; ++u) {
+            const int sub = u / nblk, blk = u - sub * nblk, slot = u % kSlots, g = u % ngt, dbuf = sub & 1;
+            mbar_wait(&S->gready[slot], (u / kSlots) & 1);
+            if (blk == 0) mbar_wait(&S->d3empty[dbuf], ((sub >> 1) & 1) ^ 1);
+            tc_fence_after_sync();
+            if (elect_one()) {
                 // dQ_blk += G . [P_h | P_l | P_m | P_h]   (A from tensor memory: hi / lo of the two 32-SNP halves)
-                const uint32_t pb2 = pt + (sub % kPStages) * kPTileBytes;
+                const uint64_t b2 = B2 + (uint64_t)((sub % kPStages) * (kPTileBytes >> 4));
+                const uint32_t d2 = tbase + kColD2 + blk * 32, a2 = tbase + slot * 64;
+                const uint32_t acc2 = sub > 0 ? 1u : 0u;
 #pragma unroll
                 for (int c = 0; c < 2; ++c)
 #pragma unroll
                     for (int t = 0; t < 2; ++t)
 #pragma unroll
                         for (int kk = 0; kk < 2; ++kk)
-                            mma_f16_ts(tbase + kColD2 + blk * 32, tbase + slot * 64 + c * 32 + t * 16 + kk * 8,
-                                       smem_desc(pb2 + (c * 4 + kk * 2) * 512, 512, 128), kIdesc2,
-                                       (sub > 0 || c > 0 || t > 0 || kk > 0) ? 1u : 0u);
+                            mma_f16_ts(d2, a2 + c * 32 + t * 16 + kk * 8, b2 + (uint64_t)((c * 4 + kk * 2) * 32), kIdesc2,
+                                       (c + t + kk) ? 1u : acc2);
                 // dP_sub += G^T . [Q_h | Q_m | Q_l]    (A = shared G^T tile, MN-major; only K steps holding real rows)
                 const int nks = min(8, (B - blk * 128 + 15) / 16);
+                const uint64_t a3 = A3 + (uint64_t)(g * (kGtBytes >> 4)), b3 = B3 + (uint64_t)(blk * (kQBlkBytes >> 4));
+                const uint32_t d3 = tbase + kColD3 + dbuf * 32;
+                const uint32_t acc3 = blk > 0 ? 1u : 0u;
+#pragma unroll
                 for (int t = 0; t < 2; ++t)
-                    for (int ks = 0; ks < nks; ++ks)
-                        mma_f16_ss(tbase + kColD3 + dbuf * 32, smem_desc(gtb + g * kGtBytes + t * 16384 + ks * 2048, 1024, 128),
-                                   smem_desc(qa + blk * kQBlkBytes + ks * 768, 384, 128), kIdesc3,
-                                   (blk > 0 || t > 0 || ks > 0) ? 1u : 0u);
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks)
+                        if (ks < nks)
+                            mma_f16_ss(d3, a3 + (uint64_t)(t * 1024 + ks * 128), b3 + (uint64_t)(ks * 48), kIdesc3,
+                                       (t + ks) ? 1u : acc3);
                 mma_commit(&S->gtfree[g]);
                 if (blk == nblk - 1) {
                     mma_commit(&S->d3full[dbuf]);
                     mma_commit(&S->pempty[sub % kPStages]);
                 }
-                if (u + kSlots < U) issue_mma1(u + kSlots);
             }
-            mma_commit(&S->alldone);
+            __syncwarp();
+            if (u + kSlots < U) issue_mma1(u + kSlots);
         }
+        if (elect_one()) mma_commit(&S->alldone);
+        __syncwarp();
     } else if (warp == 9) {
         // =============================== P sub-tile producer ===============================
         for (int sub = 0; sub < nsub; ++sub) {
