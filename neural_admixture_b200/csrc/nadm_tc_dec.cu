@@ -250,34 +250,41 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
         const uint64_t B_lh = smem_desc(pt + 128, 256, 512), B_lm = smem_desc(pt + 128, 128, 512);
         const uint64_t B2 = smem_desc(pt, 512, 128);                       // P tile as MN-major [32 x K] operand
         const uint64_t A3 = smem_desc(gtb, 1024, 128), B3 = smem_desc(qa, 384, 128);
-        int p_waited = -1;                                              // last sub-tile whose P tile we waited for
-        auto issue_mma1 = [&](int u) {
-            const int sub = u / nblk, blk = u - sub * nblk, slot = u % kSlots;
-            if (sub > p_waited) {
-                mbar_wait(&S->pfull[sub % kPStages], (sub / kPStages) & 1);
+        // Counters are advanced incrementally (no divisions on the single issuing thread's critical path).
+        // look-ahead unit (next MMA1): row block, P stage + its phase, slot
+        int l_blk = 0, l_stage = 0, l_phase = 0, l_slot = 0, l_left = U;
+        auto issue_mma1 = [&]() {
+            if (l_blk == 0) {                                           // first unit of a sub-tile: its P tile must be there
+                mbar_wait(&S->pfull[l_stage], l_phase);
                 tc_fence_after_sync();
-                p_waited = sub;
             }
             if (elect_one()) {
-                const uint64_t ao = (uint64_t)(blk * (kQBlkBytes >> 4)), bo = (uint64_t)((sub % kPStages) * (kPTileBytes >> 4));
-                const uint32_t d = tbase + slot * 64;
+                const uint64_t ao = (uint64_t)(l_blk * (kQBlkBytes >> 4)), bo = (uint64_t)(l_stage * (kPTileBytes >> 4));
+                const uint32_t d = tbase + l_slot * 64;
                 mma_f16_ss(d, A_hm + ao, B_hm + bo, kIdesc1, 0u);       // h.h + m.m
                 mma_f16_ss(d, A_hm + ao, B_mh + bo, kIdesc1, 1u);       // h.m + m.h
                 mma_f16_ss(d, A_hl + ao, B_lh + bo, kIdesc1, 1u);       // h.l + l.h
                 mma_f16_ss(d, A_ml + ao, B_lm + bo, kIdesc1, 1u);       // m.l + l.m
-                mma_commit(&S->d1full[slot]);
+                mma_commit(&S->d1full[l_slot]);
             }
             __syncwarp();
+            --l_left;
+            l_slot = (l_slot == kSlots - 1) ? 0 : l_slot + 1;
+            if (++l_blk == nblk) {
+                l_blk = 0;
+                if (++l_stage == kPStages) { l_stage = 0; l_phase ^= 1; }
+            }
         };
-        for (int u = 0; u < min(kSlots, U); ++u) issue_mma1(u);
+        for (int i = 0; i < kSlots && l_left > 0; ++i) issue_mma1();
+        const int nks_last = min(8, (B - (nblk - 1) * 128 + 15) / 16);
+        int blk = 0, sub = 0, slot = 0, slot_phase = 0, g = 0, stage = 0, dbuf = 0, d3_phase = 1;
         for (int u = 0; u < U; ++u) {
-            const int sub = u / nblk, blk = u - sub * nblk, slot = u % kSlots, g = u % ngt, dbuf = sub & 1;
-            mbar_wait(&S->gready[slot], (u / kSlots) & 1);
-            if (blk == 0) mbar_wait(&S->d3empty[dbuf], ((sub >> 1) & 1) ^ 1);
+            mbar_wait(&S->gready[slot], slot_phase);
+            if (blk == 0) mbar_wait(&S->d3empty[dbuf], d3_phase);
             tc_fence_after_sync();
             if (elect_one()) {
                 // dQ_blk += G . [P_h | P_l | P_m | P_h]   (A from tensor memory: hi / lo of the two 32-SNP halves)
-                const uint64_t b2 = B2 + (uint64_t)((sub % kPStages) * (kPTileBytes >> 4));
+                const uint64_t b2 = B2 + (uint64_t)(stage * (kPTileBytes >> 4));
                 const uint32_t d2 = tbase + kColD2 + blk * 32, a2 = tbase + slot * 64;
                 const uint32_t acc2 = sub > 0 ? 1u : 0u;
 #pragma unroll
@@ -289,25 +296,40 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
                             mma_f16_ts(d2, a2 + c * 32 + t * 16 + kk * 8, b2 + (uint64_t)((c * 4 + kk * 2) * 32), kIdesc2,
                                        (c + t + kk) ? 1u : acc2);
                 // dP_sub += G^T . [Q_h | Q_m | Q_l]    (A = shared G^T tile, MN-major; only K steps holding real rows)
-                const int nks = min(8, (B - blk * 128 + 15) / 16);
                 const uint64_t a3 = A3 + (uint64_t)(g * (kGtBytes >> 4)), b3 = B3 + (uint64_t)(blk * (kQBlkBytes >> 4));
                 const uint32_t d3 = tbase + kColD3 + dbuf * 32;
                 const uint32_t acc3 = blk > 0 ? 1u : 0u;
+                if (blk != nblk - 1 || nks_last == 8) {
 #pragma unroll
-                for (int t = 0; t < 2; ++t)
+                    for (int t = 0; t < 2; ++t)
 #pragma unroll
-                    for (int ks = 0; ks < 8; ++ks)
-                        if (ks < nks)
+                        for (int ks = 0; ks < 8; ++ks)
                             mma_f16_ss(d3, a3 + (uint64_t)(t * 1024 + ks * 128), b3 + (uint64_t)(ks * 48), kIdesc3,
                                        (t + ks) ? 1u : acc3);
+                } else {
+                    for (int t = 0; t < 2; ++t)
+                        for (int ks = 0; ks < nks_last; ++ks)
+                            mma_f16_ss(d3, a3 + (uint64_t)(t * 1024 + ks * 128), b3 + (uint64_t)(ks * 48), kIdesc3,
+                                       (t + ks) ? 1u : acc3);
+                }
                 mma_commit(&S->gtfree[g]);
                 if (blk == nblk - 1) {
                     mma_commit(&S->d3full[dbuf]);
-                    mma_commit(&S->pempty[sub % kPStages]);
+                    mma_commit(&S->pempty[stage]);
                 }
             }
             __syncwarp();
-            if (u + kSlots < U) issue_mma1(u + kSlots);
+            if (l_left > 0) issue_mma1();
+            // advance the unit counters
+            if (++slot == kSlots) { slot = 0; slot_phase ^= 1; }
+            if (++g == ngt) g = 0;
+            if (++blk == nblk) {
+                blk = 0;
+                ++sub;
+                if (++stage == kPStages) stage = 0;
+                dbuf ^= 1;
+                if (dbuf == 0) d3_phase ^= 1;
+            }
         }
         if (elect_one()) mma_commit(&S->alldone);
         __syncwarp();

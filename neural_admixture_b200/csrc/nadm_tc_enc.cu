@@ -28,7 +28,7 @@ constexpr int kAStages = 4;                // ring of widened tiles
 constexpr int kDigTile = kSub * 32;        // digit bytes per 256 K positions (4 planes x 8 components each)
 constexpr int kProdWarps = 8;
 constexpr int kProdThreads = kProdWarps * 32;
-constexpr int kPrefetch = 4;               // genotype tiles prefetched in registers per producer thread
+constexpr int kPrefetch = 8;               // genotype tiles prefetched in registers per producer thread
 constexpr int kMaxBlkTc = 16;              // 16 blocks of 128 rows per launch (16 x 32 tensor-memory columns)
 constexpr uint32_t kIdescFwd = instr_desc(kAccS32, kFmtU8, kFmtS8, /*A MN*/ false, /*B MN*/ true, 128, 32);
 constexpr uint32_t kIdescBwd = instr_desc(kAccS32, kFmtU8, kFmtS8, /*A MN*/ true, /*B MN*/ true, 128, 32);
