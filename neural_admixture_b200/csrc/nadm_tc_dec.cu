@@ -16,8 +16,9 @@
 // dQ accumulates in tensor memory over all SNP sub-tiles of the CTA (one 128 x 16 accumulator per row block), dP over
 // the row blocks of one sub-tile, after which four epilogue warps apply Adam + clamp to the 64 x k slice of P.
 //
-// Warp roles (448 threads): 0-3 / 4-7 two compute warpgroups (alternate units), 8 MMA issuer (one elected thread),
-// 9 P-tile producer, 10-13 dP/Adam epilogue.  Pipelines are mbarrier based; tcgen05.commit frees operand buffers.
+// Warp roles (576 threads): 0-11 three compute warpgroups (unit u -> warpgroup u % 3, which owns tensor-memory slot
+// u % 3), 12 MMA issuer (one elected thread), 13 P-tile producer, 14-17 dP/Adam epilogue.  Pipelines are mbarrier
+// based; tcgen05.commit frees operand buffers.
 #include "nadm_common.cuh"
 #include "nadm_tc.cuh"
 
@@ -31,7 +32,9 @@ constexpr int kGtBytes = 2 * 128 * kMS * 2;   // G^T tile: two bf16 terms x 128 
 constexpr int kPTileBytes = 4096;             // P sub-tile: 64 SNPs x 4 bf16 chunks [h | l | m | h] of 8 components
 constexpr int kQBlkBytes = 16 * 384;          // Q block: 128 rows x 3 bf16 chunks [h | m | l]
 constexpr int kPStages = 3;
-constexpr int kDecThreads = 14 * 32;
+constexpr int kWGs = 3;                       // compute warpgroups (4 warps each), one raw/G slot per warpgroup
+constexpr int kWarpIssue = 4 * kWGs, kWarpProd = kWarpIssue + 1, kWarpEpi = kWarpIssue + 2;
+constexpr int kDecThreads = (4 * kWGs + 2 + 4) * 32;
 constexpr int kSlots = 3;                     // raw / G slots of 64 tensor-memory columns, used round-robin by the units
 constexpr int kColD3 = 192, kColD2 = 256;     // tensor-memory columns: [0,192) slots, D3 2 x 32, D2 32 per row block
 constexpr uint32_t kIdesc1 = instr_desc(kAccF32, kFmtBF16, kFmtBF16, false, false, 128, kMS);
@@ -85,23 +88,22 @@ struct Elem {
     float G, l;
 };
 
-// Process 32 consecutive SNPs of one row: v[] holds raw on entry; on exit hi[] / lo[] hold the bf16x2-packed split of G.
-// w0 / w1: 2-bit codes (missing cleared) of SNPs 0-15 / 16-31.  Loss accumulators in log2 units.
-__device__ __forceinline__ void decode32(const uint32_t (&v)[32], uint32_t w0, uint32_t w1, uint32_t (&hi)[16],
-                                         uint32_t (&lo)[16], float& acc_all, float& acc_het) {
+// Process 16 consecutive SNPs of one row: v[] holds raw on entry; on exit hi[] / lo[] hold the bf16x2-packed split of G.
+// w: the 16 2-bit codes (missing cleared).  Loss accumulators in log2 units.
+__device__ __forceinline__ void decode16(const uint32_t (&v)[16], uint32_t w, uint32_t magic, uint32_t (&hi)[8],
+                                         uint32_t (&lo)[8], float& acc_all, float& acc_het) {
+    const uint32_t wh = w >> 16;
 #pragma unroll
-    for (int j2 = 0; j2 < 16; ++j2) {
+    for (int j2 = 0; j2 < 8; ++j2) {
         float g[2];
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             const int j = 2 * j2 + e;
-            const uint32_t w = (j < 16) ? w0 : w1;
-            const int jj = j & 15;
-            const uint32_t wsrc = (jj < 8) ? w : (w >> 16);
-            const int sh = 2 * (jj & 7);
+            const uint32_t wsrc = (j < 8) ? w : wh;
+            const int sh = 2 * (j & 7);
             const float raw = __uint_as_float(v[j]);
-            // code * 4^(jj&7) as an exact float via the 2^23 magic constant; x = code / 2
-            const float f = __uint_as_float((wsrc & (3u << sh)) | 0x4B000000u) - 8388608.0f;
+            // code * 4^(j&7) as an exact float via the 2^23 magic constant (kept in a register: one LOP3); x = code / 2
+            const float f = __uint_as_float((wsrc & (3u << sh)) | magic) - 8388608.0f;
             const float Rs = fminf(raw, 1.0f);
             const float prod = fmaf(-Rs, Rs, Rs);                       // R (1 - R)
             const float inv = rcp_approx(fmaxf(prod, 1e-12f));
@@ -109,9 +111,10 @@ __device__ __forceinline__ void decode32(const uint32_t (&v)[32], uint32_t w0, u
             float G = num * inv;
             G = (raw <= 1.0f) ? G : 0.0f;                               // clamp backward mask (raw >= 0 always)
             g[e] = G;
-            // BCE with torch's log clamp; X in {0, .5, 1}: a single log per element
-            const bool het = (wsrc >> sh) & 1u, hom2 = (wsrc >> sh) & 2u;
-            const float arg = hom2 ? Rs : (het ? prod : (1.0f - Rs));
+            // BCE with torch's log clamp; X in {0, .5, 1}: a single log per element.
+            // x = 0: 1 - R = 1 - |R - x| ;  x = 1: R = 1 - |R - x| ;  x = .5: weight .5 on log(R (1 - R))
+            const bool het = (wsrc >> sh) & 1u;
+            const float arg = het ? prod : (1.0f - fabsf(num));
             const float l = fmaxf(lg2_approx(arg), kLog2Clamp);
             acc_all += l;
             acc_het += het ? l : 0.0f;
@@ -160,14 +163,14 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
         mbar_init(&S->alldone, 1);
         mbar_init_fence();
     }
-    if (warp == 8) tmem_alloc<512>(&S->tmem_base);
+    if (warp == kWarpIssue) tmem_alloc<512>(&S->tmem_base);
     fence_async_smem();
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tbase = S->tmem_base;
 
-    if (warp < 8) {
+    if (warp < kWarpIssue) {
         // =============================== compute warpgroups ===============================
         const int wg = warp >> 2, q = warp & 3;
         const int rb = q * 32 + lane;                                   // row inside the block = tensor-memory lane
@@ -182,33 +185,32 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
             if (ro >= 0 && off + 16 <= pitch) r = *reinterpret_cast<const uint4*>(packed + ro + off);
             return r;
         };
+        uint32_t magic;
+        asm volatile("mov.b32 %0, 0x4B000000;" : "=r"(magic));           // opaque to the compiler: stays in a register
         if (wg < U) gw = load_codes(wg);
-        for (int u = wg; u < U; u += 2) {
+        for (int u = wg; u < U; u += kWGs) {
             const int blk = u % nblk;
-            const int slot = u % kSlots, g = u % ngt;
-            const uint4 cw = make_uint4(clear_missing(gw.x), clear_missing(gw.y), clear_missing(gw.z), clear_missing(gw.w));
-            if (u + 2 < U) gw = load_codes(u + 2);
+            const int slot = wg, g = u % ngt;
+            const uint32_t cw[4] = {clear_missing(gw.x), clear_missing(gw.y), clear_missing(gw.z), clear_missing(gw.w)};
+            if (u + kWGs < U) gw = load_codes(u + kWGs);
             const bool active = blk * 128 + q * 32 < B;                 // warp-uniform: any real row in this warp
-            mbar_wait(&S->d1full[slot], (u / kSlots) & 1);
+            mbar_wait(&S->d1full[slot], ((u / kWGs) & 1));
             tc_fence_after_sync();
             if (active) {
                 mbar_wait(&S->gtfree[g], ((u / ngt) & 1) ^ 1);
                 uint8_t* gt = GT + g * kGtBytes + (rb & 7) * 16 + (rb >> 3) * 1024;
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    uint32_t v[32], hi[16], lo[16];
-                    tmem_ld32(tlane + slot * 64 + c * 32, v);
+                for (int c = 0; c < 4; ++c) {                          // 16 SNPs at a time: raw columns [16c, 16c+16)
+                    uint32_t v[16], hi[8], lo[8];
+                    tmem_ld16(tlane + slot * 64 + c * 16, v);
                     tmem_wait_ld();
-                    decode32(v, c ? cw.z : cw.x, c ? cw.w : cw.y, hi, lo, acc_all, acc_het);
-                    tmem_st16(tlane + slot * 64 + c * 32, hi);
-                    tmem_st16(tlane + slot * 64 + c * 32 + 16, lo);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        *reinterpret_cast<uint4*>(gt + (c * 4 + i) * 128) =
-                            make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
-                        *reinterpret_cast<uint4*>(gt + 16384 + (c * 4 + i) * 128) =
-                            make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
-                    }
+                    decode16(v, cw[c], magic, hi, lo, acc_all, acc_het);
+                    tmem_st8(tlane + slot * 64 + c * 16, hi);          // G hi / lo overwrite their own raw columns
+                    tmem_st8(tlane + slot * 64 + c * 16 + 8, lo);
+                    *reinterpret_cast<uint4*>(gt + (2 * c) * 128) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<uint4*>(gt + (2 * c + 1) * 128) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+                    *reinterpret_cast<uint4*>(gt + 16384 + (2 * c) * 128) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    *reinterpret_cast<uint4*>(gt + 16384 + (2 * c + 1) * 128) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
                 }
                 tmem_wait_st();
                 fence_async_smem();
@@ -222,7 +224,7 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
         if (lane == 0) S->lossred[warp] = l;
         mbar_wait(&S->alldone, 0);
         tc_fence_after_sync();
-        for (int blk = wg; blk < nblk; blk += 2) {
+        for (int blk = wg; blk < nblk; blk += kWGs) {
             uint32_t v[32];
             tmem_ld32(tlane + kColD2 + blk * 32, v);
             tmem_wait_ld();
@@ -238,7 +240,7 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
                 reinterpret_cast<float4*>(out)[1] = o1;
             }
         }
-    } else if (warp == 8) {
+    } else if (warp == kWarpIssue) {
         // =============================== MMA issuer ===============================
         // The whole warp walks the unit sequence and waits on the barriers; one elected lane issues.  Descriptors are
         // built once; per instruction only the 14-bit start-address field (16-byte units) is advanced.
@@ -283,18 +285,20 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
             if (blk == 0) mbar_wait(&S->d3empty[dbuf], d3_phase);
             tc_fence_after_sync();
             if (elect_one()) {
-                // dQ_blk += G . [P_h | P_l | P_m | P_h]   (A from tensor memory: hi / lo of the two 32-SNP halves)
+                // dQ_blk += G . [P_h | P_l | P_m | P_h]   (A from tensor memory: per 16 SNPs, hi in 8 columns, lo in 8)
                 const uint64_t b2 = B2 + (uint64_t)(stage * (kPTileBytes >> 4));
                 const uint32_t d2 = tbase + kColD2 + blk * 32, a2 = tbase + slot * 64;
                 const uint32_t acc2 = sub > 0 ? 1u : 0u;
 #pragma unroll
-                for (int c = 0; c < 2; ++c)
+                for (int c = 0; c < 4; ++c)
 #pragma unroll
                     for (int t = 0; t < 2; ++t)
-#pragma unroll
-                        for (int kk = 0; kk < 2; ++kk)
-                            mma_f16_ts(d2, a2 + c * 32 + t * 16 + kk * 8, b2 + (uint64_t)((c * 4 + kk * 2) * 32), kIdesc2,
-                                       (c + t + kk) ? 1u : acc2);
+                        mma_f16_ts(d2, a2 + c * 16 + t * 8, b2 + (uint64_t)(c * 2 * 32), kIdesc2, (c + t) ? 1u : acc2);
+            }
+            __syncwarp();
+            // raw of the unit that reuses this slot: queued right behind the MMAs that consume the slot's G
+            if (l_left > 0) issue_mma1();
+            if (elect_one()) {
                 // dP_sub += G^T . [Q_h | Q_m | Q_l]    (A = shared G^T tile, MN-major; only K steps holding real rows)
                 const uint64_t a3 = A3 + (uint64_t)(g * (kGtBytes >> 4)), b3 = B3 + (uint64_t)(blk * (kQBlkBytes >> 4));
                 const uint32_t d3 = tbase + kColD3 + dbuf * 32;
@@ -319,7 +323,6 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
                 }
             }
             __syncwarp();
-            if (l_left > 0) issue_mma1();
             // advance the unit counters
             if (++slot == kSlots) { slot = 0; slot_phase ^= 1; }
             if (++g == ngt) g = 0;
@@ -333,7 +336,7 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
         }
         if (elect_one()) mma_commit(&S->alldone);
         __syncwarp();
-    } else if (warp == 9) {
+    } else if (warp == kWarpProd) {
         // =============================== P sub-tile producer ===============================
         for (int sub = 0; sub < nsub; ++sub) {
             const int st = sub % kPStages;
@@ -428,10 +431,10 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
     __syncthreads();
     if (tid == 0) {
         float s = 0.f;
-        for (int w = 0; w < 8; ++w) s += S->lossred[w];
+        for (int w = 0; w < kWarpIssue; ++w) s += S->lossred[w];
         loss_part[blockIdx.x] = s;
     }
-    if (warp == 8) tmem_dealloc<512>(tbase);
+    if (warp == kWarpIssue) tmem_dealloc<512>(tbase);
 }
 
 // =================================================================================================================
