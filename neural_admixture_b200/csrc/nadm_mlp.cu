@@ -265,39 +265,43 @@ __device__ __forceinline__ void adam_store(float* p, float* m, float* v, float* 
     }
 }
 
+constexpr int kRowChunks = 8;   // grid.z: the batch is split into row chunks whose partial gradients are summed in phase 2
+
+// Phase 1: partial parameter gradients of one row chunk.  grid = (ceil(H/32), 1 + ceil(sumK/8), kRowChunks).
+//   blockIdx.y == 0     : gW1[z][j][0..C) and gb1 (stored as column C) for 32 hidden units j
+//   blockIdx.y == 1 + q : gW2[z][8q .. 8q+8)[j]
+// Layout of `part`: [kRowChunks] x ( H x (C+1)  |  sumK x H ).
 __global__ void __launch_bounds__(32 * kSeg)
 mlp_bwd_params_kernel(const float* __restrict__ dL, const float* __restrict__ dHpre, const float* __restrict__ Hh,
-                      const float* __restrict__ Z, const float* __restrict__ rinv, const float* __restrict__ dwr,
-                      const float* __restrict__ suploss, int has_sup, int B, int C, int H, int sumK,
-                      nadm_mlp_params_t prm, AdamCoef adam, float* __restrict__ loss) {
+                      const float* __restrict__ Z, const float* __restrict__ rinv, const float* __restrict__ w_rms,
+                      int B, int C, int H, int sumK, float* __restrict__ part) {
     __shared__ float red[kSeg][32][NADM_MAX_C + 1];
     const int jl = threadIdx.x & 31, seg = threadIdx.x >> 5;
     const int j = blockIdx.x * 32 + jl;
     const bool jok = j < H;
-    const int rows_per_seg = (B + kSeg - 1) / kSeg;
-    const int bs = seg * rows_per_seg, be = min(B, bs + rows_per_seg);
+    const int rows_per_chunk = (B + kRowChunks - 1) / kRowChunks;
+    const int c0 = blockIdx.z * rows_per_chunk, c1 = min(B, c0 + rows_per_chunk);
+    float* mypart = part + (size_t)blockIdx.z * ((size_t)H * (C + 1) + (size_t)sumK * H);
 
     if (blockIdx.y == 0) {
         float acc[NADM_MAX_C + 1];
 #pragma unroll
         for (int c = 0; c <= NADM_MAX_C; ++c) acc[c] = 0.f;
         if (jok) {
-            for (int b = bs; b < be; ++b) {
+            for (int b = c0 + seg; b < c1; b += kSeg) {
                 const float d = dHpre[(int64_t)b * H + j];
                 if (d == 0.f) continue;
                 const float r = rinv[b];
-                // Zn is recomputed: Zn[b][c] = Z[b][c] * rinv[b] * w_rms[c]  (w_rms read before its own update below)
+                // Zn is recomputed: Zn[b][c] = Z[b][c] * rinv[b] * w_rms[c]  (w_rms is updated by a later kernel)
 #pragma unroll
                 for (int c = 0; c < NADM_MAX_C; ++c)
-                    if (c < C) acc[c] = fmaf(d, Z[(int64_t)b * C + c] * r * prm.w_rms[c], acc[c]);
+                    if (c < C) acc[c] = fmaf(d, Z[(int64_t)b * C + c] * r * w_rms[c], acc[c]);
                 acc[NADM_MAX_C] += d;
             }
         }
 #pragma unroll
         for (int c = 0; c <= NADM_MAX_C; ++c) red[seg][jl][c] = acc[c];
         __syncthreads();
-        // the w_rms values used above must all be read before block (0,0) updates w_rms: that update happens in
-        // a separate, later kernel (mlp_bwd_small_kernel), so there is no hazard here.
         for (int o = threadIdx.x; o < 32 * (C + 1); o += blockDim.x) {
             const int jj = o / (C + 1), c = o % (C + 1);
             const int jg = blockIdx.x * 32 + jj;
@@ -306,8 +310,7 @@ mlp_bwd_params_kernel(const float* __restrict__ dL, const float* __restrict__ dH
             float g = 0.f;
 #pragma unroll
             for (int s = 0; s < kSeg; ++s) g += red[s][jj][cc];
-            if (c < C) adam_store(prm.W1, prm.m_W1, prm.v_W1, prm.g_W1, (int64_t)jg * C + c, g, adam);
-            else adam_store(prm.b1, prm.m_b1, prm.v_b1, prm.g_b1, jg, g, adam);
+            mypart[(size_t)jg * (C + 1) + c] = g;
         }
     } else {
         const int k0 = (blockIdx.y - 1) * 8;
@@ -315,7 +318,7 @@ mlp_bwd_params_kernel(const float* __restrict__ dL, const float* __restrict__ dH
 #pragma unroll
         for (int q = 0; q < 8; ++q) acc[q] = 0.f;
         if (jok) {
-            for (int b = bs; b < be; ++b) {
+            for (int b = c0 + seg; b < c1; b += kSeg) {
                 const float h = Hh[(int64_t)b * H + j];
                 if (h == 0.f) continue;
 #pragma unroll
@@ -333,10 +336,27 @@ mlp_bwd_params_kernel(const float* __restrict__ dL, const float* __restrict__ dH
             float g = 0.f;
 #pragma unroll
             for (int s = 0; s < kSeg; ++s) g += red[s][jj][q];
-            adam_store(prm.W2, prm.m_W2, prm.v_W2, prm.g_W2, (int64_t)(k0 + q) * H + jg, g, adam);
+            mypart[(size_t)H * (C + 1) + (size_t)(k0 + q) * H + jg] = g;
         }
     }
-    (void)suploss; (void)has_sup; (void)dwr; (void)loss;
+}
+
+// Phase 2: sum the row-chunk partials (fixed order: deterministic) and apply Adam to W1, b1, W2.
+__global__ void __launch_bounds__(256)
+mlp_bwd_apply_kernel(const float* __restrict__ part, int C, int H, int sumK, nadm_mlp_params_t prm, AdamCoef adam) {
+    const size_t n1 = (size_t)H * (C + 1), n = n1 + (size_t)sumK * H;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float g = 0.f;
+#pragma unroll
+    for (int z = 0; z < kRowChunks; ++z) g += part[(size_t)z * n + i];
+    if (i < n1) {
+        const int jg = (int)(i / (C + 1)), c = (int)(i % (C + 1));
+        if (c < C) adam_store(prm.W1, prm.m_W1, prm.v_W1, prm.g_W1, (int64_t)jg * C + c, g, adam);
+        else adam_store(prm.b1, prm.m_b1, prm.v_b1, prm.g_b1, jg, g, adam);
+    } else {
+        adam_store(prm.W2, prm.m_W2, prm.v_W2, prm.g_W2, (int64_t)(i - n1), g, adam);
+    }
 }
 
 // db2[kk] = sum_b dL[b][kk]; dw_rms[c] = sum_b dwr[b][c]; loss += sum_b suploss[b].  One warp per output.
@@ -424,12 +444,14 @@ extern "C" int nadm_mlp_bwd(const float* dQ, const float* Q, const float* Hh, co
     NADM_REQUIRE(adam == nullptr || (p.m_w_rms && p.m_W1 && p.m_b1 && p.m_W2 && p.m_b2 && p.v_w_rms && p.v_W1 &&
                                      p.v_b1 && p.v_W2 && p.v_b2), "NULL Adam moment pointer");
     // workspace carve-up: dL (B x sumK) | dHpre (B x H) | dwr (B x C) | suploss (B)
-    const size_t need = ((size_t)B * ((size_t)hd.sumK + H + C + 1)) * sizeof(float);
+    const size_t need = ((size_t)B * ((size_t)hd.sumK + H + C + 1) +
+                         (size_t)kRowChunks * ((size_t)H * (C + 1) + (size_t)hd.sumK * H)) * sizeof(float);
     NADM_REQUIRE(need <= ws_bytes, "workspace too small for mlp_bwd (%zu > %zu)", need, ws_bytes);
     float* dL = (float*)ws;
     float* dHpre = dL + (size_t)B * hd.sumK;
     float* dwr = dHpre + (size_t)B * H;
     float* suploss = dwr + (size_t)B * C;
+    float* gpart = suploss + B;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t smem = ((size_t)kMlpRows * hd.sumK + (size_t)kMlpRows * H + (size_t)kMlpRows * NADM_MAX_C) * sizeof(float);
     NADM_REQUIRE(smem <= 200 * 1024, "hidden_size H=%d too large", H);
@@ -443,10 +465,12 @@ extern "C" int nadm_mlp_bwd(const float* dQ, const float* Q, const float* Hh, co
         dQ, Q, Hh, Z, rinv, B, C, H, hd, labels, sup_weight, p.w_rms, p.W1, p.W2, dL, dHpre, dwr, suploss, dZ);
     NADM_CHECK_LAUNCH("mlp_bwd_rows_kernel");
     const AdamCoef ac = make_adam(adam);
-    dim3 grid((H + 31) / 32, 1 + (hd.sumK + 7) / 8);
-    mlp_bwd_params_kernel<<<grid, 32 * kSeg, 0, st>>>(dL, dHpre, Hh, Z, rinv, dwr, suploss, labels != nullptr, B, C, H,
-                                                     hd.sumK, p, ac, loss);
+    dim3 grid((H + 31) / 32, 1 + (hd.sumK + 7) / 8, kRowChunks);
+    mlp_bwd_params_kernel<<<grid, 32 * kSeg, 0, st>>>(dL, dHpre, Hh, Z, rinv, p.w_rms, B, C, H, hd.sumK, gpart);
     NADM_CHECK_LAUNCH("mlp_bwd_params_kernel");
+    const size_t nparam = (size_t)H * (C + 1) + (size_t)hd.sumK * H;
+    mlp_bwd_apply_kernel<<<(unsigned)((nparam + 255) / 256), 256, 0, st>>>(gpart, C, H, hd.sumK, p, ac);
+    NADM_CHECK_LAUNCH("mlp_bwd_apply_kernel");
     mlp_bwd_small_kernel<<<1, 256, 0, st>>>(dL, dwr, suploss, labels != nullptr, B, C, hd.sumK, p, ac, loss);
     NADM_CHECK_LAUNCH("mlp_bwd_small_kernel");
     return NADM_OK;

@@ -42,6 +42,13 @@ constexpr uint32_t kIdesc2 = instr_desc(kAccF32, kFmtBF16, kFmtBF16, false, true
 constexpr uint32_t kIdesc3 = instr_desc(kAccF32, kFmtBF16, kFmtBF16, true, true, 64, 24);
 constexpr float kLog2Clamp = -144.26950408889634f;   // -100 / ln 2: torch clamps log at -100 (BCELoss)
 
+#ifdef NADM_TIMELINE
+__device__ long long g_timeline[8][512];
+#define TL(row, idx) do { if (blockIdx.x == 0 && (idx) < 512) g_timeline[row][idx] = clock64(); } while (0)
+#else
+#define TL(row, idx) do { } while (0)
+#endif
+
 struct DecSmem {
     uint64_t d1full[kSlots], gready[kSlots], gtfree[4], pfull[kPStages], pempty[kPStages], d3full[2], d3empty[2], alldone;
     uint32_t tmem_base;
@@ -194,10 +201,17 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
             const uint32_t cw[4] = {clear_missing(gw.x), clear_missing(gw.y), clear_missing(gw.z), clear_missing(gw.w)};
             if (u + kWGs < U) gw = load_codes(u + kWGs);
             const bool active = blk * 128 + q * 32 < B;                 // warp-uniform: any real row in this warp
+            if (rb == 0) TL(0, u);                                      // WG starts waiting for raw(u)
             mbar_wait(&S->d1full[slot], ((u / kWGs) & 1));
             tc_fence_after_sync();
+            if (rb == 0) TL(1, u);                                      // raw(u) seen
+#ifdef NADM_SKIPDECODE
+            if (false) {
+#else
             if (active) {
+#endif
                 mbar_wait(&S->gtfree[g], ((u / ngt) & 1) ^ 1);
+                if (rb == 0) TL(6, u);                                  // G^T buffer free
                 uint8_t* gt = GT + g * kGtBytes + (rb & 7) * 16 + (rb >> 3) * 1024;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {                          // 16 SNPs at a time: raw columns [16c, 16c+16)
@@ -216,6 +230,7 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
                 fence_async_smem();
             }
             tc_fence_before_sync();
+            if (rb == 0) TL(2, u);                                      // G(u) written
             mbar_arrive(&S->gready[slot]);
         }
         // ---- loss partial of this CTA (log2 units -> nats), dQ partial from tensor memory ----
@@ -281,9 +296,11 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
         const int nks_last = min(8, (B - (nblk - 1) * 128 + 15) / 16);
         int blk = 0, sub = 0, slot = 0, slot_phase = 0, g = 0, stage = 0, dbuf = 0, d3_phase = 1;
         for (int u = 0; u < U; ++u) {
+            if (lane == 0) TL(3, u);                                    // issuer starts waiting for G(u)
             mbar_wait(&S->gready[slot], slot_phase);
             if (blk == 0) mbar_wait(&S->d3empty[dbuf], d3_phase);
             tc_fence_after_sync();
+            if (lane == 0) TL(4, u);                                    // issuer saw G(u)
             if (elect_one()) {
                 // dQ_blk += G . [P_h | P_l | P_m | P_h]   (A from tensor memory: per 16 SNPs, hi in 8 columns, lo in 8)
                 const uint64_t b2 = B2 + (uint64_t)(stage * (kPTileBytes >> 4));
@@ -323,6 +340,7 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
                 }
             }
             __syncwarp();
+            if (lane == 0) TL(5, u);                                    // issuer done with unit u
             // advance the unit counters
             if (++slot == kSlots) { slot = 0; slot_phase ^= 1; }
             if (++g == ngt) g = 0;
@@ -445,6 +463,12 @@ bool dec_tc_supported(int B, int k) {
     const size_t fixed = (size_t)nblk * (kQBlkBytes + 1024) + kPStages * kPTileBytes + sizeof(DecSmem) + 128;
     return k <= 8 && nblk <= 8 && fixed + 3 * (size_t)kGtBytes <= (size_t)kMaxDynSmem;
 }
+
+#ifdef NADM_TIMELINE
+extern "C" int nadm_debug_timeline(long long* host_out) {
+    return (int)cudaMemcpyFromSymbol(host_out, g_timeline, sizeof(g_timeline));
+}
+#endif
 
 int launch_dec_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_idx, int64_t row0, int B, int64_t M,
                   const float* Q, float* dQ, int q_ld, int q_off, int k, float* P, float* Pm, float* Pv,
