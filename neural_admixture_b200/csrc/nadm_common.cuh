@@ -38,7 +38,7 @@ constexpr int kMaxParts = 640;        // upper bound on per-CTA partial slabs (e
 constexpr int kStreamWarps = 8;       // warps per CTA in the lane<->byte streaming kernels
 constexpr int kTileSnps = 128;        // SNPs per CTA tile in those kernels: one byte (4 SNPs) per lane
 constexpr int kEncTileSnps = 256;
-constexpr int kMaxDynSmem = 220 * 1024;  // dynamic shared memory opt-in (227 KB per CTA minus static + reserve)
+constexpr int kMaxDynSmem = 226 * 1024;  // dynamic shared memory opt-in (227 KB per CTA minus static + reserve)
 
 struct AdamCoef {
     float beta1, beta2, one_minus_beta1, one_minus_beta2, step_size, inv_bc2_sqrt, eps;
@@ -68,6 +68,7 @@ int launch_enc_bwd_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_i
                       const float* dZ, int C, float* V, float* Vm, float* Vv, const nadm_adam_t* adam, float* dV_out,
                       cudaStream_t st);
 size_t enc_tc_workspace_bytes(int B);
+bool enc_bwd_tc_supported(int B);
 // tensor-core fused decoder, nadm_tc_dec.cu
 bool dec_tc_supported(int B, int k);
 int launch_dec_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_idx, int64_t row0, int B, int64_t M,

@@ -80,31 +80,32 @@ __global__ void unpack2bit_kernel(const uint8_t* __restrict__ src, int64_t rows,
 // deterministic partial reduction: out[i*out_ld_scale...] = sum_p part[p][i]
 // =================================================================================================================
 // part: nparts x (rows x cols_p) ; out: rows x out_ld, written at column offset out_off for cols < cols_out.
-__global__ void reduce_parts_kernel(const float* __restrict__ part, int nparts, int rows, int cols_p, int cols_out,
-                                    float* __restrict__ out, int out_ld, int out_off, float scale,
-                                    const float* __restrict__ loss_part, float* __restrict__ loss) {
+// Block = 8 consecutive outputs x 32 part segments; segment sums are combined in a fixed order (deterministic).
+__global__ void __launch_bounds__(256)
+reduce_parts_kernel(const float* __restrict__ part, int nparts, int rows, int cols_p, int cols_out,
+                    float* __restrict__ out, int out_ld, int out_off, float scale,
+                    const float* __restrict__ loss_part, float* __restrict__ loss) {
+    __shared__ float red[32][8];
     const int64_t n = (int64_t)rows * cols_p;
-    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i < n) {
+    const int o = threadIdx.x & 7, seg = threadIdx.x >> 3;
+    const int64_t i = (int64_t)blockIdx.x * 8 + o;
+    float acc = 0.f;
+    if (i < n)
+        for (int q = seg; q < nparts; q += 32) acc += part[(int64_t)q * n + i];
+    red[seg][o] = acc;
+    __syncthreads();
+    if (threadIdx.x < 8 && i < n) {
+        float t = 0.f;
+#pragma unroll
+        for (int s2 = 0; s2 < 32; ++s2) t += red[s2][o];
         const int r = (int)(i / cols_p), c = (int)(i % cols_p);
-        if (c < cols_out) {
-            float acc = 0.f;
-            const float* p = part + i;
-            int q = 0;
-            for (; q + 4 <= nparts; q += 4) {
-                float a0 = p[(int64_t)q * n], a1 = p[(int64_t)(q + 1) * n];
-                float a2 = p[(int64_t)(q + 2) * n], a3 = p[(int64_t)(q + 3) * n];
-                acc += (a0 + a1) + (a2 + a3);
-            }
-            for (; q < nparts; ++q) acc += p[(int64_t)q * n];
-            out[(int64_t)r * out_ld + out_off + c] = acc * scale;
-        }
+        if (c < cols_out) out[(int64_t)r * out_ld + out_off + c] = t * scale;
     }
-    if (loss_part != nullptr && blockIdx.x == 0 && threadIdx.x < 32) {
-        double acc = 0.0;
-        for (int q = threadIdx.x; q < nparts; q += 32) acc += (double)loss_part[q];
-        acc = warp_sum_d(acc);
-        if (threadIdx.x == 0) *loss = (float)((double)*loss + acc);
+    if (loss_part != nullptr && blockIdx.x == 0 && threadIdx.x >= 32 && threadIdx.x < 64) {
+        double acc2 = 0.0;
+        for (int q = threadIdx.x - 32; q < nparts; q += 32) acc2 += (double)loss_part[q];
+        acc2 = warp_sum_d(acc2);
+        if (threadIdx.x == 32) *loss = (float)((double)*loss + acc2);
     }
 }
 
@@ -524,7 +525,7 @@ namespace nadm {
 int launch_reduce_parts(const float* part, int nparts, int rows, int cols_p, int cols_out, float* out, int out_ld,
                         int out_off, float scale, const float* loss_part, float* loss, cudaStream_t st) {
     const int64_t n = (int64_t)rows * cols_p;
-    reduce_parts_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(part, nparts, rows, cols_p, cols_out, out, out_ld,
+    reduce_parts_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(part, nparts, rows, cols_p, cols_out, out, out_ld,
                                                                     out_off, scale, loss_part, loss);
     NADM_CHECK_LAUNCH("reduce_parts_kernel");
     return NADM_OK;
@@ -569,7 +570,7 @@ static int launch_enc_fwd(const uint8_t* packed, int64_t pitch, const int64_t* r
     enc_fwd_kernel<CP><<<dim3(nslab, ngroups), RB, smem, st>>>(packed, pitch, row_idx, row0, B, M, V, C, ws, ntiles, nslab);
     NADM_CHECK_LAUNCH("enc_fwd_kernel");
     const int64_t n = (int64_t)B * CP;
-    reduce_parts_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ws, nslab, B, CP, C, Z, C, 0, 0.5f, nullptr, nullptr);
+    reduce_parts_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(ws, nslab, B, CP, C, Z, C, 0, 0.5f, nullptr, nullptr);
     NADM_CHECK_LAUNCH("reduce_parts_kernel");
     return NADM_OK;
 }
@@ -620,7 +621,7 @@ static int launch_dec(const uint8_t* packed, int64_t pitch, const int64_t* row_i
                                                          make_adam(adam), dP_out, dQpart, loss_part, ntiles);
     NADM_CHECK_LAUNCH("dec_kernel");
     const int64_t n = (int64_t)B * KP;
-    reduce_parts_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dQpart, ncta, B, KP, k, dQ, q_ld, q_off, 1.0f, loss_part, loss);
+    reduce_parts_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(dQpart, ncta, B, KP, k, dQ, q_ld, q_off, 1.0f, loss_part, loss);
     NADM_CHECK_LAUNCH("reduce_parts_kernel");
     return NADM_OK;
 }
@@ -681,7 +682,7 @@ extern "C" int nadm_encoder_bwd(const uint8_t* packed, int64_t pitch, const int6
     NADM_REQUIRE(dZ && V, "NULL pointer");
     NADM_REQUIRE(adam == nullptr || (Vm && Vv), "Adam moments are NULL");
     NADM_REQUIRE(adam != nullptr || dV_out != nullptr, "nothing to do: neither Adam nor dV_out requested");
-    if (C <= 8 && B <= 2048 && !use_generic_kernels() && (reinterpret_cast<uintptr_t>(V) & 15) == 0 &&
+    if (C <= 8 && enc_bwd_tc_supported(B) && !use_generic_kernels() && (reinterpret_cast<uintptr_t>(V) & 15) == 0 &&
         (dV_out == nullptr || (reinterpret_cast<uintptr_t>(dV_out) & 15) == 0))
         return launch_enc_bwd_tc(packed, pitch, row_idx, row0, B, M, dZ, C, V, Vm, Vv, adam, dV_out, (cudaStream_t)stream);
     if (pad_c(C) == 8)

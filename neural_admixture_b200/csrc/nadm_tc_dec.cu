@@ -163,10 +163,10 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
         *reinterpret_cast<uint4*>(a + 256) = L;
     }
     if (tid == 0) {
-        for (int i = 0; i < kSlots; ++i) { mbar_init(&S->d1full[i], 1); mbar_init(&S->gready[i], 128); }
+        for (int i = 0; i < kSlots; ++i) { mbar_init(&S->d1full[i], 1); mbar_init(&S->gready[i], 4); }
         for (int i = 0; i < 4; ++i) mbar_init(&S->gtfree[i], 1);
-        for (int i = 0; i < kPStages; ++i) { mbar_init(&S->pfull[i], 32); mbar_init(&S->pempty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&S->d3full[i], 1); mbar_init(&S->d3empty[i], 128); }
+        for (int i = 0; i < kPStages; ++i) { mbar_init(&S->pfull[i], 1); mbar_init(&S->pempty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&S->d3full[i], 1); mbar_init(&S->d3empty[i], 4); }
         mbar_init(&S->alldone, 1);
         mbar_init_fence();
     }
@@ -231,7 +231,8 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
             }
             tc_fence_before_sync();
             if (rb == 0) TL(2, u);                                      // G(u) written
-            mbar_arrive(&S->gready[slot]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S->gready[slot]);               // one arrival per warp
         }
         // ---- loss partial of this CTA (log2 units -> nats), dQ partial from tensor memory ----
         float l = -(acc_all - 0.5f * acc_het) * 0.6931471805599453f;
@@ -389,7 +390,8 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
                 *reinterpret_cast<uint4*>(t1 + 384) = H;
             }
             fence_async_smem();
-            mbar_arrive(&S->pfull[st]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S->pfull[st]);
         }
     } else {
         // =============================== dP epilogue: Adam + clamp on the 64 x k slice of P ===============================
@@ -402,7 +404,8 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
             tmem_ld32(tbase + ((uint32_t)(q * 32) << 16) + kColD3 + dbuf * 32, v);
             tmem_wait_ld();
             tc_fence_before_sync();
-            mbar_arrive(&S->d3empty[dbuf]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S->d3empty[dbuf]);
             const int64_t m = (int64_t)(s0 + sub) * kMS + q * 16 + lane;       // M = 64 accumulator: lanes 32q + (0..15)
             if (lane < 16 && m < M) {
                 float g[8];

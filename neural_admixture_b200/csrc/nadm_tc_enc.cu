@@ -11,9 +11,10 @@
 // (bit-reproducible for any grid / sharding) and carries only the fixed-point quantisation of the fp32 factor
 // (<= 2^-31 of its largest entry), i.e. it is more accurate than an fp32 FMA chain.
 //
-// Data movement: the B gathered rows of the 2-bit packed matrix are streamed once per kernel with 128-bit loads (each
-// row's 64 bytes = 256 SNPs per tile, 4 tiles prefetched in registers), widened to one byte per genotype with four
-// shift/mask operations per 16 SNPs and stored straight into the UMMA shared-memory layout; the same tile is the
+// Data movement: the B gathered rows of the 2-bit packed matrix are streamed once per kernel with 16-byte asynchronous
+// copies (cp.async, one commit group per tile, 8 tiles = 64 KB in flight per CTA; 64-byte bulk-engine copies were
+// measured 2x slower: the TMA engine is bound by copies/s, not bytes/s) into a shared-memory staging ring, widened to
+// one byte per genotype with four shift/mask operations per 16 SNPs and stored straight into the UMMA layout; the same tile is the
 // K-major operand X of the forward and the MN-major operand X^T of the backward (nadm_tc.cuh).  Inside a group of 16
 // SNPs the byte position p holds SNP sigma(p) = 4 (p % 4) + p / 4; the digit operand / epilogue use the same map.
 #include "nadm_common.cuh"
@@ -24,11 +25,12 @@ using namespace tc;
 
 constexpr int kSub = 256;                  // SNPs per genotype tile: 64 packed bytes of every row
 constexpr int kATile = 128 * kSub;         // bytes of one widened tile (128 rows x 256 SNPs)
-constexpr int kAStages = 4;                // ring of widened tiles
+constexpr int kAStages = 4;                // widened tiles: producer group g fills tiles i = g (mod 4) into stage g
 constexpr int kDigTile = kSub * 32;        // digit bytes per 256 K positions (4 planes x 8 components each)
-constexpr int kProdWarps = 8;
+constexpr int kProdWarps = 16;             // 4 producer groups of 4 warps; a group widens every 4th tile
 constexpr int kProdThreads = kProdWarps * 32;
-constexpr int kPrefetch = 8;               // genotype tiles prefetched in registers per producer thread
+constexpr int kStTile = 128 * 64;          // packed bytes of one tile in the staging ring
+constexpr int kStDepth = 2;                // tiles in flight from HBM per producer group (cp.async commit groups)
 constexpr int kMaxBlkTc = 16;              // 16 blocks of 128 rows per launch (16 x 32 tensor-memory columns)
 constexpr uint32_t kIdescFwd = instr_desc(kAccS32, kFmtU8, kFmtS8, /*A MN*/ false, /*B MN*/ true, 128, 32);
 constexpr uint32_t kIdescBwd = instr_desc(kAccS32, kFmtU8, kFmtS8, /*A MN*/ true, /*B MN*/ true, 128, 32);
@@ -99,34 +101,54 @@ __device__ __forceinline__ void store_digits(uint8_t* tile_pos, const float (&v)
     *reinterpret_cast<uint4*>(tile_pos + 128) = make_uint4(w[4], w[5], w[6], w[7]);
 }
 
-struct TileLoad {
-    uint4 w[2];
+// ---- genotype feed: HBM -> staging ring (bulk async copies) -> widened UMMA tiles ----------------------------------
+// Tile i of a CTA = rows [blk*128, blk*128+128) x SNPs [(t0+tt)*256, +256), order (tt, blk).  Producer thread tid < 128
+// issues the copy of row blk*128 + tid; all 256 producer threads widen.
+struct Feed {
+    const uint8_t* packed;
+    int64_t pitch;
+    const int32_t* rowoff;   // row number of every batch row (x pitch = byte offset)
+    int B, nblk, t0, ntile;
+    uint8_t* stage;          // this group's ring: kStDepth x kStTile; thread (wl, lane) owns 4 pieces of 16 bytes per slot
+    int c_blk, c_tt, c_i;    // next tile of this group to copy (tile index c_i = g + 4 n)
+    int c_slot;
 };
-
-// rows [blk*128, blk*128 + 128) x SNPs [t*256, t*256 + 256): thread (r = lane % 8, q = lane / 8) of producer warp pw
-// reads bytes [16 q, 16 q + 16) of the tile's 64 bytes of rows 8 (pw + 8 it) + r.
-__device__ __forceinline__ void load_tile(TileLoad& L, const uint8_t* __restrict__ packed, int64_t pitch,
-                                          const int64_t* rowoff, int B, int blk, int64_t t, int pw, int lane) {
-    const int r = lane & 7, q = lane >> 3;
-    const int64_t off = t * (kSub / 4) + q * 16;
+// every thread of the group: start the asynchronous copy of its four 16-byte pieces of the group's next tile
+__device__ __forceinline__ void feed_issue(Feed& f, int wl, int lane) {
+    if (f.c_i < f.ntile) {
+        const int r = lane & 7, q = lane >> 3;
+        const int64_t off = (int64_t)(f.t0 + f.c_tt) * (kSub / 4) + q * 16;
+        uint8_t* dst = f.stage + f.c_slot * kStTile + (wl * 32 + lane) * 16;   // piece `it` at + it * 2048 (conflict-free)
+        const bool in_pitch = off + 16 <= f.pitch;
 #pragma unroll
-    for (int it = 0; it < 2; ++it) {
-        const int b = blk * 128 + (pw + it * kProdWarps) * 8 + r;
-        L.w[it] = make_uint4(0u, 0u, 0u, 0u);
-        if (b < B && off + 16 <= pitch) L.w[it] = ldg_nc(packed + rowoff[b] + off);
+        for (int it = 0; it < 4; ++it) {
+            const int b = f.c_blk * 128 + (wl * 4 + it) * 8 + r;
+            const bool ok = in_pitch && b < f.B;
+            cp_async16(dst + it * 2048, ok ? f.packed + (int64_t)f.rowoff[b] * f.pitch + off : f.packed, ok ? 16 : 0);
+        }
+        f.c_i += 4;
+        f.c_blk += 4;
+        while (f.c_blk >= f.nblk) { f.c_blk -= f.nblk; ++f.c_tt; }
     }
+    f.c_slot = (f.c_slot + 1 == kStDepth) ? 0 : f.c_slot + 1;
+    cp_async_commit();       // always one group per call: keeps wait_group counting aligned at the tail
 }
-__device__ __forceinline__ void widen_tile(uint8_t* tile, const TileLoad& L, int B, int blk, int pw, int lane) {
+// widen the tile in staging slot `slot` (this thread's own pieces have landed once at most kStDepth-1 newer groups are
+// pending) into `tile`
+__device__ __forceinline__ void feed_widen(const Feed& f, uint8_t* tile, int slot, int blk, int wl, int lane) {
     const int r = lane & 7, q = lane >> 3;
+    cp_async_wait<kStDepth - 1>();
+    const uint8_t* st = f.stage + slot * kStTile + (wl * 32 + lane) * 16;
 #pragma unroll
-    for (int it = 0; it < 2; ++it) {
-        const int g = pw + it * kProdWarps;                      // 8-row group inside the block
-        if (blk * 128 + g * 8 >= B) continue;                    // whole group past the batch: nothing reads it
-        uint8_t* dst = tile + r * 16 + g * 2048 + (q * 4) * 128;
-        widen_store(dst, L.w[it].x);
-        widen_store(dst + 128, L.w[it].y);
-        widen_store(dst + 256, L.w[it].z);
-        widen_store(dst + 384, L.w[it].w);
+    for (int it = 0; it < 4; ++it) {
+        const int g8 = wl * 4 + it;                              // 8-row group inside the block
+        if (blk * 128 + g8 * 8 >= f.B) continue;                 // whole group past the batch: nothing reads it
+        const uint4 w = *reinterpret_cast<const uint4*>(st + it * 2048);
+        uint8_t* dst = tile + r * 16 + g8 * 2048 + (q * 4) * 128;
+        widen_store(dst, w.x);
+        widen_store(dst + 128, w.y);
+        widen_store(dst + 256, w.z);
+        widen_store(dst + 384, w.w);
     }
 }
 
@@ -149,77 +171,79 @@ __global__ void absmax_kernel(const float* __restrict__ x, int64_t n, uint32_t* 
 // =================================================================================================================
 // forward
 // =================================================================================================================
+#ifdef NADM_TIMELINE
+__device__ long long g_enc_timeline[8][512];
+#define TLE(row, idx) do { if (blockIdx.x == 0 && (idx) < 512) g_enc_timeline[row][idx] = clock64(); } while (0)
+extern "C" int nadm_debug_enc_timeline(long long* host_out) {
+    return (int)cudaMemcpyFromSymbol(host_out, g_enc_timeline, sizeof(g_enc_timeline));
+}
+#else
+#define TLE(row, idx) do { } while (0)
+#endif
+
 struct EncSmem {
     uint64_t fullA[kAStages], emptyA[kAStages], fullV[2], emptyV[2], done;
     uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(kProdThreads + 32, 1)
+constexpr int kFwdDigWarps = 2, kFwdIssueWarp = kProdWarps + kFwdDigWarps, kFwdThreads = (kFwdIssueWarp + 1) * 32;
+
+__global__ void __launch_bounds__(kFwdThreads, 1)
 enc_fwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* __restrict__ row_idx, int64_t row0,
                   int B, int64_t M, const float* __restrict__ V, int C, const uint32_t* __restrict__ vmax_bits,
                   long long* __restrict__ part, int T) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* tilesA = smem;                                         // kAStages x 32 KB
     uint8_t* tilesV = tilesA + kAStages * kATile;                   // 2 x 8 KB
-    int64_t* rowoff = reinterpret_cast<int64_t*>(tilesV + 2 * kDigTile);
-    EncSmem* S = reinterpret_cast<EncSmem*>(rowoff + ((B + 1) & ~1));
+    uint8_t* stage = tilesV + 2 * kDigTile;                         // kStDepth x 10 KB packed rows
+    int32_t* rowoff = reinterpret_cast<int32_t*>(stage + 4 * kStDepth * kStTile);
+    EncSmem* S = reinterpret_cast<EncSmem*>(rowoff + ((B + 3) & ~3));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nblk = (B + 127) / 128;
     const int t0 = (int)(((int64_t)T * blockIdx.x) / gridDim.x), t1 = (int)(((int64_t)T * (blockIdx.x + 1)) / gridDim.x);
     const int ntile = (t1 - t0) * nblk;
 
-    for (int b = tid; b < B; b += blockDim.x) rowoff[b] = ((row_idx != nullptr) ? row_idx[b] : (row0 + b)) * pitch;
+    for (int b = tid; b < B; b += blockDim.x) rowoff[b] = (int32_t)((row_idx != nullptr) ? row_idx[b] : (row0 + b));
     if (tid == 0) {
-        for (int s = 0; s < kAStages; ++s) { mbar_init(&S->fullA[s], kProdThreads); mbar_init(&S->emptyA[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&S->fullV[s], kProdThreads); mbar_init(&S->emptyV[s], 1); }
+        for (int s = 0; s < kAStages; ++s) { mbar_init(&S->fullA[s], 4); mbar_init(&S->emptyA[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&S->fullV[s], kFwdDigWarps); mbar_init(&S->emptyV[s], 1); }
         mbar_init(&S->done, 1);
         mbar_init_fence();
     }
-    if (warp == kProdWarps) tmem_alloc<512>(&S->tmem_base);
+    if (warp == kFwdIssueWarp) tmem_alloc<512>(&S->tmem_base);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tbase = S->tmem_base;
 
     if (warp < kProdWarps) {
-        // ---------------- producers: digit tiles of V and widened genotype tiles ----------------
-        const FixScale fs = fix_scale(__uint_as_float(*vmax_bits));
-        TileLoad L[kPrefetch];
-#pragma unroll
-        for (int p = 0; p < kPrefetch; ++p)
-            if (p < ntile) load_tile(L[p], packed, pitch, rowoff, B, p % nblk, t0 + p / nblk, warp, lane);
-        for (int i0 = 0; i0 < ntile; i0 += kPrefetch) {
-#pragma unroll
-            for (int p = 0; p < kPrefetch; ++p) {
-                const int i = i0 + p;
-                if (i >= ntile) break;
-                const int blk = i % nblk, tt = i / nblk;
-                if (blk == 0) {
-                    // digits of V for K positions of sub-tile t0 + tt: thread tid <-> position tid
-                    const int vs = tt & 1;
-                    const int64_t m = (int64_t)(t0 + tt) * kSub + (tid & ~15) + sigma16(tid & 15);
-                    float v[8];
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) v[c] = (m < M && c < C) ? V[m * C + c] : 0.f;
-                    mbar_wait(&S->emptyV[vs], ((tt >> 1) & 1) ^ 1);
-                    store_digits(tilesV + vs * kDigTile + (tid & 7) * 16 + (tid >> 3) * 256, v, fs.inv);
-                    fence_async_smem();
-                    mbar_arrive(&S->fullV[vs]);
-                }
-                const int s = i % kAStages;
-                mbar_wait(&S->emptyA[s], ((i / kAStages) & 1) ^ 1);
-                widen_tile(tilesA + s * kATile, L[p], B, blk, warp, lane);
-                fence_async_smem();
-                mbar_arrive(&S->fullA[s]);
-                const int nx = i + kPrefetch;
-                if (nx < ntile) load_tile(L[p], packed, pitch, rowoff, B, nx % nblk, t0 + nx / nblk, warp, lane);
-            }
+        // ---------------- producers: widened genotype tiles (group g = warp / 4 handles tiles g, g + 4, ...) ----------------
+        const int g = warp >> 2, wl = warp & 3;
+        Feed f{packed, pitch, rowoff, B, nblk, t0, ntile, stage + g * (kStDepth * kStTile), g % nblk, g / nblk, g, 0};
+        for (int p = 0; p < kStDepth; ++p) feed_issue(f, wl, lane);
+        int blk = g % nblk, slot = 0, phase = 1;
+        for (int i = g; i < ntile; i += 4) {
+            if (tid == 0) TLE(0, i);
+            mbar_wait(&S->emptyA[g], phase);
+            if (tid == 0) TLE(1, i);
+            feed_widen(f, tilesA + g * kATile, slot, blk, wl, lane);
+            if (tid == 0) TLE(3, i);
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S->fullA[g]);                // one arrival per warp of the group
+            if (tid == 0) TLE(4, i);
+            feed_issue(f, wl, lane);                                 // refill the staging slot just consumed
+            if (tid == 0) TLE(5, i);
+            phase ^= 1;
+            slot = (slot + 1 == kStDepth) ? 0 : slot + 1;
+            blk += 4;
+            while (blk >= nblk) blk -= nblk;
         }
         // ---------------- epilogue: recombine the digit planes, write this CTA's exact partial sums ----------------
         mbar_wait(&S->done, 0);
         tc_fence_after_sync();
         const int q = warp & 3;
-        for (int blk = warp >> 2; blk < nblk; blk += 2) {
+        for (int blk = warp >> 2; blk < nblk; blk += kProdWarps / 4) {
             uint32_t v[32];
             tmem_ld32(tbase + ((uint32_t)(q * 32) << 16) + blk * 32, v);
             tmem_wait_ld();
@@ -235,39 +259,97 @@ enc_fwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
                 }
             }
         }
-    } else if (lane == 0) {
-        // ---------------- MMA issuer ----------------
-        for (int i = 0; i < ntile; ++i) {
-            const int blk = i % nblk, tt = i / nblk, vs = tt & 1, s = i % kAStages;
-            if (blk == 0) mbar_wait(&S->fullV[vs], (tt >> 1) & 1);
-            mbar_wait(&S->fullA[s], (i / kAStages) & 1);
-            tc_fence_after_sync();
-            const uint32_t a0 = smem_u32(tilesA + s * kATile), b0 = smem_u32(tilesV + vs * kDigTile);
+    } else if (warp < kFwdIssueWarp) {
+        // ---------------- digit warps: int8 digit planes of V, one 256-SNP sub-tile ahead of the MMAs ----------------
+        const FixScale fs = fix_scale(__uint_as_float(*vmax_bits));
+        const int dt = tid - kProdThreads;                              // 0..63: K positions dt, dt+64, dt+128, dt+192
+        auto load_v = [&](int tt, float (&v)[4][8]) {
 #pragma unroll
-            for (int ks = 0; ks < kSub / 32; ++ks)
-                mma_i8_ss(tbase + blk * 32, smem_desc(a0 + ks * 256, 128, 2048), smem_desc(b0 + ks * 1024, 256, 128),
-                          kIdescFwd, (tt > 0 || ks > 0) ? 1u : 0u);
-            mma_commit(&S->emptyA[s]);
-            if (blk == nblk - 1) mma_commit(&S->emptyV[vs]);
+            for (int e = 0; e < 4; ++e) {
+                const int pos = dt + 64 * e;
+                const int64_t m = (int64_t)(t0 + tt) * kSub + (pos & ~15) + sigma16(pos & 15);
+                if (m < M && C == 8) {
+                    const float4 a = reinterpret_cast<const float4*>(V + m * 8)[0], b4 = reinterpret_cast<const float4*>(V + m * 8)[1];
+                    v[e][0] = a.x; v[e][1] = a.y; v[e][2] = a.z; v[e][3] = a.w;
+                    v[e][4] = b4.x; v[e][5] = b4.y; v[e][6] = b4.z; v[e][7] = b4.w;
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) v[e][c] = (m < M && c < C) ? V[m * C + c] : 0.f;
+                }
+            }
+        };
+        float vnext[4][8];
+        if (t1 > t0) load_v(0, vnext);
+        for (int tt = 0; tt < t1 - t0; ++tt) {
+            const int vs = tt & 1;
+            float v[4][8];
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+#pragma unroll
+                for (int c = 0; c < 8; ++c) v[e][c] = vnext[e][c];
+            if (t0 + tt + 1 < t1) load_v(tt + 1, vnext);
+            mbar_wait(&S->emptyV[vs], ((tt >> 1) & 1) ^ 1);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int pos = dt + 64 * e;
+                store_digits(tilesV + vs * kDigTile + (pos & 7) * 16 + (pos >> 3) * 256, v[e], fs.inv);
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S->fullV[vs]);
         }
-        mma_commit(&S->done);
+    } else {
+        // ---------------- MMA issuer: the whole warp waits, one elected lane issues; descriptors built once ----------------
+        const uint64_t A0 = smem_desc(smem_u32(tilesA), 128, 2048), B0 = smem_desc(smem_u32(tilesV), 256, 128);
+        int blk = 0, tt = 0, s = 0, s_phase = 0;
+        for (int i = 0; i < ntile; ++i) {
+            const int vs = tt & 1;
+            if (blk == 0) mbar_wait(&S->fullV[vs], (tt >> 1) & 1);
+            mbar_wait(&S->fullA[s], s_phase);
+            tc_fence_after_sync();
+            if (lane == 0) TLE(6, i);
+            if (elect_one()) {
+                const uint64_t a = A0 + (uint64_t)(s * (kATile >> 4)), b = B0 + (uint64_t)(vs * (kDigTile >> 4));
+                const uint32_t d = tbase + blk * 32, acc0 = tt > 0 ? 1u : 0u;
+#pragma unroll
+                for (int ks = 0; ks < kSub / 32; ++ks)
+                    mma_i8_ss(d, a + (uint64_t)(ks * 16), b + (uint64_t)(ks * 64), kIdescFwd, ks ? 1u : acc0);
+                mma_commit(&S->emptyA[s]);
+                if (blk == nblk - 1) mma_commit(&S->emptyV[vs]);
+            }
+            __syncwarp();
+            if (lane == 0) TLE(7, i);
+            if (++s == kAStages) { s = 0; s_phase ^= 1; }
+            if (++blk == nblk) { blk = 0; ++tt; }
+        }
+        if (elect_one()) mma_commit(&S->done);
+        __syncwarp();
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == kProdWarps) tmem_dealloc<512>(tbase);
+    if (warp == kFwdIssueWarp) tmem_dealloc<512>(tbase);
 }
 
-// Z[b, c] = 0.5 * 2^(e-30) * sum over CTAs of the exact int64 partials
-__global__ void enc_fwd_reduce_kernel(const long long* __restrict__ part, int nparts, int B, int C,
-                                      const uint32_t* __restrict__ vmax_bits, float* __restrict__ Z) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= B * 8) return;
-    const int b = i >> 3, c = i & 7;
-    if (c >= C) return;
+// Z[b, c] = 0.5 * 2^(e-30) * sum over CTAs of the exact int64 partials (integer sum: order-independent).
+// Block = the 8 components of one row x 32 part segments.
+__global__ void __launch_bounds__(256)
+enc_fwd_reduce_kernel(const long long* __restrict__ part, int nparts, int B, int C,
+                      const uint32_t* __restrict__ vmax_bits, float* __restrict__ Z) {
+    __shared__ long long red[32][8];
+    const int c = threadIdx.x & 7, seg = threadIdx.x >> 3;
+    const int b = blockIdx.x;
+    const int64_t i = (int64_t)b * 8 + c;
     long long acc = 0;
-    for (int p = 0; p < nparts; ++p) acc += part[(int64_t)p * B * 8 + i];
-    const FixScale fs = fix_scale(__uint_as_float(*vmax_bits));
-    Z[(int64_t)b * C + c] = (float)((double)acc * fs.back * 0.5);
+    for (int p = seg; p < nparts; p += 32) acc += part[(int64_t)p * B * 8 + i];
+    red[seg][c] = acc;
+    __syncthreads();
+    if (threadIdx.x < 8 && c < C) {
+        long long t = 0;
+#pragma unroll
+        for (int s2 = 0; s2 < 32; ++s2) t += red[s2][c];
+        const FixScale fs = fix_scale(__uint_as_float(*vmax_bits));
+        Z[(int64_t)b * C + c] = (float)((double)t * fs.back * 0.5);
+    }
 }
 
 // =================================================================================================================
@@ -287,16 +369,17 @@ enc_bwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
     const int nblk = (B + 127) / 128;
     uint8_t* tilesA = smem;                                         // kAStages x 32 KB
     uint8_t* digZ = tilesA + kAStages * kATile;                     // nblk x 4 KB: dZ digits, K position = batch row
-    int64_t* rowoff = reinterpret_cast<int64_t*>(digZ + nblk * 4096);
-    EncBwdSmem* S = reinterpret_cast<EncBwdSmem*>(rowoff + ((B + 1) & ~1));
+    uint8_t* stage = digZ + nblk * 4096;                            // kStDepth x 10 KB packed rows
+    int32_t* rowoff = reinterpret_cast<int32_t*>(stage + 4 * kStDepth * kStTile);
+    EncBwdSmem* S = reinterpret_cast<EncBwdSmem*>(rowoff + ((B + 3) & ~3));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int t0 = (int)(((int64_t)T * blockIdx.x) / gridDim.x), t1 = (int)(((int64_t)T * (blockIdx.x + 1)) / gridDim.x);
     const int ntile = (t1 - t0) * nblk;
 
-    for (int b = tid; b < B; b += blockDim.x) rowoff[b] = ((row_idx != nullptr) ? row_idx[b] : (row0 + b)) * pitch;
+    for (int b = tid; b < B; b += blockDim.x) rowoff[b] = (int32_t)((row_idx != nullptr) ? row_idx[b] : (row0 + b));
     if (tid == 0) {
-        for (int s = 0; s < kAStages; ++s) { mbar_init(&S->fullA[s], kProdThreads); mbar_init(&S->emptyA[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&S->dfull[s], 1); mbar_init(&S->dempty[s], 128); }
+        for (int s = 0; s < kAStages; ++s) { mbar_init(&S->fullA[s], 4); mbar_init(&S->emptyA[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&S->dfull[s], 1); mbar_init(&S->dempty[s], 4); }
         mbar_init_fence();
     }
     if (warp == kProdWarps) tmem_alloc<128>(&S->tmem_base);
@@ -324,43 +407,54 @@ enc_bwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
 
     if (warp < kProdWarps) {
         // ---------------- producers: widened genotype tiles, order (sub-tile, block) ----------------
-        TileLoad L[kPrefetch];
-#pragma unroll
-        for (int p = 0; p < kPrefetch; ++p)
-            if (p < ntile) load_tile(L[p], packed, pitch, rowoff, B, p % nblk, t0 + p / nblk, warp, lane);
-        for (int i0 = 0; i0 < ntile; i0 += kPrefetch) {
-#pragma unroll
-            for (int p = 0; p < kPrefetch; ++p) {
-                const int i = i0 + p;
-                if (i >= ntile) break;
-                const int s = i % kAStages;
-                mbar_wait(&S->emptyA[s], ((i / kAStages) & 1) ^ 1);
-                widen_tile(tilesA + s * kATile, L[p], B, i % nblk, warp, lane);
-                fence_async_smem();
-                mbar_arrive(&S->fullA[s]);
-                const int nx = i + kPrefetch;
-                if (nx < ntile) load_tile(L[p], packed, pitch, rowoff, B, nx % nblk, t0 + nx / nblk, warp, lane);
-            }
+        const int g = warp >> 2, wl = warp & 3;
+        Feed f{packed, pitch, rowoff, B, nblk, t0, ntile, stage + g * (kStDepth * kStTile), g % nblk, g / nblk, g, 0};
+        for (int p = 0; p < kStDepth; ++p) feed_issue(f, wl, lane);
+        int blk = g % nblk, slot = 0, phase = 1;
+        for (int i = g; i < ntile; i += 4) {
+            mbar_wait(&S->emptyA[g], phase);
+            feed_widen(f, tilesA + g * kATile, slot, blk, wl, lane);
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S->fullA[g]);
+            feed_issue(f, wl, lane);
+            phase ^= 1;
+            slot = (slot + 1 == kStDepth) ? 0 : slot + 1;
+            blk += 4;
+            while (blk >= nblk) blk -= nblk;
         }
     } else if (warp == kProdWarps) {
-        // ---------------- MMA issuer ----------------
-        if (lane == 0) {
-            for (int i = 0; i < ntile; ++i) {
-                const int blk = i % nblk, tt = i / nblk, buf = tt & 1, s = i % kAStages;
-                if (blk == 0) {
-                    mbar_wait(&S->dempty[buf], ((tt >> 1) & 1) ^ 1);
+        // ---------------- MMA issuer: the whole warp waits, one elected lane issues; descriptors built once ----------------
+        const uint64_t A0 = smem_desc(smem_u32(tilesA), 2048, 128), B0 = smem_desc(smem_u32(digZ), 256, 128);
+        const int nks_last = min(4, (B - (nblk - 1) * 128 + 31) / 32);      // K steps holding real batch rows
+        int blk = 0, tt = 0, s = 0, s_phase = 0;
+        for (int i = 0; i < ntile; ++i) {
+            const int buf = tt & 1;
+            if (blk == 0) mbar_wait(&S->dempty[buf], ((tt >> 1) & 1) ^ 1);
+            mbar_wait(&S->fullA[s], s_phase);
+            tc_fence_after_sync();
+            if (elect_one()) {
+                const uint64_t a = A0 + (uint64_t)(s * (kATile >> 4)), b = B0 + (uint64_t)(blk * 256);
+                const uint32_t d = tbase + buf * 64, acc0 = blk > 0 ? 1u : 0u;
+                if (blk != nblk - 1 || nks_last == 4) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)
+                            mma_i8_ss(d + h * 32, a + (uint64_t)(h * 64 + ks * 512), b + (uint64_t)(ks * 64), kIdescBwd,
+                                      ks ? 1u : acc0);
+                } else {
+                    for (int h = 0; h < 2; ++h)
+                        for (int ks = 0; ks < nks_last; ++ks)
+                            mma_i8_ss(d + h * 32, a + (uint64_t)(h * 64 + ks * 512), b + (uint64_t)(ks * 64), kIdescBwd,
+                                      ks ? 1u : acc0);
                 }
-                mbar_wait(&S->fullA[s], (i / kAStages) & 1);
-                tc_fence_after_sync();
-                const uint32_t a0 = smem_u32(tilesA + s * kATile), b0 = smem_u32(digZ + blk * 4096);
-                const int nks = min(4, (B - blk * 128 + 31) / 32);          // K steps holding real batch rows
-                for (int h = 0; h < 2; ++h)
-                    for (int ks = 0; ks < nks; ++ks)
-                        mma_i8_ss(tbase + buf * 64 + h * 32, smem_desc(a0 + h * 1024 + ks * 8192, 2048, 128),
-                                  smem_desc(b0 + ks * 1024, 256, 128), kIdescBwd, (blk > 0 || ks > 0) ? 1u : 0u);
                 mma_commit(&S->emptyA[s]);
                 if (blk == nblk - 1) mma_commit(&S->dfull[buf]);
             }
+            __syncwarp();
+            if (++s == kAStages) { s = 0; s_phase ^= 1; }
+            if (++blk == nblk) { blk = 0; ++tt; }
         }
     } else {
         // ---------------- epilogue: digit planes -> dV -> Adam on V, one SNP per thread ----------------
@@ -374,7 +468,8 @@ enc_bwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
             tmem_ld32(tbase + ((uint32_t)(q * 32) << 16) + buf * 64 + 32, v[1]);
             tmem_wait_ld();
             tc_fence_before_sync();
-            mbar_arrive(&S->dempty[buf]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S->dempty[buf]);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int pos = q * 32 + lane;
@@ -427,6 +522,11 @@ enc_bwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
 // =================================================================================================================
 // host launchers (called from the C ABI in nadm_stream.cu)
 // =================================================================================================================
+bool enc_bwd_tc_supported(int B) {
+    const int nblk = (B + 127) / 128;
+    return (size_t)kAStages * kATile + (size_t)nblk * 4096 + (size_t)4 * kStDepth * kStTile + (size_t)((B + 3) & ~3) * 4 +
+               sizeof(EncBwdSmem) + 64 <= (size_t)kMaxDynSmem;
+}
 size_t enc_tc_workspace_bytes(int B) { return (size_t)sm_count() * (size_t)B * 8 * sizeof(long long) + 256; }
 
 int launch_enc_fwd_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_idx, int64_t row0, int B, int64_t M,
@@ -442,16 +542,17 @@ int launch_enc_fwd_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_i
     const int64_t n = M * C;
     absmax_kernel<<<(unsigned)std::min<int64_t>((n / 4 + 255) / 256 + 1, 4 * sm_count()), 256, 0, st>>>(V, n, vmax);
     NADM_CHECK_LAUNCH("absmax_kernel");
-    const size_t smem = (size_t)kAStages * kATile + 2 * kDigTile + (size_t)((B + 1) & ~1) * 8 + sizeof(EncSmem) + 64;
+    const size_t smem = (size_t)kAStages * kATile + 2 * kDigTile + (size_t)4 * kStDepth * kStTile + (size_t)((B + 3) & ~3) * 4 +
+                        sizeof(EncSmem) + 64;
     static bool attr = false;
     if (!attr) {
         e = cudaFuncSetAttribute(enc_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(enc_fwd_tc)");
         attr = true;
     }
-    enc_fwd_tc_kernel<<<ncta, kProdThreads + 32, smem, st>>>(packed, pitch, row_idx, row0, B, M, V, C, vmax, part, T);
+    enc_fwd_tc_kernel<<<ncta, kFwdThreads, smem, st>>>(packed, pitch, row_idx, row0, B, M, V, C, vmax, part, T);
     NADM_CHECK_LAUNCH("enc_fwd_tc_kernel");
-    enc_fwd_reduce_kernel<<<(B * 8 + 255) / 256, 256, 0, st>>>(part, ncta, B, C, vmax, Z);
+    enc_fwd_reduce_kernel<<<B, 256, 0, st>>>(part, ncta, B, C, vmax, Z);
     NADM_CHECK_LAUNCH("enc_fwd_reduce_kernel");
     return NADM_OK;
 }
@@ -462,7 +563,7 @@ int launch_enc_bwd_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_i
     const int T = (int)((M + kSub - 1) / kSub);
     const int ncta = std::min(T, sm_count());
     const int nblk = (B + 127) / 128;
-    const size_t smem = (size_t)kAStages * kATile + (size_t)nblk * 4096 + (size_t)((B + 1) & ~1) * 8 +
+    const size_t smem = (size_t)kAStages * kATile + (size_t)nblk * 4096 + (size_t)4 * kStDepth * kStTile + (size_t)((B + 3) & ~3) * 4 +
                         sizeof(EncBwdSmem) + 64;
     NADM_REQUIRE(smem <= (size_t)kMaxDynSmem, "batch B=%d too large for encoder_bwd", B);
     static bool attr = false;
