@@ -92,7 +92,8 @@ int nadm_mlp_fwd(const float* Z, int32_t B, int32_t C, int32_t H, const float* w
  *   Q, dQ : B x q_ld (q_ld = sumK), this head occupies columns [q_off, q_off+k)
  *   P, Pm, Pv : M x k parameter and Adam moments, updated in place when adam != NULL
  *   dP_out : optional M x k raw gradient output (tests); may be NULL
- *   loss : 1 float, the head's loss is ADDED to it (zero it once per step). */
+ *   loss : 1 float, the head's loss is ADDED to it (zero it once per step); NULL = gradients only (the loss value
+ *          is not needed by the backward: the reference only reports it, neural_admixture.py:414-417). */
 int nadm_decoder_step(const uint8_t* packed, int64_t pitch, const int64_t* row_idx, int64_t row0, int32_t B,
                       int64_t M, const float* Q, float* dQ, int32_t q_ld, int32_t q_off, int32_t k,
                       float* P, float* Pm, float* Pv, const nadm_adam_t* adam /*[host], NULL = no update*/,

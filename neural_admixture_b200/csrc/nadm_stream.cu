@@ -101,7 +101,7 @@ reduce_parts_kernel(const float* __restrict__ part, int nparts, int rows, int co
         const int r = (int)(i / cols_p), c = (int)(i % cols_p);
         if (c < cols_out) out[(int64_t)r * out_ld + out_off + c] = t * scale;
     }
-    if (loss_part != nullptr && blockIdx.x == 0 && threadIdx.x >= 32 && threadIdx.x < 64) {
+    if (loss_part != nullptr && loss != nullptr && blockIdx.x == 0 && threadIdx.x >= 32 && threadIdx.x < 64) {
         double acc2 = 0.0;
         for (int q = threadIdx.x - 32; q < nparts; q += 32) acc2 += (double)loss_part[q];
         acc2 = warp_sum_d(acc2);
@@ -634,7 +634,7 @@ extern "C" int nadm_decoder_step(const uint8_t* packed, int64_t pitch, const int
     NADM_REQUIRE(B > 0 && M > 0, "empty batch or no SNPs (B=%d, M=%lld)", B, (long long)M);
     NADM_REQUIRE(k >= 1 && k <= NADM_MAX_K, "k=%d unsupported (1..%d)", k, NADM_MAX_K);
     NADM_REQUIRE(q_off >= 0 && q_off + k <= q_ld, "head columns [%d,%d) outside q_ld=%d", q_off, q_off + k, q_ld);
-    NADM_REQUIRE(Q && dQ && P && loss && ws, "NULL pointer");
+    NADM_REQUIRE(Q && dQ && P && ws, "NULL pointer");
     NADM_REQUIRE(adam == nullptr || (Pm && Pv), "Adam moments are NULL");
     cudaStream_t st = (cudaStream_t)stream;
     float* w = (float*)ws;

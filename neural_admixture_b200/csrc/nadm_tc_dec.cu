@@ -96,7 +96,10 @@ struct Elem {
 };
 
 // Process 16 consecutive SNPs of one row: v[] holds raw on entry; on exit hi[] / lo[] hold the bf16x2-packed split of G.
-// w: the 16 2-bit codes (missing cleared).  Loss accumulators in log2 units.
+// w: the 16 2-bit codes (missing cleared).  Loss accumulators in log2 units (kLoss = false: gradients only).
+// kChecked = true is the general path (raw may exceed 1 by rounding: clamp + inclusive mask of the clamp backward);
+// kChecked = false is taken when the caller has verified max(raw) <= 1 for the 16 values, where min / mask are no-ops.
+template <bool kLoss, bool kChecked>
 __device__ __forceinline__ void decode16(const uint32_t (&v)[16], uint32_t w, uint32_t magic, uint32_t (&hi)[8],
                                          uint32_t (&lo)[8], float& acc_all, float& acc_het) {
     const uint32_t wh = w >> 16;
@@ -111,20 +114,22 @@ __device__ __forceinline__ void decode16(const uint32_t (&v)[16], uint32_t w, ui
             const float raw = __uint_as_float(v[j]);
             // code * 4^(j&7) as an exact float via the 2^23 magic constant (kept in a register: one LOP3); x = code / 2
             const float f = __uint_as_float((wsrc & (3u << sh)) | magic) - 8388608.0f;
-            const float Rs = fminf(raw, 1.0f);
+            const float Rs = kChecked ? fminf(raw, 1.0f) : raw;
             const float prod = fmaf(-Rs, Rs, Rs);                       // R (1 - R)
             const float inv = rcp_approx(fmaxf(prod, 1e-12f));
             const float num = fmaf(f, -0.5f / (float)(1 << sh), Rs);     // R - x
             float G = num * inv;
-            G = (raw <= 1.0f) ? G : 0.0f;                               // clamp backward mask (raw >= 0 always)
+            if (kChecked) G = (raw <= 1.0f) ? G : 0.0f;                 // clamp backward mask (raw >= 0 always)
             g[e] = G;
-            // BCE with torch's log clamp; X in {0, .5, 1}: a single log per element.
-            // x = 0: 1 - R = 1 - |R - x| ;  x = 1: R = 1 - |R - x| ;  x = .5: weight .5 on log(R (1 - R))
-            const bool het = (wsrc >> sh) & 1u;
-            const float arg = het ? prod : (1.0f - fabsf(num));
-            const float l = fmaxf(lg2_approx(arg), kLog2Clamp);
-            acc_all += l;
-            acc_het += het ? l : 0.0f;
+            if (kLoss) {
+                // BCE with torch's log clamp; X in {0, .5, 1}: a single log per element.
+                // x = 0: 1 - R = 1 - |R - x| ;  x = 1: R = 1 - |R - x| ;  x = .5: weight .5 on log(R (1 - R))
+                const bool het = (wsrc >> sh) & 1u;
+                const float arg = het ? prod : (1.0f - fabsf(num));
+                const float l = fmaxf(lg2_approx(arg), kLog2Clamp);
+                acc_all += l;
+                acc_het += het ? l : 0.0f;
+            }
         }
         const uint32_t h = pack_bf16x2(g[0], g[1]);
         hi[j2] = h;
@@ -132,6 +137,7 @@ __device__ __forceinline__ void decode16(const uint32_t (&v)[16], uint32_t w, ui
     }
 }
 
+template <bool kLoss>
 __global__ void __launch_bounds__(kDecThreads, 1)
 dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* __restrict__ row_idx, int64_t row0, int B,
               int64_t M, const float* __restrict__ Q, int q_ld, int q_off, int k, float* __restrict__ P,
@@ -213,12 +219,17 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
                 mbar_wait(&S->gtfree[g], ((u / ngt) & 1) ^ 1);
                 if (rb == 0) TL(6, u);                                  // G^T buffer free
                 uint8_t* gt = GT + g * kGtBytes + (rb & 7) * 16 + (rb >> 3) * 1024;
-#pragma unroll
+#pragma unroll 1
                 for (int c = 0; c < 4; ++c) {                          // 16 SNPs at a time: raw columns [16c, 16c+16)
                     uint32_t v[16], hi[8], lo[8];
                     tmem_ld16(tlane + slot * 64 + c * 16, v);
                     tmem_wait_ld();
-                    decode16(v, cw[c], magic, hi, lo, acc_all, acc_het);
+                    const uint32_t w = (c & 2) ? ((c & 1) ? cw[3] : cw[2]) : ((c & 1) ? cw[1] : cw[0]);
+                    float mx = __uint_as_float(v[0]);
+#pragma unroll
+                    for (int j = 1; j < 16; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+                    if (mx <= 1.0f) decode16<kLoss, false>(v, w, magic, hi, lo, acc_all, acc_het);
+                    else decode16<kLoss, true>(v, w, magic, hi, lo, acc_all, acc_het);
                     tmem_st8(tlane + slot * 64 + c * 16, hi);          // G hi / lo overwrite their own raw columns
                     tmem_st8(tlane + slot * 64 + c * 16 + 8, lo);
                     *reinterpret_cast<uint4*>(gt + (2 * c) * 128) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
@@ -476,6 +487,7 @@ extern "C" int nadm_debug_timeline(long long* host_out) {
 int launch_dec_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_idx, int64_t row0, int B, int64_t M,
                   const float* Q, float* dQ, int q_ld, int q_off, int k, float* P, float* Pm, float* Pv,
                   const nadm_adam_t* adam, float* dP_out, float* loss, float* ws, size_t ws_bytes, cudaStream_t st) {
+    const bool want_loss = loss != nullptr;
     const int nblk = (B + 127) / 128;
     const int TS = (int)((M + kMS - 1) / kMS);
     const int ncta = std::min(TS, sm_count());
@@ -485,16 +497,22 @@ int launch_dec_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_idx, 
     NADM_REQUIRE((size_t)ncta * ((size_t)B * 8 + 1) * sizeof(float) <= ws_bytes, "workspace too small for decoder_step");
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(dec_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+        cudaError_t e = cudaFuncSetAttribute(dec_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(dec_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(dec_tc)");
         attr = true;
     }
     float* dQpart = ws;
     float* loss_part = ws + (size_t)ncta * B * 8;
-    dec_tc_kernel<<<ncta, kDecThreads, smem, st>>>(packed, pitch, row_idx, row0, B, M, Q, q_ld, q_off, k, P, Pm, Pv,
-                                                  make_adam(adam), dP_out, dQpart, loss_part, TS, ngt);
+    if (want_loss)
+        dec_tc_kernel<true><<<ncta, kDecThreads, smem, st>>>(packed, pitch, row_idx, row0, B, M, Q, q_ld, q_off, k, P, Pm, Pv,
+                                                            make_adam(adam), dP_out, dQpart, loss_part, TS, ngt);
+    else
+        dec_tc_kernel<false><<<ncta, kDecThreads, smem, st>>>(packed, pitch, row_idx, row0, B, M, Q, q_ld, q_off, k, P, Pm,
+                                                             Pv, make_adam(adam), dP_out, dQpart, loss_part, TS, ngt);
     NADM_CHECK_LAUNCH("dec_tc_kernel");
-    return launch_reduce_parts(dQpart, ncta, B, 8, k, dQ, q_ld, q_off, 1.0f, loss_part, loss, st);
+    return launch_reduce_parts(dQpart, ncta, B, 8, k, dQ, q_ld, q_off, 1.0f, want_loss ? loss_part : nullptr, loss, st);
 }
 
 }  // namespace nadm

@@ -264,12 +264,13 @@ class NeuralAdmixture:
             setattr(p, "g_" + n, None)
         return p
 
-    def _train_step(self, row_idx: Optional[torch.Tensor], labels: Optional[torch.Tensor], loss_out: torch.Tensor,
-                    pg: Optional[ops.PackedGenotypes] = None) -> None:
+    def _train_step(self, row_idx: Optional[torch.Tensor], labels: Optional[torch.Tensor],
+                    loss_out: Optional[torch.Tensor], pg: Optional[ops.PackedGenotypes] = None) -> None:
         """One minibatch: the body of the reference's ``_run_epoch`` loop (:403-414) — forward, loss, backward,
         Adam on every parameter, P clamp — as 5 library calls.  ``loss_out`` (1 float on device) receives the step's
-        loss; nothing is synchronised with the host.  The batch is rows ``row_idx`` of the resident matrix, or all
-        rows of ``pg`` (a staged batch, see ``train_from_host``)."""
+        loss; nothing is synchronised with the host.  ``loss_out=None`` skips the evaluation of the reconstruction loss
+        (its value never feeds the backward; the reference only logs it, :414-417).  The batch is rows ``row_idx`` of
+        the resident matrix, or all rows of ``pg`` (a staged batch, see ``train_from_host``)."""
         m, o = self.raw_model, self.optimizer
         if pg is None:
             pg = self.packed
@@ -285,7 +286,7 @@ class NeuralAdmixture:
         off = 0
         for i, k in enumerate(m.multihead_encoder.ks):
             ops.decoder_step(pg, fb["Q"], sb["dQ"], off, k, m.decoders.decoders[i].weight.data, o.m["P"][i], o.v["P"][i],
-                             hyper, sb["loss"], fb["ws"], row_idx=row_idx)
+                             hyper, sb["loss"] if loss_out is not None else None, fb["ws"], row_idx=row_idx)
             off += k
         if self.sharded:
             self._allreduce(sb["dq_loss"])
@@ -293,7 +294,8 @@ class NeuralAdmixture:
                     sb["dZ"], sb["loss"], fb["ws"], labels=labels,
                     sup_weight=float(self.supervised_loss_weight) if labels is not None else 0.0)
         ops.encoder_bwd(pg, sb["dZ"], m.V.data, o.m["V"], o.v["V"], hyper, fb["ws"], row_idx=row_idx)
-        loss_out.copy_(sb["loss"])
+        if loss_out is not None:
+            loss_out.copy_(sb["loss"])
 
     def epoch_order(self, N: int) -> torch.Tensor:
         """Row order of one epoch: exactly what the reference's ``RandomSampler(dataset, generator=self.generator)``
@@ -306,13 +308,14 @@ class NeuralAdmixture:
         device->host read per epoch of the per-step losses, summed in the same order."""
         N = order_dev.numel()
         nsteps = (N + self.batch_size - 1) // self.batch_size
+        every = 2 if pops is not None else 5
+        want_loss = (epoch % every == 0) or self.keep_loss_history     # the epochs whose loss the reference prints
         losses = torch.zeros(nsteps, dtype=torch.float32, device=self.device)
         for s in range(nsteps):
             idx = order_dev[s * self.batch_size:(s + 1) * self.batch_size]
             labels = pops[idx].contiguous() if pops is not None else None
-            self._train_step(idx, labels, losses[s:s + 1])
-        every = 2 if pops is not None else 5
-        loss_acc = float(losses.double().sum().item()) if (epoch % every == 0 or self.keep_loss_history) else None
+            self._train_step(idx, labels, losses[s:s + 1] if want_loss else None)
+        loss_acc = float(losses.double().sum().item()) if want_loss else None
         if loss_acc is not None:
             self.loss_history.append(loss_acc)
         if epoch % every == 0 and self.master:

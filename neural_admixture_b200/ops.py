@@ -144,7 +144,7 @@ def mlp_fwd(Z, w_rms, W1, b1, W2, b2, ks, rinv, Hh, Q) -> None:
 
 def decoder_step(pg: PackedGenotypes, Q, dQ, q_off: int, k: int, P, Pm, Pv, adam: Optional[AdamHyper], loss, ws, *,
                  row_idx=None, row0: int = 0, dP_out=None) -> None:
-    _need_cuda(Q, dQ, P, Pm, Pv, loss, ws, row_idx, dP_out)
+    _need_cuda(Q, dQ, P, Pm, Pv, loss, ws, row_idx, dP_out)   # loss may be None: gradients only
     B, q_ld = Q.shape
     assert P.shape == (pg.M, k) and P.is_contiguous() and P.dtype == torch.float32
     assert Q.is_contiguous() and dQ.is_contiguous() and dQ.shape == Q.shape

@@ -210,6 +210,31 @@ def test_decoder_step_grads(ops, dev, N, M, k, B, edge):
         assert np.abs(dP_ref).max() > 1e10
 
 
+def test_decoder_step_without_loss_is_the_same_update(ops, dev):
+    """loss = NULL (gradients only: the schedule used on epochs whose loss the reference does not print) must give
+    bit-identical dQ and P updates."""
+    rng = np.random.default_rng(11)
+    N, M, k, B = 900, 30011, 8, 800
+    G = rand_genotypes(rng, N, M)
+    pg = packed_from(ops, G, dev)
+    P0 = rng.uniform(0.0, 1.0, size=(M, k)).astype(np.float32)
+    P0[7] = 0.0
+    P0[9] = 1.0
+    Q = t(rng.dirichlet(0.3 * np.ones(k), size=B).astype(np.float32), dev)
+    idx = t(rng.permutation(N)[:B], dev, torch.int64)
+    ws = ws_for(ops, B, M, 8, 64, k, dev)
+    outs = []
+    for with_loss in (True, False):
+        P, Pm, Pv = t(P0, dev), torch.zeros((M, k), device=dev), torch.zeros((M, k), device=dev)
+        dQ = torch.zeros((B, k), device=dev)
+        loss = torch.zeros(1, device=dev)
+        ops.decoder_step(pg, Q, dQ, 0, k, P, Pm, Pv, ops.adam_hyper(2e-3, 1), loss if with_loss else None, ws, row_idx=idx)
+        outs.append((dQ.clone(), P.clone(), Pm.clone(), Pv.clone(), loss.item()))
+    for a, b in zip(outs[0][:4], outs[1][:4]):
+        assert torch.equal(a, b)
+    assert outs[0][4] > 0 and outs[1][4] == 0.0
+
+
 @pytest.mark.parametrize("N,M,C,B", [(64, 203, 8, 48), (300, 4099, 8, 300), (1000, 20000, 8, 800), (30, 6, 5, 30)])
 def test_encoder_bwd(ops, dev, N, M, C, B):
     rng = np.random.default_rng(M + 1)
