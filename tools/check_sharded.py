@@ -1,0 +1,65 @@
+#!/usr/bin/env python
+"""Multi-GPU parity of the SNP-sharded engine (NCCL) against the single-GPU engine and the CPU oracle.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/check_sharded.py
+"""
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "oracle"))
+from neural_admixture_b200 import ops  # noqa: E402
+from neural_admixture_b200.model.neural_admixture import NeuralAdmixture  # noqa: E402
+from neural_admixture_b200.model.train import snp_slice  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    rng = np.random.default_rng(5)
+    N, M, ks, C, H, B, epochs = 1500, 40_003, [5, 6, 7, 8], 8, 128, 512, 2
+    Pt = rng.uniform(0.05, 0.95, size=(6, M))
+    Qt = rng.dirichlet(0.3 * np.ones(6), size=N)
+    G = rng.binomial(2, Qt @ Pt).astype(np.uint8)
+    G[rng.random((N, M)) < 0.01] = 3
+    V = np.linalg.qr(rng.standard_normal((M, C)))[0].astype(np.float32)
+    P0 = rng.uniform(0.05, 0.95, size=(sum(ks), M)).astype(np.float32)
+
+    def run(sharded):
+        c0, c1 = snp_slice(M, rank, world) if sharded else (0, M)
+        torch.manual_seed(0)
+        na = NeuralAdmixture(None, epochs, B, 2e-3, dev, 0, world if sharded else 0, rank == 0, "nadm_b200", min(ks), max(ks))
+        na.keep_loss_history = True
+        packed = ops.PackedGenotypes.from_unpacked_host(torch.as_tensor(G), dev, c0, c1)
+        Qs, Ps, _ = na.launch_training(torch.as_tensor(P0[:, c0:c1].copy(), device=dev), packed, H, C,
+                                       torch.as_tensor(V[c0:c1].copy(), device=dev), c1 - c0, N)
+        return Qs, Ps, na.loss_history
+
+    Qs_s, Ps_s, loss_s = run(True)
+    dist.barrier()
+    if rank == 0:
+        Qs_1, Ps_1, loss_1 = run(False)
+        rel = lambda a, b: float(np.linalg.norm(a - b) / np.linalg.norm(b))
+        worst = 0.0
+        for i in range(len(ks)):
+            eq, ep = rel(Qs_s[i], Qs_1[i]), rel(Ps_s[i], Ps_1[i])
+            worst = max(worst, eq, ep)
+            print(f"head K={ks[i]}: relF(Q sharded vs single) = {eq:.2e}   relF(P) = {ep:.2e}")
+        el = max(abs(a - b) / abs(b) for a, b in zip(loss_s, loss_1))
+        print(f"epoch losses sharded {loss_s} single {loss_1} (max rel diff {el:.2e})")
+        ok = worst < 1e-4 and el < 1e-5
+        print(f"SHARDED PARITY ({world} GPUs): {'PASS' if ok else 'FAIL'}")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
