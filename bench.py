@@ -110,7 +110,7 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE, text=True,
+                                          "-lms", "20", "-i", str(index)], stdout=subprocess.PIPE, text=True,
                                          stderr=subprocess.DEVNULL)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -220,7 +220,7 @@ def cpu_reference(ks, M, B, steps, warmup, budget_s, as_line=False, n_gpus=1):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=125)
+    ap.add_argument("--steps", type=int, default=500)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
