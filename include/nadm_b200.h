@@ -129,6 +129,21 @@ int nadm_loglikelihood(const uint8_t* packed, int64_t pitch, int64_t N, int64_t 
                        const float* P, int32_t k, double eps, double* out, void* ws, size_t ws_bytes,
                        void* stream);
 
+/* ---- PLINK .bed -> sample-major 2-bit packed matrix on the device ("next" row f4 of the scope table).  Replaces
+ * SNPReader._read_bed (src/snp_reader.py:16-45) -> utils_c.read_bed (src/utils_c/utils.pyx:43-68, LUT [2,3,1,0] into an
+ * N x M uint8 host array), the allele flip `G if G.mean() < 1 else 2 - G` (snp_reader.py:110) and pack2bit_cpu_to_gpu
+ * (pack2bit.cu:65-117) without the one-byte-per-genotype intermediate.
+ *   bed     : M rows (SNPs) of bed_pitch >= ceil(N/4) bytes, the .bed payload after its 3 magic bytes (device copy)
+ *   snp0    : column of the first SNP of this call in the destination (multiple of 128): a file can be converted in
+ *             chunks of SNP rows; every chunk but the last must hold a multiple of 128 SNPs
+ *   flip    : 0 = codes as read_bed gives them; 1 = additionally g -> 2 - g (missing stays 3)
+ *   counts  : optional 4 x uint64; counts[1..3] += number of codes 1, 2, 3 read (BEFORE the flip) in this call, so
+ *             the caller can evaluate the reference's `G.mean() < 1` test; zero it first
+ * nadm_flip_packed applies g -> 2 - g in place to a packed N x M matrix (missing and the zero row tails unchanged). */
+int nadm_bed_to_packed(const uint8_t* bed, int64_t bed_pitch, int64_t N, int64_t M, int64_t snp0, int32_t flip,
+                       uint8_t* dst, int64_t dst_pitch, uint64_t* counts, void* stream);
+int nadm_flip_packed(uint8_t* packed, int64_t pitch, int64_t N, int64_t M, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

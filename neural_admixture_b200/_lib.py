@@ -51,6 +51,9 @@ SIGNATURES = {
                                    C.c_void_p]),
     "nadm_loglikelihood": (C.c_int, [c_u8p, C.c_int64, C.c_int64, C.c_int64, c_f32p, c_f32p, C.c_int32, C.c_double,
                                      C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "nadm_bed_to_packed": (C.c_int, [c_u8p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32, c_u8p, C.c_int64,
+                                     C.c_void_p, C.c_void_p]),
+    "nadm_flip_packed": (C.c_int, [c_u8p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p]),
 }
 
 _lib = None

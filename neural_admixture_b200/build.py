@@ -8,7 +8,7 @@ from pathlib import Path
 
 CSRC = Path(__file__).resolve().parent / "csrc"
 LIB = CSRC / "libnadm_b200.so"
-SOURCES = ["nadm_stream.cu", "nadm_mlp.cu", "nadm_tc_enc.cu", "nadm_tc_dec.cu"]
+SOURCES = ["nadm_stream.cu", "nadm_mlp.cu", "nadm_tc_enc.cu", "nadm_tc_dec.cu", "nadm_bed.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]
 

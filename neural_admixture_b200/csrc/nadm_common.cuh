@@ -68,6 +68,7 @@ int launch_enc_bwd_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_i
                       const float* dZ, int C, float* V, float* Vm, float* Vv, const nadm_adam_t* adam, float* dV_out,
                       cudaStream_t st);
 size_t enc_tc_workspace_bytes(int B);
+size_t mlp_bwd_workspace_bytes(int B, int C, int H, int sumK);   // nadm_mlp.cu
 bool enc_bwd_tc_supported(int B);
 // tensor-core fused decoder, nadm_tc_dec.cu
 bool dec_tc_supported(int B, int k);

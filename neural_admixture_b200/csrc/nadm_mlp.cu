@@ -140,35 +140,48 @@ mlp_fwd_kernel(const float* __restrict__ Z, int B, int C, int H, const float* __
 }
 
 // =================================================================================================================
-// backward A: per-row quantities  dL, dHpre, dZ, per-row dw_rms terms, supervised term
+// backward, phase 1: one CTA per kBwdRows batch rows does the whole backward of its rows and writes its PARTIAL
+// parameter gradients into its own slab (deterministic: no atomics).
+//   dL (softmax backward, + supervised CE on head 0) -> dH = relu'(H) . (dL W2) -> dZn = dH W1 -> RMSNorm backward -> dZ
+//   partial gradients of the CTA's rows: dW1^T[c][j] (c = C is db1), dW2[kk][j], db2[kk], dw_rms[c], supervised loss.
+// Slab layout (floats): [ (C+1) x H | sumK x H | sumK | C | 1 ], see mlp_slab_floats().
 // =================================================================================================================
+constexpr int kBwdRows = 8;
+
+__host__ __device__ inline size_t mlp_slab_floats(int C, int H, int sumK) {
+    return (size_t)(C + 1) * H + (size_t)sumK * H + (size_t)sumK + (size_t)C + 1;
+}
+
+template <int CP>   // components padded to 8 or 16
 __global__ void __launch_bounds__(kMlpThreads)
 mlp_bwd_rows_kernel(const float* __restrict__ dQ, const float* __restrict__ Q, const float* __restrict__ Hh,
                     const float* __restrict__ Z, const float* __restrict__ rinv, int B, int C, int H, Heads hd,
                     const int64_t* __restrict__ labels, float sup_weight, const float* __restrict__ w_rms,
-                    const float* __restrict__ W1, const float* __restrict__ W2, float* __restrict__ dL,
-                    float* __restrict__ dHpre, float* __restrict__ dwr, float* __restrict__ suploss,
+                    const float* __restrict__ W1, const float* __restrict__ W2, float* __restrict__ part,
                     float* __restrict__ dZ) {
     extern __shared__ __align__(16) float sm[];
-    float* dLs = sm;                                   // kMlpRows x sumK
-    float* dHs = dLs + (size_t)kMlpRows * hd.sumK;      // kMlpRows x H
-    float* dZn = dHs + (size_t)kMlpRows * H;            // kMlpRows x MAX_C
+    float* dLs = sm;                                         // kBwdRows x sumK
+    float* Zn = dLs + (size_t)kBwdRows * hd.sumK;             // kBwdRows x MAX_C   (normalised inputs, recomputed)
+    float* red = Zn + kBwdRows * CP;                  // nwarps x kBwdRows x MAX_C  (dZn partials per warp)
+    float* sups = red + (kMlpThreads / 32) * kBwdRows * CP;   // kBwdRows
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int b0 = blockIdx.x * kMlpRows;
+    const int b0 = blockIdx.x * kBwdRows;
+    const int sumK = hd.sumK;
+    float* slab = part + (size_t)blockIdx.x * mlp_slab_floats(C, H, sumK);
 
-    // softmax backward per (row, head); the supervised cross-entropy acts on head 0 only
-    for (int i = tid; i < kMlpRows * hd.n; i += blockDim.x) {
+    // ---- softmax backward per (row, head); the supervised cross-entropy acts on head 0 only ----
+    for (int i = tid; i < kBwdRows * hd.n; i += blockDim.x) {
         const int r = i / hd.n, h = i % hd.n;
         const int b = b0 + r;
         const int k = hd.k[h], off = hd.off[h];
-        float* out = dLs + r * hd.sumK + off;
+        float* out = dLs + r * sumK + off;
+        if (h == 0) sups[r] = 0.f;
         if (b >= B) {
             for (int kk = 0; kk < k; ++kk) out[kk] = 0.f;
             continue;
         }
-        const float* q = Q + (int64_t)b * hd.sumK + off;
-        const float* dq = dQ + (int64_t)b * hd.sumK + off;
-        float sl = 0.f;
+        const float* q = Q + (int64_t)b * sumK + off;
+        const float* dq = dQ + (int64_t)b * sumK + off;
         const bool sup = (labels != nullptr) && (h == 0);
         float mx = 0.f, lse = 0.f;
         int y = 0;
@@ -179,8 +192,7 @@ mlp_bwd_rows_kernel(const float* __restrict__ dQ, const float* __restrict__ Q, c
             float se = 0.f;
             for (int kk = 0; kk < k; ++kk) se += expf(q[kk] - mx);
             lse = logf(se);
-            sl = sup_weight * (lse + mx - q[y]);
-            suploss[b] = sl;
+            sups[r] = sup_weight * (lse + mx - q[y]);
         }
         float dot = 0.f;
         float g[NADM_MAX_K];
@@ -190,70 +202,114 @@ mlp_bwd_rows_kernel(const float* __restrict__ dQ, const float* __restrict__ Q, c
             g[kk] = gk;
             dot = fmaf(gk, q[kk], dot);
         }
-        for (int kk = 0; kk < k; ++kk) {
-            const float v = q[kk] * (g[kk] - dot);
-            out[kk] = v;
-            dL[(int64_t)b * hd.sumK + off + kk] = v;
-        }
+        for (int kk = 0; kk < k; ++kk) out[kk] = q[kk] * (g[kk] - dot);
+    }
+    // ---- Zn[r][c] = Z[b][c] * rinv[b] * w_rms[c] ----
+    for (int i = tid; i < kBwdRows * CP; i += blockDim.x) {
+        const int r = i / CP, c = i % CP, b = b0 + r;
+        Zn[i] = (b < B && c < C) ? Z[(int64_t)b * C + c] * rinv[b] * w_rms[c] : 0.f;
     }
     __syncthreads();
-    // dHpre[r][j] = relu'(H) * sum_kk dL[r][kk] W2[kk][j]
+
+    // ---- hidden units j = tid, tid + 256, ...: dH, partial dW2 / dW1 / db1 of these rows, dZn partial sums ----
+    float dzn[kBwdRows][CP];
+#pragma unroll
+    for (int r = 0; r < kBwdRows; ++r)
+#pragma unroll
+        for (int c = 0; c < CP; ++c) dzn[r][c] = 0.f;
+    const bool c8 = (C == 8);
     for (int j = tid; j < H; j += blockDim.x) {
-        float acc[kMlpRows];
+        float hh[kBwdRows], dH[kBwdRows];
 #pragma unroll
-        for (int r = 0; r < kMlpRows; ++r) acc[r] = 0.f;
-        for (int kk = 0; kk < hd.sumK; ++kk) {
+        for (int r = 0; r < kBwdRows; ++r) {
+            hh[r] = (b0 + r < B) ? Hh[(int64_t)(b0 + r) * H + j] : 0.f;
+            dH[r] = 0.f;
+        }
+        for (int kk = 0; kk < sumK; ++kk) {
             const float w = W2[(int64_t)kk * H + j];
+            float g2 = 0.f;
 #pragma unroll
-            for (int r = 0; r < kMlpRows; ++r) acc[r] = fmaf(dLs[r * hd.sumK + kk], w, acc[r]);
+            for (int r = 0; r < kBwdRows; ++r) {
+                const float d = dLs[r * sumK + kk];
+                dH[r] = fmaf(d, w, dH[r]);
+                g2 = fmaf(d, hh[r], g2);
+            }
+            slab[(size_t)(C + 1) * H + (size_t)kk * H + j] = g2;       // partial dW2[kk][j]
+        }
+        float gb = 0.f;
+#pragma unroll
+        for (int r = 0; r < kBwdRows; ++r) {
+            dH[r] = (hh[r] > 0.f) ? dH[r] : 0.f;                       // ReLU backward
+            gb += dH[r];
+        }
+        slab[(size_t)C * H + j] = gb;                                   // partial db1[j]
+        float w1[CP];
+        if (c8 && CP == 8) {
+            const float4 a = reinterpret_cast<const float4*>(W1 + (int64_t)j * 8)[0];
+            const float4 bq = reinterpret_cast<const float4*>(W1 + (int64_t)j * 8)[1];
+            w1[0] = a.x; w1[1] = a.y; w1[2] = a.z; w1[3] = a.w; w1[4] = bq.x; w1[5] = bq.y; w1[6] = bq.z; w1[7] = bq.w;
+        } else {
+#pragma unroll
+            for (int c = 0; c < CP; ++c) w1[c] = (c < C) ? W1[(int64_t)j * C + c] : 0.f;
         }
 #pragma unroll
-        for (int r = 0; r < kMlpRows; ++r) {
-            const int b = b0 + r;
-            float v = 0.f;
-            if (b < B) {
-                v = (Hh[(int64_t)b * H + j] > 0.f) ? acc[r] : 0.f;
-                dHpre[(int64_t)b * H + j] = v;
+        for (int c = 0; c < CP; ++c) {
+            if (c < C) {
+                float g1 = 0.f;
+#pragma unroll
+                for (int r = 0; r < kBwdRows; ++r) {
+                    g1 = fmaf(dH[r], Zn[r * CP + c], g1);
+                    dzn[r][c] = fmaf(dH[r], w1[c], dzn[r][c]);
+                }
+                slab[(size_t)c * H + j] = g1;                           // partial dW1[j][c], stored transposed
             }
-            dHs[(size_t)r * H + j] = v;
         }
     }
+    // ---- dZn: sum over the 256 threads (warp shuffles, then shared memory across warps) ----
+#pragma unroll
+    for (int r = 0; r < kBwdRows; ++r) {
+        float v[CP];
+#pragma unroll
+        for (int c = 0; c < CP; ++c) v[c] = dzn[r][c];
+        const float s = warp_reduce_vec<CP>(v, lane);          // lane c * (32 / CP) holds component c
+        if (lane % (32 / CP) == 0) red[(warp * kBwdRows + r) * CP + lane / (32 / CP)] = s;
+    }
     __syncthreads();
-    // dZn[r][c] = sum_j dHpre[r][j] W1[j][c] : one warp per (r, c)
-    for (int o = warp; o < kMlpRows * C; o += blockDim.x / 32) {
-        const int r = o / C, c = o % C;
+    // ---- RMSNorm backward (y = z * rinv * w) and the small partial gradients; thread (r, c) ----
+    if (tid < kBwdRows * CP) {
+        const int r = tid / CP, c = tid % CP, b = b0 + r;
+        float d = 0.f;
+#pragma unroll
+        for (int w = 0; w < kMlpThreads / 32; ++w) d += red[(w * kBwdRows + r) * CP + c];
+        const bool ok = (b < B) && (c < C);
+        const float z = ok ? Z[(int64_t)b * C + c] : 0.f;
+        const float wr = ok ? w_rms[c] : 0.f;
+        const float ri = (b < B) ? rinv[b] : 0.f;
+        float dot = d * wr * z;                                        // sum over c: the 16 lanes of this row
+#pragma unroll
+        for (int o = CP / 2; o >= 1; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        if (ok) dZ[(int64_t)b * C + c] = ri * d * wr - z * (ri * ri * ri * dot / (float)C);
+        red[(0 * kBwdRows + r) * CP + c] = ok ? d * z * ri : 0.f;   // per-row dw_rms term (warp 0's slots: own element)
+    }
+    __syncthreads();
+    float* small = slab + (size_t)(C + 1) * H + (size_t)sumK * H;
+    for (int o = tid; o < sumK + C + 1; o += blockDim.x) {
         float acc = 0.f;
-        for (int j = lane; j < H; j += 32) acc = fmaf(dHs[(size_t)r * H + j], W1[(int64_t)j * C + c], acc);
-        acc = warp_sum(acc);
-        if (lane == 0) dZn[r * NADM_MAX_C + c] = acc;
-    }
-    __syncthreads();
-    // RMSNorm backward: y = z * rinv * w
-    if (tid < kMlpRows) {
-        const int b = b0 + tid;
-        if (b < B) {
-            const float r = rinv[b];
-            float dot = 0.f;
-            for (int c = 0; c < C; ++c) dot = fmaf(dZn[tid * NADM_MAX_C + c] * w_rms[c], Z[(int64_t)b * C + c], dot);
-            const float coef = r * r * r * dot / (float)C;
-            for (int c = 0; c < C; ++c) {
-                const float z = Z[(int64_t)b * C + c];
-                const float dzn = dZn[tid * NADM_MAX_C + c];
-                dZ[(int64_t)b * C + c] = r * dzn * w_rms[c] - z * coef;
-                dwr[(int64_t)b * C + c] = dzn * z * r;
-            }
+        if (o < sumK) {
+            for (int r = 0; r < kBwdRows; ++r) acc += dLs[r * sumK + o];
+        } else if (o < sumK + C) {
+            for (int r = 0; r < kBwdRows; ++r) acc += red[r * CP + (o - sumK)];
+        } else {
+            for (int r = 0; r < kBwdRows; ++r) acc += sups[r];
         }
+        small[o] = acc;
     }
 }
 
 // =================================================================================================================
-// backward B: reductions over the batch -> parameter gradients, then Adam.  grid = (ceil(H/32), 1 + nchunks)
-//   blockIdx.y == 0        : dW1[j][:], db1[j]                (+ block (0,0) also does db2, dw_rms, loss terms)
-//   blockIdx.y == 1 + q    : dW2[8q .. 8q+8)[j]
-// block = 32 hidden units x 8 batch segments; partial sums over segments are combined through shared memory.
+// backward, phase 2: sum the slabs in a fixed order (deterministic) and apply Adam to W1, b1, W2, b2, w_rms; the
+// supervised loss term is added to *loss.
 // =================================================================================================================
-constexpr int kSeg = 8;
-
 __device__ __forceinline__ void adam_store(float* p, float* m, float* v, float* gout, int64_t i, float g,
                                            const AdamCoef& c) {
     if (gout != nullptr) gout[i] = g;
@@ -265,125 +321,40 @@ __device__ __forceinline__ void adam_store(float* p, float* m, float* v, float* 
     }
 }
 
-constexpr int kRowChunks = 8;   // grid.z: the batch is split into row chunks whose partial gradients are summed in phase 2
-
-// Phase 1: partial parameter gradients of one row chunk.  grid = (ceil(H/32), 1 + ceil(sumK/8), kRowChunks).
-//   blockIdx.y == 0     : gW1[z][j][0..C) and gb1 (stored as column C) for 32 hidden units j
-//   blockIdx.y == 1 + q : gW2[z][8q .. 8q+8)[j]
-// Layout of `part`: [kRowChunks] x ( H x (C+1)  |  sumK x H ).
-__global__ void __launch_bounds__(32 * kSeg)
-mlp_bwd_params_kernel(const float* __restrict__ dL, const float* __restrict__ dHpre, const float* __restrict__ Hh,
-                      const float* __restrict__ Z, const float* __restrict__ rinv, const float* __restrict__ w_rms,
-                      int B, int C, int H, int sumK, float* __restrict__ part) {
-    __shared__ float red[kSeg][32][NADM_MAX_C + 1];
-    const int jl = threadIdx.x & 31, seg = threadIdx.x >> 5;
-    const int j = blockIdx.x * 32 + jl;
-    const bool jok = j < H;
-    const int rows_per_chunk = (B + kRowChunks - 1) / kRowChunks;
-    const int c0 = blockIdx.z * rows_per_chunk, c1 = min(B, c0 + rows_per_chunk);
-    float* mypart = part + (size_t)blockIdx.z * ((size_t)H * (C + 1) + (size_t)sumK * H);
-
-    if (blockIdx.y == 0) {
-        float acc[NADM_MAX_C + 1];
-#pragma unroll
-        for (int c = 0; c <= NADM_MAX_C; ++c) acc[c] = 0.f;
-        if (jok) {
-            for (int b = c0 + seg; b < c1; b += kSeg) {
-                const float d = dHpre[(int64_t)b * H + j];
-                if (d == 0.f) continue;
-                const float r = rinv[b];
-                // Zn is recomputed: Zn[b][c] = Z[b][c] * rinv[b] * w_rms[c]  (w_rms is updated by a later kernel)
-#pragma unroll
-                for (int c = 0; c < NADM_MAX_C; ++c)
-                    if (c < C) acc[c] = fmaf(d, Z[(int64_t)b * C + c] * r * w_rms[c], acc[c]);
-                acc[NADM_MAX_C] += d;
-            }
-        }
-#pragma unroll
-        for (int c = 0; c <= NADM_MAX_C; ++c) red[seg][jl][c] = acc[c];
-        __syncthreads();
-        for (int o = threadIdx.x; o < 32 * (C + 1); o += blockDim.x) {
-            const int jj = o / (C + 1), c = o % (C + 1);
-            const int jg = blockIdx.x * 32 + jj;
-            if (jg >= H) continue;
-            const int cc = (c < C) ? c : NADM_MAX_C;
-            float g = 0.f;
-#pragma unroll
-            for (int s = 0; s < kSeg; ++s) g += red[s][jj][cc];
-            mypart[(size_t)jg * (C + 1) + c] = g;
-        }
-    } else {
-        const int k0 = (blockIdx.y - 1) * 8;
-        float acc[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) acc[q] = 0.f;
-        if (jok) {
-            for (int b = c0 + seg; b < c1; b += kSeg) {
-                const float h = Hh[(int64_t)b * H + j];
-                if (h == 0.f) continue;
-#pragma unroll
-                for (int q = 0; q < 8; ++q)
-                    if (k0 + q < sumK) acc[q] = fmaf(dL[(int64_t)b * sumK + k0 + q], h, acc[q]);
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < 8; ++q) red[seg][jl][q] = acc[q];
-        __syncthreads();
-        for (int o = threadIdx.x; o < 32 * 8; o += blockDim.x) {
-            const int q = o / 32, jj = o % 32;
-            const int jg = blockIdx.x * 32 + jj;
-            if (jg >= H || k0 + q >= sumK) continue;
-            float g = 0.f;
-#pragma unroll
-            for (int s = 0; s < kSeg; ++s) g += red[s][jj][q];
-            mypart[(size_t)H * (C + 1) + (size_t)(k0 + q) * H + jg] = g;
-        }
-    }
-}
-
-// Phase 2: sum the row-chunk partials (fixed order: deterministic) and apply Adam to W1, b1, W2.
 __global__ void __launch_bounds__(256)
-mlp_bwd_apply_kernel(const float* __restrict__ part, int C, int H, int sumK, nadm_mlp_params_t prm, AdamCoef adam) {
-    const size_t n1 = (size_t)H * (C + 1), n = n1 + (size_t)sumK * H;
+mlp_bwd_apply_kernel(const float* __restrict__ part, int nslab, int C, int H, int sumK, int has_sup,
+                     nadm_mlp_params_t prm, AdamCoef adam, float* __restrict__ loss) {
+    const size_t n = mlp_slab_floats(C, H, sumK);
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    float g = 0.f;
-#pragma unroll
-    for (int z = 0; z < kRowChunks; ++z) g += part[(size_t)z * n + i];
+    float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
+    int z = 0;
+    for (; z + 4 <= nslab; z += 4) {      // fixed association: four interleaved chains, then (g0 + g1) + (g2 + g3)
+        g0 += part[(size_t)(z + 0) * n + i];
+        g1 += part[(size_t)(z + 1) * n + i];
+        g2 += part[(size_t)(z + 2) * n + i];
+        g3 += part[(size_t)(z + 3) * n + i];
+    }
+    for (; z < nslab; ++z) g0 += part[(size_t)z * n + i];
+    const float g = (g0 + g1) + (g2 + g3);
+    const size_t n1 = (size_t)(C + 1) * H, n2 = n1 + (size_t)sumK * H;
     if (i < n1) {
-        const int jg = (int)(i / (C + 1)), c = (int)(i % (C + 1));
-        if (c < C) adam_store(prm.W1, prm.m_W1, prm.v_W1, prm.g_W1, (int64_t)jg * C + c, g, adam);
-        else adam_store(prm.b1, prm.m_b1, prm.v_b1, prm.g_b1, jg, g, adam);
-    } else {
+        const int c = (int)(i / H), j = (int)(i % H);
+        if (c < C) adam_store(prm.W1, prm.m_W1, prm.v_W1, prm.g_W1, (int64_t)j * C + c, g, adam);
+        else adam_store(prm.b1, prm.m_b1, prm.v_b1, prm.g_b1, j, g, adam);
+    } else if (i < n2) {
         adam_store(prm.W2, prm.m_W2, prm.v_W2, prm.g_W2, (int64_t)(i - n1), g, adam);
+    } else if (i < n2 + sumK) {
+        adam_store(prm.b2, prm.m_b2, prm.v_b2, prm.g_b2, (int64_t)(i - n2), g, adam);
+    } else if (i < n2 + sumK + C) {
+        adam_store(prm.w_rms, prm.m_w_rms, prm.v_w_rms, prm.g_w_rms, (int64_t)(i - n2 - sumK), g, adam);
+    } else if (has_sup) {
+        *loss += g;
     }
 }
 
-// db2[kk] = sum_b dL[b][kk]; dw_rms[c] = sum_b dwr[b][c]; loss += sum_b suploss[b].  One warp per output.
-// Runs AFTER mlp_bwd_params_kernel (which still reads the old w_rms).
-__global__ void __launch_bounds__(256)
-mlp_bwd_small_kernel(const float* __restrict__ dL, const float* __restrict__ dwr, const float* __restrict__ suploss,
-                     int has_sup, int B, int C, int sumK, nadm_mlp_params_t prm, AdamCoef adam,
-                     float* __restrict__ loss) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nwarps = blockDim.x / 32;
-    const int nout = sumK + C + (has_sup ? 1 : 0);
-    for (int o = warp; o < nout; o += nwarps) {
-        float acc = 0.f;
-        if (o < sumK) {
-            for (int b = lane; b < B; b += 32) acc += dL[(int64_t)b * sumK + o];
-        } else if (o < sumK + C) {
-            for (int b = lane; b < B; b += 32) acc += dwr[(int64_t)b * C + (o - sumK)];
-        } else {
-            for (int b = lane; b < B; b += 32) acc += suploss[b];
-        }
-        acc = warp_sum(acc);
-        if (lane == 0) {
-            if (o < sumK) adam_store(prm.b2, prm.m_b2, prm.v_b2, prm.g_b2, o, acc, adam);
-            else if (o < sumK + C) adam_store(prm.w_rms, prm.m_w_rms, prm.v_w_rms, prm.g_w_rms, o - sumK, acc, adam);
-            else *loss += acc;
-        }
-    }
+size_t mlp_bwd_workspace_bytes(int B, int C, int H, int sumK) {
+    return (size_t)((B + kBwdRows - 1) / kBwdRows) * mlp_slab_floats(C, H, sumK) * sizeof(float);
 }
 
 }  // namespace nadm
@@ -443,35 +414,26 @@ extern "C" int nadm_mlp_bwd(const float* dQ, const float* Q, const float* Hh, co
     NADM_REQUIRE(p.w_rms && p.W1 && p.b1 && p.W2 && p.b2, "NULL parameter pointer");
     NADM_REQUIRE(adam == nullptr || (p.m_w_rms && p.m_W1 && p.m_b1 && p.m_W2 && p.m_b2 && p.v_w_rms && p.v_W1 &&
                                      p.v_b1 && p.v_W2 && p.v_b2), "NULL Adam moment pointer");
-    // workspace carve-up: dL (B x sumK) | dHpre (B x H) | dwr (B x C) | suploss (B)
-    const size_t need = ((size_t)B * ((size_t)hd.sumK + H + C + 1) +
-                         (size_t)kRowChunks * ((size_t)H * (C + 1) + (size_t)hd.sumK * H)) * sizeof(float);
+    // workspace: one slab of partial parameter gradients per CTA of kBwdRows rows
+    const int nslab = (B + kBwdRows - 1) / kBwdRows;
+    const size_t need = mlp_bwd_workspace_bytes(B, C, H, hd.sumK);
     NADM_REQUIRE(need <= ws_bytes, "workspace too small for mlp_bwd (%zu > %zu)", need, ws_bytes);
-    float* dL = (float*)ws;
-    float* dHpre = dL + (size_t)B * hd.sumK;
-    float* dwr = dHpre + (size_t)B * H;
-    float* suploss = dwr + (size_t)B * C;
-    float* gpart = suploss + B;
+    float* gpart = (float*)ws;
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t smem = ((size_t)kMlpRows * hd.sumK + (size_t)kMlpRows * H + (size_t)kMlpRows * NADM_MAX_C) * sizeof(float);
-    NADM_REQUIRE(smem <= 200 * 1024, "hidden_size H=%d too large", H);
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(mlp_bwd_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(mlp_bwd_rows)");
-        attr = true;
-    }
-    mlp_bwd_rows_kernel<<<(B + kMlpRows - 1) / kMlpRows, kMlpThreads, smem, st>>>(
-        dQ, Q, Hh, Z, rinv, B, C, H, hd, labels, sup_weight, p.w_rms, p.W1, p.W2, dL, dHpre, dwr, suploss, dZ);
+    const int CP = C <= 8 ? 8 : 16;
+    const size_t smem = ((size_t)kBwdRows * hd.sumK + (size_t)kBwdRows * CP +
+                         (size_t)(kMlpThreads / 32) * kBwdRows * CP + kBwdRows) * sizeof(float);
+    if (CP == 8)
+        mlp_bwd_rows_kernel<8><<<nslab, kMlpThreads, smem, st>>>(dQ, Q, Hh, Z, rinv, B, C, H, hd, labels, sup_weight,
+                                                                 p.w_rms, p.W1, p.W2, gpart, dZ);
+    else
+        mlp_bwd_rows_kernel<16><<<nslab, kMlpThreads, smem, st>>>(dQ, Q, Hh, Z, rinv, B, C, H, hd, labels, sup_weight,
+                                                                  p.w_rms, p.W1, p.W2, gpart, dZ);
     NADM_CHECK_LAUNCH("mlp_bwd_rows_kernel");
     const AdamCoef ac = make_adam(adam);
-    dim3 grid((H + 31) / 32, 1 + (hd.sumK + 7) / 8, kRowChunks);
-    mlp_bwd_params_kernel<<<grid, 32 * kSeg, 0, st>>>(dL, dHpre, Hh, Z, rinv, p.w_rms, B, C, H, hd.sumK, gpart);
-    NADM_CHECK_LAUNCH("mlp_bwd_params_kernel");
-    const size_t nparam = (size_t)H * (C + 1) + (size_t)hd.sumK * H;
-    mlp_bwd_apply_kernel<<<(unsigned)((nparam + 255) / 256), 256, 0, st>>>(gpart, C, H, hd.sumK, p, ac);
+    const size_t nparam = mlp_slab_floats(C, H, hd.sumK);
+    mlp_bwd_apply_kernel<<<(unsigned)((nparam + 255) / 256), 256, 0, st>>>(gpart, nslab, C, H, hd.sumK,
+                                                                          labels != nullptr, p, ac, loss);
     NADM_CHECK_LAUNCH("mlp_bwd_apply_kernel");
-    mlp_bwd_small_kernel<<<1, 256, 0, st>>>(dL, dwr, suploss, labels != nullptr, B, C, hd.sumK, p, ac, loss);
-    NADM_CHECK_LAUNCH("mlp_bwd_small_kernel");
     return NADM_OK;
 }

@@ -539,8 +539,7 @@ extern "C" size_t nadm_workspace_bytes(int32_t B, int64_t M, int32_t C, int32_t 
     (void)M;
     size_t enc = (size_t)kMaxParts * (size_t)B * 16 * sizeof(float);
     size_t dec = (size_t)kMaxParts * ((size_t)B * 16 + 1) * sizeof(float);
-    size_t mlp = ((size_t)B * ((size_t)sumK + (size_t)H + (size_t)C + 2) + 64 +
-                  (size_t)8 * ((size_t)H * ((size_t)C + 1) + (size_t)sumK * (size_t)H)) * sizeof(float) + 4096;
+    size_t mlp = mlp_bwd_workspace_bytes(B, C, H, sumK) + 4096;
     size_t ll = (size_t)kMaxParts * sizeof(double) * 2;
     size_t enc_tc = enc_tc_workspace_bytes(B);
     enc = enc > enc_tc ? enc : enc_tc;

@@ -72,6 +72,37 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
                  : "memory");
 }
 
+// ---- predicated issue: the WHOLE warp executes the (convergent) descriptor arithmetic, only the lane whose `issue`
+// flag is set executes the MMA / commit.  Keeping the issuing code free of a divergent `if (elected)` region lets the
+// compiler hold descriptors and counters in uniform registers instead of moving them there (R2UR) per instruction.
+#define NADM_DEF_MMA_SS_P(NAME, KIND)                                                                            \
+    __device__ __forceinline__ void NAME(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,       \
+                                         uint32_t accumulate, uint32_t issue) {                                  \
+        asm volatile(                                                                                            \
+            "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"                      \
+            "@q tcgen05.mma.cta_group::1.kind::" KIND " [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),              \
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(issue)                                      \
+            : "memory");                                                                                         \
+    }
+NADM_DEF_MMA_SS_P(mma_i8_ss_p, "i8")
+NADM_DEF_MMA_SS_P(mma_f16_ss_p, "f16")
+#undef NADM_DEF_MMA_SS_P
+__device__ __forceinline__ void mma_f16_ts_p(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate, uint32_t issue) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(issue)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit_p(uint64_t* bar, uint32_t issue) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" ::"r"(smem_u32(bar)),
+        "r"(issue)
+        : "memory");
+}
+
 // ---- tensor memory -----------------------------------------------------------------------------------------------------
 template <int COLS>
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result) {  // one full warp
@@ -150,6 +181,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
+}
+// Wait of a warp that is NOT on the kernel's critical path (epilogues, operand producers running ahead): every failed
+// poll suspends the thread for up to `ns` nanoseconds in hardware, so the polling loop does not compete for issue slots
+// with the warps of its SM sub-partition (default try_wait polls were measured to be ~10 % of all instructions issued).
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+            : "memory");
+    } while (!ok);
 }
 // generic-proxy shared-memory writes -> visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }

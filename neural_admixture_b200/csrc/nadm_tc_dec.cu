@@ -32,11 +32,16 @@ constexpr int kGtBytes = 2 * 128 * kMS * 2;   // G^T tile: two bf16 terms x 128 
 constexpr int kPTileBytes = 4096;             // P sub-tile: 64 SNPs x 4 bf16 chunks [h | l | m | h] of 8 components
 constexpr int kQBlkBytes = 16 * 384;          // Q block: 128 rows x 3 bf16 chunks [h | m | l]
 constexpr int kPStages = 3;
-constexpr int kWGs = 3;                       // compute warpgroups (4 warps each), one raw/G slot per warpgroup
-constexpr int kWarpIssue = 4 * kWGs, kWarpProd = kWarpIssue + 1, kWarpEpi = kWarpIssue + 2;
-constexpr int kDecThreads = (4 * kWGs + 2 + 4) * 32;
-constexpr int kSlots = 3;                     // raw / G slots of 64 tensor-memory columns, used round-robin by the units
-constexpr int kColD3 = 192, kColD2 = 256;     // tensor-memory columns: [0,192) slots, D3 2 x 32, D2 32 per row block
+// Three compute warpgroups (4 warps each) work on units round-robin; a unit lives in one of SLOTS raw / G slots of 64
+// tensor-memory columns (+ one G^T tile in shared memory per slot).  SLOTS = 4 > 3 warpgroups lets a warpgroup start
+// its next unit while the issuers are still turning its previous slot around (dQ/dP MMAs, then the next raw).
+// Tensor-memory columns: [0, 64 SLOTS) slots, then the dP accumulator(s) (32 each: one for SLOTS = 4, two for 3),
+// then one 32-column dQ accumulator per row block:  SLOTS = 4: 256 + 32 + 32 nblk (nblk <= 7, B <= 896);
+// SLOTS = 3: 192 + 64 + 32 nblk (nblk <= 8).
+constexpr int kWGs = 3, kMaxSlots = 4;
+constexpr int kWarpIssueA1 = 4 * kWGs, kWarpIssueA2 = kWarpIssueA1 + 1, kWarpIssueB = kWarpIssueA1 + 2,
+              kWarpProd = kWarpIssueA1 + 3, kDecThreads = (4 * kWGs + 4 + 4) * 32;
+__host__ __device__ constexpr int dec_nd3(int SLOTS) { return SLOTS == 3 ? 2 : 1; }
 constexpr uint32_t kIdesc1 = instr_desc(kAccF32, kFmtBF16, kFmtBF16, false, false, 128, kMS);
 constexpr uint32_t kIdesc2 = instr_desc(kAccF32, kFmtBF16, kFmtBF16, false, true, 128, 32);
 constexpr uint32_t kIdesc3 = instr_desc(kAccF32, kFmtBF16, kFmtBF16, true, true, 64, 24);
@@ -50,8 +55,9 @@ __device__ long long g_timeline[8][512];
 #endif
 
 struct DecSmem {
-    uint64_t d1full[kSlots], gready[kSlots], gtfree[4], pfull[kPStages], pempty[kPStages], d3full[2], d3empty[2], alldone;
-    uint32_t tmem_base;
+    uint64_t d1full[kMaxSlots], gready[kMaxSlots], gtfree[kMaxSlots], slotfree[kMaxSlots], pfull[kPStages],
+        pempty[kPStages], d3full[2], d3empty[2], alldone;
+    uint32_t tmem_base, magic;
     float lossred[16];
 };
 
@@ -89,19 +95,15 @@ __device__ __forceinline__ void split3_row(const float (&x)[8], uint4& H, uint4&
     L = make_uint4(l[0] | (l[1] << 16), l[2] | (l[3] << 16), l[4] | (l[5] << 16), l[6] | (l[7] << 16));
 }
 
-// One element: raw (>= 0 by construction), code field f2 = code * 4^jj as an exact float.
-//   G and the two loss terms.  x = code / 2.
-struct Elem {
-    float G, l;
-};
-
 // Process 16 consecutive SNPs of one row: v[] holds raw on entry; on exit hi[] / lo[] hold the bf16x2-packed split of G.
-// w: the 16 2-bit codes (missing cleared).  Loss accumulators in log2 units (kLoss = false: gradients only).
-// kChecked = true is the general path (raw may exceed 1 by rounding: clamp + inclusive mask of the clamp backward);
-// kChecked = false is taken when the caller has verified max(raw) <= 1 for the 16 values, where min / mask are no-ops.
-template <bool kLoss, bool kChecked>
-__device__ __forceinline__ void decode16(const uint32_t (&v)[16], uint32_t w, uint32_t magic, uint32_t (&hi)[8],
-                                         uint32_t (&lo)[8], float& acc_all, float& acc_het) {
+// w: the 16 2-bit codes (missing cleared).  Loss accumulators in log2 units, kept apart for x in {0, 1} (acc_hom) and
+// x = 1/2 (acc_het, weight 1/2); kLoss = false: gradients only.
+//
+// General path: raw may exceed 1 by rounding (clamp + inclusive mask of the clamp backward), R (1 - R) may fall
+// below the 1e-12 floor of BCELoss' backward, log may hit torch's -100 clamp.  One log per element.
+template <bool kLoss>
+__device__ __forceinline__ void decode16_general(const uint32_t (&v)[16], uint32_t w, uint32_t magic, uint32_t (&hi)[8],
+                                                 uint32_t (&lo)[8], float& acc_hom, float& acc_het) {
     const uint32_t wh = w >> 16;
 #pragma unroll
     for (int j2 = 0; j2 < 8; ++j2) {
@@ -114,20 +116,18 @@ __device__ __forceinline__ void decode16(const uint32_t (&v)[16], uint32_t w, ui
             const float raw = __uint_as_float(v[j]);
             // code * 4^(j&7) as an exact float via the 2^23 magic constant (kept in a register: one LOP3); x = code / 2
             const float f = __uint_as_float((wsrc & (3u << sh)) | magic) - 8388608.0f;
-            const float Rs = kChecked ? fminf(raw, 1.0f) : raw;
+            const float Rs = fminf(raw, 1.0f);
             const float prod = fmaf(-Rs, Rs, Rs);                       // R (1 - R)
             const float inv = rcp_approx(fmaxf(prod, 1e-12f));
             const float num = fmaf(f, -0.5f / (float)(1 << sh), Rs);     // R - x
-            float G = num * inv;
-            if (kChecked) G = (raw <= 1.0f) ? G : 0.0f;                 // clamp backward mask (raw >= 0 always)
-            g[e] = G;
+            g[e] = (raw <= 1.0f) ? num * inv : 0.0f;                    // clamp backward mask (raw >= 0 always)
             if (kLoss) {
                 // BCE with torch's log clamp; X in {0, .5, 1}: a single log per element.
                 // x = 0: 1 - R = 1 - |R - x| ;  x = 1: R = 1 - |R - x| ;  x = .5: weight .5 on log(R (1 - R))
                 const bool het = (wsrc >> sh) & 1u;
                 const float arg = het ? prod : (1.0f - fabsf(num));
                 const float l = fmaxf(lg2_approx(arg), kLog2Clamp);
-                acc_all += l;
+                acc_hom += het ? 0.0f : l;
                 acc_het += het ? l : 0.0f;
             }
         }
@@ -137,12 +137,65 @@ __device__ __forceinline__ void decode16(const uint32_t (&v)[16], uint32_t w, ui
     }
 }
 
+// Fast path, taken when every R (1 - R) of the 16 values (prod[], computed by the caller from the unclamped raw) is at
+// least kProdFast = 2^-15: then 0 < raw < 1 (no clamp, mask = 1), the 1e-12 floor and the -100 log clamp cannot bind,
+// and each BCE argument t (R, 1 - R or R (1 - R)) lies in [2^-15, 1].  The loss is accumulated as PRODUCTS of the
+// RECIPROCAL arguments, which the gradient already provides (x in {0,1}: 1/t = |G|; x = 1/2: 1/t = inv), 8 elements
+// per product (<= 2^120: no overflow), so 16 elements cost 4 logs and one multiply each instead of 16 logs:
+// sum_j log t_j = -log prod_j (1 / t_j).
+constexpr float kProdFast = 3.0517578125e-05f;
 template <bool kLoss>
+__device__ __forceinline__ void decode16_fast(const uint32_t (&v)[16], const float (&prod)[16], uint32_t w,
+                                              uint32_t magic, uint32_t (&hi)[8], uint32_t (&lo)[8], float& acc_hom,
+                                              float& acc_het) {
+    const uint32_t wh = w >> 16;
+    float p_hom = 1.0f, p_het = 1.0f;
+#pragma unroll
+    for (int j2 = 0; j2 < 8; ++j2) {
+        float g[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int j = 2 * j2 + e;
+            const uint32_t wsrc = (j < 8) ? w : wh;
+            const int sh = 2 * (j & 7);
+            const float raw = __uint_as_float(v[j]);
+            const float inv = rcp_approx(prod[j]);
+#ifndef NADM_DEC_PRED
+            const float f = __uint_as_float((wsrc & (3u << sh)) | magic) - 8388608.0f;
+            const float num = fmaf(f, -0.5f / (float)(1 << sh), raw);    // R - x
+#else   // measured alternative (kept out: ptxas builds the predicates one by one, 16.6 instead of 14.2 instr / element)
+            float num = raw;
+            if ((wsrc >> sh) & 1u) num = raw - 0.5f;
+            if ((wsrc >> sh) & 2u) num = raw - 1.0f;
+#endif
+            g[e] = num * inv;
+            if (kLoss) {
+                // x in {0,1}: |G| = 1 / (1 - |R - x|), the reciprocal of the BCE argument;  x = 1/2: inv = 1 / (R (1 - R))
+                if ((wsrc >> sh) & 1u) p_het *= inv;
+                else p_hom *= fabsf(g[e]);
+            }
+        }
+        const uint32_t h = pack_bf16x2(g[0], g[1]);
+        hi[j2] = h;
+        lo[j2] = pack_bf16x2(g[0] - __uint_as_float(h << 16), g[1] - __uint_as_float(h & 0xFFFF0000u));
+        if (kLoss && (j2 & 3) == 3) {
+            acc_hom -= lg2_approx(p_hom);
+            acc_het -= lg2_approx(p_het);
+            p_hom = 1.0f;
+            p_het = 1.0f;
+        }
+    }
+}
+
+template <bool kLoss, int SLOTS>
 __global__ void __launch_bounds__(kDecThreads, 1)
 dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* __restrict__ row_idx, int64_t row0, int B,
               int64_t M, const float* __restrict__ Q, int q_ld, int q_off, int k, float* __restrict__ P,
               float* __restrict__ Pm, float* __restrict__ Pv, AdamCoef adam, float* __restrict__ dP_out,
-              float* __restrict__ dQpart, float* __restrict__ loss_part, int TS, int ngt) {
+              float* __restrict__ dQpart, float* __restrict__ loss_part, int TS) {
+    constexpr int kSlots = SLOTS, kWarpIssue = kWarpIssueA1;
+    constexpr int ngt = SLOTS;   // one G^T tile per slot (see the issuer warps for why not more)
+    constexpr int kND3 = dec_nd3(SLOTS), kColD3 = 64 * SLOTS, kColD2 = kColD3 + 32 * kND3;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int nblk = (B + 127) / 128;
     uint8_t* QA = smem;                                   // nblk x 6 KB : bf16 h/m/l of Q (MMA1 A K-major, MMA3 B MN-major)
@@ -169,11 +222,16 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
         *reinterpret_cast<uint4*>(a + 256) = L;
     }
     if (tid == 0) {
-        for (int i = 0; i < kSlots; ++i) { mbar_init(&S->d1full[i], 1); mbar_init(&S->gready[i], 4); }
-        for (int i = 0; i < 4; ++i) mbar_init(&S->gtfree[i], 1);
-        for (int i = 0; i < kPStages; ++i) { mbar_init(&S->pfull[i], 1); mbar_init(&S->pempty[i], 1); }
+        for (int i = 0; i < kMaxSlots; ++i) {
+            mbar_init(&S->d1full[i], 1);
+            mbar_init(&S->gready[i], 4);
+            mbar_init(&S->gtfree[i], 1);
+            mbar_init(&S->slotfree[i], 1);
+        }
+        for (int i = 0; i < kPStages; ++i) { mbar_init(&S->pfull[i], 1); mbar_init(&S->pempty[i], 2); }
         for (int i = 0; i < 2; ++i) { mbar_init(&S->d3full[i], 1); mbar_init(&S->d3empty[i], 4); }
         mbar_init(&S->alldone, 1);
+        S->magic = 0x4B000000u;
         mbar_init_fence();
     }
     if (warp == kWarpIssue) tmem_alloc<512>(&S->tmem_base);
@@ -188,27 +246,34 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
         const int wg = warp >> 2, q = warp & 3;
         const int rb = q * 32 + lane;                                   // row inside the block = tensor-memory lane
         const uint32_t tlane = tbase + ((uint32_t)(q * 32) << 16);
-        float acc_all = 0.f, acc_het = 0.f;
+        float acc_hom = 0.f, acc_het = 0.f;
         uint4 gw = make_uint4(0u, 0u, 0u, 0u);
-        auto load_codes = [&](int u) {
-            const int blk = u % nblk;
-            const int64_t ro = rowoff[blk * 128 + rb];
-            const int64_t off = (int64_t)(s0 + u / nblk) * (kMS / 4);
+        auto load_codes = [&](int blk_, int sub_) {
+            const int64_t ro = rowoff[blk_ * 128 + rb];
+            const int64_t off = (int64_t)(s0 + sub_) * (kMS / 4);
             uint4 r = make_uint4(0u, 0u, 0u, 0u);
             if (ro >= 0 && off + 16 <= pitch) r = *reinterpret_cast<const uint4*>(packed + ro + off);
             return r;
         };
-        uint32_t magic;
-        asm volatile("mov.b32 %0, 0x4B000000;" : "=r"(magic));           // opaque to the compiler: stays in a register
-        if (wg < U) gw = load_codes(wg);
+        const uint32_t magic = S->magic;   // 2^23 as bits, read from shared memory so that it stays in a REGISTER:
+                                           // (w & field) | magic is then one LOP3 (an immediate would cost a second)
+        // unit counters, advanced incrementally by kWGs units (no divisions in the loop):
+        //   u = sub * nblk + blk = uq * kSlots + slot;  (nblk_, nsub_) belong to the prefetched unit u + kWGs
+        int blk = wg % nblk, sub = wg / nblk, slot = wg % kSlots, uq = wg / kSlots;
+        int nblk_ = blk, nsub_ = sub;
+        auto advance = [&](int& b_, int& s_) {
+            b_ += kWGs;
+            while (b_ >= nblk) { b_ -= nblk; ++s_; }
+        };
+        if (wg < U) gw = load_codes(blk, sub);
         for (int u = wg; u < U; u += kWGs) {
-            const int blk = u % nblk;
-            const int slot = wg, g = u % ngt;
+            const int g = slot;                                         // G^T tile of this unit = its slot
             const uint32_t cw[4] = {clear_missing(gw.x), clear_missing(gw.y), clear_missing(gw.z), clear_missing(gw.w)};
-            if (u + kWGs < U) gw = load_codes(u + kWGs);
+            advance(nblk_, nsub_);
+            if (u + kWGs < U) gw = load_codes(nblk_, nsub_);
             const bool active = blk * 128 + q * 32 < B;                 // warp-uniform: any real row in this warp
             if (rb == 0) TL(0, u);                                      // WG starts waiting for raw(u)
-            mbar_wait(&S->d1full[slot], ((u / kWGs) & 1));
+            mbar_wait(&S->d1full[slot], (uq & 1));
             tc_fence_after_sync();
             if (rb == 0) TL(1, u);                                      // raw(u) seen
 #ifdef NADM_SKIPDECODE
@@ -216,7 +281,7 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
 #else
             if (active) {
 #endif
-                mbar_wait(&S->gtfree[g], ((u / ngt) & 1) ^ 1);
+                mbar_wait(&S->gtfree[g], (uq & 1) ^ 1);
                 if (rb == 0) TL(6, u);                                  // G^T buffer free
                 uint8_t* gt = GT + g * kGtBytes + (rb & 7) * 16 + (rb >> 3) * 1024;
 #pragma unroll 1
@@ -225,11 +290,14 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
                     tmem_ld16(tlane + slot * 64 + c * 16, v);
                     tmem_wait_ld();
                     const uint32_t w = (c & 2) ? ((c & 1) ? cw[3] : cw[2]) : ((c & 1) ? cw[1] : cw[0]);
-                    float mx = __uint_as_float(v[0]);
+                    float prod[16];
 #pragma unroll
-                    for (int j = 1; j < 16; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
-                    if (mx <= 1.0f) decode16<kLoss, false>(v, w, magic, hi, lo, acc_all, acc_het);
-                    else decode16<kLoss, true>(v, w, magic, hi, lo, acc_all, acc_het);
+                    for (int j = 0; j < 16; ++j) prod[j] = fmaf(-__uint_as_float(v[j]), __uint_as_float(v[j]), __uint_as_float(v[j]));
+                    float mn = prod[0];
+#pragma unroll
+                    for (int j = 1; j < 16; ++j) mn = fminf(mn, prod[j]);
+                    if (mn >= kProdFast) decode16_fast<kLoss>(v, prod, w, magic, hi, lo, acc_hom, acc_het);
+                    else decode16_general<kLoss>(v, w, magic, hi, lo, acc_hom, acc_het);
                     tmem_st8(tlane + slot * 64 + c * 16, hi);          // G hi / lo overwrite their own raw columns
                     tmem_st8(tlane + slot * 64 + c * 16 + 8, lo);
                     *reinterpret_cast<uint4*>(gt + (2 * c) * 128) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
@@ -244,9 +312,13 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
             if (rb == 0) TL(2, u);                                      // G(u) written
             __syncwarp();
             if (lane == 0) mbar_arrive(&S->gready[slot]);               // one arrival per warp
+            blk = nblk_;
+            sub = nsub_;
+            slot += kWGs;
+            if (slot >= kSlots) { slot -= kSlots; ++uq; }
         }
         // ---- loss partial of this CTA (log2 units -> nats), dQ partial from tensor memory ----
-        float l = -(acc_all - 0.5f * acc_het) * 0.6931471805599453f;
+        float l = -(acc_hom + 0.5f * acc_het) * 0.6931471805599453f;
         l = warp_sum(l);
         if (lane == 0) S->lossred[warp] = l;
         mbar_wait(&S->alldone, 0);
@@ -267,69 +339,92 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
                 reinterpret_cast<float4*>(out)[1] = o1;
             }
         }
-    } else if (warp == kWarpIssue) {
-        // =============================== MMA issuer ===============================
-        // The whole warp walks the unit sequence and waits on the barriers; one elected lane issues.  Descriptors are
-        // built once; per instruction only the 14-bit start-address field (16-byte units) is advanced.
-        const uint32_t qa = smem_u32(QA), pt = smem_u32(PT), gtb = smem_u32(GT);
+    } else if (warp == kWarpIssueA1) {
+        // =============================== MMA issuer A1: raw = Q.P^T (MMA1) ===============================
+        // Issuing is split over THREE warps (on three different SM sub-partitions).  One thread issuing all 28 MMAs of a
+        // unit plus its bookkeeping (~235 dependent instructions, scheduled against the compute warps of its
+        // sub-partition) was measured to BE the kernel's critical path: 2170 cycles per unit, compute warpgroups waiting
+        // for raw 62 % of the time; two issuers: 1530 cycles per unit, the raw/dQ issuer still saturated.
+        //   A1: MMA1 of unit l into slot l % SLOTS, once A2's MMA2 of unit l - SLOTS has consumed that slot's G (slotfree)
+        //   A2: MMA2 (dQ += G.P, A operand = the slot's G in tensor memory), then tcgen05.commit -> slotfree[slot]
+        //   B : MMA3 (dP += G^T.Q, shared-memory operands only), commit -> gtfree[slot]
+        // A2 and B both wait on gready[slot]; neither can fall a whole barrier phase behind, because unit u + SLOTS cannot
+        // be decoded before A1 has produced its raw (which needs A2's slotfree of unit u) and B has released the slot's
+        // G^T tile (gtfree of unit u; one tile per slot).
+        // The whole warp runs the (convergent) loop; only the elected lane's MMAs / commits are executed.  Descriptors
+        // are built once; per instruction only the 14-bit start-address field (16-byte units) is advanced.
+        const uint32_t qa = smem_u32(QA), pt = smem_u32(PT);
         // Q chunks [h m l] (128 B apart, 8-row groups 384 B apart); P chunks [h l m h] (8-row groups 512 B apart).
         // A K=16 instruction multiplies two chunk pairs: start address = first chunk, LBO = distance to the second.
         const uint64_t A_hm = smem_desc(qa, 128, 384), A_hl = smem_desc(qa, 256, 384), A_ml = smem_desc(qa + 128, 128, 384);
         const uint64_t B_hm = smem_desc(pt, 256, 512), B_mh = smem_desc(pt + 256, 128, 512);
         const uint64_t B_lh = smem_desc(pt + 128, 256, 512), B_lm = smem_desc(pt + 128, 128, 512);
-        const uint64_t B2 = smem_desc(pt, 512, 128);                       // P tile as MN-major [32 x K] operand
-        const uint64_t A3 = smem_desc(gtb, 1024, 128), B3 = smem_desc(qa, 384, 128);
-        // Counters are advanced incrementally (no divisions on the single issuing thread's critical path).
-        // look-ahead unit (next MMA1): row block, P stage + its phase, slot
-        int l_blk = 0, l_stage = 0, l_phase = 0, l_slot = 0, l_left = U;
-        auto issue_mma1 = [&]() {
-            if (l_blk == 0) {                                           // first unit of a sub-tile: its P tile must be there
-                mbar_wait(&S->pfull[l_stage], l_phase);
-                tc_fence_after_sync();
-            }
-            if (elect_one()) {
-                const uint64_t ao = (uint64_t)(l_blk * (kQBlkBytes >> 4)), bo = (uint64_t)(l_stage * (kPTileBytes >> 4));
-                const uint32_t d = tbase + l_slot * 64;
-                mma_f16_ss(d, A_hm + ao, B_hm + bo, kIdesc1, 0u);       // h.h + m.m
-                mma_f16_ss(d, A_hm + ao, B_mh + bo, kIdesc1, 1u);       // h.m + m.h
-                mma_f16_ss(d, A_hl + ao, B_lh + bo, kIdesc1, 1u);       // h.l + l.h
-                mma_f16_ss(d, A_ml + ao, B_lm + bo, kIdesc1, 1u);       // m.l + l.m
-                mma_commit(&S->d1full[l_slot]);
-            }
-            __syncwarp();
-            --l_left;
-            l_slot = (l_slot == kSlots - 1) ? 0 : l_slot + 1;
+        const uint32_t leader = elect_one() ? 1u : 0u;                  // the one lane that executes the MMAs / commits
+        int l_blk = 0, l_stage = 0, l_phase = 0, l_slot = 0, l_sphase = 1;
+        for (int l = 0; l < U; ++l) {
+            mbar_wait(&S->slotfree[l_slot], l_sphase);                  // first round: passes at once (fresh barrier)
+            if (l_blk == 0) mbar_wait(&S->pfull[l_stage], l_phase);     // first unit of a sub-tile: its P tile must be there
+            tc_fence_after_sync();
+            const uint64_t ao = (uint64_t)(l_blk * (kQBlkBytes >> 4)), bo = (uint64_t)(l_stage * (kPTileBytes >> 4));
+            const uint32_t d = tbase + l_slot * 64;
+            mma_f16_ss_p(d, A_hm + ao, B_hm + bo, kIdesc1, 0u, leader);       // h.h + m.m
+            mma_f16_ss_p(d, A_hm + ao, B_mh + bo, kIdesc1, 1u, leader);       // h.m + m.h
+            mma_f16_ss_p(d, A_hl + ao, B_lh + bo, kIdesc1, 1u, leader);       // h.l + l.h
+            mma_f16_ss_p(d, A_ml + ao, B_lm + bo, kIdesc1, 1u, leader);       // m.l + l.m
+            mma_commit_p(&S->d1full[l_slot], leader);
+            if (l_blk == nblk - 1) mma_commit_p(&S->pempty[l_stage], leader); // this warp's reads of the P stage are issued
+            if (++l_slot == kSlots) { l_slot = 0; l_sphase ^= 1; }
             if (++l_blk == nblk) {
                 l_blk = 0;
                 if (++l_stage == kPStages) { l_stage = 0; l_phase ^= 1; }
             }
-        };
-        for (int i = 0; i < kSlots && l_left > 0; ++i) issue_mma1();
-        const int nks_last = min(8, (B - (nblk - 1) * 128 + 15) / 16);
-        int blk = 0, sub = 0, slot = 0, slot_phase = 0, g = 0, stage = 0, dbuf = 0, d3_phase = 1;
+        }
+        __syncwarp();
+    } else if (warp == kWarpIssueA2) {
+        // =============================== MMA issuer A2: dQ_blk += G . [P_h | P_l | P_m | P_h] (MMA2) ===============================
+        // A operand from tensor memory: per 16 SNPs, G hi in 8 columns and G lo in 8; B = the P tile re-read MN-major.
+        const uint64_t B2 = smem_desc(smem_u32(PT), 512, 128);
+        const uint32_t leader = elect_one() ? 1u : 0u;
+        int blk = 0, sub = 0, slot = 0, slot_phase = 0, stage = 0;
         for (int u = 0; u < U; ++u) {
             if (lane == 0) TL(3, u);                                    // issuer starts waiting for G(u)
             mbar_wait(&S->gready[slot], slot_phase);
-            if (blk == 0) mbar_wait(&S->d3empty[dbuf], d3_phase);
             tc_fence_after_sync();
             if (lane == 0) TL(4, u);                                    // issuer saw G(u)
-            if (elect_one()) {
-                // dQ_blk += G . [P_h | P_l | P_m | P_h]   (A from tensor memory: per 16 SNPs, hi in 8 columns, lo in 8)
-                const uint64_t b2 = B2 + (uint64_t)(stage * (kPTileBytes >> 4));
-                const uint32_t d2 = tbase + kColD2 + blk * 32, a2 = tbase + slot * 64;
-                const uint32_t acc2 = sub > 0 ? 1u : 0u;
+            const uint64_t b2 = B2 + (uint64_t)(stage * (kPTileBytes >> 4));
+            const uint32_t d2 = tbase + kColD2 + blk * 32, a2 = tbase + slot * 64;
+            const uint32_t acc2 = sub > 0 ? 1u : 0u;
 #pragma unroll
-                for (int c = 0; c < 4; ++c)
+            for (int c = 0; c < 4; ++c)
 #pragma unroll
-                    for (int t = 0; t < 2; ++t)
-                        mma_f16_ts(d2, a2 + c * 16 + t * 8, b2 + (uint64_t)(c * 2 * 32), kIdesc2, (c + t) ? 1u : acc2);
+                for (int t = 0; t < 2; ++t)
+                    mma_f16_ts_p(d2, a2 + c * 16 + t * 8, b2 + (uint64_t)(c * 2 * 32), kIdesc2, (c + t) ? 1u : acc2, leader);
+            mma_commit_p(&S->slotfree[slot], leader);                   // the slot's G has been consumed: A1 may overwrite it
+            if (blk == nblk - 1) mma_commit_p(&S->pempty[stage], leader);
+            if (lane == 0) TL(5, u);                                    // issuer done with unit u
+            if (++slot == kSlots) { slot = 0; slot_phase ^= 1; }
+            if (++blk == nblk) {
+                blk = 0;
+                ++sub;
+                if (++stage == kPStages) stage = 0;
             }
-            __syncwarp();
-            // raw of the unit that reuses this slot: queued right behind the MMAs that consume the slot's G
-            if (l_left > 0) issue_mma1();
-            if (elect_one()) {
-                // dP_sub += G^T . [Q_h | Q_m | Q_l]    (A = shared G^T tile, MN-major; only K steps holding real rows)
-                const uint64_t a3 = A3 + (uint64_t)(g * (kGtBytes >> 4)), b3 = B3 + (uint64_t)(blk * (kQBlkBytes >> 4));
+        }
+        mma_commit_p(&S->alldone, leader);
+        __syncwarp();
+    } else if (warp == kWarpIssueB) {
+        // =============================== MMA issuer B: dP_sub += G^T . [Q_h | Q_m | Q_l] (MMA3) ===============================
+        // A = the shared G^T tile of the unit's slot, MN-major; B = the Q block re-read MN-major; only K steps holding
+        // real rows are issued for the last row block.
+        const uint64_t A3 = smem_desc(smem_u32(GT), 1024, 128), B3 = smem_desc(smem_u32(QA), 384, 128);
+        const int nks_last = min(8, (B - (nblk - 1) * 128 + 15) / 16);
+        const uint32_t leader = elect_one() ? 1u : 0u;
+        int blk = 0, slot = 0, slot_phase = 0, dbuf = 0, d3_phase = 1;
+        for (int u = 0; u < U; ++u) {
+            mbar_wait(&S->gready[slot], slot_phase);
+            if (blk == 0) mbar_wait(&S->d3empty[dbuf], d3_phase);
+            tc_fence_after_sync();
+            {
+                const uint64_t a3 = A3 + (uint64_t)(slot * (kGtBytes >> 4)), b3 = B3 + (uint64_t)(blk * (kQBlkBytes >> 4));
                 const uint32_t d3 = tbase + kColD3 + dbuf * 32;
                 const uint32_t acc3 = blk > 0 ? 1u : 0u;
                 if (blk != nblk - 1 || nks_last == 8) {
@@ -337,35 +432,24 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
                     for (int t = 0; t < 2; ++t)
 #pragma unroll
                         for (int ks = 0; ks < 8; ++ks)
-                            mma_f16_ss(d3, a3 + (uint64_t)(t * 1024 + ks * 128), b3 + (uint64_t)(ks * 48), kIdesc3,
-                                       (t + ks) ? 1u : acc3);
+                            mma_f16_ss_p(d3, a3 + (uint64_t)(t * 1024 + ks * 128), b3 + (uint64_t)(ks * 48), kIdesc3,
+                                         (t + ks) ? 1u : acc3, leader);
                 } else {
                     for (int t = 0; t < 2; ++t)
                         for (int ks = 0; ks < nks_last; ++ks)
-                            mma_f16_ss(d3, a3 + (uint64_t)(t * 1024 + ks * 128), b3 + (uint64_t)(ks * 48), kIdesc3,
-                                       (t + ks) ? 1u : acc3);
+                            mma_f16_ss_p(d3, a3 + (uint64_t)(t * 1024 + ks * 128), b3 + (uint64_t)(ks * 48), kIdesc3,
+                                         (t + ks) ? 1u : acc3, leader);
                 }
-                mma_commit(&S->gtfree[g]);
-                if (blk == nblk - 1) {
-                    mma_commit(&S->d3full[dbuf]);
-                    mma_commit(&S->pempty[stage]);
-                }
+                mma_commit_p(&S->gtfree[slot], leader);
+                if (blk == nblk - 1) mma_commit_p(&S->d3full[dbuf], leader);
             }
-            __syncwarp();
-            if (lane == 0) TL(5, u);                                    // issuer done with unit u
-            // advance the unit counters
+            if (lane == 0) TL(7, u);                                    // issuer B done with unit u
             if (++slot == kSlots) { slot = 0; slot_phase ^= 1; }
-            if (++g == ngt) g = 0;
             if (++blk == nblk) {
                 blk = 0;
-                ++sub;
-                if (++stage == kPStages) stage = 0;
-                dbuf ^= 1;
-                if (dbuf == 0) d3_phase ^= 1;
+                if (++dbuf == kND3) { dbuf = 0; d3_phase ^= 1; }
             }
         }
-        if (elect_one()) mma_commit(&S->alldone);
-        __syncwarp();
     } else if (warp == kWarpProd) {
         // =============================== P sub-tile producer ===============================
         for (int sub = 0; sub < nsub; ++sub) {
@@ -387,7 +471,7 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
                     }
                 }
             }
-            mbar_wait(&S->pempty[st], ((sub / kPStages) & 1) ^ 1);
+            mbar_wait_relaxed(&S->pempty[st], ((sub / kPStages) & 1) ^ 1, 400);
             uint8_t* tile = PT + st * kPTileBytes;
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
@@ -408,8 +492,8 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
         // =============================== dP epilogue: Adam + clamp on the 64 x k slice of P ===============================
         const int q = warp & 3;
         for (int sub = 0; sub < nsub; ++sub) {
-            const int dbuf = sub & 1;
-            mbar_wait(&S->d3full[dbuf], (sub >> 1) & 1);
+            const int dbuf = sub % kND3;
+            mbar_wait_relaxed(&S->d3full[dbuf], (sub / kND3) & 1, 200);
             tc_fence_after_sync();
             uint32_t v[32];
             tmem_ld32(tbase + ((uint32_t)(q * 32) << 16) + kColD3 + dbuf * 32, v);
@@ -484,6 +568,37 @@ extern "C" int nadm_debug_timeline(long long* host_out) {
 }
 #endif
 
+template <bool kLoss, int SLOTS>
+static int dec_launch_one(int ncta, size_t smem, cudaStream_t st, const uint8_t* packed, int64_t pitch,
+                          const int64_t* row_idx, int64_t row0, int B, int64_t M, const float* Q, int q_ld, int q_off,
+                          int k, float* P, float* Pm, float* Pv, const AdamCoef& adam, float* dP_out, float* dQpart,
+                          float* loss_part, int TS) {
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(dec_tc_kernel<kLoss, SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             kMaxDynSmem);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(dec_tc)");
+        attr = true;
+    }
+    dec_tc_kernel<kLoss, SLOTS><<<ncta, kDecThreads, smem, st>>>(packed, pitch, row_idx, row0, B, M, Q, q_ld, q_off, k, P,
+                                                                Pm, Pv, adam, dP_out, dQpart, loss_part, TS);
+    NADM_CHECK_LAUNCH("dec_tc_kernel");
+    return NADM_OK;
+}
+
+// raw / G slots: 4 whenever tensor memory (nblk <= 7, i.e. B <= 896) and shared memory allow it, else 3.
+// NADM_DEC_SLOTS=3 forces 3 (A/B measurements).
+static int dec_pick_slots(int nblk, size_t fixed) {
+    static int forced = -1;
+    if (forced < 0) {
+        const char* e = getenv("NADM_DEC_SLOTS");
+        forced = e ? atoi(e) : 0;
+    }
+    int slots = (nblk <= 7 && fixed + 4 * (size_t)kGtBytes <= (size_t)kMaxDynSmem) ? 4 : 3;
+    if (forced == 3) slots = 3;
+    return slots;
+}
+
 int launch_dec_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_idx, int64_t row0, int B, int64_t M,
                   const float* Q, float* dQ, int q_ld, int q_off, int k, float* P, float* Pm, float* Pv,
                   const nadm_adam_t* adam, float* dP_out, float* loss, float* ws, size_t ws_bytes, cudaStream_t st) {
@@ -492,26 +607,23 @@ int launch_dec_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_idx, 
     const int TS = (int)((M + kMS - 1) / kMS);
     const int ncta = std::min(TS, sm_count());
     const size_t fixed = (size_t)nblk * (kQBlkBytes + 1024) + kPStages * kPTileBytes + sizeof(DecSmem) + 128;
-    const int ngt = (fixed + 4 * (size_t)kGtBytes <= (size_t)kMaxDynSmem) ? 4 : 3;
-    const size_t smem = fixed + (size_t)ngt * kGtBytes;
+    const int slots = dec_pick_slots(nblk, fixed);
+    const size_t smem = fixed + (size_t)slots * kGtBytes;             // one G^T tile per slot
     NADM_REQUIRE((size_t)ncta * ((size_t)B * 8 + 1) * sizeof(float) <= ws_bytes, "workspace too small for decoder_step");
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(dec_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(dec_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(dec_tc)");
-        attr = true;
-    }
     float* dQpart = ws;
     float* loss_part = ws + (size_t)ncta * B * 8;
-    if (want_loss)
-        dec_tc_kernel<true><<<ncta, kDecThreads, smem, st>>>(packed, pitch, row_idx, row0, B, M, Q, q_ld, q_off, k, P, Pm, Pv,
-                                                            make_adam(adam), dP_out, dQpart, loss_part, TS, ngt);
-    else
-        dec_tc_kernel<false><<<ncta, kDecThreads, smem, st>>>(packed, pitch, row_idx, row0, B, M, Q, q_ld, q_off, k, P, Pm,
-                                                             Pv, make_adam(adam), dP_out, dQpart, loss_part, TS, ngt);
-    NADM_CHECK_LAUNCH("dec_tc_kernel");
+    const AdamCoef ac = make_adam(adam);
+    int rc;
+#define NADM_DEC_GO(L, W)                                                                                              \
+    rc = dec_launch_one<L, W>(ncta, smem, st, packed, pitch, row_idx, row0, B, M, Q, q_ld, q_off, k, P, Pm, Pv, ac, dP_out, \
+                              dQpart, loss_part, TS)
+    if (slots == 4) {
+        if (want_loss) NADM_DEC_GO(true, 4); else NADM_DEC_GO(false, 4);
+    } else {
+        if (want_loss) NADM_DEC_GO(true, 3); else NADM_DEC_GO(false, 3);
+    }
+#undef NADM_DEC_GO
+    if (rc != NADM_OK) return rc;
     return launch_reduce_parts(dQpart, ncta, B, 8, k, dQ, q_ld, q_off, 1.0f, want_loss ? loss_part : nullptr, loss, st);
 }
 

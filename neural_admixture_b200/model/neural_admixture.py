@@ -160,6 +160,21 @@ class Q_P(torch.nn.Module):
             off += k
         return probs, buf
 
+    def infer_packed(self, pg: ops.PackedGenotypes, batch: int = 2048, allreduce=None) -> List[torch.Tensor]:
+        """Q for every row of a packed matrix, sequential row batches, outputs preallocated (the reference's
+        inference loop, src/inference.py:71-77, and post-training Q pass, :369-383, grow Q with ``torch.cat`` per
+        batch).  The batch size does not change any row's result.  ``allreduce`` sums the partial projections of the
+        SNP shards (sharded runs: every rank passes its own column slice and receives the full Q)."""
+        self.bind()
+        ks = self.multihead_encoder.ks
+        outs = [torch.empty((pg.N, k), dtype=torch.float32, device=pg.storage.device) for k in ks]
+        for r0 in range(0, pg.N, batch):
+            nb = min(batch, pg.N - r0)
+            probs, _ = self.encode_packed(pg, row0=r0, B=nb, allreduce=allreduce)
+            for o, p in zip(outs, probs):
+                o[r0:r0 + nb].copy_(p)
+        return outs
+
     def _return_training(self, probs):
         raise NadmError("Q_P.forward in training mode is not materialised by the B200 engine (the B x M reconstruction "
                         "never exists in memory); train through NeuralAdmixture.launch_training")
@@ -413,15 +428,7 @@ class NeuralAdmixture:
         return out
 
     def infer_Q(self, batch: int) -> List[torch.Tensor]:
-        ks = self.raw_model.multihead_encoder.ks
-        outs = [torch.empty((self.N, k), dtype=torch.float32, device=self.device) for k in ks]
-        for r0 in range(0, self.N, batch):
-            B = min(batch, self.N - r0)
-            probs, _ = self.raw_model.encode_packed(self.packed, row0=r0, B=B,
-                                                    allreduce=self._allreduce if self.sharded else None)
-            for o, p in zip(outs, probs):
-                o[r0:r0 + B].copy_(p)
-        return outs
+        return self.raw_model.infer_packed(self.packed, batch, allreduce=self._allreduce if self.sharded else None)
 
     def gather_P(self) -> List[torch.Tensor]:
         """Full M x k P per head on every rank (concatenating the SNP shards in rank order)."""

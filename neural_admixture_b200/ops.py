@@ -185,3 +185,20 @@ def loglikelihood(pg: PackedGenotypes, Q: torch.Tensor, P: torch.Tensor, ws: tor
     check(_lib.load().nadm_loglikelihood(_ptr(pg.storage), pg.pitch, pg.N, pg.M, _ptr(Q), _ptr(P), k, eps, _ptr(out),
                                          _ptr(ws), ws.numel() * ws.element_size(), _stream()))
     return float(out.item())
+
+
+def bed_to_packed(bed: torch.Tensor, N: int, dst: PackedGenotypes, snp0: int = 0, flip: bool = False,
+                  counts: Optional[torch.Tensor] = None) -> None:
+    """bed: (SNPs of this chunk) x ceil(N/4) uint8 on the device — rows of the .bed payload; writes columns
+    [snp0, snp0 + bed.shape[0]) of ``dst``.  counts: optional 4 x int64 device tensor (codes 1, 2, 3 accumulate)."""
+    _need_cuda(bed, counts)
+    assert bed.dtype == torch.uint8 and bed.dim() == 2 and bed.stride(1) == 1
+    assert counts is None or (counts.dtype == torch.int64 and counts.numel() == 4 and counts.is_contiguous())
+    Mc = bed.shape[0]
+    check(_lib.load().nadm_bed_to_packed(_ptr(bed), bed.stride(0) if Mc > 1 else bed.shape[1], N, Mc, snp0, int(flip),
+                                         _ptr(dst.storage), dst.pitch, _ptr(counts), _stream()))
+
+
+def flip_packed(pg: PackedGenotypes) -> None:
+    """In place g -> 2 - g (missing unchanged): the reference's minor-allele orientation (snp_reader.py:110)."""
+    check(_lib.load().nadm_flip_packed(_ptr(pg.storage), pg.pitch, pg.N, pg.M, _stream()))

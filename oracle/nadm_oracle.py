@@ -67,6 +67,28 @@ def unpack2bit(packed: np.ndarray, M: int) -> np.ndarray:
 # --------------------------------------------------------------------------------------------------------------
 
 
+# --------------------------------------------------------------------------------------------------------------
+# PLINK .bed decoding  (src/utils_c/utils.pyx:43-68 read_bed; src/snp_reader.py:16-45 _read_bed, :109-110 read_data)
+# --------------------------------------------------------------------------------------------------------------
+
+
+def read_bed(bed_bytes: np.ndarray, N: int) -> np.ndarray:
+    """bed_bytes: M x ceil(N/4) uint8, the .bed payload after its 3 magic bytes, one row per SNP (snp_reader.py:33-38).
+    Sample 4b+i sits in bits 2i..2i+1 of byte b; field -> genotype code through the table [2, 3, 1, 0]
+    (utils.pyx:51,58-67).  Returns the N x M uint8 matrix ``read_bed`` fills (codes 0, 1, 2, 3 = missing)."""
+    lut = np.array([2, 3, 1, 0], dtype=np.uint8)
+    M = bed_bytes.shape[0]
+    fields = np.stack([(bed_bytes >> (2 * i)) & 3 for i in range(4)], axis=2).reshape(M, -1)[:, :N]
+    return np.ascontiguousarray(lut[fields].T)
+
+
+def orient_alleles(G: np.ndarray) -> np.ndarray:
+    """``G if G.mean() < 1 else 2 - G`` in uint8 arithmetic (snp_reader.py:110): missing 3 becomes 255, whose two low
+    bits — all that pack2bit keeps (pack2bit.cu:29) — are 3 again."""
+    assert int(G.min()) == 0 and int(G.max()) in (2, 3)          # snp_reader.py:109
+    return G if G.mean() < 1 else (2 - G).astype(np.uint8)
+
+
 @dataclass
 class OracleState:
     """Parameters of Q_P in the reference's own layouts (model/neural_admixture.py:126-144).

@@ -20,6 +20,8 @@ Fixtures (all small npz):
   train_k3.npz       NeuralAdmixture.launch_training, 4 epochs, ragged last batch
   train_k3to5.npz    multi-head K=3..5
   train_sup_k3.npz   supervised mode
+  bed_demo_slices.npz  1500 SNP rows of the demo .bed (+ injected missing fields), as stored and with the homozygous
+                     fields exchanged, each with the N x M uint8 matrix SNPReader.read_data returns (flip in case b)
   demo_k7.npz        the shipped demo BED through read_bed -> RSVD -> GMM init -> 5 epochs (K=7, seed 42), plus the
                      shipped demo_run.7.{Q,P}.expected for reference
 """
@@ -232,6 +234,54 @@ def make_demo(ref_model, ref_root: str):
     np.savez_compressed(HERE / "demo_k7.npz", **z)
 
 
+def make_bed(ref_root: str, out: Path):
+    """PLINK .bed files through the reference's own reader (src/snp_reader.py: SNPReader.read_data -> Cython
+    utils_c.read_bed + the `2 - G` allele flip).  Two cases: a slice of the shipped demo BED (mean < 1: no flip) and
+    the same slice with the two homozygous fields exchanged in the file (mean >= 1: the reference flips it), both with
+    N = 105 (N % 4 = 1: padding fields in the last byte of every SNP row)."""
+    import shutil
+    import tempfile
+    from neural_admixture.src.snp_reader import SNPReader
+    demo = Path(ref_root) / "demo" / "data" / "demo_data"
+    N = sum(1 for _ in open(str(demo) + ".fam"))
+    nb = (N + 3) // 4
+    raw = np.fromfile(str(demo) + ".bed", dtype=np.uint8)
+    magic, payload = raw[:3], raw[3:].reshape(-1, nb)
+    M = 1500
+    rng = np.random.default_rng(5)
+    rows = np.sort(rng.choice(payload.shape[0], size=M, replace=False))
+    bed_a = payload[rows].copy()
+    miss = rng.random(bed_a.shape) < 0.01                       # sprinkle missing fields (01) into sample 4b
+    bed_a[miss] = (bed_a[miss] & 0xFC) | 0x01
+    # exchange fields 00 <-> 11 everywhere (hom A1 <-> hom A2): the matrix mean rises above 1
+    hi, lo = (bed_a >> 1) & 0x55, bed_a & 0x55
+    same = ~(hi ^ lo) & 0x55
+    bed_b = bed_a ^ (same | (same << 1))
+    res = {"N": np.int64(N), "M": np.int64(M)}
+    tmp = Path(tempfile.mkdtemp())
+    try:
+        for tag, bed in (("a", bed_a), ("b", bed_b)):
+            base = tmp / f"case_{tag}"
+            with open(str(base) + ".bed", "wb") as f:
+                f.write(magic.tobytes())
+                f.write(bed.tobytes())
+            shutil.copy(str(demo) + ".fam", str(base) + ".fam")
+            G = SNPReader().read_data(str(base) + ".bed")
+            res[f"bed_{tag}"] = bed
+            res[f"G_{tag}"] = np.asarray(G, dtype=np.uint8)
+            res[f"flipped_{tag}"] = np.bool_(not (np.asarray(G) == _lut_read(bed, N)).all())
+    finally:
+        shutil.rmtree(tmp)
+    assert not res["flipped_a"] and res["flipped_b"]
+    np.savez_compressed(out, **res)
+
+
+def _lut_read(bed, N):
+    lut = np.array([2, 3, 1, 0], dtype=np.uint8)
+    f = np.stack([(bed >> (2 * i)) & 3 for i in range(4)], axis=2).reshape(bed.shape[0], -1)[:, :N]
+    return lut[f].T
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("ref_root", help="built scratch copy of /root/reference (see module docstring)")
@@ -246,6 +296,7 @@ def main():
     make_step(ref_model, HERE / "step_k5.npz")
     make_trainings(ref_model)
     make_demo(ref_model, args.ref_root)
+    make_bed(args.ref_root, HERE / "bed_demo_slices.npz")
     for f in sorted(HERE.glob("*.npz")):
         print(f.name, f.stat().st_size)
 

@@ -416,6 +416,60 @@ def test_infer_forward_surface(ops, dev):
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# PLINK .bed -> packed device layout (next row f4): bit-exact vs the oracle and vs the reference reader's output
+# ---------------------------------------------------------------------------------------------------------------
+def test_bed_to_packed_golden(ops, dev, tmp_path):
+    from neural_admixture_b200.src import snp_reader
+    g = load_golden("bed_demo_slices.npz")
+    N, M = int(g["N"]), int(g["M"])
+    for tag in "ab":
+        base = tmp_path / f"case_{tag}"
+        with open(str(base) + ".bed", "wb") as f:
+            f.write(bytes([0x6C, 0x1B, 0x01]))
+            f.write(g[f"bed_{tag}"].tobytes())
+        with open(str(base) + ".fam", "w") as f:
+            f.write("".join(f"f{i} i{i} 0 0 0 -9\n" for i in range(N)))
+        pg = snp_reader.read_bed_packed(str(base) + ".bed", dev, chunk_snps=512)     # 3 chunks, ragged last one
+        assert pg.N == N and pg.M == M
+        want = orc.pack2bit(g[f"G_{tag}"])                     # the reference's matrix through its pack layout
+        got = pg.storage.cpu().numpy()
+        assert np.array_equal(got[:, :want.shape[1]], want)
+        assert not got[:, want.shape[1]:].any()                # zero row tails
+        # a rank's SNP slice (sharded runs) holds the same codes as the slice of the full matrix, when unflipped
+        if tag == "a":
+            sl = snp_reader.read_bed_packed(str(base) + ".bed", dev, col0=256, col1=1300)
+            assert np.array_equal(sl.storage.cpu().numpy()[:, :(1300 - 256 + 3) // 4], orc.pack2bit(g["G_a"][:, 256:1300]))
+
+
+@pytest.mark.parametrize("N,M", [(1, 1), (7, 130), (256, 128), (1000, 1000), (1027, 333)])
+def test_bed_to_packed_random(ops, dev, N, M):
+    rng = np.random.default_rng(N * 7 + M)
+    nb = (N + 3) // 4
+    bed = rng.integers(0, 256, size=(M, nb), dtype=np.uint8)
+    raw = orc.read_bed(bed, N)
+    pg = ops.PackedGenotypes.empty(N, M, dev)
+    pg.storage.fill_(0xAB)                                     # the kernel must overwrite every byte it owns
+    counts = torch.zeros(4, dtype=torch.int64, device=dev)
+    ops.bed_to_packed(t(bed, dev, torch.uint8), N, pg, counts=counts)
+    want = orc.pack2bit(raw)
+    got = pg.storage.cpu().numpy()
+    assert np.array_equal(got[:, :want.shape[1]], want)
+    pc128 = ((M + 127) // 128) * 32                            # tiles are 128 SNPs wide: zero up to the tile edge
+    assert not got[:, want.shape[1]:min(pc128, got.shape[1])].any()
+    c = counts.cpu().numpy()
+    assert [int(c[1]), int(c[2]), int(c[3])] == [int((raw == v).sum()) for v in (1, 2, 3)]
+    # flip: 2 - G in uint8, packed (missing stays 3); in-place flip of the packed matrix gives the same
+    pg2 = ops.PackedGenotypes.empty(N, M, dev)
+    ops.bed_to_packed(t(bed, dev, torch.uint8), N, pg2, flip=True)
+    want_f = orc.pack2bit((2 - raw).astype(np.uint8))
+    assert np.array_equal(pg2.storage.cpu().numpy()[:, :want.shape[1]], want_f)
+    pg.storage[:, pc128:].zero_() if pc128 < pg.pitch else None
+    ops.flip_packed(pg)
+    assert np.array_equal(pg.storage.cpu().numpy()[:, :want.shape[1]], want_f)
+    assert not pg.storage.cpu().numpy()[:, want.shape[1]:].any()
+
+
+# ---------------------------------------------------------------------------------------------------------------
 # full-size properties (config 2: 10k x 100k, K = 8; B = 800) — no oracle needed
 # ---------------------------------------------------------------------------------------------------------------
 def test_fullsize_properties(ops, dev):

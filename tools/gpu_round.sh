@@ -1,0 +1,48 @@
+#!/bin/bash
+# One GPU-box visit: parity tests, A/B bench legs, ncu launch list + one full capture.  Outputs under gpurun_out/.
+# usage: tools/gpu_round.sh <tag> [steps...]   steps: test ab bench launches ncu_dec ncu_enc ncu_mlp
+set -u
+TAG=$1; shift
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > $OUT/gpu.txt 2>&1
+for step in "$@"; do
+case $step in
+test)
+  timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/pytest.log; tail -5 $OUT/pytest.log;;
+ab)
+  for wg in 3 4; do export NADM_DEC_SLOTS=$wg;
+    timeout 600 python bench.py --rows 20000 --steps 60 --warmup 5 --no-cpu --no-e2e > $OUT/ab_wg$wg.json 2> $OUT/ab_wg$wg.err
+    python - <<PY
+import json
+try:
+    d=json.loads(open("$OUT/ab_wg$wg.json").read().strip().splitlines()[-1])
+    print("WG=$wg ms/step", round(d["ms_per_step"],4), "dec ms", round(d["roofline"]["ms_per_launch"],4), "grad_only ms", round(d["grad_only"]["ms_per_step"],4))
+except Exception as e:
+    print("WG=$wg failed", e)
+PY
+  done; unset NADM_DEC_SLOTS;;
+bench)
+  timeout 1200 python bench.py > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?"; tail -c 3000 $OUT/bench.json;;
+launches)
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base demangled -k regex:nadm:: -c 400 --csv --log-file $OUT/launches.csv \
+     python bench.py --rows 20000 --steps 3 --warmup 3 --no-cpu --no-e2e > $OUT/launches_bench.log 2>&1
+  python tools/launch_summary.py $OUT/launches.csv | tee $OUT/launch_summary.txt;;
+ncu_dec)
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:dec_tc_kernel --launch-skip 4 -c 1 \
+     -o $OUT/dec_full -f python bench.py --rows 20000 --steps 3 --warmup 3 --no-cpu --no-e2e > $OUT/ncu_dec.log 2>&1; echo "ncu_dec rc=$?";;
+ncu_enc)
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:enc_.*_tc_kernel --launch-skip 8 -c 2 \
+     -o $OUT/enc_full -f python bench.py --rows 20000 --steps 3 --warmup 3 --no-cpu --no-e2e > $OUT/ncu_enc.log 2>&1; echo "ncu_enc rc=$?";;
+ncu_mlp)
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:mlp_ --launch-skip 20 -c 5 \
+     -o $OUT/mlp_full -f python bench.py --rows 20000 --steps 3 --warmup 3 --no-cpu --no-e2e > $OUT/ncu_mlp.log 2>&1; echo "ncu_mlp rc=$?";;
+timeline_enc)
+  timeout 300 python tools/timeline_enc.py > $OUT/timeline_enc.txt 2>&1; tail -30 $OUT/timeline_enc.txt;;
+timeline)
+  timeout 300 python tools/timeline.py libnadm_b200_tl.so > $OUT/timeline.txt 2>&1; tail -8 $OUT/timeline.txt;;
+breakdown)
+  timeout 600 python tools/step_breakdown.py --out $OUT/breakdown.json 2> $OUT/breakdown.err | tail -1;;
+esac
+done
+ls -la $OUT

@@ -26,7 +26,13 @@ lib = L.load()
 lib.nadm_debug_timeline.argtypes = [ctypes.c_void_p]
 rc = lib.nadm_debug_timeline(out.ctypes.data)
 t0 = out[0][0]
-names = ["wg_wait_start", "wg_raw_seen", "wg_G_written", "iss_wait_start", "iss_G_seen", "iss_done", "wg_gt_free"]
+names = ["wg_wait_start", "wg_raw_seen", "wg_G_written", "issA_wait", "issA_G_seen", "issA_done", "wg_gt_free", "issB_done"]
 print("unit " + " ".join(f"{n:>14s}" for n in names))
-for u in range(60, 78):
-    print(f"{u:4d} " + " ".join(f"{int(out[r][u] - t0):14d}" for r in range(7)))
+for u in range(60, 84):
+    print(f"{u:4d} " + " ".join(f"{int(out[r][u] - t0):14d}" for r in range(8)))
+span = out[5][300] - out[5][100]
+print(f"cycles per unit (units 100..300, issuer A done): {span / 200:.1f}")
+dec = (out[2][100:300] - out[1][100:300]).mean()
+wait = (out[1][100:300] - out[0][100:300]).mean()
+print(f"compute warpgroup: decode {dec:.0f} cycles/unit, wait for raw {wait:.0f} cycles/unit")
+print(f"issuer A: wait for G {(out[4][100:300] - out[3][100:300]).mean():.0f}, issue {(out[5][100:300] - out[4][100:300]).mean():.0f} cycles/unit")
