@@ -282,8 +282,8 @@ def main():
     losses = torch.zeros(total + 8, dtype=torch.float32, device=dev)
 
     def run_steps(s0, n):
-        for s in range(s0, s0 + n):
-            na._train_step(order[s * B:(s + 1) * B], None, losses[s:s + 1])
+        # the public step loop: CUDA-graph replayed steps (NADM_NO_GRAPH=1: eager launches), loss evaluated every step
+        losses[s0:s0 + n].copy_(na.train_steps(order, n, True, first=s0))
 
     def sync_all():
         torch.cuda.synchronize()
@@ -295,7 +295,7 @@ def main():
     run_steps(0, args.warmup)
     sampler = ClockSampler(local) if rank == 0 else None
     sync_all()
-    l0 = ops.launch_count()
+    l0 = ops.launch_count() + na.graph_kernel_launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if sampler:
         sampler.mark_start()
@@ -305,16 +305,16 @@ def main():
     sync_all()
     if sampler:
         sampler.mark_stop()
-    launches = ops.launch_count() - l0
+    launches = ops.launch_count() + na.graph_kernel_launches - l0
     ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
     # same loop without evaluating the reconstruction loss (what NeuralAdmixture does on epochs whose loss the reference
     # does not print: 4 of 5 epochs) — reported next to the headline, which evaluates the loss on every step
     n_go = min(args.steps, 40)
+    na.train_steps(order, 1, False, first=args.warmup)           # (captures the loss-free step graph outside the timing)
     sync_all()
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     g0.record()
-    for s_ in range(args.warmup, args.warmup + n_go):
-        na._train_step(order[s_ * B:(s_ + 1) * B], None, None)
+    na.train_steps(order, n_go, False, first=args.warmup)
     g1.record()
     sync_all()
     ms_go = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
@@ -410,6 +410,7 @@ def main():
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": clocks, "loss": {"first_timed_step": loss_first, "last_timed_step": loss_last,
                                            "schedule": "evaluated on every timed step, as the reference does"},
+                "step_launch": "cuda-graph replay (one graph launch per step)" if na.use_graph else "eager launches",
                 "grad_only": {"value": B * n_go / (float(ms_go.item()) * 1e-3), "unit": UNIT, "steps": n_go,
                               "ms_per_step": float(ms_go.item()) / n_go,
                               "what": "same step with the loss value not evaluated (loss pointer NULL)"}}

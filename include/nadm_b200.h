@@ -42,14 +42,21 @@ extern "C" {
 #define NADM_MAX_HEADS 32
 
 /* Adam hyper-parameters of one optimizer step (torch.optim.Adam, betas (0.9,0.95): neural_admixture.py:197-204).
- * `step` is the 1-based step count AFTER increment (torch's state['step']). */
+ * `step` is the 1-based step count AFTER increment (torch's state['step']).
+ * `device_coef`: optional DEVICE pointer to the NADM_ADAM_COEF_BYTES coefficient block that nadm_step_begin writes.
+ * When it is not NULL the kernels read the step's bias-corrected coefficients from it and ignore lr/betas/eps/step, so
+ * the launch arguments of a training step no longer change from step to step and the whole step can be captured
+ * into a CUDA graph and replayed. */
 typedef struct nadm_adam {
     float lr;
     float beta1;
     float beta2;
     float eps;
     int32_t step;
+    int32_t reserved;          /* 0 */
+    const void* device_coef;
 } nadm_adam_t;
+#define NADM_ADAM_COEF_BYTES 32
 
 int nadm_version(void);
 const char* nadm_last_error(void);
@@ -143,6 +150,17 @@ int nadm_loglikelihood(const uint8_t* packed, int64_t pitch, int64_t N, int64_t 
 int nadm_bed_to_packed(const uint8_t* bed, int64_t bed_pitch, int64_t N, int64_t M, int64_t snp0, int32_t flip,
                        uint8_t* dst, int64_t dst_pitch, uint64_t* counts, void* stream);
 int nadm_flip_packed(uint8_t* packed, int64_t pitch, int64_t N, int64_t M, void* stream);
+
+/* ---- device-side step bookkeeping: what makes a training step replayable as a CUDA graph (the reference's loop
+ * body, neural_admixture.py:403-414, re-launches ~25 eager kernels from Python every step).
+ * counters: 2 x int64 on the device: [0] = index of the next minibatch inside `order`, [1] = optimizer steps done.
+ * nadm_step_begin: row_idx_out[i] = order[counters[0] * stride + i] for i < B (the minibatch's rows: the sampler's
+ *   permutation, src/loaders.py:26-33, lives on the device), and the Adam coefficients of step counters[1] + 1
+ *   (hyper: lr, betas, eps [host]) -> coef_out (device, NADM_ADAM_COEF_BYTES).
+ * nadm_step_end: losses_out[counters[0]] = *loss when both are given; counters[0] += 1; counters[1] += 1. */
+int nadm_step_begin(const int64_t* order, int64_t order_len, int64_t* counters, int64_t stride, int32_t B,
+                    int64_t* row_idx_out, const nadm_adam_t* hyper, void* coef_out, void* stream);
+int nadm_step_end(int64_t* counters, const float* loss, float* losses_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -19,7 +19,7 @@ class NadmError(RuntimeError):
 class AdamHyper(C.Structure):
     """nadm_adam_t"""
     _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
-                ("step", C.c_int32)]
+                ("step", C.c_int32), ("reserved", C.c_int32), ("device_coef", C.c_void_p)]
 
 
 class MlpParams(C.Structure):
@@ -54,6 +54,9 @@ SIGNATURES = {
     "nadm_bed_to_packed": (C.c_int, [c_u8p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32, c_u8p, C.c_int64,
                                      C.c_void_p, C.c_void_p]),
     "nadm_flip_packed": (C.c_int, [c_u8p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p]),
+    "nadm_step_begin": (C.c_int, [c_i64p, C.c_int64, c_i64p, C.c_int64, C.c_int32, c_i64p, C.POINTER(AdamHyper),
+                                  C.c_void_p, C.c_void_p]),
+    "nadm_step_end": (C.c_int, [c_i64p, c_f32p, c_f32p, C.c_void_p]),
 }
 
 _lib = None

@@ -43,21 +43,27 @@ constexpr int kMaxDynSmem = 226 * 1024;  // dynamic shared memory opt-in (227 KB
 struct AdamCoef {
     float beta1, beta2, one_minus_beta1, one_minus_beta2, step_size, inv_bc2_sqrt, eps;
     int enabled;
+    const void* dev;   // optional device copy of the first 32 bytes (nadm_adam_t.device_coef): read at kernel start
 };
+
+inline void adam_coefficients(float lr, float beta1, float beta2, float eps, long long step, AdamCoef& c) {
+    double bc1 = 1.0 - pow((double)beta1, (double)step);
+    double bc2 = 1.0 - pow((double)beta2, (double)step);
+    c.beta1 = beta1;
+    c.beta2 = beta2;
+    c.one_minus_beta1 = 1.0f - beta1;
+    c.one_minus_beta2 = 1.0f - beta2;
+    c.step_size = (float)((double)lr / bc1);
+    c.inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
+    c.eps = eps;
+    c.enabled = 1;
+}
 
 inline AdamCoef make_adam(const nadm_adam_t* a) {
     AdamCoef c{};
     if (!a) return c;
-    double bc1 = 1.0 - pow((double)a->beta1, (double)a->step);
-    double bc2 = 1.0 - pow((double)a->beta2, (double)a->step);
-    c.beta1 = a->beta1;
-    c.beta2 = a->beta2;
-    c.one_minus_beta1 = 1.0f - a->beta1;
-    c.one_minus_beta2 = 1.0f - a->beta2;
-    c.step_size = (float)((double)a->lr / bc1);
-    c.inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
-    c.eps = a->eps;
-    c.enabled = 1;
+    adam_coefficients(a->lr, a->beta1, a->beta2, a->eps, a->step, c);
+    c.dev = a->device_coef;
     return c;
 }
 
@@ -83,6 +89,16 @@ bool use_generic_kernels();   // NADM_GENERIC=1: force the CUDA-core formulation
 #ifdef __CUDACC__
 // torch.optim.Adam (no weight decay / amsgrad), same operation order as torch's fused kernel:
 //   m = lerp(m, g, 1-b1); v = b2*v + (1-b2)*g*g; p -= step_size * m / (sqrt(v)/sqrt(bc2) + eps)
+// kernels call this once on their by-value copy: coefficients written on the device by nadm_step_begin win
+__device__ __forceinline__ AdamCoef adam_resolve(AdamCoef a) {
+    if (a.dev != nullptr) {
+        const float4 x = reinterpret_cast<const float4*>(a.dev)[0], y = reinterpret_cast<const float4*>(a.dev)[1];
+        a.beta1 = x.x; a.beta2 = x.y; a.one_minus_beta1 = x.z; a.one_minus_beta2 = x.w;
+        a.step_size = y.x; a.inv_bc2_sqrt = y.y; a.eps = y.z;
+        a.enabled = 1;
+    }
+    return a;
+}
 __device__ __forceinline__ float adam_apply(float p, float g, float& m, float& v, const AdamCoef& c) {
     m = m + (g - m) * c.one_minus_beta1;
     v = c.beta2 * v + c.one_minus_beta2 * g * g;

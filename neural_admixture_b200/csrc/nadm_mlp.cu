@@ -323,7 +323,8 @@ __device__ __forceinline__ void adam_store(float* p, float* m, float* v, float* 
 
 __global__ void __launch_bounds__(256)
 mlp_bwd_apply_kernel(const float* __restrict__ part, int nslab, int C, int H, int sumK, int has_sup,
-                     nadm_mlp_params_t prm, AdamCoef adam, float* __restrict__ loss) {
+                     nadm_mlp_params_t prm, AdamCoef adam_in, float* __restrict__ loss) {
+    const AdamCoef adam = adam_resolve(adam_in);
     const size_t n = mlp_slab_floats(C, H, sumK);
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;

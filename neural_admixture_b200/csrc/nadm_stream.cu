@@ -230,8 +230,9 @@ template <int KP>
 __global__ void __launch_bounds__(kStreamWarps * 32)
 dec_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* __restrict__ row_idx, int64_t row0, int B,
            int64_t M, const float* __restrict__ Q, int q_ld, int q_off, int k, float* __restrict__ P,
-           float* __restrict__ Pm, float* __restrict__ Pv, AdamCoef adam, float* __restrict__ dP_out,
+           float* __restrict__ Pm, float* __restrict__ Pv, AdamCoef adam_in, float* __restrict__ dP_out,
            float* __restrict__ dQpart, float* __restrict__ loss_part, int ntiles) {
+    const AdamCoef adam = adam_resolve(adam_in);
     extern __shared__ __align__(16) uint8_t smem[];
     constexpr int W = kStreamWarps;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -357,7 +358,8 @@ template <int CP>
 __global__ void __launch_bounds__(kStreamWarps * 32)
 enc_bwd_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* __restrict__ row_idx, int64_t row0,
                int B, int64_t M, const float* __restrict__ dZ, int C, float* __restrict__ V, float* __restrict__ Vm,
-               float* __restrict__ Vv, AdamCoef adam, float* __restrict__ dV_out, int ntiles) {
+               float* __restrict__ Vv, AdamCoef adam_in, float* __restrict__ dV_out, int ntiles) {
+    const AdamCoef adam = adam_resolve(adam_in);
     extern __shared__ __align__(16) uint8_t smem[];
     constexpr int W = kStreamWarps;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -533,6 +535,58 @@ int launch_reduce_parts(const float* part, int nparts, int rows, int cols_p, int
 }  // namespace nadm
 
 static inline int pad_c(int C) { return C <= 8 ? 8 : 16; }
+// =================================================================================================================
+// device-side step bookkeeping (CUDA-graph replayable steps): see nadm_b200.h
+// =================================================================================================================
+namespace nadm {
+__global__ void step_begin_kernel(const int64_t* __restrict__ order, int64_t order_len, const int64_t* __restrict__ counters,
+                                  int64_t stride, int B, int64_t* __restrict__ row_idx_out, float lr, float beta1,
+                                  float beta2, float eps, float* __restrict__ coef_out) {
+    const int64_t s = counters[0];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B; i += gridDim.x * blockDim.x) {
+        const int64_t j = s * stride + i;
+        row_idx_out[i] = (j < order_len) ? order[j] : 0;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const double t = (double)(counters[1] + 1);
+        const double bc1 = 1.0 - pow((double)beta1, t), bc2 = 1.0 - pow((double)beta2, t);
+        coef_out[0] = beta1;
+        coef_out[1] = beta2;
+        coef_out[2] = 1.0f - beta1;
+        coef_out[3] = 1.0f - beta2;
+        coef_out[4] = (float)((double)lr / bc1);
+        coef_out[5] = (float)(1.0 / sqrt(bc2));
+        coef_out[6] = eps;
+        reinterpret_cast<int*>(coef_out)[7] = 1;
+    }
+}
+__global__ void step_end_kernel(int64_t* __restrict__ counters, const float* __restrict__ loss, float* __restrict__ losses_out) {
+    const int64_t s = counters[0];
+    if (loss != nullptr && losses_out != nullptr) losses_out[s] = *loss;
+    counters[0] = s + 1;
+    counters[1] += 1;
+}
+}  // namespace nadm
+
+extern "C" int nadm_step_begin(const int64_t* order, int64_t order_len, int64_t* counters, int64_t stride, int32_t B,
+                               int64_t* row_idx_out, const nadm_adam_t* hyper, void* coef_out, void* stream) {
+    NADM_REQUIRE(order && counters && row_idx_out && hyper && coef_out, "NULL pointer");
+    NADM_REQUIRE(B > 0 && stride >= B && order_len > 0, "bad minibatch geometry (B=%d, stride=%lld)", B, (long long)stride);
+    NADM_REQUIRE(((uintptr_t)coef_out & 15) == 0, "coef_out must be 16-byte aligned");
+    nadm::step_begin_kernel<<<(B + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        order, order_len, counters, stride, B, row_idx_out, hyper->lr, hyper->beta1, hyper->beta2, hyper->eps,
+        (float*)coef_out);
+    NADM_CHECK_LAUNCH("step_begin_kernel");
+    return NADM_OK;
+}
+
+extern "C" int nadm_step_end(int64_t* counters, const float* loss, float* losses_out, void* stream) {
+    NADM_REQUIRE(counters, "NULL pointer");
+    nadm::step_end_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(counters, loss, losses_out);
+    NADM_CHECK_LAUNCH("step_end_kernel");
+    return NADM_OK;
+}
+
 static inline int pad_k(int k) { return k <= 4 ? 4 : (k <= 8 ? 8 : 16); }
 
 extern "C" size_t nadm_workspace_bytes(int32_t B, int64_t M, int32_t C, int32_t H, int32_t sumK) {

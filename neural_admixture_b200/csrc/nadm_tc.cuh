@@ -182,18 +182,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
-// Wait of a warp that is NOT on the kernel's critical path (epilogues, operand producers running ahead): every failed
-// poll suspends the thread for up to `ns` nanoseconds in hardware, so the polling loop does not compete for issue slots
-// with the warps of its SM sub-partition (default try_wait polls were measured to be ~10 % of all instructions issued).
+// Wait of a warp that is NOT on the kernel's critical path (epilogues, operand producers running ahead): failed polls
+// are spaced by nanosleep so that the polling loop does not compete for issue slots with the warps of its SM
+// sub-partition (back-to-back try_wait polls were measured to be 10-20 % of all instructions issued; the try_wait
+// suspend-time hint does not space them: the hardware wakes the thread after ~25 ns regardless).
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, uint32_t ns) {
-    uint32_t ok;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-            : "=r"(ok)
-            : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
-            : "memory");
-    } while (!ok);
+    while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
+}
+// named barrier among `nthreads` threads (whole warps) of the CTA; id 1..15 (0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
 }
 // generic-proxy shared-memory writes -> visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }

@@ -191,9 +191,10 @@ template <bool kLoss, int SLOTS>
 __global__ void __launch_bounds__(kDecThreads, 1)
 dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* __restrict__ row_idx, int64_t row0, int B,
               int64_t M, const float* __restrict__ Q, int q_ld, int q_off, int k, float* __restrict__ P,
-              float* __restrict__ Pm, float* __restrict__ Pv, AdamCoef adam, float* __restrict__ dP_out,
+              float* __restrict__ Pm, float* __restrict__ Pv, AdamCoef adam_in, float* __restrict__ dP_out,
               float* __restrict__ dQpart, float* __restrict__ loss_part, int TS) {
     constexpr int kSlots = SLOTS, kWarpIssue = kWarpIssueA1;
+    const AdamCoef adam = adam_resolve(adam_in);
     constexpr int ngt = SLOTS;   // one G^T tile per slot (see the issuer warps for why not more)
     constexpr int kND3 = dec_nd3(SLOTS), kColD3 = 64 * SLOTS, kColD2 = kColD3 + 32 * kND3;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -471,7 +472,7 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
                     }
                 }
             }
-            mbar_wait_relaxed(&S->pempty[st], ((sub / kPStages) & 1) ^ 1, 400);
+            mbar_wait_relaxed(&S->pempty[st], ((sub / kPStages) & 1) ^ 1, 256);
             uint8_t* tile = PT + st * kPTileBytes;
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
@@ -493,7 +494,9 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
         const int q = warp & 3;
         for (int sub = 0; sub < nsub; ++sub) {
             const int dbuf = sub % kND3;
-            mbar_wait_relaxed(&S->d3full[dbuf], (sub / kND3) & 1, 200);
+            // one warp polls, the other three sleep on a named barrier
+            if (warp == kWarpProd + 1) mbar_wait_relaxed(&S->d3full[dbuf], (sub / kND3) & 1, 64);
+            named_bar_sync(1, 128);
             tc_fence_after_sync();
             uint32_t v[32];
             tmem_ld32(tbase + ((uint32_t)(q * 32) << 16) + kColD3 + dbuf * 32, v);

@@ -139,16 +139,19 @@ __device__ __forceinline__ void feed_widen(const Feed& f, uint8_t* tile, int slo
     const int r = lane & 7, q = lane >> 3;
     cp_async_wait<kStDepth - 1>();
     const uint8_t* st = f.stage + slot * kStTile + (wl * 32 + lane) * 16;
+    // all four pieces are loaded before any is widened (one exposed shared-memory latency instead of four); 8-row
+    // groups past the batch were zero-filled by the copy and widen to zeros that no MMA K step reads
+    uint4 w[4];
+#pragma unroll
+    for (int it = 0; it < 4; ++it) w[it] = *reinterpret_cast<const uint4*>(st + it * 2048);
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
         const int g8 = wl * 4 + it;                              // 8-row group inside the block
-        if (blk * 128 + g8 * 8 >= f.B) continue;                 // whole group past the batch: nothing reads it
-        const uint4 w = *reinterpret_cast<const uint4*>(st + it * 2048);
         uint8_t* dst = tile + r * 16 + g8 * 2048 + (q * 4) * 128;
-        widen_store(dst, w.x);
-        widen_store(dst + 128, w.y);
-        widen_store(dst + 256, w.z);
-        widen_store(dst + 384, w.w);
+        widen_store(dst, w[it].x);
+        widen_store(dst + 128, w[it].y);
+        widen_store(dst + 256, w[it].z);
+        widen_store(dst + 384, w[it].w);
     }
 }
 
@@ -186,8 +189,14 @@ struct EncSmem {
     uint32_t tmem_base;
 };
 
-constexpr int kFwdDigWarps = 2, kFwdIssueWarp = kProdWarps + kFwdDigWarps, kFwdThreads = (kFwdIssueWarp + 1) * 32;
+// Two MMA-issuer warps: a single issuing thread (waits + descriptor arithmetic + 8 MMAs + commits per tile, ~770 cycles
+// measured against 320 cycles of tensor-pipe time) was the kernel's critical path.  Issuer p issues K steps 4p..4p+3 of
+// EVERY tile into its own accumulator set (tensor-memory columns (p nblk + blk) 32); the epilogue adds the two int32
+// sets.  (Giving each issuer every other tile instead is unsafe: an issuer that skips phases of a stage's mbarrier
+// cannot tell the phases apart by parity.)  With 1 issuer or more than 8 row blocks: one accumulator set.
+constexpr int kFwdDigWarps = 2, kFwdIssueWarp = kProdWarps + kFwdDigWarps, kFwdThreads = (kFwdIssueWarp + 2) * 32;
 
+template <int NISS>   // MMA issuer warps in use: 2, or 1 (the second issuer warp then idles)
 __global__ void __launch_bounds__(kFwdThreads, 1)
 enc_fwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* __restrict__ row_idx, int64_t row0,
                   int B, int64_t M, const float* __restrict__ V, int C, const uint32_t* __restrict__ vmax_bits,
@@ -205,9 +214,9 @@ enc_fwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
 
     for (int b = tid; b < B; b += blockDim.x) rowoff[b] = (int32_t)((row_idx != nullptr) ? row_idx[b] : (row0 + b));
     if (tid == 0) {
-        for (int s = 0; s < kAStages; ++s) { mbar_init(&S->fullA[s], 4); mbar_init(&S->emptyA[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&S->fullV[s], kFwdDigWarps); mbar_init(&S->emptyV[s], 1); }
-        mbar_init(&S->done, 1);
+        for (int s = 0; s < kAStages; ++s) { mbar_init(&S->fullA[s], 4); mbar_init(&S->emptyA[s], NISS); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&S->fullV[s], kFwdDigWarps); mbar_init(&S->emptyV[s], NISS); }
+        mbar_init(&S->done, NISS);
         mbar_init_fence();
     }
     if (warp == kFwdIssueWarp) tmem_alloc<512>(&S->tmem_base);
@@ -246,6 +255,13 @@ enc_fwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
         for (int blk = warp >> 2; blk < nblk; blk += kProdWarps / 4) {
             uint32_t v[32];
             tmem_ld32(tbase + ((uint32_t)(q * 32) << 16) + blk * 32, v);
+            if (NISS == 2) {
+                uint32_t v1[32];
+                tmem_ld32(tbase + ((uint32_t)(q * 32) << 16) + (nblk + blk) * 32, v1);
+                tmem_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = (uint32_t)((int)v[j] + (int)v1[j]);
+            }
             tmem_wait_ld();
             const int b = blk * 128 + q * 32 + lane;
             if (b < B) {
@@ -288,7 +304,7 @@ enc_fwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
 #pragma unroll
                 for (int c = 0; c < 8; ++c) v[e][c] = vnext[e][c];
             if (t0 + tt + 1 < t1) load_v(tt + 1, vnext);
-            mbar_wait(&S->emptyV[vs], ((tt >> 1) & 1) ^ 1);
+            mbar_wait_relaxed(&S->emptyV[vs], ((tt >> 1) & 1) ^ 1, 128);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int pos = dt + 64 * e;
@@ -299,30 +315,32 @@ enc_fwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
             if (lane == 0) mbar_arrive(&S->fullV[vs]);
         }
     } else {
-        // ---------------- MMA issuer: the whole warp waits, one elected lane issues; descriptors built once ----------------
+        // ---------------- MMA issuers (warp parity p = row-block parity of its tiles): the whole warp runs the convergent
+        // loop, only the elected lane's MMAs / commits execute; descriptors built once ----------------
+        const int par = warp - kFwdIssueWarp;
         const uint64_t A0 = smem_desc(smem_u32(tilesA), 128, 2048), B0 = smem_desc(smem_u32(tilesV), 256, 128);
+        const uint32_t leader = elect_one() ? 1u : 0u;
+        constexpr int kSteps = (kSub / 32) / NISS;                      // K steps of a tile issued by one issuer
         int blk = 0, tt = 0, s = 0, s_phase = 0;
-        for (int i = 0; i < ntile; ++i) {
+        for (int i = 0; i < ntile && par < NISS; ++i) {
             const int vs = tt & 1;
             if (blk == 0) mbar_wait(&S->fullV[vs], (tt >> 1) & 1);
             mbar_wait(&S->fullA[s], s_phase);
             tc_fence_after_sync();
             if (lane == 0) TLE(6, i);
-            if (elect_one()) {
-                const uint64_t a = A0 + (uint64_t)(s * (kATile >> 4)), b = B0 + (uint64_t)(vs * (kDigTile >> 4));
-                const uint32_t d = tbase + blk * 32, acc0 = tt > 0 ? 1u : 0u;
+            const uint64_t a = A0 + (uint64_t)(s * (kATile >> 4) + par * kSteps * 16);
+            const uint64_t b = B0 + (uint64_t)(vs * (kDigTile >> 4) + par * kSteps * 64);
+            const uint32_t d = tbase + (par * nblk + blk) * 32, acc0 = tt > 0 ? 1u : 0u;
 #pragma unroll
-                for (int ks = 0; ks < kSub / 32; ++ks)
-                    mma_i8_ss(d, a + (uint64_t)(ks * 16), b + (uint64_t)(ks * 64), kIdescFwd, ks ? 1u : acc0);
-                mma_commit(&S->emptyA[s]);
-                if (blk == nblk - 1) mma_commit(&S->emptyV[vs]);
-            }
-            __syncwarp();
+            for (int ks = 0; ks < kSteps; ++ks)
+                mma_i8_ss_p(d, a + (uint64_t)(ks * 16), b + (uint64_t)(ks * 64), kIdescFwd, ks ? 1u : acc0, leader);
+            mma_commit_p(&S->emptyA[s], leader);
+            if (blk == nblk - 1) mma_commit_p(&S->emptyV[vs], leader);
             if (lane == 0) TLE(7, i);
             if (++s == kAStages) { s = 0; s_phase ^= 1; }
             if (++blk == nblk) { blk = 0; ++tt; }
         }
-        if (elect_one()) mma_commit(&S->done);
+        if (par < NISS) mma_commit_p(&S->done, leader);
         __syncwarp();
     }
     tc_fence_before_sync();
@@ -361,10 +379,14 @@ struct EncBwdSmem {
     float red[32];
 };
 
-__global__ void __launch_bounds__(kProdThreads + 32 + 128, 1)
+// warps: 16 producers, 2 MMA issuers (issuer h owns the 128-SNP half h of every tile: separate accumulators), 4 epilogue
+constexpr int kBwdThreads = kProdThreads + 64 + 128;
+template <int NISS>   // MMA issuer warps in use: 2, or 1 (issuer 0 then issues both halves, issuer 1 idles)
+__global__ void __launch_bounds__(kBwdThreads, 1)
 enc_bwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* __restrict__ row_idx, int64_t row0,
                   int B, int64_t M, const float* __restrict__ dZ, int C, float* __restrict__ V, float* __restrict__ Vm,
-                  float* __restrict__ Vv, AdamCoef adam, float* __restrict__ dV_out, int T) {
+                  float* __restrict__ Vv, AdamCoef adam_in, float* __restrict__ dV_out, int T) {
+    const AdamCoef adam = adam_resolve(adam_in);
     extern __shared__ __align__(1024) uint8_t smem[];
     const int nblk = (B + 127) / 128;
     uint8_t* tilesA = smem;                                         // kAStages x 32 KB
@@ -378,8 +400,8 @@ enc_bwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
 
     for (int b = tid; b < B; b += blockDim.x) rowoff[b] = (int32_t)((row_idx != nullptr) ? row_idx[b] : (row0 + b));
     if (tid == 0) {
-        for (int s = 0; s < kAStages; ++s) { mbar_init(&S->fullA[s], 4); mbar_init(&S->emptyA[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&S->dfull[s], 1); mbar_init(&S->dempty[s], 4); }
+        for (int s = 0; s < kAStages; ++s) { mbar_init(&S->fullA[s], 4); mbar_init(&S->emptyA[s], NISS); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&S->dfull[s], NISS); mbar_init(&S->dempty[s], 4); }
         mbar_init_fence();
     }
     if (warp == kProdWarps) tmem_alloc<128>(&S->tmem_base);
@@ -423,45 +445,48 @@ enc_bwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
             blk += 4;
             while (blk >= nblk) blk -= nblk;
         }
-    } else if (warp == kProdWarps) {
-        // ---------------- MMA issuer: the whole warp waits, one elected lane issues; descriptors built once ----------------
-        const uint64_t A0 = smem_desc(smem_u32(tilesA), 2048, 128), B0 = smem_desc(smem_u32(digZ), 256, 128);
+    } else if (warp <= kProdWarps + 1) {
+        // ---------------- MMA issuers: issuer h = warp - kProdWarps issues the 4 K steps of half h of every tile (a single
+        // issuing thread was the critical path); convergent loop, only the elected lane's MMAs / commits execute ----------------
+        const int h = warp - kProdWarps;
+        const uint64_t A0 = smem_desc(smem_u32(tilesA), 2048, 128) + (uint64_t)(h * 64), B0 = smem_desc(smem_u32(digZ), 256, 128);
+        constexpr int kHalves = 3 - NISS;                              // halves issued by one issuer: 1 (two issuers) or 2
         const int nks_last = min(4, (B - (nblk - 1) * 128 + 31) / 32);      // K steps holding real batch rows
+        const uint32_t leader = elect_one() ? 1u : 0u;
         int blk = 0, tt = 0, s = 0, s_phase = 0;
-        for (int i = 0; i < ntile; ++i) {
+        for (int i = 0; i < ntile && h < NISS; ++i) {
             const int buf = tt & 1;
             if (blk == 0) mbar_wait(&S->dempty[buf], ((tt >> 1) & 1) ^ 1);
             mbar_wait(&S->fullA[s], s_phase);
             tc_fence_after_sync();
-            if (elect_one()) {
-                const uint64_t a = A0 + (uint64_t)(s * (kATile >> 4)), b = B0 + (uint64_t)(blk * 256);
-                const uint32_t d = tbase + buf * 64, acc0 = blk > 0 ? 1u : 0u;
-                if (blk != nblk - 1 || nks_last == 4) {
+            const uint64_t a = A0 + (uint64_t)(s * (kATile >> 4)), b = B0 + (uint64_t)(blk * 256);
+            const uint32_t d = tbase + buf * 64 + h * 32, acc0 = blk > 0 ? 1u : 0u;
+            if (blk != nblk - 1 || nks_last == 4) {
 #pragma unroll
-                    for (int h = 0; h < 2; ++h)
+                for (int hh = 0; hh < kHalves; ++hh)
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks)
-                            mma_i8_ss(d + h * 32, a + (uint64_t)(h * 64 + ks * 512), b + (uint64_t)(ks * 64), kIdescBwd,
-                                      ks ? 1u : acc0);
-                } else {
-                    for (int h = 0; h < 2; ++h)
-                        for (int ks = 0; ks < nks_last; ++ks)
-                            mma_i8_ss(d + h * 32, a + (uint64_t)(h * 64 + ks * 512), b + (uint64_t)(ks * 64), kIdescBwd,
-                                      ks ? 1u : acc0);
-                }
-                mma_commit(&S->emptyA[s]);
-                if (blk == nblk - 1) mma_commit(&S->dfull[buf]);
+                    for (int ks = 0; ks < 4; ++ks)
+                        mma_i8_ss_p(d + hh * 32, a + (uint64_t)(hh * 64 + ks * 512), b + (uint64_t)(ks * 64), kIdescBwd,
+                                    ks ? 1u : acc0, leader);
+            } else {
+                for (int hh = 0; hh < kHalves; ++hh)
+                    for (int ks = 0; ks < nks_last; ++ks)
+                        mma_i8_ss_p(d + hh * 32, a + (uint64_t)(hh * 64 + ks * 512), b + (uint64_t)(ks * 64), kIdescBwd,
+                                    ks ? 1u : acc0, leader);
             }
-            __syncwarp();
+            mma_commit_p(&S->emptyA[s], leader);
+            if (blk == nblk - 1) mma_commit_p(&S->dfull[buf], leader);
             if (++s == kAStages) { s = 0; s_phase ^= 1; }
             if (++blk == nblk) { blk = 0; ++tt; }
         }
+        __syncwarp();
     } else {
         // ---------------- epilogue: digit planes -> dV -> Adam on V, one SNP per thread ----------------
         const int q = warp & 3;             // tensor-memory lane quadrant this warp may access (warp id % 4)
         for (int tt = 0; tt < t1 - t0; ++tt) {
             const int buf = tt & 1;
-            mbar_wait(&S->dfull[buf], (tt >> 1) & 1);
+            if (warp == kProdWarps + 2) mbar_wait_relaxed(&S->dfull[buf], (tt >> 1) & 1, 64);   // one warp polls
+            named_bar_sync(1, 128);
             tc_fence_after_sync();
             uint32_t v[2][32];
             tmem_ld32(tbase + ((uint32_t)(q * 32) << 16) + buf * 64, v[0]);
@@ -522,6 +547,16 @@ enc_bwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
 // =================================================================================================================
 // host launchers (called from the C ABI in nadm_stream.cu)
 // =================================================================================================================
+// MMA issuer warps per encoder kernel: NADM_ENC_ISSUERS=1|2 (A/B measurements; default below)
+static int enc_issuers() {
+    static int n = 0;
+    if (n == 0) {
+        const char* e = getenv("NADM_ENC_ISSUERS");
+        n = (e != nullptr && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 2;
+    }
+    return n;
+}
+
 bool enc_bwd_tc_supported(int B) {
     const int nblk = (B + 127) / 128;
     return (size_t)kAStages * kATile + (size_t)nblk * 4096 + (size_t)4 * kStDepth * kStTile + (size_t)((B + 3) & ~3) * 4 +
@@ -546,11 +581,16 @@ int launch_enc_fwd_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_i
                         sizeof(EncSmem) + 64;
     static bool attr = false;
     if (!attr) {
-        e = cudaFuncSetAttribute(enc_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+        e = cudaFuncSetAttribute(enc_fwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(enc_fwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(enc_fwd_tc)");
         attr = true;
     }
-    enc_fwd_tc_kernel<<<ncta, kFwdThreads, smem, st>>>(packed, pitch, row_idx, row0, B, M, V, C, vmax, part, T);
+    if (enc_issuers() == 2 && B <= 1024)          // two accumulator sets: 2 x 32 columns per row block, 512 in all
+        enc_fwd_tc_kernel<2><<<ncta, kFwdThreads, smem, st>>>(packed, pitch, row_idx, row0, B, M, V, C, vmax, part, T);
+    else
+        enc_fwd_tc_kernel<1><<<ncta, kFwdThreads, smem, st>>>(packed, pitch, row_idx, row0, B, M, V, C, vmax, part, T);
     NADM_CHECK_LAUNCH("enc_fwd_tc_kernel");
     enc_fwd_reduce_kernel<<<B, 256, 0, st>>>(part, ncta, B, C, vmax, Z);
     NADM_CHECK_LAUNCH("enc_fwd_reduce_kernel");
@@ -568,12 +608,18 @@ int launch_enc_bwd_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_i
     NADM_REQUIRE(smem <= (size_t)kMaxDynSmem, "batch B=%d too large for encoder_bwd", B);
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(enc_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+        cudaError_t e = cudaFuncSetAttribute(enc_bwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(enc_bwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(enc_bwd_tc)");
         attr = true;
     }
-    enc_bwd_tc_kernel<<<ncta, kProdThreads + 32 + 128, smem, st>>>(packed, pitch, row_idx, row0, B, M, dZ, C, V, Vm, Vv,
-                                                                  make_adam(adam), dV_out, T);
+    if (enc_issuers() == 2)
+        enc_bwd_tc_kernel<2><<<ncta, kBwdThreads, smem, st>>>(packed, pitch, row_idx, row0, B, M, dZ, C, V, Vm, Vv,
+                                                             make_adam(adam), dV_out, T);
+    else
+        enc_bwd_tc_kernel<1><<<ncta, kBwdThreads, smem, st>>>(packed, pitch, row_idx, row0, B, M, dZ, C, V, Vm, Vv,
+                                                             make_adam(adam), dV_out, T);
     NADM_CHECK_LAUNCH("enc_bwd_tc_kernel");
     return NADM_OK;
 }

@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import json
 import logging
+import os
 import sys
 from pathlib import Path
 from typing import Dict, List, Optional, Tuple
@@ -280,12 +281,14 @@ class NeuralAdmixture:
         return p
 
     def _train_step(self, row_idx: Optional[torch.Tensor], labels: Optional[torch.Tensor],
-                    loss_out: Optional[torch.Tensor], pg: Optional[ops.PackedGenotypes] = None) -> None:
+                    loss_out: Optional[torch.Tensor], pg: Optional[ops.PackedGenotypes] = None, hyper=None) -> None:
         """One minibatch: the body of the reference's ``_run_epoch`` loop (:403-414) — forward, loss, backward,
         Adam on every parameter, P clamp — as 5 library calls.  ``loss_out`` (1 float on device) receives the step's
         loss; nothing is synchronised with the host.  ``loss_out=None`` skips the evaluation of the reconstruction loss
         (its value never feeds the backward; the reference only logs it, :414-417).  The batch is rows ``row_idx`` of
-        the resident matrix, or all rows of ``pg`` (a staged batch, see ``train_from_host``)."""
+        the resident matrix, or all rows of ``pg`` (a staged batch, see ``train_from_host``).  ``hyper``: Adam
+        hyper-parameters whose coefficients live on the device (graph replay, see ``train_steps``); by default the
+        host-side step count is advanced and its coefficients are passed by value."""
         m, o = self.raw_model, self.optimizer
         if pg is None:
             pg = self.packed
@@ -296,8 +299,9 @@ class NeuralAdmixture:
                                     allreduce=self._allreduce if self.sharded else None)
         sb = self._step_buffers(B)
         sb["loss"].zero_()
-        o.step_count += 1
-        hyper = o.hyper()
+        if hyper is None:
+            o.step_count += 1
+            hyper = o.hyper()
         off = 0
         for i, k in enumerate(m.multihead_encoder.ks):
             ops.decoder_step(pg, fb["Q"], sb["dQ"], off, k, m.decoders.decoders[i].weight.data, o.m["P"][i], o.v["P"][i],
@@ -312,6 +316,84 @@ class NeuralAdmixture:
         if loss_out is not None:
             loss_out.copy_(sb["loss"])
 
+    # ---- CUDA-graph replayed steps ------------------------------------------------------------------------------------
+    use_graph = os.environ.get("NADM_NO_GRAPH", "0") != "1"
+    graph_kernel_launches = 0     # library kernels executed through graph replays (they bypass nadm_launch_count)
+
+    def _graph_state(self, order_len: int) -> dict:
+        gs = getattr(self, "_gs", None)
+        if gs is None or gs["order"].numel() < order_len:
+            dev = self.device
+            gs = {"order": torch.zeros(order_len, dtype=torch.int64, device=dev),
+                  "counters": torch.zeros(2, dtype=torch.int64, device=dev),
+                  "coef": torch.zeros(8, dtype=torch.float32, device=dev),
+                  "loss1": torch.zeros(1, dtype=torch.float32, device=dev),
+                  "losses": torch.zeros(order_len, dtype=torch.float32, device=dev), "idx": {}, "graphs": {},
+                  "pops": None}
+            self._gs = gs
+        return gs
+
+    def _get_graph(self, gs: dict, Bs: int, want_loss: bool, sup: bool):
+        """The whole step for a minibatch of ``Bs`` rows as ONE replayable CUDA graph: ``nadm_step_begin`` (rows of the
+        minibatch out of the device-resident permutation + this step's Adam coefficients, both indexed by a device
+        counter), the five hot-path calls (and, sharded, their two all-reduces), ``nadm_step_end``.  Nothing in the
+        graph depends on host state, so an epoch is ``nsteps`` graph launches."""
+        key = (Bs, want_loss, sup)
+        g = gs["graphs"].get(key)
+        if g is not None:
+            return g
+        o = self.optimizer
+        self.raw_model.bind()
+        self.raw_model._fwd_buffers(Bs)
+        self._step_buffers(Bs)
+        idx = gs["idx"].setdefault(Bs, torch.zeros(Bs, dtype=torch.int64, device=self.device))
+        h_host = ops.adam_hyper(o.lr, 0, o.betas[0], o.betas[1], o.eps)
+        h_dev = ops.adam_hyper(o.lr, 0, o.betas[0], o.betas[1], o.eps, device_coef=gs["coef"])
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        before = ops.launch_count()
+        with torch.cuda.graph(g):
+            ops.step_begin(gs["order"], gs["counters"], self.batch_size, Bs, idx, h_host, gs["coef"])
+            labels = gs["pops"][idx] if sup else None
+            self._train_step(idx, labels, gs["loss1"] if want_loss else None, hyper=h_dev)
+            ops.step_end(gs["counters"], gs["loss1"] if want_loss else None, gs["losses"] if want_loss else None)
+        g.nadm_kernels = ops.launch_count() - before          # library kernels per replay (bench.py's gpu_launches)
+        gs["graphs"][key] = g
+        return g
+
+    def train_steps(self, order_dev: torch.Tensor, nsteps: int, want_loss: bool = True,
+                    pops: Optional[torch.Tensor] = None, first: int = 0) -> Optional[torch.Tensor]:
+        """``nsteps`` consecutive minibatches of the row order ``order_dev`` (int64, device): minibatch ``s`` is
+        ``order_dev[(first + s) * batch_size : (first + s + 1) * batch_size]`` (the last one may be ragged).  The body of
+        the reference's epoch loop (:403-414) per minibatch; returns the per-step losses (device tensor) or None.
+        Steps are replayed CUDA graphs unless ``NADM_NO_GRAPH=1`` (or capture is impossible), then eager calls."""
+        o, Bfull, n = self.optimizer, self.batch_size, order_dev.numel()
+        if self.use_graph:
+            try:
+                gs = self._graph_state(n)
+                if gs["order"].data_ptr() != order_dev.data_ptr():
+                    gs["order"][:n].copy_(order_dev)
+                gs["pops"] = pops
+                gs["counters"].copy_(torch.tensor([first, o.step_count], dtype=torch.int64))
+                graphs = [self._get_graph(gs, min(Bfull, n - (first + s) * Bfull), want_loss, pops is not None)
+                          for s in range(nsteps)]
+            except Exception as e:  # capture not possible (e.g. a collective that cannot be captured): eager steps
+                log.info(f"    CUDA-graph capture unavailable ({type(e).__name__}: {e}); running eager steps.")
+                type(self).use_graph = False
+                graphs = None
+            if graphs is not None:
+                for g in graphs:
+                    g.replay()
+                    self.graph_kernel_launches += g.nadm_kernels
+                o.step_count += nsteps
+                return gs["losses"][first:first + nsteps] if want_loss else None
+        losses = torch.zeros(nsteps, dtype=torch.float32, device=self.device) if want_loss else None
+        for s in range(nsteps):
+            idx = order_dev[(first + s) * Bfull:(first + s + 1) * Bfull]
+            labels = pops[idx].contiguous() if pops is not None else None
+            self._train_step(idx, labels, losses[s:s + 1] if want_loss else None)
+        return losses
+
     def epoch_order(self, N: int) -> torch.Tensor:
         """Row order of one epoch: exactly what the reference's ``RandomSampler(dataset, generator=self.generator)``
         yields (src/loaders.py:29-30, generator from :283)."""
@@ -325,11 +407,7 @@ class NeuralAdmixture:
         nsteps = (N + self.batch_size - 1) // self.batch_size
         every = 2 if pops is not None else 5
         want_loss = (epoch % every == 0) or self.keep_loss_history     # the epochs whose loss the reference prints
-        losses = torch.zeros(nsteps, dtype=torch.float32, device=self.device)
-        for s in range(nsteps):
-            idx = order_dev[s * self.batch_size:(s + 1) * self.batch_size]
-            labels = pops[idx].contiguous() if pops is not None else None
-            self._train_step(idx, labels, losses[s:s + 1] if want_loss else None)
+        losses = self.train_steps(order_dev, nsteps, want_loss, pops)
         loss_acc = float(losses.double().sum().item()) if want_loss else None
         if loss_acc is not None:
             self.loss_history.append(loss_acc)

@@ -70,8 +70,11 @@ def _ks_array(ks: Sequence[int]):
     return (C.c_int32 * len(ks))(*[int(k) for k in ks])
 
 
-def adam_hyper(lr: float, step: int, beta1: float = 0.9, beta2: float = 0.95, eps: float = 1e-8) -> AdamHyper:
-    return AdamHyper(lr, beta1, beta2, eps, step)
+def adam_hyper(lr: float, step: int, beta1: float = 0.9, beta2: float = 0.95, eps: float = 1e-8,
+               device_coef: Optional[torch.Tensor] = None) -> AdamHyper:
+    """nadm_adam_t.  ``device_coef`` (8 x float32 CUDA tensor written by ``step_begin``): the kernels read the step's
+    coefficients from the device, so the step's launch arguments are the same every step (CUDA-graph replay)."""
+    return AdamHyper(lr, beta1, beta2, eps, step, 0, None if device_coef is None else device_coef.data_ptr())
 
 
 class PackedGenotypes:
@@ -202,3 +205,18 @@ def bed_to_packed(bed: torch.Tensor, N: int, dst: PackedGenotypes, snp0: int = 0
 def flip_packed(pg: PackedGenotypes) -> None:
     """In place g -> 2 - g (missing unchanged): the reference's minor-allele orientation (snp_reader.py:110)."""
     check(_lib.load().nadm_flip_packed(_ptr(pg.storage), pg.pitch, pg.N, pg.M, _stream()))
+
+
+def step_begin(order: torch.Tensor, counters: torch.Tensor, stride: int, B: int, row_idx_out: torch.Tensor,
+               hyper: AdamHyper, coef_out: torch.Tensor) -> None:
+    """Device-side start of a step: the minibatch's rows out of the device-resident permutation and the Adam
+    coefficients of the step, both indexed by ``counters`` (2 x int64 on the device)."""
+    _need_cuda(order, counters, row_idx_out, coef_out)
+    assert order.dtype == torch.int64 and counters.dtype == torch.int64 and counters.numel() == 2
+    assert row_idx_out.dtype == torch.int64 and row_idx_out.numel() >= B and coef_out.numel() * coef_out.element_size() >= 32
+    check(_lib.load().nadm_step_begin(_ptr(order), order.numel(), _ptr(counters), stride, B, _ptr(row_idx_out),
+                                      C.byref(hyper), _ptr(coef_out), _stream()))
+
+
+def step_end(counters: torch.Tensor, loss: Optional[torch.Tensor], losses_out: Optional[torch.Tensor]) -> None:
+    check(_lib.load().nadm_step_end(_ptr(counters), _ptr(loss), _ptr(losses_out), _stream()))

@@ -470,6 +470,34 @@ def test_bed_to_packed_random(ops, dev, N, M):
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# CUDA-graph replayed steps == eager steps (same kernels; Adam coefficients computed on the device)
+# ---------------------------------------------------------------------------------------------------------------
+def test_graph_replayed_steps_match_eager(dev, monkeypatch):
+    from neural_admixture_b200 import ops
+    from neural_admixture_b200.model.neural_admixture import NeuralAdmixture
+    rng = np.random.default_rng(3)
+    N, M, K, C, H, B = 333, 2051, 4, 8, 64, 100                # 4 steps per epoch, ragged last batch (33 rows)
+    G = rand_genotypes(rng, N, M)
+    V = np.linalg.qr(rng.standard_normal((M, C)))[0].astype(np.float32)
+    P0 = rng.uniform(0.05, 0.95, size=(K, M)).astype(np.float32)
+    y = torch.as_tensor(rng.integers(0, K, size=N))
+    outs = []
+    for graph in (True, False):
+        monkeypatch.setattr(NeuralAdmixture, "use_graph", graph)
+        torch.manual_seed(5)
+        na = NeuralAdmixture(K, 3, B, 2e-3, dev, 7, 0, True, "nadm_b200", None, None)
+        na.keep_loss_history = True
+        pg = packed_from(ops, G, dev)
+        Qs, Ps, _ = na.launch_training(torch.as_tensor(P0, device=dev), pg, H, C, torch.as_tensor(V, device=dev), M, N, y)
+        assert na.use_graph == graph                              # no silent fall-back to eager
+        assert (na.graph_kernel_launches > 0) == graph
+        outs.append((Qs[0], Ps[0], np.array(na.loss_history), na.optimizer.step_count))
+    assert outs[0][3] == outs[1][3] == 12
+    assert relF(outs[0][0], outs[1][0]) < 1e-6 and relF(outs[0][1], outs[1][1]) < 1e-6
+    np.testing.assert_allclose(outs[0][2], outs[1][2], rtol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------------------------
 # full-size properties (config 2: 10k x 100k, K = 8; B = 800) — no oracle needed
 # ---------------------------------------------------------------------------------------------------------------
 def test_fullsize_properties(ops, dev):

@@ -9,10 +9,10 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > 
 for step in "$@"; do
 case $step in
 test)
-  timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/pytest.log; tail -5 $OUT/pytest.log;;
+  timeout 240 python -m pytest tests -m gpu -x -q --timeout 60 > $OUT/pytest.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/pytest.log; tail -5 $OUT/pytest.log;;
 ab)
   for wg in 3 4; do export NADM_DEC_SLOTS=$wg;
-    timeout 600 python bench.py --rows 20000 --steps 60 --warmup 5 --no-cpu --no-e2e > $OUT/ab_wg$wg.json 2> $OUT/ab_wg$wg.err
+    timeout 150 python bench.py --rows 20000 --steps 60 --warmup 5 --no-cpu --no-e2e > $OUT/ab_wg$wg.json 2> $OUT/ab_wg$wg.err
     python - <<PY
 import json
 try:
@@ -25,24 +25,26 @@ PY
 bench)
   timeout 1200 python bench.py > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?"; tail -c 3000 $OUT/bench.json;;
 launches)
-  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base demangled -k regex:nadm:: -c 400 --csv --log-file $OUT/launches.csv \
+  timeout 240 ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base demangled -k regex:nadm:: -c 400 --csv --log-file $OUT/launches.csv \
      python bench.py --rows 20000 --steps 3 --warmup 3 --no-cpu --no-e2e > $OUT/launches_bench.log 2>&1
   python tools/launch_summary.py $OUT/launches.csv | tee $OUT/launch_summary.txt;;
 ncu_dec)
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:dec_tc_kernel --launch-skip 4 -c 1 \
+  timeout 240 ncu --set full --clock-control none --import-source on -k regex:dec_tc_kernel --launch-skip 4 -c 1 \
      -o $OUT/dec_full -f python bench.py --rows 20000 --steps 3 --warmup 3 --no-cpu --no-e2e > $OUT/ncu_dec.log 2>&1; echo "ncu_dec rc=$?";;
 ncu_enc)
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:enc_.*_tc_kernel --launch-skip 8 -c 2 \
+  timeout 240 ncu --set full --clock-control none --import-source on -k regex:enc_.*_tc_kernel --launch-skip 8 -c 2 \
      -o $OUT/enc_full -f python bench.py --rows 20000 --steps 3 --warmup 3 --no-cpu --no-e2e > $OUT/ncu_enc.log 2>&1; echo "ncu_enc rc=$?";;
 ncu_mlp)
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:mlp_ --launch-skip 20 -c 5 \
+  timeout 240 ncu --set full --clock-control none --import-source on -k regex:mlp_ --launch-skip 20 -c 5 \
      -o $OUT/mlp_full -f python bench.py --rows 20000 --steps 3 --warmup 3 --no-cpu --no-e2e > $OUT/ncu_mlp.log 2>&1; echo "ncu_mlp rc=$?";;
+encprobe)
+  for w in fwd bwd; do for m in 20000 100000; do NADM_ENC_ISSUERS=2 timeout 40 python tools/enc_probe.py $w $m 2>&1 | tail -1; echo "probe $w $m rc=$?"; done; done;;
 timeline_enc)
-  timeout 300 python tools/timeline_enc.py > $OUT/timeline_enc.txt 2>&1; tail -30 $OUT/timeline_enc.txt;;
+  timeout 90 python tools/timeline_enc.py > $OUT/timeline_enc.txt 2>&1; tail -30 $OUT/timeline_enc.txt;;
 timeline)
-  timeout 300 python tools/timeline.py libnadm_b200_tl.so > $OUT/timeline.txt 2>&1; tail -8 $OUT/timeline.txt;;
+  timeout 90 python tools/timeline.py libnadm_b200_tl.so > $OUT/timeline.txt 2>&1; tail -8 $OUT/timeline.txt;;
 breakdown)
-  timeout 600 python tools/step_breakdown.py --out $OUT/breakdown.json 2> $OUT/breakdown.err | tail -1;;
+  timeout 150 python tools/step_breakdown.py --out $OUT/breakdown.json 2> $OUT/breakdown.err | tail -1;;
 esac
 done
 ls -la $OUT

@@ -60,15 +60,13 @@ def wrap(n):
 for n in names:
     setattr(ops, n, wrap(n))
 
-for s in range(10):
-    na._train_step(order[s * B:(s + 1) * B], None, losses[s:s + 1])
+na.train_steps(order, 10, True, first=0)
 torch.cuda.synchronize()
 # plain timing (no per-call events)
 t0 = time.perf_counter()
 a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 a0.record()
-for s in range(10, 10 + a.steps):
-    na._train_step(order[s * B:(s + 1) * B], None, losses[s:s + 1])
+na.train_steps(order, a.steps, True, first=10)
 a1.record()
 host_ms = (time.perf_counter() - t0) * 1e3 / a.steps
 torch.cuda.synchronize()
