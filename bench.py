@@ -354,8 +354,9 @@ def main():
     dec_bytes = len(ks) * B * pitch_bytes + 24 * M_loc * sumK       # genotype pass per head + {P,m,v} read+write
     step_bytes = (2 + len(ks)) * B * pitch_bytes + 24 * M_loc * (NCOMP + sumK)
     traffic = None
-    try:
-        traffic = json.loads((ROOT / "profiles" / "r1_ncu_summary.json").read_text())["dec_tc_kernel"]["dram_bytes"]
+    try:   # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture
+        summ = json.loads((ROOT / "profiles" / "r1b_ncu_summary.json").read_text())
+        traffic = next(v["dram_bytes"] for k, v in summ.items() if k.startswith("dec_tc_kernel"))
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": "dec_tc_kernel (tcgen05 fused decoder: Q.P^T + BCE + backward + dQ/dP + Adam + clamp)",
@@ -389,6 +390,7 @@ def main():
                        "pinned host memory (double-buffered side stream), the fused step runs, loss read back"}
         assert all(math.isfinite(x) for x in hl)
 
+    step_launch = "cuda-graph replay (one graph launch per step)" if na.use_graph else "eager launches"
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         host = None
@@ -410,7 +412,7 @@ def main():
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": clocks, "loss": {"first_timed_step": loss_first, "last_timed_step": loss_last,
                                            "schedule": "evaluated on every timed step, as the reference does"},
-                "step_launch": "cuda-graph replay (one graph launch per step)" if na.use_graph else "eager launches",
+                "step_launch": step_launch,
                 "grad_only": {"value": B * n_go / (float(ms_go.item()) * 1e-3), "unit": UNIT, "steps": n_go,
                               "ms_per_step": float(ms_go.item()) / n_go,
                               "what": "same step with the loss value not evaluated (loss pointer NULL)"}}

@@ -321,28 +321,35 @@ __device__ __forceinline__ void adam_store(float* p, float* m, float* v, float* 
     }
 }
 
-__global__ void __launch_bounds__(256)
+constexpr int kApplyParams = 64, kApplyGroups = 4;   // a block sums 64 parameters' slabs in 4 interleaved groups
+
+__global__ void __launch_bounds__(kApplyParams * kApplyGroups)
 mlp_bwd_apply_kernel(const float* __restrict__ part, int nslab, int C, int H, int sumK, int has_sup,
                      nadm_mlp_params_t prm, AdamCoef adam_in, float* __restrict__ loss) {
     const AdamCoef adam = adam_resolve(adam_in);
+    __shared__ float red[kApplyGroups][kApplyParams];
     const size_t n = mlp_slab_floats(C, H, sumK);
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
-    int z = 0;
-    for (; z + 4 <= nslab; z += 4) {      // fixed association: four interleaved chains, then (g0 + g1) + (g2 + g3)
-        g0 += part[(size_t)(z + 0) * n + i];
-        g1 += part[(size_t)(z + 1) * n + i];
-        g2 += part[(size_t)(z + 2) * n + i];
-        g3 += part[(size_t)(z + 3) * n + i];
+    const int j = threadIdx.x % kApplyParams, grp = threadIdx.x / kApplyParams;
+    const size_t i = (size_t)blockIdx.x * kApplyParams + j;
+    // slabs grp, grp + 4, ...: two interleaved chains per thread, fixed association -> deterministic
+    float g0 = 0.f, g1 = 0.f;
+    if (i < n) {
+        int z = grp;
+        for (; z + kApplyGroups < nslab; z += 2 * kApplyGroups) {
+            g0 += part[(size_t)z * n + i];
+            g1 += part[(size_t)(z + kApplyGroups) * n + i];
+        }
+        if (z < nslab) g0 += part[(size_t)z * n + i];
     }
-    for (; z < nslab; ++z) g0 += part[(size_t)z * n + i];
-    const float g = (g0 + g1) + (g2 + g3);
+    red[grp][j] = g0 + g1;
+    __syncthreads();
+    if (grp != 0 || i >= n) return;
+    const float g = (red[0][j] + red[1][j]) + (red[2][j] + red[3][j]);
     const size_t n1 = (size_t)(C + 1) * H, n2 = n1 + (size_t)sumK * H;
     if (i < n1) {
-        const int c = (int)(i / H), j = (int)(i % H);
-        if (c < C) adam_store(prm.W1, prm.m_W1, prm.v_W1, prm.g_W1, (int64_t)j * C + c, g, adam);
-        else adam_store(prm.b1, prm.m_b1, prm.v_b1, prm.g_b1, j, g, adam);
+        const int c = (int)(i / H), jj = (int)(i % H);
+        if (c < C) adam_store(prm.W1, prm.m_W1, prm.v_W1, prm.g_W1, (int64_t)jj * C + c, g, adam);
+        else adam_store(prm.b1, prm.m_b1, prm.v_b1, prm.g_b1, jj, g, adam);
     } else if (i < n2) {
         adam_store(prm.W2, prm.m_W2, prm.v_W2, prm.g_W2, (int64_t)(i - n1), g, adam);
     } else if (i < n2 + sumK) {
@@ -433,7 +440,7 @@ extern "C" int nadm_mlp_bwd(const float* dQ, const float* Q, const float* Hh, co
     NADM_CHECK_LAUNCH("mlp_bwd_rows_kernel");
     const AdamCoef ac = make_adam(adam);
     const size_t nparam = mlp_slab_floats(C, H, hd.sumK);
-    mlp_bwd_apply_kernel<<<(unsigned)((nparam + 255) / 256), 256, 0, st>>>(gpart, nslab, C, H, hd.sumK,
+    mlp_bwd_apply_kernel<<<(unsigned)((nparam + kApplyParams - 1) / kApplyParams), kApplyParams * kApplyGroups, 0, st>>>(gpart, nslab, C, H, hd.sumK,
                                                                           labels != nullptr, p, ac, loss);
     NADM_CHECK_LAUNCH("mlp_bwd_apply_kernel");
     return NADM_OK;

@@ -41,6 +41,9 @@ def main():
         packed = ops.PackedGenotypes.from_unpacked_host(torch.as_tensor(G), dev, c0, c1)
         Qs, Ps, _ = na.launch_training(torch.as_tensor(P0[:, c0:c1].copy(), device=dev), packed, H, C,
                                        torch.as_tensor(V[c0:c1].copy(), device=dev), c1 - c0, N)
+        if rank == 0:
+            print(f"  {'sharded' if sharded else 'single '} run: cuda-graph steps = {na.use_graph}, "
+                  f"graph-replayed kernels = {na.graph_kernel_launches}")
         return Qs, Ps, na.loss_history
 
     Qs_s, Ps_s, loss_s = run(True)
