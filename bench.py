@@ -418,7 +418,23 @@ def main():
                               "what": "same step with the loss value not evaluated (loss pointer NULL)"}}
         print(json.dumps(line), flush=True)
     if world > 1:
+        # Tear down in this order: the captured step graphs hold NCCL kernels, and destroying the process group while
+        # they are alive was observed to hang at exit.  A watchdog guarantees the process ends in any case (the line
+        # above is already printed and flushed).
+        import gc
+        wd = threading.Timer(20.0, lambda: os._exit(0))
+        wd.daemon = True
+        wd.start()
+        try:
+            na.release_graphs()
+        except (NameError, AttributeError):
+            pass
+        na = None
+        gc.collect()
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -156,10 +156,11 @@ int nadm_flip_packed(uint8_t* packed, int64_t pitch, int64_t N, int64_t M, void*
  * counters: 2 x int64 on the device: [0] = index of the next minibatch inside `order`, [1] = optimizer steps done.
  * nadm_step_begin: row_idx_out[i] = order[counters[0] * stride + i] for i < B (the minibatch's rows: the sampler's
  *   permutation, src/loaders.py:26-33, lives on the device), and the Adam coefficients of step counters[1] + 1
- *   (hyper: lr, betas, eps [host]) -> coef_out (device, NADM_ADAM_COEF_BYTES).
+ *   (hyper: lr, betas, eps [host]) -> coef_out (device, NADM_ADAM_COEF_BYTES); *loss_accum = 0 when not NULL (the
+ *   step's loss accumulator, which nadm_decoder_step / nadm_mlp_bwd add to).
  * nadm_step_end: losses_out[counters[0]] = *loss when both are given; counters[0] += 1; counters[1] += 1. */
 int nadm_step_begin(const int64_t* order, int64_t order_len, int64_t* counters, int64_t stride, int32_t B,
-                    int64_t* row_idx_out, const nadm_adam_t* hyper, void* coef_out, void* stream);
+                    int64_t* row_idx_out, const nadm_adam_t* hyper, void* coef_out, float* loss_accum, void* stream);
 int nadm_step_end(int64_t* counters, const float* loss, float* losses_out, void* stream);
 
 #ifdef __cplusplus

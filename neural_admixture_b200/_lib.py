@@ -55,7 +55,7 @@ SIGNATURES = {
                                      C.c_void_p, C.c_void_p]),
     "nadm_flip_packed": (C.c_int, [c_u8p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p]),
     "nadm_step_begin": (C.c_int, [c_i64p, C.c_int64, c_i64p, C.c_int64, C.c_int32, c_i64p, C.POINTER(AdamHyper),
-                                  C.c_void_p, C.c_void_p]),
+                                  C.c_void_p, c_f32p, C.c_void_p]),
     "nadm_step_end": (C.c_int, [c_i64p, c_f32p, c_f32p, C.c_void_p]),
 }
 

@@ -541,7 +541,7 @@ static inline int pad_c(int C) { return C <= 8 ? 8 : 16; }
 namespace nadm {
 __global__ void step_begin_kernel(const int64_t* __restrict__ order, int64_t order_len, const int64_t* __restrict__ counters,
                                   int64_t stride, int B, int64_t* __restrict__ row_idx_out, float lr, float beta1,
-                                  float beta2, float eps, float* __restrict__ coef_out) {
+                                  float beta2, float eps, float* __restrict__ coef_out, float* __restrict__ loss_accum) {
     const int64_t s = counters[0];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B; i += gridDim.x * blockDim.x) {
         const int64_t j = s * stride + i;
@@ -558,6 +558,7 @@ __global__ void step_begin_kernel(const int64_t* __restrict__ order, int64_t ord
         coef_out[5] = (float)(1.0 / sqrt(bc2));
         coef_out[6] = eps;
         reinterpret_cast<int*>(coef_out)[7] = 1;
+        if (loss_accum != nullptr) *loss_accum = 0.f;
     }
 }
 __global__ void step_end_kernel(int64_t* __restrict__ counters, const float* __restrict__ loss, float* __restrict__ losses_out) {
@@ -569,13 +570,14 @@ __global__ void step_end_kernel(int64_t* __restrict__ counters, const float* __r
 }  // namespace nadm
 
 extern "C" int nadm_step_begin(const int64_t* order, int64_t order_len, int64_t* counters, int64_t stride, int32_t B,
-                               int64_t* row_idx_out, const nadm_adam_t* hyper, void* coef_out, void* stream) {
+                               int64_t* row_idx_out, const nadm_adam_t* hyper, void* coef_out, float* loss_accum,
+                               void* stream) {
     NADM_REQUIRE(order && counters && row_idx_out && hyper && coef_out, "NULL pointer");
     NADM_REQUIRE(B > 0 && stride >= B && order_len > 0, "bad minibatch geometry (B=%d, stride=%lld)", B, (long long)stride);
     NADM_REQUIRE(((uintptr_t)coef_out & 15) == 0, "coef_out must be 16-byte aligned");
     nadm::step_begin_kernel<<<(B + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
         order, order_len, counters, stride, B, row_idx_out, hyper->lr, hyper->beta1, hyper->beta2, hyper->eps,
-        (float*)coef_out);
+        (float*)coef_out, loss_accum);
     NADM_CHECK_LAUNCH("step_begin_kernel");
     return NADM_OK;
 }

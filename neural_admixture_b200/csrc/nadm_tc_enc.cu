@@ -156,22 +156,6 @@ __device__ __forceinline__ void feed_widen(const Feed& f, uint8_t* tile, int slo
 }
 
 // =================================================================================================================
-// |max| of a float array (scale of the fixed-point split), result as float bits via atomicMax
-// =================================================================================================================
-__global__ void absmax_kernel(const float* __restrict__ x, int64_t n, uint32_t* __restrict__ out) {
-    float m = 0.f;
-    const int64_t n4 = n / 4;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-        const float4 v = reinterpret_cast<const float4*>(x)[i];
-        m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
-    }
-    if (blockIdx.x == 0 && threadIdx.x < (int)(n - n4 * 4)) m = fmaxf(m, fabsf(x[n4 * 4 + threadIdx.x]));
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));
-}
-
-// =================================================================================================================
 // forward
 // =================================================================================================================
 #ifdef NADM_TIMELINE
@@ -187,6 +171,7 @@ extern "C" int nadm_debug_enc_timeline(long long* host_out) {
 struct EncSmem {
     uint64_t fullA[kAStages], emptyA[kAStages], fullV[2], emptyV[2], done;
     uint32_t tmem_base;
+    float red[32];       // per-warp |max| of this CTA's slice of V
 };
 
 // Two MMA-issuer warps: a single issuing thread (waits + descriptor arithmetic + 8 MMAs + commits per tile, ~770 cycles
@@ -199,7 +184,7 @@ constexpr int kFwdDigWarps = 2, kFwdIssueWarp = kProdWarps + kFwdDigWarps, kFwdT
 template <int NISS>   // MMA issuer warps in use: 2, or 1 (the second issuer warp then idles)
 __global__ void __launch_bounds__(kFwdThreads, 1)
 enc_fwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* __restrict__ row_idx, int64_t row0,
-                  int B, int64_t M, const float* __restrict__ V, int C, const uint32_t* __restrict__ vmax_bits,
+                  int B, int64_t M, const float* __restrict__ V, int C, float* __restrict__ cta_vmax,
                   long long* __restrict__ part, int T) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* tilesA = smem;                                         // kAStages x 32 KB
@@ -220,10 +205,34 @@ enc_fwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
         mbar_init_fence();
     }
     if (warp == kFwdIssueWarp) tmem_alloc<512>(&S->tmem_base);
+    // |max| of THIS CTA's rows of V: the fixed-point scale is per CTA (its partial sums are exact integers at that scale;
+    // the reduction kernel converts each CTA's partial with the CTA's own power-of-two scale).  No grid-wide pass over V.
+    {
+        const int64_t m0 = (int64_t)t0 * kSub, m1 = min((int64_t)t1 * kSub, M);
+        const int64_t n = (m1 > m0) ? (m1 - m0) * C : 0;
+        const float* v0 = V + m0 * C;
+        float mx = 0.f;
+        if ((reinterpret_cast<uintptr_t>(v0) & 15) == 0) {
+            const int64_t n4 = n / 4;
+            for (int64_t i = tid; i < n4; i += blockDim.x) {
+                const float4 x = reinterpret_cast<const float4*>(v0)[i];
+                mx = fmaxf(fmaxf(mx, fmaxf(fabsf(x.x), fabsf(x.y))), fmaxf(fabsf(x.z), fabsf(x.w)));
+            }
+            for (int64_t i = n4 * 4 + tid; i < n; i += blockDim.x) mx = fmaxf(mx, fabsf(v0[i]));
+        } else {
+            for (int64_t i = tid; i < n; i += blockDim.x) mx = fmaxf(mx, fabsf(v0[i]));
+        }
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if (lane == 0) S->red[warp] = mx;
+    }
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tbase = S->tmem_base;
+    float vmax = 0.f;
+    for (int w = 0; w < kFwdThreads / 32; ++w) vmax = fmaxf(vmax, S->red[w]);
+    if (tid == 0) cta_vmax[blockIdx.x] = vmax;
 
     if (warp < kProdWarps) {
         // ---------------- producers: widened genotype tiles (group g = warp / 4 handles tiles g, g + 4, ...) ----------------
@@ -277,7 +286,7 @@ enc_fwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
         }
     } else if (warp < kFwdIssueWarp) {
         // ---------------- digit warps: int8 digit planes of V, one 256-SNP sub-tile ahead of the MMAs ----------------
-        const FixScale fs = fix_scale(__uint_as_float(*vmax_bits));
+        const FixScale fs = fix_scale(vmax);
         const int dt = tid - kProdThreads;                              // 0..63: K positions dt, dt+64, dt+128, dt+192
         auto load_v = [&](int tt, float (&v)[4][8]) {
 #pragma unroll
@@ -348,25 +357,28 @@ enc_fwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
     if (warp == kFwdIssueWarp) tmem_dealloc<512>(tbase);
 }
 
-// Z[b, c] = 0.5 * 2^(e-30) * sum over CTAs of the exact int64 partials (integer sum: order-independent).
-// Block = the 8 components of one row x 32 part segments.
+// Z[b, c] = 0.5 * sum over CTAs p of part_p[b, c] * 2^(e_p - 30): every CTA's partial is an exact integer at the CTA's own
+// power-of-two scale (exactly representable in double, as is the product); the CTAs are summed in double in a fixed
+// order (deterministic).  Block = the 8 components of one row x 32 part segments.
 __global__ void __launch_bounds__(256)
 enc_fwd_reduce_kernel(const long long* __restrict__ part, int nparts, int B, int C,
-                      const uint32_t* __restrict__ vmax_bits, float* __restrict__ Z) {
-    __shared__ long long red[32][8];
+                      const float* __restrict__ cta_vmax, float* __restrict__ Z) {
+    __shared__ double red[32][8];
+    __shared__ double back[kMaxParts];
+    for (int p = threadIdx.x; p < nparts; p += blockDim.x) back[p] = fix_scale(cta_vmax[p]).back;
+    __syncthreads();
     const int c = threadIdx.x & 7, seg = threadIdx.x >> 3;
     const int b = blockIdx.x;
     const int64_t i = (int64_t)b * 8 + c;
-    long long acc = 0;
-    for (int p = seg; p < nparts; p += 32) acc += part[(int64_t)p * B * 8 + i];
+    double acc = 0.0;
+    for (int p = seg; p < nparts; p += 32) acc += (double)part[(int64_t)p * B * 8 + i] * back[p];
     red[seg][c] = acc;
     __syncthreads();
     if (threadIdx.x < 8 && c < C) {
-        long long t = 0;
+        double t = 0.0;
 #pragma unroll
         for (int s2 = 0; s2 < 32; ++s2) t += red[s2][c];
-        const FixScale fs = fix_scale(__uint_as_float(*vmax_bits));
-        Z[(int64_t)b * C + c] = (float)((double)t * fs.back * 0.5);
+        Z[(int64_t)b * C + c] = (float)(t * 0.5);
     }
 }
 
@@ -562,21 +574,18 @@ bool enc_bwd_tc_supported(int B) {
     return (size_t)kAStages * kATile + (size_t)nblk * 4096 + (size_t)4 * kStDepth * kStTile + (size_t)((B + 3) & ~3) * 4 +
                sizeof(EncBwdSmem) + 64 <= (size_t)kMaxDynSmem;
 }
-size_t enc_tc_workspace_bytes(int B) { return (size_t)sm_count() * (size_t)B * 8 * sizeof(long long) + 256; }
+constexpr size_t kEncWsHeader = 4096;   // per-CTA scales in front of the partial sums
+size_t enc_tc_workspace_bytes(int B) { return (size_t)sm_count() * (size_t)B * 8 * sizeof(long long) + kEncWsHeader; }
 
 int launch_enc_fwd_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_idx, int64_t row0, int B, int64_t M,
                       const float* V, int C, float* Z, void* ws, size_t ws_bytes, cudaStream_t st) {
     const int T = (int)((M + kSub - 1) / kSub);
     const int ncta = std::min(T, sm_count());
-    const size_t need = (size_t)ncta * B * 8 * sizeof(long long) + 256;
+    const size_t need = (size_t)ncta * B * 8 * sizeof(long long) + kEncWsHeader;
     NADM_REQUIRE(need <= ws_bytes, "workspace too small for encoder_fwd (%zu > %zu)", need, ws_bytes);
-    uint32_t* vmax = reinterpret_cast<uint32_t*>(ws);
-    long long* part = reinterpret_cast<long long*>(reinterpret_cast<uint8_t*>(ws) + 256);
-    cudaError_t e = cudaMemsetAsync(vmax, 0, 4, st);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(vmax)");
-    const int64_t n = M * C;
-    absmax_kernel<<<(unsigned)std::min<int64_t>((n / 4 + 255) / 256 + 1, 4 * sm_count()), 256, 0, st>>>(V, n, vmax);
-    NADM_CHECK_LAUNCH("absmax_kernel");
+    float* vmax = reinterpret_cast<float*>(ws);                     // per-CTA |max| of its slice of V (ncta floats)
+    long long* part = reinterpret_cast<long long*>(reinterpret_cast<uint8_t*>(ws) + kEncWsHeader);
+    cudaError_t e;
     const size_t smem = (size_t)kAStages * kATile + 2 * kDigTile + (size_t)4 * kStDepth * kStTile + (size_t)((B + 3) & ~3) * 4 +
                         sizeof(EncSmem) + 64;
     static bool attr = false;

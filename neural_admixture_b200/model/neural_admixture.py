@@ -281,14 +281,16 @@ class NeuralAdmixture:
         return p
 
     def _train_step(self, row_idx: Optional[torch.Tensor], labels: Optional[torch.Tensor],
-                    loss_out: Optional[torch.Tensor], pg: Optional[ops.PackedGenotypes] = None, hyper=None) -> None:
+                    loss_out: Optional[torch.Tensor], pg: Optional[ops.PackedGenotypes] = None, hyper=None,
+                    managed_loss: bool = False) -> None:
         """One minibatch: the body of the reference's ``_run_epoch`` loop (:403-414) — forward, loss, backward,
         Adam on every parameter, P clamp — as 5 library calls.  ``loss_out`` (1 float on device) receives the step's
         loss; nothing is synchronised with the host.  ``loss_out=None`` skips the evaluation of the reconstruction loss
         (its value never feeds the backward; the reference only logs it, :414-417).  The batch is rows ``row_idx`` of
         the resident matrix, or all rows of ``pg`` (a staged batch, see ``train_from_host``).  ``hyper``: Adam
         hyper-parameters whose coefficients live on the device (graph replay, see ``train_steps``); by default the
-        host-side step count is advanced and its coefficients are passed by value."""
+        host-side step count is advanced and its coefficients are passed by value.  ``managed_loss``: the caller
+        (``nadm_step_begin`` / ``nadm_step_end``) zeroes and collects the step's loss accumulator itself."""
         m, o = self.raw_model, self.optimizer
         if pg is None:
             pg = self.packed
@@ -298,7 +300,8 @@ class NeuralAdmixture:
         probs, fb = m.encode_packed(pg, row_idx=row_idx, row0=0, B=B,
                                     allreduce=self._allreduce if self.sharded else None)
         sb = self._step_buffers(B)
-        sb["loss"].zero_()
+        if not managed_loss:
+            sb["loss"].zero_()
         if hyper is None:
             o.step_count += 1
             hyper = o.hyper()
@@ -313,7 +316,7 @@ class NeuralAdmixture:
                     sb["dZ"], sb["loss"], fb["ws"], labels=labels,
                     sup_weight=float(self.supervised_loss_weight) if labels is not None else 0.0)
         ops.encoder_bwd(pg, sb["dZ"], m.V.data, o.m["V"], o.v["V"], hyper, fb["ws"], row_idx=row_idx)
-        if loss_out is not None:
+        if loss_out is not None and not managed_loss:
             loss_out.copy_(sb["loss"])
 
     # ---- CUDA-graph replayed steps ------------------------------------------------------------------------------------
@@ -345,7 +348,7 @@ class NeuralAdmixture:
         o = self.optimizer
         self.raw_model.bind()
         self.raw_model._fwd_buffers(Bs)
-        self._step_buffers(Bs)
+        loss_acc = self._step_buffers(Bs)["loss"]
         idx = gs["idx"].setdefault(Bs, torch.zeros(Bs, dtype=torch.int64, device=self.device))
         h_host = ops.adam_hyper(o.lr, 0, o.betas[0], o.betas[1], o.eps)
         h_dev = ops.adam_hyper(o.lr, 0, o.betas[0], o.betas[1], o.eps, device_coef=gs["coef"])
@@ -353,13 +356,20 @@ class NeuralAdmixture:
         g = torch.cuda.CUDAGraph()
         before = ops.launch_count()
         with torch.cuda.graph(g):
-            ops.step_begin(gs["order"], gs["counters"], self.batch_size, Bs, idx, h_host, gs["coef"])
+            ops.step_begin(gs["order"], gs["counters"], self.batch_size, Bs, idx, h_host, gs["coef"], loss_acc)
             labels = gs["pops"][idx] if sup else None
-            self._train_step(idx, labels, gs["loss1"] if want_loss else None, hyper=h_dev)
-            ops.step_end(gs["counters"], gs["loss1"] if want_loss else None, gs["losses"] if want_loss else None)
+            self._train_step(idx, labels, loss_acc if want_loss else None, hyper=h_dev, managed_loss=True)
+            ops.step_end(gs["counters"], loss_acc if want_loss else None, gs["losses"] if want_loss else None)
         g.nadm_kernels = ops.launch_count() - before          # library kernels per replay (bench.py's gpu_launches)
         gs["graphs"][key] = g
         return g
+
+    def release_graphs(self) -> None:
+        """Drop the captured step graphs (they hold the sharded step's NCCL kernels: release them before the process
+        group is destroyed)."""
+        if getattr(self, "_gs", None) is not None:
+            torch.cuda.synchronize(self.device)
+            self._gs = None
 
     def train_steps(self, order_dev: torch.Tensor, nsteps: int, want_loss: bool = True,
                     pops: Optional[torch.Tensor] = None, first: int = 0) -> Optional[torch.Tensor]:
@@ -455,6 +465,7 @@ class NeuralAdmixture:
 
         # inference of Q for every sample, sequential batches of min(N, 1024) (reference :368-383)
         Qs = self.infer_Q(min(N, 1024))
+        self.release_graphs()
         if self.master:
             log.info("")
             log.info("    Training finished!")

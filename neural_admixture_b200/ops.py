@@ -208,14 +208,14 @@ def flip_packed(pg: PackedGenotypes) -> None:
 
 
 def step_begin(order: torch.Tensor, counters: torch.Tensor, stride: int, B: int, row_idx_out: torch.Tensor,
-               hyper: AdamHyper, coef_out: torch.Tensor) -> None:
+               hyper: AdamHyper, coef_out: torch.Tensor, loss_accum: Optional[torch.Tensor] = None) -> None:
     """Device-side start of a step: the minibatch's rows out of the device-resident permutation and the Adam
     coefficients of the step, both indexed by ``counters`` (2 x int64 on the device)."""
     _need_cuda(order, counters, row_idx_out, coef_out)
     assert order.dtype == torch.int64 and counters.dtype == torch.int64 and counters.numel() == 2
     assert row_idx_out.dtype == torch.int64 and row_idx_out.numel() >= B and coef_out.numel() * coef_out.element_size() >= 32
     check(_lib.load().nadm_step_begin(_ptr(order), order.numel(), _ptr(counters), stride, B, _ptr(row_idx_out),
-                                      C.byref(hyper), _ptr(coef_out), _stream()))
+                                      C.byref(hyper), _ptr(coef_out), _ptr(loss_accum), _stream()))
 
 
 def step_end(counters: torch.Tensor, loss: Optional[torch.Tensor], losses_out: Optional[torch.Tensor]) -> None:
