@@ -133,17 +133,19 @@ __device__ __forceinline__ void feed_issue(Feed& f, int wl, int lane) {
     f.c_slot = (f.c_slot + 1 == kStDepth) ? 0 : f.c_slot + 1;
     cp_async_commit();       // always one group per call: keeps wait_group counting aligned at the tail
 }
-// widen the tile in staging slot `slot` (this thread's own pieces have landed once at most kStDepth-1 newer groups are
-// pending) into `tile`
-__device__ __forceinline__ void feed_widen(const Feed& f, uint8_t* tile, int slot, int blk, int wl, int lane) {
-    const int r = lane & 7, q = lane >> 3;
+// load this thread's four staged pieces of the tile in staging slot `slot` into registers (they have landed once at most
+// kStDepth-1 newer copy groups are pending).  After this the slot may be refilled (feed_issue) while the pieces are
+// widened: the refill overlaps the wait for the MMAs to release the widened-tile stage.
+__device__ __forceinline__ void feed_load(const Feed& f, int slot, int wl, int lane, uint4 (&w)[4]) {
     cp_async_wait<kStDepth - 1>();
     const uint8_t* st = f.stage + slot * kStTile + (wl * 32 + lane) * 16;
-    // all four pieces are loaded before any is widened (one exposed shared-memory latency instead of four); 8-row
-    // groups past the batch were zero-filled by the copy and widen to zeros that no MMA K step reads
-    uint4 w[4];
 #pragma unroll
     for (int it = 0; it < 4; ++it) w[it] = *reinterpret_cast<const uint4*>(st + it * 2048);
+}
+// widen the four pieces into `tile`; 8-row groups past the batch were zero-filled by the copy and widen to zeros that
+// no MMA K step reads
+__device__ __forceinline__ void feed_store(uint8_t* tile, int wl, int lane, const uint4 (&w)[4]) {
+    const int r = lane & 7, q = lane >> 3;
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
         const int g8 = wl * 4 + it;                              // 8-row group inside the block
@@ -214,6 +216,7 @@ enc_fwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
         float mx = 0.f;
         if ((reinterpret_cast<uintptr_t>(v0) & 15) == 0) {
             const int64_t n4 = n / 4;
+#pragma unroll 8
             for (int64_t i = tid; i < n4; i += blockDim.x) {
                 const float4 x = reinterpret_cast<const float4*>(v0)[i];
                 mx = fmaxf(fmaxf(mx, fmaxf(fabsf(x.x), fabsf(x.y))), fmaxf(fabsf(x.z), fabsf(x.w)));
@@ -241,17 +244,19 @@ enc_fwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
         for (int p = 0; p < kStDepth; ++p) feed_issue(f, wl, lane);
         int blk = g % nblk, slot = 0, phase = 1;
         for (int i = g; i < ntile; i += 4) {
+            uint4 w[4];
             if (tid == 0) TLE(0, i);
+            feed_load(f, slot, wl, lane, w);
+            feed_issue(f, wl, lane);                                 // refill the staging slot just read
+            if (tid == 0) TLE(5, i);
             mbar_wait(&S->emptyA[g], phase);
             if (tid == 0) TLE(1, i);
-            feed_widen(f, tilesA + g * kATile, slot, blk, wl, lane);
+            feed_store(tilesA + g * kATile, wl, lane, w);
             if (tid == 0) TLE(3, i);
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&S->fullA[g]);                // one arrival per warp of the group
             if (tid == 0) TLE(4, i);
-            feed_issue(f, wl, lane);                                 // refill the staging slot just consumed
-            if (tid == 0) TLE(5, i);
             phase ^= 1;
             slot = (slot + 1 == kStDepth) ? 0 : slot + 1;
             blk += 4;
@@ -419,7 +424,15 @@ enc_bwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
     if (warp == kProdWarps) tmem_alloc<128>(&S->tmem_base);
     // |max| of dZ over the batch (every CTA computes the same value)
     float mx = 0.f;
-    for (int i = tid; i < B * C; i += blockDim.x) mx = fmaxf(mx, fabsf(dZ[i]));
+    if ((reinterpret_cast<uintptr_t>(dZ) & 15) == 0 && ((B * C) & 3) == 0) {
+#pragma unroll 4
+        for (int i = tid; i < (B * C) / 4; i += blockDim.x) {
+            const float4 x = reinterpret_cast<const float4*>(dZ)[i];
+            mx = fmaxf(fmaxf(mx, fmaxf(fabsf(x.x), fabsf(x.y))), fmaxf(fabsf(x.z), fabsf(x.w)));
+        }
+    } else {
+        for (int i = tid; i < B * C; i += blockDim.x) mx = fmaxf(mx, fabsf(dZ[i]));
+    }
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     if (lane == 0) S->red[warp] = mx;
@@ -446,12 +459,14 @@ enc_bwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
         for (int p = 0; p < kStDepth; ++p) feed_issue(f, wl, lane);
         int blk = g % nblk, slot = 0, phase = 1;
         for (int i = g; i < ntile; i += 4) {
+            uint4 w[4];
+            feed_load(f, slot, wl, lane, w);
+            feed_issue(f, wl, lane);                                 // refill the staging slot just read
             mbar_wait(&S->emptyA[g], phase);
-            feed_widen(f, tilesA + g * kATile, slot, blk, wl, lane);
+            feed_store(tilesA + g * kATile, wl, lane, w);
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&S->fullA[g]);
-            feed_issue(f, wl, lane);
             phase ^= 1;
             slot = (slot + 1 == kStDepth) ? 0 : slot + 1;
             blk += 4;
