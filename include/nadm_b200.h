@@ -163,6 +163,19 @@ int nadm_step_begin(const int64_t* order, int64_t order_len, int64_t* counters, 
                     int64_t* row_idx_out, const nadm_adam_t* hyper, void* coef_out, float* loss_accum, void* stream);
 int nadm_step_end(int64_t* counters, const float* loss, float* losses_out, void* stream);
 
+/* ---- randomized-SVD products on the packed matrix ("next" row f2).  Replace multiply_A_omega / multiply_QT_A
+ * (src/utils_c/rsvd.pyx:16-50, driven by src/svd.py:49-71): naive OpenMP triple loops over the N x M uint8 matrix.
+ * They multiply by the reader's uint8 VALUES — 0, 1, 2 and, for a missing genotype, `missing_value`: 3 as read_bed
+ * writes it, 255 after the reader's `2 - G` allele flip (snp_reader.py:110) — with no halving and no missing -> 0.
+ * Same exact-integer tensor-core contraction as nadm_encoder_fwd / nadm_encoder_bwd (fixed-point digits of the fp32
+ * factor); at most 8 columns per call, wider factors go in column chunks.
+ *   nadm_geno_matmul  : Y  [N x K] = A Omega     Omega: M x K row-major
+ *   nadm_geno_matmul_t: Bt [M x K] = A^T Q       Q: N x K row-major  (the reference's B = Q^T A is Bt^T) */
+int nadm_geno_matmul(const uint8_t* packed, int64_t pitch, int64_t N, int64_t M, const float* Omega, int32_t K,
+                     int32_t missing_value, float* Y, void* ws, size_t ws_bytes, void* stream);
+int nadm_geno_matmul_t(const uint8_t* packed, int64_t pitch, int64_t N, int64_t M, const float* Q, int32_t K,
+                       int32_t missing_value, float* Bt, void* ws, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -69,10 +69,10 @@ inline AdamCoef make_adam(const nadm_adam_t* a) {
 
 // tensor-core (tcgen05) encoder kernels, nadm_tc_enc.cu
 int launch_enc_fwd_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_idx, int64_t row0, int B, int64_t M,
-                      const float* V, int C, float* Z, void* ws, size_t ws_bytes, cudaStream_t st);
+                      const float* V, int C, float* Z, void* ws, size_t ws_bytes, cudaStream_t st, int raw_mv = -1);
 int launch_enc_bwd_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_idx, int64_t row0, int B, int64_t M,
                       const float* dZ, int C, float* V, float* Vm, float* Vv, const nadm_adam_t* adam, float* dV_out,
-                      cudaStream_t st);
+                      cudaStream_t st, int raw_mv = -1, int accumulate = 0);
 size_t enc_tc_workspace_bytes(int B);
 size_t mlp_bwd_workspace_bytes(int B, int C, int H, int sumK);   // nadm_mlp.cu
 bool enc_bwd_tc_supported(int B);

@@ -745,6 +745,44 @@ extern "C" int nadm_encoder_bwd(const uint8_t* packed, int64_t pitch, const int6
     return launch_enc_bwd<16>(packed, pitch, row_idx, row0, B, M, dZ, C, V, Vm, Vv, adam, dV_out, (cudaStream_t)stream);
 }
 
+// ---- randomized-SVD products on the packed matrix (scope row f2) -------------------------------------------------------
+extern "C" int nadm_geno_matmul(const uint8_t* packed, int64_t pitch, int64_t N, int64_t M, const float* Omega, int32_t K,
+                                int32_t missing_value, float* Y, void* ws, size_t ws_bytes, void* stream) {
+    if (int rc = check_packed(packed, pitch, M)) return rc;
+    NADM_REQUIRE(N > 0 && M > 0, "empty matrix");
+    NADM_REQUIRE(K >= 1 && K <= 8, "K=%d: at most 8 columns per call (process wider factors in column chunks)", K);
+    NADM_REQUIRE(missing_value >= 0 && missing_value <= 255, "missing_value must be a uint8 value");
+    NADM_REQUIRE(Omega && Y && ws, "NULL pointer");
+    NADM_REQUIRE((reinterpret_cast<uintptr_t>(Omega) & 15) == 0, "Omega must be 16-byte aligned");
+    for (int64_t r0 = 0; r0 < N; r0 += 1024) {        // 1024 rows per launch (two accumulator sets in tensor memory)
+        const int nb = (int)std::min<int64_t>(1024, N - r0);
+        if (int rc = launch_enc_fwd_tc(packed, pitch, nullptr, r0, nb, M, Omega, K, Y + r0 * K, ws, ws_bytes,
+                                       (cudaStream_t)stream, missing_value))
+            return rc;
+    }
+    return NADM_OK;
+}
+
+extern "C" int nadm_geno_matmul_t(const uint8_t* packed, int64_t pitch, int64_t N, int64_t M, const float* Q, int32_t K,
+                                  int32_t missing_value, float* Bt, void* ws, size_t ws_bytes, void* stream) {
+    (void)ws; (void)ws_bytes;
+    if (int rc = check_packed(packed, pitch, M)) return rc;
+    NADM_REQUIRE(N > 0 && M > 0, "empty matrix");
+    NADM_REQUIRE(K >= 1 && K <= 8, "K=%d: at most 8 columns per call (process wider factors in column chunks)", K);
+    NADM_REQUIRE(missing_value >= 0 && missing_value <= 255, "missing_value must be a uint8 value");
+    NADM_REQUIRE(Q && Bt, "NULL pointer");
+    NADM_REQUIRE((reinterpret_cast<uintptr_t>(Bt) & 15) == 0, "Bt must be 16-byte aligned");
+    int batch = 1024;                                 // largest multiple of 128 rows the backward kernel's smem takes
+    while (batch > 128 && !enc_bwd_tc_supported(batch)) batch -= 128;
+    for (int64_t r0 = 0; r0 < N; r0 += batch) {       // row batches accumulate into Bt in a fixed order (deterministic)
+        const int nb = (int)std::min<int64_t>(batch, N - r0);
+        if (int rc = launch_enc_bwd_tc(packed, pitch, nullptr, r0, nb, M, Q + r0 * K, K, Bt, nullptr, nullptr, nullptr, Bt,
+                                       (cudaStream_t)stream, missing_value, r0 > 0 ? 1 : 0))
+            return rc;
+    }
+    return NADM_OK;
+}
+
 extern "C" int nadm_loglikelihood(const uint8_t* packed, int64_t pitch, int64_t N, int64_t M, const float* Q,
                                   const float* P, int32_t k, double eps, double* out, void* ws, size_t ws_bytes,
                                   void* stream) {

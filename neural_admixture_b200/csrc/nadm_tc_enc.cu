@@ -45,14 +45,28 @@ __device__ __forceinline__ uint4 ldg_nc(const uint8_t* p) {
     return r;
 }
 
-// 16 packed SNPs -> 16 bytes (codes 0,1,2; missing cleared), byte position p <-> SNP sigma16(p)
-__device__ __forceinline__ void widen_store(uint8_t* dst, uint32_t w) {
-    const uint32_t c = clear_missing(w);
+// 16 packed SNPs -> 16 bytes, byte position p <-> SNP sigma16(p).  RAW = false: codes 0,1,2 with missing (3) cleared
+// (the training path: x = code / 2, missing -> 0).  RAW = true: the reader's uint8 VALUES 0,1,2 and `missing_value` for
+// code 3 (what the reference's randomized-SVD products multiply by, rsvd.pyx:16-50); mvx = 3 ^ missing_value.
+template <bool RAW>
+__device__ __forceinline__ void widen_store(uint8_t* dst, uint32_t w, uint32_t mvx) {
     uint4 o;
-    o.x = c & 0x03030303u;
-    o.y = (c >> 2) & 0x03030303u;
-    o.z = (c >> 4) & 0x03030303u;
-    o.w = (c >> 6) & 0x03030303u;
+    if (!RAW) {
+        const uint32_t c = clear_missing(w);
+        o.x = c & 0x03030303u;
+        o.y = (c >> 2) & 0x03030303u;
+        o.z = (c >> 4) & 0x03030303u;
+        o.w = (c >> 6) & 0x03030303u;
+    } else {
+        uint32_t b[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t v = (w >> (2 * k)) & 0x03030303u;
+            const uint32_t m3 = v & (v >> 1) & 0x01010101u;          // bytes equal to 3
+            b[k] = v ^ (m3 * mvx);
+        }
+        o = make_uint4(b[0], b[1], b[2], b[3]);
+    }
     *reinterpret_cast<uint4*>(dst) = o;
 }
 
@@ -144,16 +158,17 @@ __device__ __forceinline__ void feed_load(const Feed& f, int slot, int wl, int l
 }
 // widen the four pieces into `tile`; 8-row groups past the batch were zero-filled by the copy and widen to zeros that
 // no MMA K step reads
-__device__ __forceinline__ void feed_store(uint8_t* tile, int wl, int lane, const uint4 (&w)[4]) {
+template <bool RAW>
+__device__ __forceinline__ void feed_store(uint8_t* tile, int wl, int lane, const uint4 (&w)[4], uint32_t mvx) {
     const int r = lane & 7, q = lane >> 3;
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
         const int g8 = wl * 4 + it;                              // 8-row group inside the block
         uint8_t* dst = tile + r * 16 + g8 * 2048 + (q * 4) * 128;
-        widen_store(dst, w[it].x);
-        widen_store(dst + 128, w[it].y);
-        widen_store(dst + 256, w[it].z);
-        widen_store(dst + 384, w[it].w);
+        widen_store<RAW>(dst, w[it].x, mvx);
+        widen_store<RAW>(dst + 128, w[it].y, mvx);
+        widen_store<RAW>(dst + 256, w[it].z, mvx);
+        widen_store<RAW>(dst + 384, w[it].w, mvx);
     }
 }
 
@@ -183,11 +198,11 @@ struct EncSmem {
 // cannot tell the phases apart by parity.)  With 1 issuer or more than 8 row blocks: one accumulator set.
 constexpr int kFwdDigWarps = 2, kFwdIssueWarp = kProdWarps + kFwdDigWarps, kFwdThreads = (kFwdIssueWarp + 2) * 32;
 
-template <int NISS>   // MMA issuer warps in use: 2, or 1 (the second issuer warp then idles)
+template <int NISS, bool RAW>   // NISS: MMA issuer warps in use (2, or 1: the second then idles); RAW: see widen_store
 __global__ void __launch_bounds__(kFwdThreads, 1)
 enc_fwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* __restrict__ row_idx, int64_t row0,
                   int B, int64_t M, const float* __restrict__ V, int C, float* __restrict__ cta_vmax,
-                  long long* __restrict__ part, int T) {
+                  long long* __restrict__ part, int T, uint32_t mvx) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* tilesA = smem;                                         // kAStages x 32 KB
     uint8_t* tilesV = tilesA + kAStages * kATile;                   // 2 x 8 KB
@@ -251,7 +266,7 @@ enc_fwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
             if (tid == 0) TLE(5, i);
             mbar_wait(&S->emptyA[g], phase);
             if (tid == 0) TLE(1, i);
-            feed_store(tilesA + g * kATile, wl, lane, w);
+            feed_store<RAW>(tilesA + g * kATile, wl, lane, w, mvx);
             if (tid == 0) TLE(3, i);
             fence_async_smem();
             __syncwarp();
@@ -367,7 +382,7 @@ enc_fwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
 // order (deterministic).  Block = the 8 components of one row x 32 part segments.
 __global__ void __launch_bounds__(256)
 enc_fwd_reduce_kernel(const long long* __restrict__ part, int nparts, int B, int C,
-                      const float* __restrict__ cta_vmax, float* __restrict__ Z) {
+                      const float* __restrict__ cta_vmax, float* __restrict__ Z, double out_scale) {
     __shared__ double red[32][8];
     __shared__ double back[kMaxParts];
     for (int p = threadIdx.x; p < nparts; p += blockDim.x) back[p] = fix_scale(cta_vmax[p]).back;
@@ -383,7 +398,7 @@ enc_fwd_reduce_kernel(const long long* __restrict__ part, int nparts, int B, int
         double t = 0.0;
 #pragma unroll
         for (int s2 = 0; s2 < 32; ++s2) t += red[s2][c];
-        Z[(int64_t)b * C + c] = (float)(t * 0.5);
+        Z[(int64_t)b * C + c] = (float)(t * out_scale);
     }
 }
 
@@ -398,11 +413,12 @@ struct EncBwdSmem {
 
 // warps: 16 producers, 2 MMA issuers (issuer h owns the 128-SNP half h of every tile: separate accumulators), 4 epilogue
 constexpr int kBwdThreads = kProdThreads + 64 + 128;
-template <int NISS>   // MMA issuer warps in use: 2, or 1 (issuer 0 then issues both halves, issuer 1 idles)
+template <int NISS, bool RAW>   // NISS: MMA issuer warps in use (2, or 1: issuer 0 then issues both halves)
 __global__ void __launch_bounds__(kBwdThreads, 1)
 enc_bwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* __restrict__ row_idx, int64_t row0,
                   int B, int64_t M, const float* __restrict__ dZ, int C, float* __restrict__ V, float* __restrict__ Vm,
-                  float* __restrict__ Vv, AdamCoef adam_in, float* __restrict__ dV_out, int T) {
+                  float* __restrict__ Vv, AdamCoef adam_in, float* __restrict__ dV_out, int T, uint32_t mvx,
+                  double out_scale, int accumulate) {
     const AdamCoef adam = adam_resolve(adam_in);
     extern __shared__ __align__(1024) uint8_t smem[];
     const int nblk = (B + 127) / 128;
@@ -463,7 +479,7 @@ enc_bwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
             feed_load(f, slot, wl, lane, w);
             feed_issue(f, wl, lane);                                 // refill the staging slot just read
             mbar_wait(&S->emptyA[g], phase);
-            feed_store(tilesA + g * kATile, wl, lane, w);
+            feed_store<RAW>(tilesA + g * kATile, wl, lane, w, mvx);
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&S->fullA[g]);
@@ -529,10 +545,16 @@ enc_bwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
                 if (m >= M) continue;
                 float g[8];
 #pragma unroll
-                for (int c = 0; c < 8; ++c) g[c] = (float)((double)combine4(v[h], c) * fs.back * 0.5);
+                for (int c = 0; c < 8; ++c) g[c] = (float)((double)combine4(v[h], c) * fs.back * out_scale);
                 if (C == 8) {
                     float4* gv = reinterpret_cast<float4*>(g);
                     if (dV_out != nullptr) {
+                        if (accumulate) {                              // += over successive row batches (nadm_geno_matmul_t)
+                            const float4 a0 = reinterpret_cast<float4*>(dV_out + m * 8)[0];
+                            const float4 a1 = reinterpret_cast<float4*>(dV_out + m * 8)[1];
+                            gv[0] = make_float4(gv[0].x + a0.x, gv[0].y + a0.y, gv[0].z + a0.z, gv[0].w + a0.w);
+                            gv[1] = make_float4(gv[1].x + a1.x, gv[1].y + a1.y, gv[1].z + a1.z, gv[1].w + a1.w);
+                        }
                         reinterpret_cast<float4*>(dV_out + m * 8)[0] = gv[0];
                         reinterpret_cast<float4*>(dV_out + m * 8)[1] = gv[1];
                     }
@@ -554,7 +576,7 @@ enc_bwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
                 } else {
                     for (int c = 0; c < C; ++c) {
                         const int64_t vi = m * C + c;
-                        if (dV_out != nullptr) dV_out[vi] = g[c];
+                        if (dV_out != nullptr) dV_out[vi] = accumulate ? dV_out[vi] + g[c] : g[c];
                         if (adam.enabled) {
                             float mm = Vm[vi], vv = Vv[vi];
                             V[vi] = adam_apply(V[vi], g[c], mm, vv, adam);
@@ -592,38 +614,45 @@ bool enc_bwd_tc_supported(int B) {
 constexpr size_t kEncWsHeader = 4096;   // per-CTA scales in front of the partial sums
 size_t enc_tc_workspace_bytes(int B) { return (size_t)sm_count() * (size_t)B * 8 * sizeof(long long) + kEncWsHeader; }
 
+// raw_mv < 0: training semantics (x = code / 2, missing -> 0).  raw_mv >= 0: raw uint8 values, code 3 -> raw_mv.
 int launch_enc_fwd_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_idx, int64_t row0, int B, int64_t M,
-                      const float* V, int C, float* Z, void* ws, size_t ws_bytes, cudaStream_t st) {
+                      const float* V, int C, float* Z, void* ws, size_t ws_bytes, cudaStream_t st, int raw_mv) {
     const int T = (int)((M + kSub - 1) / kSub);
     const int ncta = std::min(T, sm_count());
     const size_t need = (size_t)ncta * B * 8 * sizeof(long long) + kEncWsHeader;
     NADM_REQUIRE(need <= ws_bytes, "workspace too small for encoder_fwd (%zu > %zu)", need, ws_bytes);
     float* vmax = reinterpret_cast<float*>(ws);                     // per-CTA |max| of its slice of V (ncta floats)
     long long* part = reinterpret_cast<long long*>(reinterpret_cast<uint8_t*>(ws) + kEncWsHeader);
-    cudaError_t e;
     const size_t smem = (size_t)kAStages * kATile + 2 * kDigTile + (size_t)4 * kStDepth * kStTile + (size_t)((B + 3) & ~3) * 4 +
                         sizeof(EncSmem) + 64;
     static bool attr = false;
     if (!attr) {
-        e = cudaFuncSetAttribute(enc_fwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+        cudaError_t e = cudaFuncSetAttribute(enc_fwd_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(enc_fwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+            e = cudaFuncSetAttribute(enc_fwd_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(enc_fwd_tc_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(enc_fwd_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(enc_fwd_tc)");
         attr = true;
     }
-    if (enc_issuers() == 2 && B <= 1024)          // two accumulator sets: 2 x 32 columns per row block, 512 in all
-        enc_fwd_tc_kernel<2><<<ncta, kFwdThreads, smem, st>>>(packed, pitch, row_idx, row0, B, M, V, C, vmax, part, T);
-    else
-        enc_fwd_tc_kernel<1><<<ncta, kFwdThreads, smem, st>>>(packed, pitch, row_idx, row0, B, M, V, C, vmax, part, T);
+    const bool two = enc_issuers() == 2 && B <= 1024;     // two accumulator sets: 2 x 32 columns per row block, 512 in all
+    const uint32_t mvx = raw_mv >= 0 ? (3u ^ (uint32_t)(raw_mv & 0xFF)) : 0u;
+#define NADM_FWD_GO(N_, R_) \
+    enc_fwd_tc_kernel<N_, R_><<<ncta, kFwdThreads, smem, st>>>(packed, pitch, row_idx, row0, B, M, V, C, vmax, part, T, mvx)
+    if (raw_mv >= 0) { if (two) NADM_FWD_GO(2, true); else NADM_FWD_GO(1, true); }
+    else { if (two) NADM_FWD_GO(2, false); else NADM_FWD_GO(1, false); }
+#undef NADM_FWD_GO
     NADM_CHECK_LAUNCH("enc_fwd_tc_kernel");
-    enc_fwd_reduce_kernel<<<B, 256, 0, st>>>(part, ncta, B, C, vmax, Z);
+    enc_fwd_reduce_kernel<<<B, 256, 0, st>>>(part, ncta, B, C, vmax, Z, raw_mv >= 0 ? 1.0 : 0.5);
     NADM_CHECK_LAUNCH("enc_fwd_reduce_kernel");
     return NADM_OK;
 }
 
 int launch_enc_bwd_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_idx, int64_t row0, int B, int64_t M,
                       const float* dZ, int C, float* V, float* Vm, float* Vv, const nadm_adam_t* adam, float* dV_out,
-                      cudaStream_t st) {
+                      cudaStream_t st, int raw_mv, int accumulate) {
     const int T = (int)((M + kSub - 1) / kSub);
     const int ncta = std::min(T, sm_count());
     const int nblk = (B + 127) / 128;
@@ -632,18 +661,25 @@ int launch_enc_bwd_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_i
     NADM_REQUIRE(smem <= (size_t)kMaxDynSmem, "batch B=%d too large for encoder_bwd", B);
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(enc_bwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+        cudaError_t e = cudaFuncSetAttribute(enc_bwd_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(enc_bwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+            e = cudaFuncSetAttribute(enc_bwd_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(enc_bwd_tc_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(enc_bwd_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(enc_bwd_tc)");
         attr = true;
     }
-    if (enc_issuers() == 2)
-        enc_bwd_tc_kernel<2><<<ncta, kBwdThreads, smem, st>>>(packed, pitch, row_idx, row0, B, M, dZ, C, V, Vm, Vv,
-                                                             make_adam(adam), dV_out, T);
-    else
-        enc_bwd_tc_kernel<1><<<ncta, kBwdThreads, smem, st>>>(packed, pitch, row_idx, row0, B, M, dZ, C, V, Vm, Vv,
-                                                             make_adam(adam), dV_out, T);
+    const bool two = enc_issuers() == 2;
+    const uint32_t mvx = raw_mv >= 0 ? (3u ^ (uint32_t)(raw_mv & 0xFF)) : 0u;
+    const double scale = raw_mv >= 0 ? 1.0 : 0.5;
+#define NADM_BWD_GO(N_, R_)                                                                                            \
+    enc_bwd_tc_kernel<N_, R_><<<ncta, kBwdThreads, smem, st>>>(packed, pitch, row_idx, row0, B, M, dZ, C, V, Vm, Vv,  \
+                                                              make_adam(adam), dV_out, T, mvx, scale, accumulate)
+    if (raw_mv >= 0) { if (two) NADM_BWD_GO(2, true); else NADM_BWD_GO(1, true); }
+    else { if (two) NADM_BWD_GO(2, false); else NADM_BWD_GO(1, false); }
+#undef NADM_BWD_GO
     NADM_CHECK_LAUNCH("enc_bwd_tc_kernel");
     return NADM_OK;
 }

@@ -220,3 +220,37 @@ def step_begin(order: torch.Tensor, counters: torch.Tensor, stride: int, B: int,
 
 def step_end(counters: torch.Tensor, loss: Optional[torch.Tensor], losses_out: Optional[torch.Tensor]) -> None:
     check(_lib.load().nadm_step_end(_ptr(counters), _ptr(loss), _ptr(losses_out), _stream()))
+
+
+def geno_matmul(pg: PackedGenotypes, Omega: torch.Tensor, ws: torch.Tensor, missing_value: int = 3) -> torch.Tensor:
+    """Y = A @ Omega (N x K) with A the uint8 genotype VALUES (code 3 -> ``missing_value``); Omega: M x K float32 on the
+    device, any K (processed in column chunks of 8).  Role of rsvd.multiply_A_omega (rsvd.pyx:56-71)."""
+    _need_cuda(Omega, ws)
+    assert Omega.dtype == torch.float32 and Omega.dim() == 2 and Omega.shape[0] == pg.M
+    K = Omega.shape[1]
+    Y = torch.empty((pg.N, K), dtype=torch.float32, device=Omega.device)
+    for c0 in range(0, K, 8):
+        c1 = min(K, c0 + 8)
+        om = Omega[:, c0:c1].contiguous()
+        y = torch.empty((pg.N, c1 - c0), dtype=torch.float32, device=Omega.device)
+        check(_lib.load().nadm_geno_matmul(_ptr(pg.storage), pg.pitch, pg.N, pg.M, _ptr(om), c1 - c0, missing_value,
+                                           _ptr(y), _ptr(ws), ws.numel() * ws.element_size(), _stream()))
+        Y[:, c0:c1] = y
+    return Y
+
+
+def geno_matmul_t(pg: PackedGenotypes, QT: torch.Tensor, ws: torch.Tensor, missing_value: int = 3) -> torch.Tensor:
+    """B = QT @ A (K x M) with A the uint8 genotype VALUES; QT: K x N float32 on the device, any K.  Role of
+    rsvd.multiply_QT_A (rsvd.pyx:74-93)."""
+    _need_cuda(QT, ws)
+    assert QT.dtype == torch.float32 and QT.dim() == 2 and QT.shape[1] == pg.N
+    K = QT.shape[0]
+    Bm = torch.empty((K, pg.M), dtype=torch.float32, device=QT.device)
+    for c0 in range(0, K, 8):
+        c1 = min(K, c0 + 8)
+        q = QT[c0:c1].T.contiguous()                                  # N x k
+        bt = torch.empty((pg.M, c1 - c0), dtype=torch.float32, device=QT.device)
+        check(_lib.load().nadm_geno_matmul_t(_ptr(pg.storage), pg.pitch, pg.N, pg.M, _ptr(q), c1 - c0, missing_value,
+                                             _ptr(bt), _ptr(ws), ws.numel() * ws.element_size(), _stream()))
+        Bm[c0:c1] = bt.T
+    return Bm

@@ -89,6 +89,42 @@ def orient_alleles(G: np.ndarray) -> np.ndarray:
     return G if G.mean() < 1 else (2 - G).astype(np.uint8)
 
 
+# --------------------------------------------------------------------------------------------------------------
+# randomized SVD  (src/svd.py:39-83; products src/utils_c/rsvd.pyx:16-50)
+# --------------------------------------------------------------------------------------------------------------
+
+
+def multiply_A_omega(A: np.ndarray, Omega: np.ndarray) -> np.ndarray:
+    """Y[i, j] = sum_l float(A[i, l]) * Omega[l, j] over the raw uint8 values (rsvd.pyx:16-32), in float64."""
+    return A.astype(np.float64) @ Omega.astype(np.float64)
+
+
+def multiply_QT_A(QT: np.ndarray, A: np.ndarray) -> np.ndarray:
+    """B[i, j] = sum_l QT[i, l] * float(A[l, j]) (rsvd.pyx:34-50), in float64."""
+    return QT.astype(np.float64) @ A.astype(np.float64)
+
+
+def svd_flip(V: np.ndarray, U: np.ndarray) -> np.ndarray:
+    """src/svd.py:16-37."""
+    idx = np.argmax(np.abs(U), axis=0)
+    return V * np.sign(U[idx, np.arange(U.shape[1])])[:, None]
+
+
+def rsvd(A: np.ndarray, k: int = 8, seed: int = 42, oversampling: int = 10, power_iterations: int = 2) -> np.ndarray:
+    """src/svd.py:39-83 with float64 products (the reference's are float32 running sums)."""
+    rng = np.random.default_rng(seed)
+    k_prime = max(k + oversampling, 20)
+    Omega = rng.standard_normal(size=(A.shape[1], k_prime), dtype=np.float32)
+    Y = multiply_A_omega(A, Omega)
+    for _ in range(power_iterations):
+        Qy, _ = np.linalg.qr(Y, mode="reduced")
+        Y = multiply_A_omega(A, multiply_QT_A(Qy.T, A).T)
+    Q, _ = np.linalg.qr(Y, mode="reduced")
+    B = multiply_QT_A(Q.T, A)
+    Ut, St, Vt = np.linalg.svd(B, full_matrices=False)
+    return svd_flip(Vt, Ut)[:k]
+
+
 @dataclass
 class OracleState:
     """Parameters of Q_P in the reference's own layouts (model/neural_admixture.py:126-144).

@@ -22,6 +22,8 @@ Fixtures (all small npz):
   train_sup_k3.npz   supervised mode
   bed_demo_slices.npz  1500 SNP rows of the demo .bed (+ injected missing fields), as stored and with the homozygous
                      fields exchanged, each with the N x M uint8 matrix SNPReader.read_data returns (flip in case b)
+  rsvd_demo_slices.npz  the reference's rsvd.multiply_A_omega / multiply_QT_A / RSVD on the two matrices of
+                     bed_demo_slices.npz (missing = 3 and, flipped, 255)
   demo_k7.npz        the shipped demo BED through read_bed -> RSVD -> GMM init -> 5 epochs (K=7, seed 42), plus the
                      shipped demo_run.7.{Q,P}.expected for reference
 """
@@ -282,6 +284,27 @@ def _lut_read(bed, N):
     return lut[f].T
 
 
+def make_rsvd(ref_root: str, out: Path):
+    """The reference's randomized-SVD building blocks on genotype matrices that contain missing values as the reference's
+    reader leaves them (3, and 255 after its `2 - G` flip): the two Cython products (rsvd.pyx) and the full RSVD
+    (svd.py:39-83, k = 8, seed 42)."""
+    from neural_admixture.src.utils_c import rsvd as ref_rsvd
+    from neural_admixture.src.svd import RSVD
+    g = np.load(HERE / "bed_demo_slices.npz")
+    rng = np.random.default_rng(11)
+    res = {}
+    for tag in "ab":
+        A = np.ascontiguousarray(g[f"G_{tag}"])                  # 105 x 1500 uint8; case b holds 255 for missing
+        N, M = A.shape
+        Om = rng.standard_normal((M, 20)).astype(np.float32)
+        QT = rng.standard_normal((20, N)).astype(np.float32)
+        res[f"Omega_{tag}"], res[f"QT_{tag}"] = Om, QT
+        res[f"Y_{tag}"] = ref_rsvd.multiply_A_omega(A, Om)
+        res[f"B_{tag}"] = ref_rsvd.multiply_QT_A(QT, A)
+        res[f"Vt_{tag}"] = RSVD(A, N, M, 8, 42).astype(np.float32)
+    np.savez_compressed(out, **res)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("ref_root", help="built scratch copy of /root/reference (see module docstring)")
@@ -297,6 +320,7 @@ def main():
     make_trainings(ref_model)
     make_demo(ref_model, args.ref_root)
     make_bed(args.ref_root, HERE / "bed_demo_slices.npz")
+    make_rsvd(args.ref_root, HERE / "rsvd_demo_slices.npz")
     for f in sorted(HERE.glob("*.npz")):
         print(f.name, f.stat().st_size)
 

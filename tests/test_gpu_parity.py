@@ -470,6 +470,40 @@ def test_bed_to_packed_random(ops, dev, N, M):
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# randomized SVD on the packed matrix (next row f2): products and full RSVD vs the reference's own outputs
+# ---------------------------------------------------------------------------------------------------------------
+def test_rsvd_products_and_rsvd_golden(ops, dev):
+    from neural_admixture_b200.src import svd
+    g, b = load_golden("rsvd_demo_slices.npz"), load_golden("bed_demo_slices.npz")
+    for tag, mv in (("a", 3), ("b", 255)):
+        A = b[f"G_{tag}"]                                          # reference matrix: missing = 3 / 255 (flipped)
+        pg = packed_from(ops, A, dev)                              # packing keeps the two low bits: 255 -> 3
+        ws = ws_for(ops, 1024, A.shape[1], 8, 8, 8, dev)
+        Y = ops.geno_matmul(pg, t(g[f"Omega_{tag}"], dev), ws, mv).cpu().numpy()
+        Bm = ops.geno_matmul_t(pg, t(g[f"QT_{tag}"], dev), ws, mv).cpu().numpy()
+        assert relF(Y, orc.multiply_A_omega(A, g[f"Omega_{tag}"])) < 2e-7          # vs fp64 oracle
+        assert relF(Bm, orc.multiply_QT_A(g[f"QT_{tag}"], A)) < 2e-7
+        assert relF(Y, g[f"Y_{tag}"]) < 1e-6 and relF(Bm, g[f"B_{tag}"]) < 1e-6     # vs the reference's fp32 loops
+        Vt = svd.RSVD(pg, A.shape[0], A.shape[1], 8, 42, missing_value=mv)
+        assert Vt.shape == (8, A.shape[1])
+        assert relF(Vt, g[f"Vt_{tag}"]) < 1e-4
+        assert relF(Vt, orc.rsvd(A, 8, 42)) < 1e-4
+
+
+def test_geno_matmul_row_batches(ops, dev):
+    """More rows than one launch takes (1024): forward batches are independent, transposed batches accumulate."""
+    rng = np.random.default_rng(8)
+    N, M, K = 2500, 1111, 11
+    A = rand_genotypes(rng, N, M)
+    pg = packed_from(ops, A, dev)
+    ws = ws_for(ops, 1024, M, 8, 8, 8, dev)
+    Om = rng.standard_normal((M, K)).astype(np.float32)
+    QT = rng.standard_normal((K, N)).astype(np.float32)
+    assert relF(ops.geno_matmul(pg, t(Om, dev), ws, 3).cpu().numpy(), orc.multiply_A_omega(A, Om)) < 2e-7
+    assert relF(ops.geno_matmul_t(pg, t(QT, dev), ws, 3).cpu().numpy(), orc.multiply_QT_A(QT, A)) < 3e-7
+
+
+# ---------------------------------------------------------------------------------------------------------------
 # CUDA-graph replayed steps == eager steps (same kernels; Adam coefficients computed on the device)
 # ---------------------------------------------------------------------------------------------------------------
 def test_graph_replayed_steps_match_eager(dev, monkeypatch):
