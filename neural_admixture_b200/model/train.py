@@ -119,3 +119,66 @@ def train(epochs: int, batch_size: int, learning_rate: float, K: int, seed: int,
                                      torch.as_tensor(Ps[i], device=device).contiguous(), ws)
             log.info(f"    Log-likelihood: {logl:2f}." if K is not None else f"    Log-likelihood for K={k}: {logl:2f}.")
     return Ps, Qs, raw
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The same pipeline with the genotypes ONLY in the device-resident packed layout (single GPU): nothing below touches an
+# N x M one-byte-per-genotype array (50 GB at 100k x 500k), so real data of the benchmark's size can be fitted.
+# ------------------------------------------------------------------------------------------------------------------
+def gmm_initial_P_packed(pg: ops.PackedGenotypes, V: np.ndarray, ks, seed: int, missing_value: int = 3) -> np.ndarray:
+    """``gmm_initial_P`` with the PCA projection on the device: ``(data / 2) @ V.T`` over the raw uint8 values
+    (reference :49-53: no missing -> 0 there, a missing entry counts 3 / 2, or 255 / 2 after the reader's flip) is
+    ``0.5 * nadm_geno_matmul``; the Gaussian mixture on the N x C projection stays scikit-learn's (:61-67)."""
+    from sklearn.mixture import GaussianMixture
+    dev = pg.storage.device
+    ws = torch.empty(ops.workspace_bytes(1024, pg.M, 8, 8, 8), dtype=torch.uint8, device=dev)
+    Vt = torch.as_tensor(np.ascontiguousarray(V.T), dtype=torch.float32, device=dev)          # M x C
+    X_pca = (0.5 * ops.geno_matmul(pg, Vt, ws, missing_value)).cpu().numpy().astype("float64")
+    log.info("")
+    log.info("    Running Gaussian Mixture in PCA subspace...")
+    log.info("")
+    Ps = []
+    for k in ks:
+        gmm = GaussianMixture(n_components=k, n_init=5, init_params="k-means++", tol=1e-4, covariance_type="full",
+                              max_iter=100, random_state=seed).fit(X_pca)
+        Ps.append(np.clip(gmm.means_ @ V, 5e-6, 1 - 5e-6))
+    return np.concatenate(Ps, axis=0)
+
+
+def train_packed(epochs: int, batch_size: int, learning_rate: float, K: int, seed: int, pg: ops.PackedGenotypes,
+                 hidden_size: int, V: np.ndarray, pops=None, min_k: int = None, max_k: int = None,
+                 missing_value: int = 3):
+    """``train`` (reference model/train.py:19-149) for genotypes that exist only as a ``PackedGenotypes`` on the device
+    (e.g. from ``src.snp_reader.read_bed_packed``; V from ``src.svd.RSVD`` on the same object).  Returns
+    ``(Ps, Qs, model)``.  ``missing_value``: see ``gmm_initial_P_packed``."""
+    device, N, M = pg.storage.device, pg.N, pg.M
+    ks = [K] if K is not None else list(range(min_k, max_k + 1))
+    y = None
+    if pops is None:
+        P = gmm_initial_P_packed(pg, V, ks, seed, missing_value)
+    else:
+        log.info("")
+        log.info("    Running Supervised Mode...")
+        log.info("")
+        anc = {a: i for i, a in enumerate(sorted(np.unique([a for a in pops])))}
+        assert len(anc) == K, (f"Number of ancestries in training ground truth ({len(anc)}) is not equal to the "
+                               f"value of K ({K})")
+        y_num = np.array([anc[a] for a in pops], dtype=np.int64)
+        # per-label mean of the raw uint8 values, not halved (reference :78-82): one-hot labels^T @ A / counts
+        onehot = torch.zeros((K, N), dtype=torch.float32, device=device)
+        onehot[torch.as_tensor(y_num, device=device), torch.arange(N, device=device)] = 1.0
+        ws = torch.empty(ops.workspace_bytes(1024, M, 8, 8, 8), dtype=torch.uint8, device=device)
+        sums = ops.geno_matmul_t(pg, onehot, ws, missing_value)
+        P = (sums / onehot.sum(dim=1, keepdim=True)).cpu().numpy()
+        y = torch.as_tensor(y_num, dtype=torch.int64, device=device)
+    P_init = torch.as_tensor(P, dtype=torch.float32, device=device).contiguous()
+    V_dev = torch.as_tensor(np.ascontiguousarray(V.T), dtype=torch.float32, device=device)
+    model = NeuralAdmixture(K, epochs, batch_size, learning_rate, device, seed, 0, True, "nadm_b200", min_k, max_k)
+    Qs, Ps, raw = model.launch_training(P_init, pg, hidden_size, V_dev.shape[1], V_dev, M, N, y)
+    ws = torch.empty(ops.workspace_bytes(min(N, 1024), M, V_dev.shape[1], hidden_size, sum(ks)), dtype=torch.uint8,
+                     device=device)
+    for i, k in enumerate(ks):
+        logl = ops.loglikelihood(pg, torch.as_tensor(Qs[i], device=device).contiguous(),
+                                 torch.as_tensor(Ps[i], device=device).contiguous(), ws)
+        log.info(f"    Log-likelihood: {logl:2f}." if K is not None else f"    Log-likelihood for K={k}: {logl:2f}.")
+    return Ps, Qs, raw

@@ -503,6 +503,31 @@ def test_geno_matmul_row_batches(ops, dev):
     assert relF(ops.geno_matmul_t(pg, t(QT, dev), ws, 3).cpu().numpy(), orc.multiply_QT_A(QT, A)) < 3e-7
 
 
+def test_train_packed_pipeline_matches_host_pipeline(dev, tmp_path):
+    """.bed -> packed -> device RSVD -> device PCA projection + GMM init -> training, never materialising N x M bytes,
+    gives the same initial P and the same fit as the pipeline fed with the reference reader's uint8 matrix."""
+    from neural_admixture_b200.model import train as tr
+    from neural_admixture_b200.src import snp_reader, svd
+    b = load_golden("bed_demo_slices.npz")
+    N, M = int(b["N"]), int(b["M"])
+    base = tmp_path / "case_a"
+    with open(str(base) + ".bed", "wb") as f:
+        f.write(bytes([0x6C, 0x1B, 0x01]))
+        f.write(b["bed_a"].tobytes())
+    with open(str(base) + ".fam", "w") as f:
+        f.write("".join(f"f{i} i{i} 0 0 0 -9\n" for i in range(N)))
+    pg = snp_reader.read_bed_packed(str(base) + ".bed", dev)
+    V = svd.RSVD(pg, N, M, 8, 42)                                   # C x M
+    P_dev = tr.gmm_initial_P_packed(pg, V, [4], 42)
+    P_host = tr.gmm_initial_P(b["G_a"], V, [4], 8, 42)
+    assert relF(P_dev, P_host) < 1e-5
+    torch.manual_seed(1)
+    Ps1, Qs1, _ = tr.train_packed(3, 64, 2e-3, 4, 42, pg, 64, V)
+    torch.manual_seed(1)
+    Ps2, Qs2, _ = tr.train(3, 64, 2e-3, 4, 42, torch.as_tensor(b["G_a"]), dev, 0, 64, True, V, None, n_components=8)
+    assert relF(Qs1[0], Qs2[0]) < 1e-4 and relF(Ps1[0], Ps2[0]) < 1e-4
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # CUDA-graph replayed steps == eager steps (same kernels; Adam coefficients computed on the device)
 # ---------------------------------------------------------------------------------------------------------------
