@@ -88,15 +88,26 @@ mlp_fwd_kernel(const float* __restrict__ Z, int B, int C, int H, const float* __
         }
     }
     __syncthreads();
+#pragma unroll 4
     for (int j = tid; j < H; j += blockDim.x) {
         float acc[kMlpRows];
         const float bj = b1[j];
 #pragma unroll
         for (int r = 0; r < kMlpRows; ++r) acc[r] = bj;
-        for (int c = 0; c < C; ++c) {
-            const float w = W1[(int64_t)j * C + c];
+        if (C == 8) {                                   // the default width: two 128-bit loads per hidden unit
+            const float4 wa = reinterpret_cast<const float4*>(W1 + (int64_t)j * 8)[0];
+            const float4 wb = reinterpret_cast<const float4*>(W1 + (int64_t)j * 8)[1];
+            const float w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
 #pragma unroll
-            for (int r = 0; r < kMlpRows; ++r) acc[r] = fmaf(Zn[r * NADM_MAX_C + c], w, acc[r]);
+            for (int c = 0; c < 8; ++c)
+#pragma unroll
+                for (int r = 0; r < kMlpRows; ++r) acc[r] = fmaf(Zn[r * NADM_MAX_C + c], w[c], acc[r]);
+        } else {
+            for (int c = 0; c < C; ++c) {
+                const float w = W1[(int64_t)j * C + c];
+#pragma unroll
+                for (int r = 0; r < kMlpRows; ++r) acc[r] = fmaf(Zn[r * NADM_MAX_C + c], w, acc[r]);
+            }
         }
 #pragma unroll
         for (int r = 0; r < kMlpRows; ++r) {
@@ -111,6 +122,7 @@ mlp_fwd_kernel(const float* __restrict__ Z, int B, int C, int H, const float* __
         float acc[kMlpRows];
 #pragma unroll
         for (int r = 0; r < kMlpRows; ++r) acc[r] = 0.f;
+#pragma unroll 8
         for (int j = lane; j < H; j += 32) {
             const float w = W2[(int64_t)kk * H + j];
 #pragma unroll

@@ -121,7 +121,7 @@ __device__ __forceinline__ void store_digits(uint8_t* tile_pos, const float (&v)
 struct Feed {
     const uint8_t* packed;
     int64_t pitch;
-    const int32_t* rowoff;   // row number of every batch row (x pitch = byte offset)
+    const uint32_t* rowoff;  // byte offset / 16 (row number x pitch / 16; pitch % 16 == 0) of every batch row
     int B, nblk, t0, ntile;
     uint8_t* stage;          // this group's ring: kStDepth x kStTile; thread (wl, lane) owns 4 pieces of 16 bytes per slot
     int c_blk, c_tt, c_i;    // next tile of this group to copy (tile index c_i = g + 4 n)
@@ -138,7 +138,7 @@ __device__ __forceinline__ void feed_issue(Feed& f, int wl, int lane) {
         for (int it = 0; it < 4; ++it) {
             const int b = f.c_blk * 128 + (wl * 4 + it) * 8 + r;
             const bool ok = in_pitch && b < f.B;
-            cp_async16(dst + it * 2048, ok ? f.packed + (int64_t)f.rowoff[b] * f.pitch + off : f.packed, ok ? 16 : 0);
+            cp_async16(dst + it * 2048, ok ? f.packed + ((uint64_t)f.rowoff[b] << 4) + off : f.packed, ok ? 16 : 0);
         }
         f.c_i += 4;
         f.c_blk += 4;
@@ -207,14 +207,15 @@ enc_fwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
     uint8_t* tilesA = smem;                                         // kAStages x 32 KB
     uint8_t* tilesV = tilesA + kAStages * kATile;                   // 2 x 8 KB
     uint8_t* stage = tilesV + 2 * kDigTile;                         // kStDepth x 10 KB packed rows
-    int32_t* rowoff = reinterpret_cast<int32_t*>(stage + 4 * kStDepth * kStTile);
+    uint32_t* rowoff = reinterpret_cast<uint32_t*>(stage + 4 * kStDepth * kStTile);
     EncSmem* S = reinterpret_cast<EncSmem*>(rowoff + ((B + 3) & ~3));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nblk = (B + 127) / 128;
     const int t0 = (int)(((int64_t)T * blockIdx.x) / gridDim.x), t1 = (int)(((int64_t)T * (blockIdx.x + 1)) / gridDim.x);
     const int ntile = (t1 - t0) * nblk;
 
-    for (int b = tid; b < B; b += blockDim.x) rowoff[b] = (int32_t)((row_idx != nullptr) ? row_idx[b] : (row0 + b));
+    for (int b = tid; b < B; b += blockDim.x)
+        rowoff[b] = (uint32_t)((((row_idx != nullptr) ? row_idx[b] : (row0 + b)) * pitch) >> 4);
     if (tid == 0) {
         for (int s = 0; s < kAStages; ++s) { mbar_init(&S->fullA[s], 4); mbar_init(&S->emptyA[s], NISS); }
         for (int s = 0; s < 2; ++s) { mbar_init(&S->fullV[s], kFwdDigWarps); mbar_init(&S->emptyV[s], NISS); }
@@ -425,13 +426,14 @@ enc_bwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
     uint8_t* tilesA = smem;                                         // kAStages x 32 KB
     uint8_t* digZ = tilesA + kAStages * kATile;                     // nblk x 4 KB: dZ digits, K position = batch row
     uint8_t* stage = digZ + nblk * 4096;                            // kStDepth x 10 KB packed rows
-    int32_t* rowoff = reinterpret_cast<int32_t*>(stage + 4 * kStDepth * kStTile);
+    uint32_t* rowoff = reinterpret_cast<uint32_t*>(stage + 4 * kStDepth * kStTile);
     EncBwdSmem* S = reinterpret_cast<EncBwdSmem*>(rowoff + ((B + 3) & ~3));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int t0 = (int)(((int64_t)T * blockIdx.x) / gridDim.x), t1 = (int)(((int64_t)T * (blockIdx.x + 1)) / gridDim.x);
     const int ntile = (t1 - t0) * nblk;
 
-    for (int b = tid; b < B; b += blockDim.x) rowoff[b] = (int32_t)((row_idx != nullptr) ? row_idx[b] : (row0 + b));
+    for (int b = tid; b < B; b += blockDim.x)
+        rowoff[b] = (uint32_t)((((row_idx != nullptr) ? row_idx[b] : (row0 + b)) * pitch) >> 4);
     if (tid == 0) {
         for (int s = 0; s < kAStages; ++s) { mbar_init(&S->fullA[s], 4); mbar_init(&S->emptyA[s], NISS); }
         for (int s = 0; s < 2; ++s) { mbar_init(&S->dfull[s], NISS); mbar_init(&S->dempty[s], 4); }

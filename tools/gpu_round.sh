@@ -43,6 +43,10 @@ sharded)
   NADM_NO_GRAPH=1 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 2 --steps 200 --warmup 5 --no-e2e > $OUT/bench2_eager.json 2> $OUT/bench2_eager.err; echo "bench2 eager rc=$?"; python -c "import json;d=json.loads(open('$OUT/bench2_eager.json').read().strip().splitlines()[-1]);print('eager 2gpu ms/step',d['ms_per_step'])";;
 exit2)
   timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29514 bench.py --gpus 2 --steps 100 --warmup 5 --rows 20000 --no-e2e > $OUT/bench2q.json 2> $OUT/bench2q.err; echo "bench2 quick rc=$?"; python -c "import json;d=json.loads(open('$OUT/bench2q.json').read().strip().splitlines()[-1]);print('2gpu ms/step',d['ms_per_step'], d['step_launch'])";;
+smoke)
+  timeout 200 python -c 'import __graft_entry__ as g; g.smoke()' 2>&1 | tail -3;;
+refarm)
+  timeout 400 python bench.py --impl reference --steps 5 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err; echo "ref rc=$?"; tail -c 900 $OUT/bench_ref.json;;
 encprobe)
   for w in fwd bwd; do for m in 20000 100000; do NADM_ENC_ISSUERS=2 timeout 40 python tools/enc_probe.py $w $m 2>&1 | tail -1; echo "probe $w $m rc=$?"; done; done;;
 timeline_enc)
