@@ -186,16 +186,20 @@ extern "C" int nadm_debug_enc_timeline(long long* host_out) {
 #endif
 
 struct EncSmem {
-    uint64_t fullA[kAStages], emptyA[kAStages], fullV[2], emptyV[2], done;
+    uint64_t fullA[kAStages], emptyA[kAStages], fullV[2], emptyV[2], done, fdone;
     uint32_t tmem_base;
+    uint32_t finit[2];   // per issuer: bit blk set = its accumulator of row block blk has been written
     float red[32];       // per-warp |max| of this CTA's slice of V
 };
 
 // Two MMA-issuer warps: a single issuing thread (waits + descriptor arithmetic + 8 MMAs + commits per tile, ~770 cycles
-// measured against 320 cycles of tensor-pipe time) was the kernel's critical path.  Issuer p issues K steps 4p..4p+3 of
-// EVERY tile into its own accumulator set (tensor-memory columns (p nblk + blk) 32); the epilogue adds the two int32
-// sets.  (Giving each issuer every other tile instead is unsafe: an issuer that skips phases of a stage's mbarrier
-// cannot tell the phases apart by parity.)  With 1 issuer or more than 8 row blocks: one accumulator set.
+// measured against 320 cycles of tensor-pipe time) was the kernel's critical path.  Issuer p owns the widened-tile
+// stages 2p and 2p+1 (producer groups 2p, 2p+1), i.e. the tiles i with (i >> 1) & 1 == p, and issues all 8 K steps of
+// its tiles into its OWN accumulator set (tensor-memory columns (p nblk + blk) 32); the epilogue adds the two int32
+// sets.  Each issuer sees every phase of the mbarriers of its own stages.  (Splitting the tiles by row-block parity is
+// unsafe — an issuer that skips phases of a stage's mbarrier cannot tell them apart by parity: a timing-dependent hang;
+// splitting the K steps of every tile keeps the per-tile overhead on both issuers and gains nothing.)
+// With 1 issuer, fewer than 3 or more than 8 row blocks: one accumulator set.
 constexpr int kFwdDigWarps = 2, kFwdIssueWarp = kProdWarps + kFwdDigWarps, kFwdThreads = (kFwdIssueWarp + 2) * 32;
 
 template <int NISS, bool RAW>   // NISS: MMA issuer warps in use (2, or 1: the second then idles); RAW: see widen_store
@@ -217,9 +221,11 @@ enc_fwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
     for (int b = tid; b < B; b += blockDim.x)
         rowoff[b] = (uint32_t)((((row_idx != nullptr) ? row_idx[b] : (row0 + b)) * pitch) >> 4);
     if (tid == 0) {
-        for (int s = 0; s < kAStages; ++s) { mbar_init(&S->fullA[s], 4); mbar_init(&S->emptyA[s], NISS); }
+        for (int s = 0; s < kAStages; ++s) { mbar_init(&S->fullA[s], 4); mbar_init(&S->emptyA[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&S->fullV[s], kFwdDigWarps); mbar_init(&S->emptyV[s], NISS); }
         mbar_init(&S->done, NISS);
+        mbar_init(&S->fdone, NISS);
+        S->finit[0] = S->finit[1] = 0u;
         mbar_init_fence();
     }
     if (warp == kFwdIssueWarp) tmem_alloc<512>(&S->tmem_base);
@@ -280,27 +286,33 @@ enc_fwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
         }
         // ---------------- epilogue: recombine the digit planes, write this CTA's exact partial sums ----------------
         mbar_wait(&S->done, 0);
+        mbar_wait(&S->fdone, 0);
         tc_fence_after_sync();
+        const uint32_t init0 = S->finit[0], init1 = S->finit[1];
         const int q = warp & 3;
         for (int blk = warp >> 2; blk < nblk; blk += kProdWarps / 4) {
             uint32_t v[32];
             tmem_ld32(tbase + ((uint32_t)(q * 32) << 16) + blk * 32, v);
-            if (NISS == 2) {
+            tmem_wait_ld();
+            if (!((init0 >> blk) & 1u)) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0u;
+            }
+            if (NISS == 2 && ((init1 >> blk) & 1u)) {
                 uint32_t v1[32];
                 tmem_ld32(tbase + ((uint32_t)(q * 32) << 16) + (nblk + blk) * 32, v1);
                 tmem_wait_ld();
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = (uint32_t)((int)v[j] + (int)v1[j]);
             }
-            tmem_wait_ld();
             const int b = blk * 128 + q * 32 + lane;
             if (b < B) {
                 long long* out = part + ((int64_t)blockIdx.x * B + b) * 8;
 #pragma unroll
                 for (int c = 0; c < 8; c += 2) {
                     longlong2 z;
-                    z.x = (ntile > 0) ? combine4(v, c) : 0;
-                    z.y = (ntile > 0) ? combine4(v, c + 1) : 0;
+                    z.x = combine4(v, c);
+                    z.y = combine4(v, c + 1);
                     *reinterpret_cast<longlong2*>(out + c) = z;
                 }
             }
@@ -345,32 +357,41 @@ enc_fwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
             if (lane == 0) mbar_arrive(&S->fullV[vs]);
         }
     } else {
-        // ---------------- MMA issuers (warp parity p = row-block parity of its tiles): the whole warp runs the convergent
-        // loop, only the elected lane's MMAs / commits execute; descriptors built once ----------------
+        // ---------------- MMA issuers: the whole warp runs the convergent loop, only the elected lane's MMAs / commits
+        // execute; descriptors built once.  Issuer `par` takes the tiles in its two stages ----------------
         const int par = warp - kFwdIssueWarp;
-        const uint64_t A0 = smem_desc(smem_u32(tilesA), 128, 2048), B0 = smem_desc(smem_u32(tilesV), 256, 128);
-        const uint32_t leader = elect_one() ? 1u : 0u;
-        constexpr int kSteps = (kSub / 32) / NISS;                      // K steps of a tile issued by one issuer
-        int blk = 0, tt = 0, s = 0, s_phase = 0;
-        for (int i = 0; i < ntile && par < NISS; ++i) {
-            const int vs = tt & 1;
-            if (blk == 0) mbar_wait(&S->fullV[vs], (tt >> 1) & 1);
-            mbar_wait(&S->fullA[s], s_phase);
-            tc_fence_after_sync();
-            if (lane == 0) TLE(6, i);
-            const uint64_t a = A0 + (uint64_t)(s * (kATile >> 4) + par * kSteps * 16);
-            const uint64_t b = B0 + (uint64_t)(vs * (kDigTile >> 4) + par * kSteps * 64);
-            const uint32_t d = tbase + (par * nblk + blk) * 32, acc0 = tt > 0 ? 1u : 0u;
+        if (par < NISS) {
+            const uint64_t A0 = smem_desc(smem_u32(tilesA), 128, 2048), B0 = smem_desc(smem_u32(tilesV), 256, 128);
+            const uint32_t leader = elect_one() ? 1u : 0u;
+            uint32_t inited = 0u;
+            int i = 0;                                                   // tile index, order (sub-tile, row block)
+            for (int tt = 0; tt < t1 - t0; ++tt) {
+                const int vs = tt & 1;
+                mbar_wait(&S->fullV[vs], (tt >> 1) & 1);                 // every issuer waits for every sub-tile's digits
+                for (int blk = 0; blk < nblk; ++blk, ++i) {
+                    if (NISS == 2 && ((i >> 1) & 1) != par) continue;
+                    const int s = i & (kAStages - 1);
+                    mbar_wait(&S->fullA[s], (i >> 2) & 1);
+                    tc_fence_after_sync();
+                    if (lane == 0) TLE(6, i);
+                    const uint64_t a = A0 + (uint64_t)(s * (kATile >> 4)), b = B0 + (uint64_t)(vs * (kDigTile >> 4));
+                    const uint32_t d = tbase + (par * nblk + blk) * 32, acc0 = (inited >> blk) & 1u;
 #pragma unroll
-            for (int ks = 0; ks < kSteps; ++ks)
-                mma_i8_ss_p(d, a + (uint64_t)(ks * 16), b + (uint64_t)(ks * 64), kIdescFwd, ks ? 1u : acc0, leader);
-            mma_commit_p(&S->emptyA[s], leader);
-            if (blk == nblk - 1) mma_commit_p(&S->emptyV[vs], leader);
-            if (lane == 0) TLE(7, i);
-            if (++s == kAStages) { s = 0; s_phase ^= 1; }
-            if (++blk == nblk) { blk = 0; ++tt; }
+                    for (int ks = 0; ks < kSub / 32; ++ks)
+                        mma_i8_ss_p(d, a + (uint64_t)(ks * 16), b + (uint64_t)(ks * 64), kIdescFwd, ks ? 1u : acc0, leader);
+                    inited |= 1u << blk;
+                    mma_commit_p(&S->emptyA[s], leader);
+                    if (lane == 0) TLE(7, i);
+                }
+                mma_commit_p(&S->emptyV[vs], leader);
+            }
+            if (lane == 0) {
+                S->finit[par] = inited;
+                __threadfence_block();
+                mbar_arrive(&S->fdone);
+            }
+            mma_commit_p(&S->done, leader);
         }
-        if (par < NISS) mma_commit_p(&S->done, leader);
         __syncwarp();
     }
     tc_fence_before_sync();
@@ -412,7 +433,7 @@ struct EncBwdSmem {
     float red[32];
 };
 
-// warps: 16 producers, 2 MMA issuers (issuer h owns the 128-SNP half h of every tile: separate accumulators), 4 epilogue
+// warps: 16 producers, 2 MMA issuers (issuer p owns stages 2p, 2p+1 and its own accumulator set, as in the forward), 4 epilogue
 constexpr int kBwdThreads = kProdThreads + 64 + 128;
 template <int NISS, bool RAW>   // NISS: MMA issuer warps in use (2, or 1: issuer 0 then issues both halves)
 __global__ void __launch_bounds__(kBwdThreads, 1)
@@ -435,11 +456,11 @@ enc_bwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
     for (int b = tid; b < B; b += blockDim.x)
         rowoff[b] = (uint32_t)((((row_idx != nullptr) ? row_idx[b] : (row0 + b)) * pitch) >> 4);
     if (tid == 0) {
-        for (int s = 0; s < kAStages; ++s) { mbar_init(&S->fullA[s], 4); mbar_init(&S->emptyA[s], NISS); }
+        for (int s = 0; s < kAStages; ++s) { mbar_init(&S->fullA[s], 4); mbar_init(&S->emptyA[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&S->dfull[s], NISS); mbar_init(&S->dempty[s], 4); }
         mbar_init_fence();
     }
-    if (warp == kProdWarps) tmem_alloc<128>(&S->tmem_base);
+    if (warp == kProdWarps) tmem_alloc<256>(&S->tmem_base);
     // |max| of dZ over the batch (every CTA computes the same value)
     float mx = 0.f;
     if ((reinterpret_cast<uintptr_t>(dZ) & 15) == 0 && ((B * C) & 3) == 0) {
@@ -491,38 +512,44 @@ enc_bwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
             while (blk >= nblk) blk -= nblk;
         }
     } else if (warp <= kProdWarps + 1) {
-        // ---------------- MMA issuers: issuer h = warp - kProdWarps issues the 4 K steps of half h of every tile (a single
-        // issuing thread was the critical path); convergent loop, only the elected lane's MMAs / commits execute ----------------
-        const int h = warp - kProdWarps;
-        const uint64_t A0 = smem_desc(smem_u32(tilesA), 2048, 128) + (uint64_t)(h * 64), B0 = smem_desc(smem_u32(digZ), 256, 128);
-        constexpr int kHalves = 3 - NISS;                              // halves issued by one issuer: 1 (two issuers) or 2
-        const int nks_last = min(4, (B - (nblk - 1) * 128 + 31) / 32);      // K steps holding real batch rows
-        const uint32_t leader = elect_one() ? 1u : 0u;
-        int blk = 0, tt = 0, s = 0, s_phase = 0;
-        for (int i = 0; i < ntile && h < NISS; ++i) {
-            const int buf = tt & 1;
-            if (blk == 0) mbar_wait(&S->dempty[buf], ((tt >> 1) & 1) ^ 1);
-            mbar_wait(&S->fullA[s], s_phase);
-            tc_fence_after_sync();
-            const uint64_t a = A0 + (uint64_t)(s * (kATile >> 4)), b = B0 + (uint64_t)(blk * 256);
-            const uint32_t d = tbase + buf * 64 + h * 32, acc0 = blk > 0 ? 1u : 0u;
-            if (blk != nblk - 1 || nks_last == 4) {
+        // ---------------- MMA issuers: issuer p = warp - kProdWarps takes the tiles of its two stages ((i >> 1) & 1 == p;
+        // with >= 3 row blocks every sub-tile has tiles of both) and accumulates both 128-SNP halves into its own set:
+        // tensor-memory columns (buf NISS + p) 64 + h 32.  Convergent loop, elected lane issues ----------------
+        const int p = warp - kProdWarps;
+        if (p < NISS) {
+            const uint64_t A0 = smem_desc(smem_u32(tilesA), 2048, 128), B0 = smem_desc(smem_u32(digZ), 256, 128);
+            const int nks_last = min(4, (B - (nblk - 1) * 128 + 31) / 32);  // K steps holding real batch rows
+            const uint32_t leader = elect_one() ? 1u : 0u;
+            int i = 0;
+            for (int tt = 0; tt < t1 - t0; ++tt) {
+                const int buf = tt & 1;
+                mbar_wait(&S->dempty[buf], ((tt >> 1) & 1) ^ 1);
+                uint32_t acc0 = 0u;
+                for (int blk = 0; blk < nblk; ++blk, ++i) {
+                    if (NISS == 2 && ((i >> 1) & 1) != p) continue;
+                    const int s = i & (kAStages - 1);
+                    mbar_wait(&S->fullA[s], (i >> 2) & 1);
+                    tc_fence_after_sync();
+                    const uint64_t a = A0 + (uint64_t)(s * (kATile >> 4)), b = B0 + (uint64_t)(blk * 256);
+                    const uint32_t d = tbase + (buf * NISS + p) * 64;
+                    if (blk != nblk - 1 || nks_last == 4) {
 #pragma unroll
-                for (int hh = 0; hh < kHalves; ++hh)
+                        for (int h = 0; h < 2; ++h)
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks)
-                        mma_i8_ss_p(d + hh * 32, a + (uint64_t)(hh * 64 + ks * 512), b + (uint64_t)(ks * 64), kIdescBwd,
-                                    ks ? 1u : acc0, leader);
-            } else {
-                for (int hh = 0; hh < kHalves; ++hh)
-                    for (int ks = 0; ks < nks_last; ++ks)
-                        mma_i8_ss_p(d + hh * 32, a + (uint64_t)(hh * 64 + ks * 512), b + (uint64_t)(ks * 64), kIdescBwd,
-                                    ks ? 1u : acc0, leader);
+                            for (int ks = 0; ks < 4; ++ks)
+                                mma_i8_ss_p(d + h * 32, a + (uint64_t)(h * 64 + ks * 512), b + (uint64_t)(ks * 64), kIdescBwd,
+                                            ks ? 1u : acc0, leader);
+                    } else {
+                        for (int h = 0; h < 2; ++h)
+                            for (int ks = 0; ks < nks_last; ++ks)
+                                mma_i8_ss_p(d + h * 32, a + (uint64_t)(h * 64 + ks * 512), b + (uint64_t)(ks * 64), kIdescBwd,
+                                            ks ? 1u : acc0, leader);
+                    }
+                    acc0 = 1u;
+                    mma_commit_p(&S->emptyA[s], leader);
+                }
+                mma_commit_p(&S->dfull[buf], leader);
             }
-            mma_commit_p(&S->emptyA[s], leader);
-            if (blk == nblk - 1) mma_commit_p(&S->dfull[buf], leader);
-            if (++s == kAStages) { s = 0; s_phase ^= 1; }
-            if (++blk == nblk) { blk = 0; ++tt; }
         }
         __syncwarp();
     } else {
@@ -533,10 +560,22 @@ enc_bwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
             if (warp == kProdWarps + 2) mbar_wait_relaxed(&S->dfull[buf], (tt >> 1) & 1, 64);   // one warp polls
             named_bar_sync(1, 128);
             tc_fence_after_sync();
-            uint32_t v[2][32];
-            tmem_ld32(tbase + ((uint32_t)(q * 32) << 16) + buf * 64, v[0]);
-            tmem_ld32(tbase + ((uint32_t)(q * 32) << 16) + buf * 64 + 32, v[1]);
-            tmem_wait_ld();
+            // recombine the digit planes of each accumulator set right after loading it (int64, exact) and add the sets:
+            // 32 live accumulator registers at a time instead of 96
+            long long z[2][8];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) z[h][c] = 0;
+#pragma unroll
+                for (int set = 0; set < NISS; ++set) {
+                    uint32_t v[32];
+                    tmem_ld32(tbase + ((uint32_t)(q * 32) << 16) + (buf * NISS + set) * 64 + h * 32, v);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) z[h][c] += combine4(v, c);
+                }
+            }
             tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&S->dempty[buf]);
@@ -547,7 +586,7 @@ enc_bwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
                 if (m >= M) continue;
                 float g[8];
 #pragma unroll
-                for (int c = 0; c < 8; ++c) g[c] = (float)((double)combine4(v[h], c) * fs.back * out_scale);
+                for (int c = 0; c < 8; ++c) g[c] = (float)((double)z[h][c] * fs.back * out_scale);
                 if (C == 8) {
                     float4* gv = reinterpret_cast<float4*>(g);
                     if (dV_out != nullptr) {
@@ -592,7 +631,7 @@ enc_bwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == kProdWarps) tmem_dealloc<128>(tbase);
+    if (warp == kProdWarps) tmem_dealloc<256>(tbase);
 }
 
 // =================================================================================================================
@@ -639,7 +678,8 @@ int launch_enc_fwd_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_i
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(enc_fwd_tc)");
         attr = true;
     }
-    const bool two = enc_issuers() == 2 && B <= 1024;     // two accumulator sets: 2 x 32 columns per row block, 512 in all
+    const int nblk_ = (B + 127) / 128;
+    const bool two = enc_issuers() == 2 && nblk_ >= 3 && nblk_ <= 8;   // two accumulator sets: 2 x 32 columns per row block
     const uint32_t mvx = raw_mv >= 0 ? (3u ^ (uint32_t)(raw_mv & 0xFF)) : 0u;
 #define NADM_FWD_GO(N_, R_) \
     enc_fwd_tc_kernel<N_, R_><<<ncta, kFwdThreads, smem, st>>>(packed, pitch, row_idx, row0, B, M, V, C, vmax, part, T, mvx)
@@ -673,7 +713,7 @@ int launch_enc_bwd_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_i
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(enc_bwd_tc)");
         attr = true;
     }
-    const bool two = enc_issuers() == 2;
+    const bool two = enc_issuers() == 2 && nblk >= 3;       // both issuers then have tiles in every sub-tile
     const uint32_t mvx = raw_mv >= 0 ? (3u ^ (uint32_t)(raw_mv & 0xFF)) : 0u;
     const double scale = raw_mv >= 0 ? 1.0 : 0.5;
 #define NADM_BWD_GO(N_, R_)                                                                                            \
