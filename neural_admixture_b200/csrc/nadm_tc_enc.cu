@@ -127,18 +127,26 @@ struct Feed {
     int c_blk, c_tt, c_i;    // next tile of this group to copy (tile index c_i = g + 4 n)
     int c_slot;
 };
-// every thread of the group: start the asynchronous copy of its four 16-byte pieces of the group's next tile
+// every thread of the group: start the asynchronous copy of its four 16-byte pieces of the group's next tile.
+// Pieces of rows past the batch (or past the row pitch) are zeroed with a plain shared-memory store instead of a
+// zero-fill copy: the variable source size of cp.async costs ~8 address-fixup instructions per copy.
+__device__ __forceinline__ void cp_async16_full(void* smem, const void* gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
 __device__ __forceinline__ void feed_issue(Feed& f, int wl, int lane) {
     if (f.c_i < f.ntile) {
         const int r = lane & 7, q = lane >> 3;
         const int64_t off = (int64_t)(f.t0 + f.c_tt) * (kSub / 4) + q * 16;
         uint8_t* dst = f.stage + f.c_slot * kStTile + (wl * 32 + lane) * 16;   // piece `it` at + it * 2048 (conflict-free)
-        const bool in_pitch = off + 16 <= f.pitch;
+        const uint8_t* base = f.packed + off;
+        const int b0 = f.c_blk * 128 + wl * 32 + r;                            // piece `it` holds row b0 + 8 it
+        const int nrows = (off + 16 <= f.pitch) ? f.B : 0;
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
-            const int b = f.c_blk * 128 + (wl * 4 + it) * 8 + r;
-            const bool ok = in_pitch && b < f.B;
-            cp_async16(dst + it * 2048, ok ? f.packed + ((uint64_t)f.rowoff[b] << 4) + off : f.packed, ok ? 16 : 0);
+            const int b = b0 + it * 8;
+            if (b < nrows) cp_async16_full(dst + it * 2048, base + ((uint64_t)f.rowoff[b] << 4));
+            else *reinterpret_cast<uint4*>(dst + it * 2048) = make_uint4(0u, 0u, 0u, 0u);
         }
         f.c_i += 4;
         f.c_blk += 4;
@@ -217,6 +225,7 @@ enc_fwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
     const int nblk = (B + 127) / 128;
     const int t0 = (int)(((int64_t)T * blockIdx.x) / gridDim.x), t1 = (int)(((int64_t)T * (blockIdx.x + 1)) / gridDim.x);
     const int ntile = (t1 - t0) * nblk;
+    if (tid == 0) TLE(2, 0);                                            // kernel entry
 
     for (int b = tid; b < B; b += blockDim.x)
         rowoff[b] = (uint32_t)((((row_idx != nullptr) ? row_idx[b] : (row0 + b)) * pitch) >> 4);
@@ -258,6 +267,7 @@ enc_fwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
     float vmax = 0.f;
     for (int w = 0; w < kFwdThreads / 32; ++w) vmax = fmaxf(vmax, S->red[w]);
     if (tid == 0) cta_vmax[blockIdx.x] = vmax;
+    if (tid == 0) TLE(2, 1);                                            // setup done
 
     if (warp < kProdWarps) {
         // ---------------- producers: widened genotype tiles (group g = warp / 4 handles tiles g, g + 4, ...) ----------------
@@ -285,8 +295,10 @@ enc_fwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
             while (blk >= nblk) blk -= nblk;
         }
         // ---------------- epilogue: recombine the digit planes, write this CTA's exact partial sums ----------------
+        if (tid == 0) TLE(2, 2);                                        // producers done
         mbar_wait(&S->done, 0);
         mbar_wait(&S->fdone, 0);
+        if (tid == 0) TLE(2, 3);                                        // MMAs done
         tc_fence_after_sync();
         const uint32_t init0 = S->finit[0], init1 = S->finit[1];
         const int q = warp & 3;
@@ -396,6 +408,7 @@ enc_fwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
     }
     tc_fence_before_sync();
     __syncthreads();
+    if (tid == 0) TLE(2, 4);                                            // epilogue done
     if (warp == kFwdIssueWarp) tmem_dealloc<512>(tbase);
 }
 

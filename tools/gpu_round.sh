@@ -47,6 +47,8 @@ smoke)
   timeout 200 python -c 'import __graft_entry__ as g; g.smoke()' 2>&1 | tail -3;;
 refarm)
   timeout 400 python bench.py --impl reference --steps 5 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err; echo "ref rc=$?"; tail -c 900 $OUT/bench_ref.json;;
+l2probe)
+  for w in fwd bwd; do for n in 200 20000; do timeout 60 python tools/enc_probe.py $w 500000 $n 2>&1 | tail -1; done; done;;
 encprobe)
   for w in fwd bwd; do for m in 20000 100000; do NADM_ENC_ISSUERS=2 timeout 40 python tools/enc_probe.py $w $m 2>&1 | tail -1; echo "probe $w $m rc=$?"; done; done;;
 timeline_enc)

@@ -28,3 +28,8 @@ names = ["p_start", "p_emptyA", "p_cpwait", "p_widened", "p_arrived", "p_issued"
 print("tile " + " ".join(f"{n:>10s}" for n in names))
 for u in range(40, 62):
     print(f"{u:4d} " + " ".join(f"{int(out[r][u] - t0):10d}" for r in range(8)))
+
+t = out[2]
+print("phases (cycles): setup", int(t[1] - t[0]), " first tile start after setup", int(out[0][0] - t[1]),
+      " producers' loop", int(t[2] - out[0][0]), " drain MMAs", int(t[3] - t[2]), " epilogue", int(t[4] - t[3]),
+      " total", int(t[4] - t[0]))
