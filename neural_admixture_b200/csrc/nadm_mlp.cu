@@ -230,6 +230,7 @@ mlp_bwd_rows_kernel(const float* __restrict__ dQ, const float* __restrict__ Q, c
 #pragma unroll
         for (int c = 0; c < CP; ++c) dzn[r][c] = 0.f;
     const bool c8 = (C == 8);
+#pragma unroll 2
     for (int j = tid; j < H; j += blockDim.x) {
         float hh[kBwdRows], dH[kBwdRows];
 #pragma unroll
@@ -333,7 +334,7 @@ __device__ __forceinline__ void adam_store(float* p, float* m, float* v, float* 
     }
 }
 
-constexpr int kApplyParams = 64, kApplyGroups = 4;   // a block sums 64 parameters' slabs in 4 interleaved groups
+constexpr int kApplyParams = 64, kApplyGroups = 8;   // a block sums 64 parameters' slabs in 8 interleaved groups
 
 __global__ void __launch_bounds__(kApplyParams * kApplyGroups)
 mlp_bwd_apply_kernel(const float* __restrict__ part, int nslab, int C, int H, int sumK, int has_sup,
@@ -356,7 +357,9 @@ mlp_bwd_apply_kernel(const float* __restrict__ part, int nslab, int C, int H, in
     red[grp][j] = g0 + g1;
     __syncthreads();
     if (grp != 0 || i >= n) return;
-    const float g = (red[0][j] + red[1][j]) + (red[2][j] + red[3][j]);
+    float g = 0.f;
+#pragma unroll
+    for (int q = 0; q < kApplyGroups; q += 2) g += red[q][j] + red[q + 1][j];      // fixed order
     const size_t n1 = (size_t)(C + 1) * H, n2 = n1 + (size_t)sumK * H;
     if (i < n1) {
         const int c = (int)(i / H), jj = (int)(i % H);

@@ -83,6 +83,8 @@ class PackedGenotypes:
     def __init__(self, storage: torch.Tensor, N: int, M: int):
         assert storage.dtype == torch.uint8 and storage.dim() == 2 and storage.is_cuda and storage.is_contiguous()
         assert storage.shape[0] == N and storage.shape[1] % 16 == 0 and storage.shape[1] >= (M + 3) // 4
+        # the tensor-core encoder kernels keep row offsets as 32-bit counts of 16 bytes
+        assert N * storage.shape[1] < 2 ** 36, "packed matrix must be smaller than 64 GiB per device"
         self.storage, self.N, self.M = storage, N, M
 
     @property
