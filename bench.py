@@ -366,6 +366,26 @@ def main():
                 "step": {"algorithmic_bytes": step_bytes, "achieved": step_bytes / (ms_step * 1e-3) / 1e9,
                          "frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak}}
 
+    # ---- forward-only half of the path (post-training Q pass / `infer`, BASELINE configs[4]): Q for consecutive rows ----
+    n_inf = min(N, 16384)
+    inf_pg = ops.PackedGenotypes(pg.storage[:n_inf], n_inf, M_loc)
+    allred = (lambda t_: dist.all_reduce(t_, op=dist.ReduceOp.SUM)) if world > 1 else None
+    na.raw_model.infer_packed(inf_pg, 2048, allreduce=allred)
+    sync_all()
+    i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    i0.record()
+    for _ in range(3):
+        na.raw_model.infer_packed(inf_pg, 2048, allreduce=allred)
+    i1.record()
+    sync_all()
+    t_inf = torch.tensor([i0.elapsed_time(i1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_inf, op=dist.ReduceOp.MAX)
+    infer = {"value": 3 * n_inf / (float(t_inf.item()) * 1e-3), "unit": UNIT, "rows": n_inf, "batch": 2048,
+             "algorithmic_gbs": 3 * n_inf * pitch_bytes / (float(t_inf.item()) * 1e-3) / 1e9,
+             "what": "Q_P.infer_packed: encoder projection + MLP + softmax on consecutive rows of the resident packed "
+                     "matrix (the reference's inference loop / post-training Q pass), not part of the headline"}
+
     # ---- end to end: minibatches streamed from pinned host memory, loss read back every step ---------------------
     e2e, host = None, None
     if not args.no_e2e:
@@ -412,7 +432,7 @@ def main():
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": clocks, "loss": {"first_timed_step": loss_first, "last_timed_step": loss_last,
                                            "schedule": "evaluated on every timed step, as the reference does"},
-                "step_launch": step_launch,
+                "step_launch": step_launch, "infer": infer,
                 "grad_only": {"value": B * n_go / (float(ms_go.item()) * 1e-3), "unit": UNIT, "steps": n_go,
                               "ms_per_step": float(ms_go.item()) / n_go,
                               "what": "same step with the loss value not evaluated (loss pointer NULL)"}}

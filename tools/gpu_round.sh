@@ -49,6 +49,10 @@ refarm)
   timeout 400 python bench.py --impl reference --steps 5 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err; echo "ref rc=$?"; tail -c 900 $OUT/bench_ref.json;;
 l2probe)
   for w in fwd bwd; do for n in 200 20000; do timeout 60 python tools/enc_probe.py $w 500000 $n 2>&1 | tail -1; done; done;;
+sanitize)
+  timeout 280 compute-sanitizer --tool memcheck --print-limit 20 python -c 'import __graft_entry__ as g; g.smoke()' > $OUT/memcheck.txt 2>&1; echo "memcheck rc=$?"; tail -6 $OUT/memcheck.txt;;
+exit4)
+  timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29515 bench.py --gpus 4 --steps 100 --warmup 5 --rows 20000 --no-e2e > $OUT/bench4q.json 2> $OUT/bench4q.err; echo "bench4 quick rc=$?"; python -c "import json;d=json.loads(open('$OUT/bench4q.json').read().strip().splitlines()[-1]);print('4gpu ms/step',d['ms_per_step'], d['step_launch'], d['infer']['value'])";;
 encprobe)
   for w in fwd bwd; do for m in 20000 100000; do NADM_ENC_ISSUERS=2 timeout 40 python tools/enc_probe.py $w $m 2>&1 | tail -1; echo "probe $w $m rc=$?"; done; done;;
 timeline_enc)
