@@ -3,9 +3,11 @@ call fails, this module raises."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
-LIB_PATH = Path(__file__).resolve().parent / "csrc" / "libnadm_b200.so"
+# NADM_LIB=<file name under csrc/> selects an A/B build variant of the SAME library (tools/gpu_round.sh); never a fallback
+LIB_PATH = Path(__file__).resolve().parent / "csrc" / os.environ.get("NADM_LIB", "libnadm_b200.so")
 
 c_u8p = C.c_void_p
 c_f32p = C.c_void_p

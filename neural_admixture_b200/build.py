@@ -40,5 +40,15 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return LIB
 
 
+def build_variant(name: str, extra_flags: list[str]) -> Path:
+    """A/B variant of the library under csrc/<name> (selected at run time with NADM_LIB=<name>)."""
+    out = CSRC / name
+    res = subprocess.run([_nvcc(), *NVCC_FLAGS, *extra_flags, "-o", str(out), *[str(CSRC / s) for s in SOURCES]],
+                         capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"nvcc failed:\n{res.stdout}\n{res.stderr}")
+    return out
+
+
 if __name__ == "__main__":
     print(build(force=True, verbose=True))

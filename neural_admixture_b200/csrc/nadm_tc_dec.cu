@@ -57,7 +57,7 @@ __device__ long long g_timeline[8][512];
 struct DecSmem {
     uint64_t d1full[kMaxSlots], gready[kMaxSlots], gtfree[kMaxSlots], slotfree[kMaxSlots], pfull[kPStages],
         pempty[kPStages], d3full[2], d3empty[2], alldone;
-    uint32_t tmem_base, magic;
+    uint32_t tmem_base, magic, magic21, pad_;
     float lossred[16];
 };
 
@@ -144,40 +144,42 @@ __device__ __forceinline__ void decode16_general(const uint32_t (&v)[16], uint32
 // per product (<= 2^120: no overflow), so 16 elements cost 4 logs and one multiply each instead of 16 logs:
 // sum_j log t_j = -log prod_j (1 / t_j).
 constexpr float kProdFast = 3.0517578125e-05f;
+// The fp32 arithmetic of the fast path is issued as PACKED pairs (sm_100 FFMA2 / FADD2 / FMUL2 via __ffma2_rn & co.:
+// one issue slot per two elements, results bit-identical to the scalar .rn instructions; negation / |.| fold into
+// operand modifiers).  The kernel is bound by instruction issue, not by the fp32 pipe.
 template <bool kLoss>
-__device__ __forceinline__ void decode16_fast(const uint32_t (&v)[16], const float (&prod)[16], uint32_t w,
-                                              uint32_t magic, uint32_t (&hi)[8], uint32_t (&lo)[8], float& acc_hom,
-                                              float& acc_het) {
+__device__ __forceinline__ void decode16_fast(const uint32_t (&v)[16], const float2 (&prod)[8], uint32_t w,
+                                              uint32_t magic, uint32_t magic21, uint32_t (&hi)[8], uint32_t (&lo)[8],
+                                              float& acc_hom, float& acc_het) {
     const uint32_t wh = w >> 16;
     float p_hom = 1.0f, p_het = 1.0f;
 #pragma unroll
     for (int j2 = 0; j2 < 8; ++j2) {
-        float g[2];
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const int j = 2 * j2 + e;
-            const uint32_t wsrc = (j < 8) ? w : wh;
-            const int sh = 2 * (j & 7);
-            const float raw = __uint_as_float(v[j]);
-            const float inv = rcp_approx(prod[j]);
-#ifndef NADM_DEC_PRED
-            const float f = __uint_as_float((wsrc & (3u << sh)) | magic) - 8388608.0f;
-            const float num = fmaf(f, -0.5f / (float)(1 << sh), raw);    // R - x
-#else   // measured alternative (kept out: ptxas builds the predicates one by one, 16.6 instead of 14.2 instr / element)
-            float num = raw;
-            if ((wsrc >> sh) & 1u) num = raw - 0.5f;
-            if ((wsrc >> sh) & 2u) num = raw - 1.0f;
-#endif
-            g[e] = num * inv;
-            if (kLoss) {
-                // x in {0,1}: |G| = 1 / (1 - |R - x|), the reciprocal of the BCE argument;  x = 1/2: inv = 1 / (R (1 - R))
-                if ((wsrc >> sh) & 1u) p_het *= inv;
-                else p_hom *= fabsf(g[e]);
-            }
+        const int j = 2 * j2;
+        const uint32_t wsrc = (j < 8) ? w : wh;
+        const int sh = 2 * (j & 7);                                      // element j: bits sh, sh+1; j+1: sh+2, sh+3
+        const float2 raw = make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+        const float2 inv = make_float2(rcp_approx(prod[j2].x), rcp_approx(prod[j2].y));
+        // code * 4^(j&7) as an exact float via the 2^23 magic constant (kept in a register: one LOP3 per element).  The
+        // odd element's field sits two bits higher: OR-ing it into 2^21 (ulp 1/4) instead of 2^23 (ulp 1) gives it the
+        // SAME scale as the even element, so the pair shares one multiplier (an immediate of the packed FFMA2).
+        const float2 fm = make_float2(__uint_as_float((wsrc & (3u << sh)) | magic),
+                                      __uint_as_float((wsrc & (12u << sh)) | magic21));
+        const float2 f = __fadd2_rn(fm, make_float2(-8388608.0f, -2097152.0f));
+        const float cs = -0.5f / (float)(1 << sh);
+        const float2 num = __ffma2_rn(f, make_float2(cs, cs), raw);      // R - x
+        const float2 g = __fmul2_rn(num, inv);
+        if (kLoss) {
+            // x in {0,1}: |G| = 1 / (1 - |R - x|), the reciprocal of the BCE argument;  x = 1/2: inv = 1 / (R (1 - R))
+            if ((wsrc >> sh) & 1u) p_het *= inv.x;
+            else p_hom *= fabsf(g.x);
+            if ((wsrc >> sh) & 4u) p_het *= inv.y;
+            else p_hom *= fabsf(g.y);
         }
-        const uint32_t h = pack_bf16x2(g[0], g[1]);
+        const uint32_t h = pack_bf16x2(g.x, g.y);
         hi[j2] = h;
-        lo[j2] = pack_bf16x2(g[0] - __uint_as_float(h << 16), g[1] - __uint_as_float(h & 0xFFFF0000u));
+        const float2 l = __fadd2_rn(g, make_float2(-__uint_as_float(h << 16), -__uint_as_float(h & 0xFFFF0000u)));
+        lo[j2] = pack_bf16x2(l.x, l.y);
         if (kLoss && (j2 & 3) == 3) {
             acc_hom -= lg2_approx(p_hom);
             acc_het -= lg2_approx(p_het);
@@ -233,6 +235,7 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
         for (int i = 0; i < 2; ++i) { mbar_init(&S->d3full[i], 1); mbar_init(&S->d3empty[i], 4); }
         mbar_init(&S->alldone, 1);
         S->magic = 0x4B000000u;
+        S->magic21 = 0x4A000000u;
         mbar_init_fence();
     }
     if (warp == kWarpIssue) tmem_alloc<512>(&S->tmem_base);
@@ -256,6 +259,7 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
             if (ro >= 0 && off + 16 <= pitch) r = *reinterpret_cast<const uint4*>(packed + ro + off);
             return r;
         };
+        const uint32_t magic21 = S->magic21;
         const uint32_t magic = S->magic;   // 2^23 as bits, read from shared memory so that it stays in a REGISTER:
                                            // (w & field) | magic is then one LOP3 (an immediate would cost a second)
         // unit counters, advanced incrementally by kWGs units (no divisions in the loop):
@@ -285,19 +289,20 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
                 mbar_wait(&S->gtfree[g], (uq & 1) ^ 1);
                 if (rb == 0) TL(6, u);                                  // G^T buffer free
                 uint8_t* gt = GT + g * kGtBytes + (rb & 7) * 16 + (rb >> 3) * 1024;
-#pragma unroll 1
-                for (int c = 0; c < 4; ++c) {                          // 16 SNPs at a time: raw columns [16c, 16c+16)
-                    uint32_t v[16], hi[8], lo[8];
-                    tmem_ld16(tlane + slot * 64 + c * 16, v);
-                    tmem_wait_ld();
+                // 16 SNPs at a time: raw columns [16c, 16c+16) of the slot -> G hi / lo
+                auto decode_group = [&](int c, const uint32_t (&v)[16]) {
+                    uint32_t hi[8], lo[8];
                     const uint32_t w = (c & 2) ? ((c & 1) ? cw[3] : cw[2]) : ((c & 1) ? cw[1] : cw[0]);
-                    float prod[16];
+                    float2 prod[8];                                   // R (1 - R), packed pairs (FFMA2)
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) prod[j] = fmaf(-__uint_as_float(v[j]), __uint_as_float(v[j]), __uint_as_float(v[j]));
-                    float mn = prod[0];
+                    for (int j = 0; j < 8; ++j) {
+                        const float2 r2 = make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+                        prod[j] = __ffma2_rn(make_float2(-r2.x, -r2.y), r2, r2);
+                    }
+                    float mn = fminf(prod[0].x, prod[0].y);
 #pragma unroll
-                    for (int j = 1; j < 16; ++j) mn = fminf(mn, prod[j]);
-                    if (mn >= kProdFast) decode16_fast<kLoss>(v, prod, w, magic, hi, lo, acc_hom, acc_het);
+                    for (int j = 1; j < 8; ++j) mn = fminf(mn, fminf(prod[j].x, prod[j].y));
+                    if (mn >= kProdFast) decode16_fast<kLoss>(v, prod, w, magic, magic21, hi, lo, acc_hom, acc_het);
                     else decode16_general<kLoss>(v, w, magic, hi, lo, acc_hom, acc_het);
                     tmem_st8(tlane + slot * 64 + c * 16, hi);          // G hi / lo overwrite their own raw columns
                     tmem_st8(tlane + slot * 64 + c * 16 + 8, lo);
@@ -305,7 +310,29 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
                     *reinterpret_cast<uint4*>(gt + (2 * c + 1) * 128) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
                     *reinterpret_cast<uint4*>(gt + 16384 + (2 * c) * 128) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                     *reinterpret_cast<uint4*>(gt + 16384 + (2 * c + 1) * 128) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                };
+#ifdef NADM_DEC_PREFETCH
+                // software-pipelined tensor-memory reads: the load of group c + 1 is in flight while group c is decoded
+                uint32_t va[16], vb[16];
+                tmem_ld16(tlane + slot * 64, va);
+#pragma unroll 1
+                for (int c2 = 0; c2 < 2; ++c2) {
+                    tmem_wait_ld();
+                    tmem_ld16(tlane + slot * 64 + (2 * c2 + 1) * 16, vb);
+                    decode_group(2 * c2, va);
+                    tmem_wait_ld();
+                    if (c2 == 0) tmem_ld16(tlane + slot * 64 + 32, va);
+                    decode_group(2 * c2 + 1, vb);
                 }
+#else
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t v[16];
+                    tmem_ld16(tlane + slot * 64 + c * 16, v);
+                    tmem_wait_ld();
+                    decode_group(c, v);
+                }
+#endif
                 tmem_wait_st();
                 fence_async_smem();
             }

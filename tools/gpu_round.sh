@@ -22,6 +22,18 @@ except Exception as e:
     print("WG=$wg failed", e)
 PY
   done; unset NADM_DEC_SLOTS;;
+abpf)
+  for lib in libnadm_b200.so libnadm_b200_pf.so; do
+    NADM_LIB=$lib timeout 150 python bench.py --rows 20000 --steps 60 --warmup 5 --no-cpu --no-e2e > $OUT/ab_$lib.json 2> $OUT/ab_$lib.err
+    python - <<PY
+import json
+try:
+    d=json.loads(open("$OUT/ab_$lib.json").read().strip().splitlines()[-1])
+    print("$lib ms/step", round(d["ms_per_step"],4), "dec ms", round(d["roofline"]["ms_per_launch"],4), "grad_only ms", round(d["grad_only"]["ms_per_step"],4))
+except Exception as e:
+    print("$lib failed", e)
+PY
+  done;;
 bench)
   timeout 1200 python bench.py > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?"; tail -c 3000 $OUT/bench.json;;
 launches)
