@@ -28,6 +28,13 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
     return d;
 }
 
+// Advance a descriptor's start address by `units16` 16-byte units.  Only the low word changes (the 14-bit address field
+// of a valid shared-memory address cannot carry out of bits 0..13), so this is ONE 32-bit add instead of a 64-bit
+// add-with-carry pair per descriptor on the issuer's instruction stream.
+__device__ __forceinline__ uint64_t desc_add(uint64_t d, uint32_t units16) {
+    return (d & 0xFFFFFFFF00000000ull) | (uint64_t)((uint32_t)d + units16);
+}
+
 // ---- instruction descriptor ---------------------------------------------------------------------------------------
 enum : uint32_t { kFmtF16 = 0, kFmtBF16 = 1, kFmtTF32 = 2, kFmtU8 = 0, kFmtS8 = 1 };
 enum : uint32_t { kAccF16 = 0, kAccF32 = 1, kAccS32 = 2 };

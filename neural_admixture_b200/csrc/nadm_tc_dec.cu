@@ -55,8 +55,8 @@ __device__ long long g_timeline[8][512];
 #endif
 
 struct DecSmem {
-    uint64_t d1full[kMaxSlots], gready[kMaxSlots], gtfree[kMaxSlots], slotfree[kMaxSlots], pfull[kPStages],
-        pempty[kPStages], d3full[2], d3empty[2], alldone;
+    uint64_t d1full[kMaxSlots], gready[kMaxSlots], gtfree[kMaxSlots], slotfree[kMaxSlots], m1go[kMaxSlots],
+        pfull[kPStages], pempty[kPStages], d3full[2], d3empty[2], alldone;
     uint32_t tmem_base, magic, magic21, pad_;
     float lossred[16];
 };
@@ -230,6 +230,7 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
             mbar_init(&S->gready[i], 4);
             mbar_init(&S->gtfree[i], 1);
             mbar_init(&S->slotfree[i], 1);
+            mbar_init(&S->m1go[i], 1);
         }
         for (int i = 0; i < kPStages; ++i) { mbar_init(&S->pfull[i], 1); mbar_init(&S->pempty[i], 2); }
         for (int i = 0; i < 2; ++i) { mbar_init(&S->d3full[i], 1); mbar_init(&S->d3empty[i], 4); }
@@ -286,8 +287,10 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
 #else
             if (active) {
 #endif
+#ifndef NADM_DEC_GTFREE_LATE
                 mbar_wait(&S->gtfree[g], (uq & 1) ^ 1);
                 if (rb == 0) TL(6, u);                                  // G^T buffer free
+#endif
                 uint8_t* gt = GT + g * kGtBytes + (rb & 7) * 16 + (rb >> 3) * 1024;
                 // 16 SNPs at a time: raw columns [16c, 16c+16) of the slot -> G hi / lo
                 auto decode_group = [&](int c, const uint32_t (&v)[16]) {
@@ -306,6 +309,12 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
                     else decode16_general<kLoss>(v, w, magic, hi, lo, acc_hom, acc_het);
                     tmem_st8(tlane + slot * 64 + c * 16, hi);          // G hi / lo overwrite their own raw columns
                     tmem_st8(tlane + slot * 64 + c * 16 + 8, lo);
+#ifdef NADM_DEC_GTFREE_LATE   // measured alternative: wait for the G^T tile only before its first store
+                    if (c == 0) {
+                        mbar_wait(&S->gtfree[g], (uq & 1) ^ 1);
+                        if (rb == 0) TL(6, u);
+                    }
+#endif
                     *reinterpret_cast<uint4*>(gt + (2 * c) * 128) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                     *reinterpret_cast<uint4*>(gt + (2 * c + 1) * 128) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
                     *reinterpret_cast<uint4*>(gt + 16384 + (2 * c) * 128) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -368,6 +377,7 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
             }
         }
     } else if (warp == kWarpIssueA1) {
+#ifdef NADM_DEC_SPLIT_A
         // =============================== MMA issuer A1: raw = Q.P^T (MMA1) ===============================
         // Issuing is split over THREE warps (on three different SM sub-partitions).  One thread issuing all 28 MMAs of a
         // unit plus its bookkeeping (~235 dependent instructions, scheduled against the compute warps of its
@@ -393,14 +403,17 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
             mbar_wait(&S->slotfree[l_slot], l_sphase);                  // first round: passes at once (fresh barrier)
             if (l_blk == 0) mbar_wait(&S->pfull[l_stage], l_phase);     // first unit of a sub-tile: its P tile must be there
             tc_fence_after_sync();
-            const uint64_t ao = (uint64_t)(l_blk * (kQBlkBytes >> 4)), bo = (uint64_t)(l_stage * (kPTileBytes >> 4));
+            const uint32_t ao = (uint32_t)(l_blk * (kQBlkBytes >> 4)), bo = (uint32_t)(l_stage * (kPTileBytes >> 4));
             const uint32_t d = tbase + l_slot * 64;
-            mma_f16_ss_p(d, A_hm + ao, B_hm + bo, kIdesc1, 0u, leader);       // h.h + m.m
-            mma_f16_ss_p(d, A_hm + ao, B_mh + bo, kIdesc1, 1u, leader);       // h.m + m.h
-            mma_f16_ss_p(d, A_hl + ao, B_lh + bo, kIdesc1, 1u, leader);       // h.l + l.h
-            mma_f16_ss_p(d, A_ml + ao, B_lm + bo, kIdesc1, 1u, leader);       // m.l + l.m
+            mma_f16_ss_p(d, desc_add(A_hm, ao), desc_add(B_hm, bo), kIdesc1, 0u, leader);   // h.h + m.m
+            mma_f16_ss_p(d, desc_add(A_hm, ao), desc_add(B_mh, bo), kIdesc1, 1u, leader);   // h.m + m.h
+            mma_f16_ss_p(d, desc_add(A_hl, ao), desc_add(B_lh, bo), kIdesc1, 1u, leader);   // h.l + l.h
+            mma_f16_ss_p(d, desc_add(A_ml, ao), desc_add(B_lm, bo), kIdesc1, 1u, leader);   // m.l + l.m
             mma_commit_p(&S->d1full[l_slot], leader);
             if (l_blk == nblk - 1) mma_commit_p(&S->pempty[l_stage], leader); // this warp's reads of the P stage are issued
+#ifdef NADM_DEC_M1PRIO
+            if (leader) mbar_arrive(&S->m1go[l_slot]);                  // issuer B may now queue MMA3 of unit l - SLOTS
+#endif
             if (++l_slot == kSlots) { l_slot = 0; l_sphase ^= 1; }
             if (++l_blk == nblk) {
                 l_blk = 0;
@@ -408,7 +421,72 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
             }
         }
         __syncwarp();
+#endif   // (merged issuer: this warp only allocates / frees tensor memory)
     } else if (warp == kWarpIssueA2) {
+#ifndef NADM_DEC_SPLIT_A
+        // =============================== MMA issuer A: dQ_blk += G . [P_h | P_l | P_m | P_h] (MMA2), then raw of the
+        // unit that takes over the slot (MMA1) ===============================
+        // MMA2(u) reads the slot's G from tensor memory and MMA1(u + SLOTS) overwrites the same columns with the next
+        // raw.  Both are issued by THIS thread, and tcgen05.mma instructions of one thread execute in issue order, so
+        // no barrier is needed between them: the slot's turn-around (gready -> raw of its next unit) is the issue and
+        // execution time of 12 MMAs.  With the two on different warps (NADM_DEC_SPLIT_A) the tcgen05.commit ->
+        // mbarrier -> polling-warp hop in between made the turn-around about as long as the stagger between the three
+        // warpgroups, which then waited for raw ~20 % of the time (ncu warp-state samples at their d1full wait).
+        const uint32_t qa = smem_u32(QA), pt = smem_u32(PT);
+        // Q chunks [h m l] (128 B apart, 8-row groups 384 B apart); P chunks [h l m h] (8-row groups 512 B apart).
+        // A K=16 instruction multiplies two chunk pairs: start address = first chunk, LBO = distance to the second.
+        const uint64_t A_hm = smem_desc(qa, 128, 384), A_hl = smem_desc(qa, 256, 384), A_ml = smem_desc(qa + 128, 128, 384);
+        const uint64_t B_hm = smem_desc(pt, 256, 512), B_mh = smem_desc(pt + 256, 128, 512);
+        const uint64_t B_lh = smem_desc(pt + 128, 256, 512), B_lm = smem_desc(pt + 128, 128, 512);
+        const uint64_t B2 = smem_desc(pt, 512, 128);
+        const uint32_t leader = elect_one() ? 1u : 0u;                  // the one lane that executes the MMAs / commits
+        int l_blk = 0, l_stage = 0, l_phase = 0, l_slot = 0;
+        auto issue_mma1 = [&]() {
+            if (l_blk == 0) mbar_wait(&S->pfull[l_stage], l_phase);     // first unit of a sub-tile: its P tile must be there
+            tc_fence_after_sync();
+            const uint32_t ao = (uint32_t)(l_blk * (kQBlkBytes >> 4)), bo = (uint32_t)(l_stage * (kPTileBytes >> 4));
+            const uint32_t d = tbase + l_slot * 64;
+            mma_f16_ss_p(d, desc_add(A_hm, ao), desc_add(B_hm, bo), kIdesc1, 0u, leader);   // h.h + m.m
+            mma_f16_ss_p(d, desc_add(A_hm, ao), desc_add(B_mh, bo), kIdesc1, 1u, leader);   // h.m + m.h
+            mma_f16_ss_p(d, desc_add(A_hl, ao), desc_add(B_lh, bo), kIdesc1, 1u, leader);   // h.l + l.h
+            mma_f16_ss_p(d, desc_add(A_ml, ao), desc_add(B_lm, bo), kIdesc1, 1u, leader);   // m.l + l.m
+            mma_commit_p(&S->d1full[l_slot], leader);
+            if (l_blk == nblk - 1) mma_commit_p(&S->pempty[l_stage], leader); // MMA1's reads of the P stage are issued
+            if (++l_slot == kSlots) l_slot = 0;
+            if (++l_blk == nblk) {
+                l_blk = 0;
+                if (++l_stage == kPStages) { l_stage = 0; l_phase ^= 1; }
+            }
+        };
+        for (int l = 0; l < kSlots && l < U; ++l) issue_mma1();         // fill the slots
+        int blk = 0, sub = 0, slot = 0, slot_phase = 0, stage = 0;
+        for (int u = 0; u < U; ++u) {
+            if (lane == 0) TL(3, u);                                    // issuer starts waiting for G(u)
+            mbar_wait(&S->gready[slot], slot_phase);
+            tc_fence_after_sync();
+            if (lane == 0) TL(4, u);                                    // issuer saw G(u)
+            const uint64_t b2 = desc_add(B2, (uint32_t)(stage * (kPTileBytes >> 4)));
+            const uint32_t d2 = tbase + kColD2 + blk * 32, a2 = tbase + slot * 64;
+            const uint32_t acc2 = sub > 0 ? 1u : 0u;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+                for (int t = 0; t < 2; ++t)
+                    mma_f16_ts_p(d2, a2 + c * 16 + t * 8, desc_add(b2, (uint32_t)(c * 2 * 32)), kIdesc2, (c + t) ? 1u : acc2,
+                                 leader);
+            if (blk == nblk - 1) mma_commit_p(&S->pempty[stage], leader); // MMA2's reads of the P stage are issued
+            if (u + kSlots < U) issue_mma1();                           // raw of unit u + SLOTS into the slot just consumed
+            if (lane == 0) TL(5, u);                                    // issuer done with unit u
+            if (++slot == kSlots) { slot = 0; slot_phase ^= 1; }
+            if (++blk == nblk) {
+                blk = 0;
+                ++sub;
+                if (++stage == kPStages) stage = 0;
+            }
+        }
+        mma_commit_p(&S->alldone, leader);
+        __syncwarp();
+#else
         // =============================== MMA issuer A2: dQ_blk += G . [P_h | P_l | P_m | P_h] (MMA2) ===============================
         // A operand from tensor memory: per 16 SNPs, G hi in 8 columns and G lo in 8; B = the P tile re-read MN-major.
         const uint64_t B2 = smem_desc(smem_u32(PT), 512, 128);
@@ -419,14 +497,15 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
             mbar_wait(&S->gready[slot], slot_phase);
             tc_fence_after_sync();
             if (lane == 0) TL(4, u);                                    // issuer saw G(u)
-            const uint64_t b2 = B2 + (uint64_t)(stage * (kPTileBytes >> 4));
+            const uint64_t b2 = desc_add(B2, (uint32_t)(stage * (kPTileBytes >> 4)));
             const uint32_t d2 = tbase + kColD2 + blk * 32, a2 = tbase + slot * 64;
             const uint32_t acc2 = sub > 0 ? 1u : 0u;
 #pragma unroll
             for (int c = 0; c < 4; ++c)
 #pragma unroll
                 for (int t = 0; t < 2; ++t)
-                    mma_f16_ts_p(d2, a2 + c * 16 + t * 8, b2 + (uint64_t)(c * 2 * 32), kIdesc2, (c + t) ? 1u : acc2, leader);
+                    mma_f16_ts_p(d2, a2 + c * 16 + t * 8, desc_add(b2, (uint32_t)(c * 2 * 32)), kIdesc2, (c + t) ? 1u : acc2,
+                                 leader);
             mma_commit_p(&S->slotfree[slot], leader);                   // the slot's G has been consumed: A1 may overwrite it
             if (blk == nblk - 1) mma_commit_p(&S->pempty[stage], leader);
             if (lane == 0) TL(5, u);                                    // issuer done with unit u
@@ -439,6 +518,7 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
         }
         mma_commit_p(&S->alldone, leader);
         __syncwarp();
+#endif
     } else if (warp == kWarpIssueB) {
         // =============================== MMA issuer B: dP_sub += G^T . [Q_h | Q_m | Q_l] (MMA3) ===============================
         // A = the shared G^T tile of the unit's slot, MN-major; B = the Q block re-read MN-major; only K steps holding
@@ -450,9 +530,16 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
         for (int u = 0; u < U; ++u) {
             mbar_wait(&S->gready[slot], slot_phase);
             if (blk == 0) mbar_wait(&S->d3empty[dbuf], d3_phase);
+#ifdef NADM_DEC_M1PRIO   // measured: no effect (kept out)
+            // Tensor-pipe order per slot: MMA2(u) -> MMA1(u + SLOTS) -> MMA3(u).  raw(u + SLOTS) is what a compute
+            // warpgroup is about to wait for, whereas the G^T tile MMA3(u) releases is needed only after the first 16
+            // SNPs of unit u + SLOTS are decoded: queueing the 16 MMA3 first (368 tensor cycles) delayed raw by that much.
+            if (u + kSlots < U) mbar_wait(&S->m1go[slot], slot_phase ^ 1);
+#endif
             tc_fence_after_sync();
             {
-                const uint64_t a3 = A3 + (uint64_t)(slot * (kGtBytes >> 4)), b3 = B3 + (uint64_t)(blk * (kQBlkBytes >> 4));
+                const uint64_t a3 = desc_add(A3, (uint32_t)(slot * (kGtBytes >> 4))),
+                               b3 = desc_add(B3, (uint32_t)(blk * (kQBlkBytes >> 4)));
                 const uint32_t d3 = tbase + kColD3 + dbuf * 32;
                 const uint32_t acc3 = blk > 0 ? 1u : 0u;
                 if (blk != nblk - 1 || nks_last == 8) {
@@ -460,13 +547,13 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
                     for (int t = 0; t < 2; ++t)
 #pragma unroll
                         for (int ks = 0; ks < 8; ++ks)
-                            mma_f16_ss_p(d3, a3 + (uint64_t)(t * 1024 + ks * 128), b3 + (uint64_t)(ks * 48), kIdesc3,
-                                         (t + ks) ? 1u : acc3, leader);
+                            mma_f16_ss_p(d3, desc_add(a3, (uint32_t)(t * 1024 + ks * 128)), desc_add(b3, (uint32_t)(ks * 48)),
+                                         kIdesc3, (t + ks) ? 1u : acc3, leader);
                 } else {
                     for (int t = 0; t < 2; ++t)
                         for (int ks = 0; ks < nks_last; ++ks)
-                            mma_f16_ss_p(d3, a3 + (uint64_t)(t * 1024 + ks * 128), b3 + (uint64_t)(ks * 48), kIdesc3,
-                                         (t + ks) ? 1u : acc3, leader);
+                            mma_f16_ss_p(d3, desc_add(a3, (uint32_t)(t * 1024 + ks * 128)), desc_add(b3, (uint32_t)(ks * 48)),
+                                         kIdesc3, (t + ks) ? 1u : acc3, leader);
                 }
                 mma_commit_p(&S->gtfree[slot], leader);
                 if (blk == nblk - 1) mma_commit_p(&S->d3full[dbuf], leader);
@@ -521,8 +608,16 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
         const int q = warp & 3;
         for (int sub = 0; sub < nsub; ++sub) {
             const int dbuf = sub % kND3;
-            // one warp polls, the other three sleep on a named barrier
-            if (warp == kWarpProd + 1) mbar_wait_relaxed(&S->d3full[dbuf], (sub / kND3) & 1, 64);
+            // one warp polls, the other three sleep on a named barrier.  The poller is the epilogue warp of the SM
+            // sub-partition that hosts no busy issuer (warp ids 12..15 -> sub-partitions 0..3; 12 is idle once MMA1 and
+            // MMA2 share an issuer): polling costs ~5 % of a sub-partition's issue slots, and the kernel runs at the
+            // pace of the busiest one.
+#ifndef NADM_DEC_SPLIT_A
+            constexpr int kPoller = kWarpProd + 1;
+#else
+            constexpr int kPoller = kWarpProd + 4;
+#endif
+            if (warp == kPoller) mbar_wait_relaxed(&S->d3full[dbuf], (sub / kND3) & 1, 64);
             named_bar_sync(1, 128);
             tc_fence_after_sync();
             uint32_t v[32];

@@ -23,7 +23,7 @@ except Exception as e:
 PY
   done; unset NADM_DEC_SLOTS;;
 abpf)
-  for lib in libnadm_b200.so libnadm_b200_pf.so; do
+  for lib in ${NADM_AB_LIBS:-libnadm_b200.so libnadm_b200_pf.so}; do
     NADM_LIB=$lib timeout 150 python bench.py --rows 20000 --steps 60 --warmup 5 --no-cpu --no-e2e > $OUT/ab_$lib.json 2> $OUT/ab_$lib.err
     python - <<PY
 import json
