@@ -16,9 +16,10 @@
 // dQ accumulates in tensor memory over all SNP sub-tiles of the CTA (one 128 x 16 accumulator per row block), dP over
 // the row blocks of one sub-tile, after which four epilogue warps apply Adam + clamp to the 64 x k slice of P.
 //
-// Warp roles (576 threads): 0-11 three compute warpgroups (unit u -> warpgroup u % 3, which owns tensor-memory slot
-// u % 3), 12 MMA issuer (one elected thread), 13 P-tile producer, 14-17 dP/Adam epilogue.  Pipelines are mbarrier
-// based; tcgen05.commit frees operand buffers.
+// Warp roles (640 threads): 0-11 three compute warpgroups (unit u -> warpgroup u % 3, raw / G slot u % SLOTS), 12 tensor
+// memory allocation only, 13 MMA issuer A (MMA2 of a unit, then MMA1 of the unit that takes over its slot), 14 MMA
+// issuer B (MMA3), 15 P-tile producer, 16-19 dP/Adam epilogue.  Pipelines are mbarrier based; tcgen05.commit frees
+// operand buffers.
 #include "nadm_common.cuh"
 #include "nadm_tc.cuh"
 
@@ -55,8 +56,8 @@ __device__ long long g_timeline[8][512];
 #endif
 
 struct DecSmem {
-    uint64_t d1full[kMaxSlots], gready[kMaxSlots], gtfree[kMaxSlots], slotfree[kMaxSlots], m1go[kMaxSlots],
-        pfull[kPStages], pempty[kPStages], d3full[2], d3empty[2], alldone;
+    uint64_t d1full[kMaxSlots], gready[kMaxSlots], gtfree[kMaxSlots], pfull[kPStages], pempty[kPStages], d3full[2],
+        d3empty[2], alldone;
     uint32_t tmem_base, magic, magic21, pad_;
     float lossred[16];
 };
@@ -229,8 +230,6 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
             mbar_init(&S->d1full[i], 1);
             mbar_init(&S->gready[i], 4);
             mbar_init(&S->gtfree[i], 1);
-            mbar_init(&S->slotfree[i], 1);
-            mbar_init(&S->m1go[i], 1);
         }
         for (int i = 0; i < kPStages; ++i) { mbar_init(&S->pfull[i], 1); mbar_init(&S->pempty[i], 2); }
         for (int i = 0; i < 2; ++i) { mbar_init(&S->d3full[i], 1); mbar_init(&S->d3empty[i], 4); }
@@ -287,10 +286,8 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
 #else
             if (active) {
 #endif
-#ifndef NADM_DEC_GTFREE_LATE
                 mbar_wait(&S->gtfree[g], (uq & 1) ^ 1);
                 if (rb == 0) TL(6, u);                                  // G^T buffer free
-#endif
                 uint8_t* gt = GT + g * kGtBytes + (rb & 7) * 16 + (rb >> 3) * 1024;
                 // 16 SNPs at a time: raw columns [16c, 16c+16) of the slot -> G hi / lo
                 auto decode_group = [&](int c, const uint32_t (&v)[16]) {
@@ -302,38 +299,20 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
                         const float2 r2 = make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
                         prod[j] = __ffma2_rn(make_float2(-r2.x, -r2.y), r2, r2);
                     }
-                    float mn = fminf(prod[0].x, prod[0].y);
-#pragma unroll
-                    for (int j = 1; j < 8; ++j) mn = fminf(mn, fminf(prod[j].x, prod[j].y));
+                    // min over the 16 products as a 3-input tree (depth 3) instead of a chain of 8 dependent FMNMX3
+                    const float t0 = fminf(fminf(prod[0].x, prod[0].y), prod[1].x), t1 = fminf(fminf(prod[1].y, prod[2].x), prod[2].y);
+                    const float t2 = fminf(fminf(prod[3].x, prod[3].y), prod[4].x), t3 = fminf(fminf(prod[4].y, prod[5].x), prod[5].y);
+                    const float t4 = fminf(fminf(prod[6].x, prod[6].y), prod[7].x);
+                    const float mn = fminf(fminf(fminf(t0, t1), t2), fminf(fminf(t3, t4), prod[7].y));
                     if (mn >= kProdFast) decode16_fast<kLoss>(v, prod, w, magic, magic21, hi, lo, acc_hom, acc_het);
                     else decode16_general<kLoss>(v, w, magic, hi, lo, acc_hom, acc_het);
                     tmem_st8(tlane + slot * 64 + c * 16, hi);          // G hi / lo overwrite their own raw columns
                     tmem_st8(tlane + slot * 64 + c * 16 + 8, lo);
-#ifdef NADM_DEC_GTFREE_LATE   // measured alternative: wait for the G^T tile only before its first store
-                    if (c == 0) {
-                        mbar_wait(&S->gtfree[g], (uq & 1) ^ 1);
-                        if (rb == 0) TL(6, u);
-                    }
-#endif
                     *reinterpret_cast<uint4*>(gt + (2 * c) * 128) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                     *reinterpret_cast<uint4*>(gt + (2 * c + 1) * 128) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
                     *reinterpret_cast<uint4*>(gt + 16384 + (2 * c) * 128) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                     *reinterpret_cast<uint4*>(gt + 16384 + (2 * c + 1) * 128) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
                 };
-#ifdef NADM_DEC_PREFETCH
-                // software-pipelined tensor-memory reads: the load of group c + 1 is in flight while group c is decoded
-                uint32_t va[16], vb[16];
-                tmem_ld16(tlane + slot * 64, va);
-#pragma unroll 1
-                for (int c2 = 0; c2 < 2; ++c2) {
-                    tmem_wait_ld();
-                    tmem_ld16(tlane + slot * 64 + (2 * c2 + 1) * 16, vb);
-                    decode_group(2 * c2, va);
-                    tmem_wait_ld();
-                    if (c2 == 0) tmem_ld16(tlane + slot * 64 + 32, va);
-                    decode_group(2 * c2 + 1, vb);
-                }
-#else
 #pragma unroll 1
                 for (int c = 0; c < 4; ++c) {
                     uint32_t v[16];
@@ -341,7 +320,6 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
                     tmem_wait_ld();
                     decode_group(c, v);
                 }
-#endif
                 tmem_wait_st();
                 fence_async_smem();
             }
@@ -377,59 +355,14 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
             }
         }
     } else if (warp == kWarpIssueA1) {
-#ifdef NADM_DEC_SPLIT_A
-        // =============================== MMA issuer A1: raw = Q.P^T (MMA1) ===============================
-        // Issuing is split over THREE warps (on three different SM sub-partitions).  One thread issuing all 28 MMAs of a
-        // unit plus its bookkeeping (~235 dependent instructions, scheduled against the compute warps of its
-        // sub-partition) was measured to BE the kernel's critical path: 2170 cycles per unit, compute warpgroups waiting
-        // for raw 62 % of the time; two issuers: 1530 cycles per unit, the raw/dQ issuer still saturated.
-        //   A1: MMA1 of unit l into slot l % SLOTS, once A2's MMA2 of unit l - SLOTS has consumed that slot's G (slotfree)
-        //   A2: MMA2 (dQ += G.P, A operand = the slot's G in tensor memory), then tcgen05.commit -> slotfree[slot]
-        //   B : MMA3 (dP += G^T.Q, shared-memory operands only), commit -> gtfree[slot]
-        // A2 and B both wait on gready[slot]; neither can fall a whole barrier phase behind, because unit u + SLOTS cannot
-        // be decoded before A1 has produced its raw (which needs A2's slotfree of unit u) and B has released the slot's
-        // G^T tile (gtfree of unit u; one tile per slot).
-        // The whole warp runs the (convergent) loop; only the elected lane's MMAs / commits are executed.  Descriptors
-        // are built once; per instruction only the 14-bit start-address field (16-byte units) is advanced.
-        const uint32_t qa = smem_u32(QA), pt = smem_u32(PT);
-        // Q chunks [h m l] (128 B apart, 8-row groups 384 B apart); P chunks [h l m h] (8-row groups 512 B apart).
-        // A K=16 instruction multiplies two chunk pairs: start address = first chunk, LBO = distance to the second.
-        const uint64_t A_hm = smem_desc(qa, 128, 384), A_hl = smem_desc(qa, 256, 384), A_ml = smem_desc(qa + 128, 128, 384);
-        const uint64_t B_hm = smem_desc(pt, 256, 512), B_mh = smem_desc(pt + 256, 128, 512);
-        const uint64_t B_lh = smem_desc(pt + 128, 256, 512), B_lm = smem_desc(pt + 128, 128, 512);
-        const uint32_t leader = elect_one() ? 1u : 0u;                  // the one lane that executes the MMAs / commits
-        int l_blk = 0, l_stage = 0, l_phase = 0, l_slot = 0, l_sphase = 1;
-        for (int l = 0; l < U; ++l) {
-            mbar_wait(&S->slotfree[l_slot], l_sphase);                  // first round: passes at once (fresh barrier)
-            if (l_blk == 0) mbar_wait(&S->pfull[l_stage], l_phase);     // first unit of a sub-tile: its P tile must be there
-            tc_fence_after_sync();
-            const uint32_t ao = (uint32_t)(l_blk * (kQBlkBytes >> 4)), bo = (uint32_t)(l_stage * (kPTileBytes >> 4));
-            const uint32_t d = tbase + l_slot * 64;
-            mma_f16_ss_p(d, desc_add(A_hm, ao), desc_add(B_hm, bo), kIdesc1, 0u, leader);   // h.h + m.m
-            mma_f16_ss_p(d, desc_add(A_hm, ao), desc_add(B_mh, bo), kIdesc1, 1u, leader);   // h.m + m.h
-            mma_f16_ss_p(d, desc_add(A_hl, ao), desc_add(B_lh, bo), kIdesc1, 1u, leader);   // h.l + l.h
-            mma_f16_ss_p(d, desc_add(A_ml, ao), desc_add(B_lm, bo), kIdesc1, 1u, leader);   // m.l + l.m
-            mma_commit_p(&S->d1full[l_slot], leader);
-            if (l_blk == nblk - 1) mma_commit_p(&S->pempty[l_stage], leader); // this warp's reads of the P stage are issued
-#ifdef NADM_DEC_M1PRIO
-            if (leader) mbar_arrive(&S->m1go[l_slot]);                  // issuer B may now queue MMA3 of unit l - SLOTS
-#endif
-            if (++l_slot == kSlots) { l_slot = 0; l_sphase ^= 1; }
-            if (++l_blk == nblk) {
-                l_blk = 0;
-                if (++l_stage == kPStages) { l_stage = 0; l_phase ^= 1; }
-            }
-        }
-        __syncwarp();
-#endif   // (merged issuer: this warp only allocates / frees tensor memory)
+        // (this warp only allocates and frees tensor memory: MMA1 moved to issuer A below)
     } else if (warp == kWarpIssueA2) {
-#ifndef NADM_DEC_SPLIT_A
         // =============================== MMA issuer A: dQ_blk += G . [P_h | P_l | P_m | P_h] (MMA2), then raw of the
         // unit that takes over the slot (MMA1) ===============================
         // MMA2(u) reads the slot's G from tensor memory and MMA1(u + SLOTS) overwrites the same columns with the next
         // raw.  Both are issued by THIS thread, and tcgen05.mma instructions of one thread execute in issue order, so
         // no barrier is needed between them: the slot's turn-around (gready -> raw of its next unit) is the issue and
-        // execution time of 12 MMAs.  With the two on different warps (NADM_DEC_SPLIT_A) the tcgen05.commit ->
+        // execution time of 12 MMAs.  With the two on different warps (earlier builds) the tcgen05.commit ->
         // mbarrier -> polling-warp hop in between made the turn-around about as long as the stagger between the three
         // warpgroups, which then waited for raw ~20 % of the time (ncu warp-state samples at their d1full wait).
         const uint32_t qa = smem_u32(QA), pt = smem_u32(PT);
@@ -486,39 +419,6 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
         }
         mma_commit_p(&S->alldone, leader);
         __syncwarp();
-#else
-        // =============================== MMA issuer A2: dQ_blk += G . [P_h | P_l | P_m | P_h] (MMA2) ===============================
-        // A operand from tensor memory: per 16 SNPs, G hi in 8 columns and G lo in 8; B = the P tile re-read MN-major.
-        const uint64_t B2 = smem_desc(smem_u32(PT), 512, 128);
-        const uint32_t leader = elect_one() ? 1u : 0u;
-        int blk = 0, sub = 0, slot = 0, slot_phase = 0, stage = 0;
-        for (int u = 0; u < U; ++u) {
-            if (lane == 0) TL(3, u);                                    // issuer starts waiting for G(u)
-            mbar_wait(&S->gready[slot], slot_phase);
-            tc_fence_after_sync();
-            if (lane == 0) TL(4, u);                                    // issuer saw G(u)
-            const uint64_t b2 = desc_add(B2, (uint32_t)(stage * (kPTileBytes >> 4)));
-            const uint32_t d2 = tbase + kColD2 + blk * 32, a2 = tbase + slot * 64;
-            const uint32_t acc2 = sub > 0 ? 1u : 0u;
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-#pragma unroll
-                for (int t = 0; t < 2; ++t)
-                    mma_f16_ts_p(d2, a2 + c * 16 + t * 8, desc_add(b2, (uint32_t)(c * 2 * 32)), kIdesc2, (c + t) ? 1u : acc2,
-                                 leader);
-            mma_commit_p(&S->slotfree[slot], leader);                   // the slot's G has been consumed: A1 may overwrite it
-            if (blk == nblk - 1) mma_commit_p(&S->pempty[stage], leader);
-            if (lane == 0) TL(5, u);                                    // issuer done with unit u
-            if (++slot == kSlots) { slot = 0; slot_phase ^= 1; }
-            if (++blk == nblk) {
-                blk = 0;
-                ++sub;
-                if (++stage == kPStages) stage = 0;
-            }
-        }
-        mma_commit_p(&S->alldone, leader);
-        __syncwarp();
-#endif
     } else if (warp == kWarpIssueB) {
         // =============================== MMA issuer B: dP_sub += G^T . [Q_h | Q_m | Q_l] (MMA3) ===============================
         // A = the shared G^T tile of the unit's slot, MN-major; B = the Q block re-read MN-major; only K steps holding
@@ -530,12 +430,6 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
         for (int u = 0; u < U; ++u) {
             mbar_wait(&S->gready[slot], slot_phase);
             if (blk == 0) mbar_wait(&S->d3empty[dbuf], d3_phase);
-#ifdef NADM_DEC_M1PRIO   // measured: no effect (kept out)
-            // Tensor-pipe order per slot: MMA2(u) -> MMA1(u + SLOTS) -> MMA3(u).  raw(u + SLOTS) is what a compute
-            // warpgroup is about to wait for, whereas the G^T tile MMA3(u) releases is needed only after the first 16
-            // SNPs of unit u + SLOTS are decoded: queueing the 16 MMA3 first (368 tensor cycles) delayed raw by that much.
-            if (u + kSlots < U) mbar_wait(&S->m1go[slot], slot_phase ^ 1);
-#endif
             tc_fence_after_sync();
             {
                 const uint64_t a3 = desc_add(A3, (uint32_t)(slot * (kGtBytes >> 4))),
@@ -612,11 +506,7 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
             // sub-partition that hosts no busy issuer (warp ids 12..15 -> sub-partitions 0..3; 12 is idle once MMA1 and
             // MMA2 share an issuer): polling costs ~5 % of a sub-partition's issue slots, and the kernel runs at the
             // pace of the busiest one.
-#ifndef NADM_DEC_SPLIT_A
             constexpr int kPoller = kWarpProd + 1;
-#else
-            constexpr int kPoller = kWarpProd + 4;
-#endif
             if (warp == kPoller) mbar_wait_relaxed(&S->d3full[dbuf], (sub / kND3) & 1, 64);
             named_bar_sync(1, 128);
             tc_fence_after_sync();
