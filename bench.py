@@ -355,7 +355,7 @@ def main():
     step_bytes = (2 + len(ks)) * B * pitch_bytes + 24 * M_loc * (NCOMP + sumK)
     traffic = None
     try:   # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture
-        summ = json.loads((ROOT / "profiles" / "r1b_ncu_summary.json").read_text())
+        summ = json.loads((ROOT / "profiles" / "r1c_ncu_summary.json").read_text())
         traffic = next(v["dram_bytes"] for k, v in summ.items() if k.startswith("dec_tc_kernel"))
     except Exception:
         pass

@@ -53,6 +53,8 @@ sharded)
   timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/check_sharded.py > $OUT/sharded.txt 2>&1; echo "sharded rc=$?"; tail -9 $OUT/sharded.txt
   timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 200 --warmup 5 --no-e2e > $OUT/bench2.json 2> $OUT/bench2.err; echo "bench2 rc=$?"; tail -c 1500 $OUT/bench2.json; tail -3 $OUT/bench2.err
   NADM_NO_GRAPH=1 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 2 --steps 200 --warmup 5 --no-e2e > $OUT/bench2_eager.json 2> $OUT/bench2_eager.err; echo "bench2 eager rc=$?"; python -c "import json;d=json.loads(open('$OUT/bench2_eager.json').read().strip().splitlines()[-1]);print('eager 2gpu ms/step',d['ms_per_step'])";;
+shard2)
+  timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/check_sharded.py > $OUT/sharded.txt 2>&1; echo "sharded rc=$?"; tail -9 $OUT/sharded.txt;;
 exit2)
   timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29514 bench.py --gpus 2 --steps 100 --warmup 5 --rows 20000 --no-e2e > $OUT/bench2q.json 2> $OUT/bench2q.err; echo "bench2 quick rc=$?"; python -c "import json;d=json.loads(open('$OUT/bench2q.json').read().strip().splitlines()[-1]);print('2gpu ms/step',d['ms_per_step'], d['step_launch'])";;
 smoke)
