@@ -40,6 +40,15 @@ int sm_count() {
     return cached[dev];
 }
 
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("NADM_NO_PDL");
+        v = (e != nullptr && e[0] == '1') ? 0 : 1;
+    }
+    return v == 1;
+}
+
 bool use_generic_kernels() {
     static int cached = -1;
     if (cached < 0) {
@@ -68,6 +77,7 @@ mlp_fwd_kernel(const float* __restrict__ Z, int B, int C, int H, const float* __
                const float* __restrict__ W1, const float* __restrict__ b1, const float* __restrict__ W2,
                const float* __restrict__ b2, Heads hd, float* __restrict__ rinv_out, float* __restrict__ Hh,
                float* __restrict__ Q) {
+    pdl_prologue();
     extern __shared__ __align__(16) float sm[];
     float* Zn = sm;                         // kMlpRows x C
     float* Hs = Zn + kMlpRows * NADM_MAX_C;  // kMlpRows x H
@@ -171,6 +181,7 @@ mlp_bwd_rows_kernel(const float* __restrict__ dQ, const float* __restrict__ Q, c
                     const int64_t* __restrict__ labels, float sup_weight, const float* __restrict__ w_rms,
                     const float* __restrict__ W1, const float* __restrict__ W2, float* __restrict__ part,
                     float* __restrict__ dZ) {
+    pdl_prologue();
     extern __shared__ __align__(16) float sm[];
     float* dLs = sm;                                         // kBwdRows x sumK
     float* Zn = dLs + (size_t)kBwdRows * hd.sumK;             // kBwdRows x MAX_C   (normalised inputs, recomputed)
@@ -339,6 +350,7 @@ constexpr int kApplyParams = 64, kApplyGroups = 8;   // a block sums 64 paramete
 __global__ void __launch_bounds__(kApplyParams * kApplyGroups)
 mlp_bwd_apply_kernel(const float* __restrict__ part, int nslab, int C, int H, int sumK, int has_sup,
                      nadm_mlp_params_t prm, AdamCoef adam_in, float* __restrict__ loss) {
+    pdl_prologue();
     const AdamCoef adam = adam_resolve(adam_in);
     __shared__ float red[kApplyGroups][kApplyParams];
     const size_t n = mlp_slab_floats(C, H, sumK);
@@ -418,8 +430,8 @@ extern "C" int nadm_mlp_fwd(const float* Z, int32_t B, int32_t C, int32_t H, con
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(mlp_fwd)");
         attr = true;
     }
-    mlp_fwd_kernel<<<(B + kMlpRows - 1) / kMlpRows, kMlpThreads, smem, (cudaStream_t)stream>>>(
-        Z, B, C, H, w_rms, W1, b1, W2, b2, hd, rinv, Hh, Q);
+    launch_pdl(mlp_fwd_kernel, dim3((B + kMlpRows - 1) / kMlpRows), dim3(kMlpThreads), smem, (cudaStream_t)stream, Z, B, C, H,
+               w_rms, W1, b1, W2, b2, hd, rinv, Hh, Q);
     NADM_CHECK_LAUNCH("mlp_fwd_kernel");
     return NADM_OK;
 }
@@ -447,16 +459,16 @@ extern "C" int nadm_mlp_bwd(const float* dQ, const float* Q, const float* Hh, co
     const size_t smem = ((size_t)kBwdRows * hd.sumK + (size_t)kBwdRows * CP +
                          (size_t)(kMlpThreads / 32) * kBwdRows * CP + kBwdRows) * sizeof(float);
     if (CP == 8)
-        mlp_bwd_rows_kernel<8><<<nslab, kMlpThreads, smem, st>>>(dQ, Q, Hh, Z, rinv, B, C, H, hd, labels, sup_weight,
-                                                                 p.w_rms, p.W1, p.W2, gpart, dZ);
+        launch_pdl(mlp_bwd_rows_kernel<8>, dim3(nslab), dim3(kMlpThreads), smem, st, dQ, Q, Hh, Z, rinv, B, C, H, hd, labels,
+                   sup_weight, p.w_rms, p.W1, p.W2, gpart, dZ);
     else
-        mlp_bwd_rows_kernel<16><<<nslab, kMlpThreads, smem, st>>>(dQ, Q, Hh, Z, rinv, B, C, H, hd, labels, sup_weight,
-                                                                  p.w_rms, p.W1, p.W2, gpart, dZ);
+        launch_pdl(mlp_bwd_rows_kernel<16>, dim3(nslab), dim3(kMlpThreads), smem, st, dQ, Q, Hh, Z, rinv, B, C, H, hd, labels,
+                   sup_weight, p.w_rms, p.W1, p.W2, gpart, dZ);
     NADM_CHECK_LAUNCH("mlp_bwd_rows_kernel");
     const AdamCoef ac = make_adam(adam);
     const size_t nparam = mlp_slab_floats(C, H, hd.sumK);
-    mlp_bwd_apply_kernel<<<(unsigned)((nparam + kApplyParams - 1) / kApplyParams), kApplyParams * kApplyGroups, 0, st>>>(gpart, nslab, C, H, hd.sumK,
-                                                                          labels != nullptr, p, ac, loss);
+    launch_pdl(mlp_bwd_apply_kernel, dim3((unsigned)((nparam + kApplyParams - 1) / kApplyParams)), dim3(kApplyParams * kApplyGroups),
+               0, st, gpart, nslab, C, H, hd.sumK, (int)(labels != nullptr), p, ac, loss);
     NADM_CHECK_LAUNCH("mlp_bwd_apply_kernel");
     return NADM_OK;
 }

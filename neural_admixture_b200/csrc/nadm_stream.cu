@@ -85,6 +85,7 @@ __global__ void __launch_bounds__(256)
 reduce_parts_kernel(const float* __restrict__ part, int nparts, int rows, int cols_p, int cols_out,
                     float* __restrict__ out, int out_ld, int out_off, float scale,
                     const float* __restrict__ loss_part, float* __restrict__ loss) {
+    pdl_prologue();
     __shared__ float red[32][8];
     const int64_t n = (int64_t)rows * cols_p;
     const int o = threadIdx.x & 7, seg = threadIdx.x >> 3;
@@ -527,8 +528,8 @@ namespace nadm {
 int launch_reduce_parts(const float* part, int nparts, int rows, int cols_p, int cols_out, float* out, int out_ld,
                         int out_off, float scale, const float* loss_part, float* loss, cudaStream_t st) {
     const int64_t n = (int64_t)rows * cols_p;
-    reduce_parts_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(part, nparts, rows, cols_p, cols_out, out, out_ld,
-                                                                    out_off, scale, loss_part, loss);
+    launch_pdl(reduce_parts_kernel, dim3((unsigned)((n + 7) / 8)), dim3(256), 0, st, part, nparts, rows, cols_p, cols_out, out,
+               out_ld, out_off, scale, loss_part, loss);
     NADM_CHECK_LAUNCH("reduce_parts_kernel");
     return NADM_OK;
 }
@@ -542,6 +543,7 @@ namespace nadm {
 __global__ void step_begin_kernel(const int64_t* __restrict__ order, int64_t order_len, const int64_t* __restrict__ counters,
                                   int64_t stride, int B, int64_t* __restrict__ row_idx_out, float lr, float beta1,
                                   float beta2, float eps, float* __restrict__ coef_out, float* __restrict__ loss_accum) {
+    pdl_prologue();
     const int64_t s = counters[0];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B; i += gridDim.x * blockDim.x) {
         const int64_t j = s * stride + i;
@@ -562,6 +564,7 @@ __global__ void step_begin_kernel(const int64_t* __restrict__ order, int64_t ord
     }
 }
 __global__ void step_end_kernel(int64_t* __restrict__ counters, const float* __restrict__ loss, float* __restrict__ losses_out) {
+    pdl_prologue();
     const int64_t s = counters[0];
     if (loss != nullptr && losses_out != nullptr) losses_out[s] = *loss;
     counters[0] = s + 1;
@@ -575,16 +578,16 @@ extern "C" int nadm_step_begin(const int64_t* order, int64_t order_len, int64_t*
     NADM_REQUIRE(order && counters && row_idx_out && hyper && coef_out, "NULL pointer");
     NADM_REQUIRE(B > 0 && stride >= B && order_len > 0, "bad minibatch geometry (B=%d, stride=%lld)", B, (long long)stride);
     NADM_REQUIRE(((uintptr_t)coef_out & 15) == 0, "coef_out must be 16-byte aligned");
-    nadm::step_begin_kernel<<<(B + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
-        order, order_len, counters, stride, B, row_idx_out, hyper->lr, hyper->beta1, hyper->beta2, hyper->eps,
-        (float*)coef_out, loss_accum);
+    nadm::launch_pdl(nadm::step_begin_kernel, dim3((B + 255) / 256), dim3(256), 0, (cudaStream_t)stream, order, order_len,
+                     counters, stride, B, row_idx_out, hyper->lr, hyper->beta1, hyper->beta2, hyper->eps, (float*)coef_out,
+                     loss_accum);
     NADM_CHECK_LAUNCH("step_begin_kernel");
     return NADM_OK;
 }
 
 extern "C" int nadm_step_end(int64_t* counters, const float* loss, float* losses_out, void* stream) {
     NADM_REQUIRE(counters, "NULL pointer");
-    nadm::step_end_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(counters, loss, losses_out);
+    nadm::launch_pdl(nadm::step_end_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, counters, loss, losses_out);
     NADM_CHECK_LAUNCH("step_end_kernel");
     return NADM_OK;
 }

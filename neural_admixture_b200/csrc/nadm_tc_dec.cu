@@ -196,6 +196,7 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
               int64_t M, const float* __restrict__ Q, int q_ld, int q_off, int k, float* __restrict__ P,
               float* __restrict__ Pm, float* __restrict__ Pv, AdamCoef adam_in, float* __restrict__ dP_out,
               float* __restrict__ dQpart, float* __restrict__ loss_part, int TS) {
+    pdl_prologue();
     constexpr int kSlots = SLOTS, kWarpIssue = kWarpIssueA1;
     const AdamCoef adam = adam_resolve(adam_in);
     constexpr int ngt = SLOTS;   // one G^T tile per slot (see the issuer warps for why not more)
@@ -595,8 +596,8 @@ static int dec_launch_one(int ncta, size_t smem, cudaStream_t st, const uint8_t*
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(dec_tc)");
         attr = true;
     }
-    dec_tc_kernel<kLoss, SLOTS><<<ncta, kDecThreads, smem, st>>>(packed, pitch, row_idx, row0, B, M, Q, q_ld, q_off, k, P,
-                                                                Pm, Pv, adam, dP_out, dQpart, loss_part, TS);
+    launch_pdl(dec_tc_kernel<kLoss, SLOTS>, dim3(ncta), dim3(kDecThreads), smem, st, packed, pitch, row_idx, row0, B, M, Q, q_ld,
+               q_off, k, P, Pm, Pv, adam, dP_out, dQpart, loss_part, TS);
     NADM_CHECK_LAUNCH("dec_tc_kernel");
     return NADM_OK;
 }

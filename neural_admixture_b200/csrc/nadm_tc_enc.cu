@@ -215,6 +215,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1)
 enc_fwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* __restrict__ row_idx, int64_t row0,
                   int B, int64_t M, const float* __restrict__ V, int C, float* __restrict__ cta_vmax,
                   long long* __restrict__ part, int T, uint32_t mvx) {
+    pdl_prologue();
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* tilesA = smem;                                         // kAStages x 32 KB
     uint8_t* tilesV = tilesA + kAStages * kATile;                   // 2 x 8 KB
@@ -418,6 +419,7 @@ enc_fwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
 __global__ void __launch_bounds__(256)
 enc_fwd_reduce_kernel(const long long* __restrict__ part, int nparts, int B, int C,
                       const float* __restrict__ cta_vmax, float* __restrict__ Z, double out_scale) {
+    pdl_prologue();
     __shared__ double red[32][8];
     __shared__ double back[kMaxParts];
     for (int p = threadIdx.x; p < nparts; p += blockDim.x) back[p] = fix_scale(cta_vmax[p]).back;
@@ -454,6 +456,7 @@ enc_bwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
                   int B, int64_t M, const float* __restrict__ dZ, int C, float* __restrict__ V, float* __restrict__ Vm,
                   float* __restrict__ Vv, AdamCoef adam_in, float* __restrict__ dV_out, int T, uint32_t mvx,
                   double out_scale, int accumulate) {
+    pdl_prologue();
     const AdamCoef adam = adam_resolve(adam_in);
     extern __shared__ __align__(1024) uint8_t smem[];
     const int nblk = (B + 127) / 128;
@@ -695,12 +698,12 @@ int launch_enc_fwd_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_i
     const bool two = enc_issuers() == 2 && nblk_ >= 3 && nblk_ <= 8;   // two accumulator sets: 2 x 32 columns per row block
     const uint32_t mvx = raw_mv >= 0 ? (3u ^ (uint32_t)(raw_mv & 0xFF)) : 0u;
 #define NADM_FWD_GO(N_, R_) \
-    enc_fwd_tc_kernel<N_, R_><<<ncta, kFwdThreads, smem, st>>>(packed, pitch, row_idx, row0, B, M, V, C, vmax, part, T, mvx)
+    launch_pdl(enc_fwd_tc_kernel<N_, R_>, dim3(ncta), dim3(kFwdThreads), smem, st, packed, pitch, row_idx, row0, B, M, V, C, vmax, part, T, mvx)
     if (raw_mv >= 0) { if (two) NADM_FWD_GO(2, true); else NADM_FWD_GO(1, true); }
     else { if (two) NADM_FWD_GO(2, false); else NADM_FWD_GO(1, false); }
 #undef NADM_FWD_GO
     NADM_CHECK_LAUNCH("enc_fwd_tc_kernel");
-    enc_fwd_reduce_kernel<<<B, 256, 0, st>>>(part, ncta, B, C, vmax, Z, raw_mv >= 0 ? 1.0 : 0.5);
+    launch_pdl(enc_fwd_reduce_kernel, dim3(B), dim3(256), 0, st, part, ncta, B, C, vmax, Z, raw_mv >= 0 ? 1.0 : 0.5);
     NADM_CHECK_LAUNCH("enc_fwd_reduce_kernel");
     return NADM_OK;
 }
@@ -730,8 +733,8 @@ int launch_enc_bwd_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_i
     const uint32_t mvx = raw_mv >= 0 ? (3u ^ (uint32_t)(raw_mv & 0xFF)) : 0u;
     const double scale = raw_mv >= 0 ? 1.0 : 0.5;
 #define NADM_BWD_GO(N_, R_)                                                                                            \
-    enc_bwd_tc_kernel<N_, R_><<<ncta, kBwdThreads, smem, st>>>(packed, pitch, row_idx, row0, B, M, dZ, C, V, Vm, Vv,  \
-                                                              make_adam(adam), dV_out, T, mvx, scale, accumulate)
+    launch_pdl(enc_bwd_tc_kernel<N_, R_>, dim3(ncta), dim3(kBwdThreads), smem, st, packed, pitch, row_idx, row0, B, M, dZ, C, \
+               V, Vm, Vv, make_adam(adam), dV_out, T, mvx, scale, accumulate)
     if (raw_mv >= 0) { if (two) NADM_BWD_GO(2, true); else NADM_BWD_GO(1, true); }
     else { if (two) NADM_BWD_GO(2, false); else NADM_BWD_GO(1, false); }
 #undef NADM_BWD_GO

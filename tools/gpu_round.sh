@@ -34,6 +34,18 @@ except Exception as e:
     print("$lib failed", e)
 PY
   done;;
+abpdl)
+  for nopdl in 1 0 1 0; do
+    NADM_NO_PDL=$nopdl timeout 150 python bench.py --rows 20000 --steps 100 --warmup 5 --no-cpu --no-e2e > $OUT/ab_nopdl$nopdl.json 2> $OUT/ab_nopdl$nopdl.err
+    python - <<PY
+import json
+try:
+    d=json.loads(open("$OUT/ab_nopdl$nopdl.json").read().strip().splitlines()[-1])
+    print("NADM_NO_PDL=$nopdl ms/step", round(d["ms_per_step"],4), "dec ms", round(d["roofline"]["ms_per_launch"],4), "grad_only ms", round(d["grad_only"]["ms_per_step"],4), "infer", round(d["infer"]["value"]))
+except Exception as e:
+    print("NADM_NO_PDL=$nopdl failed", e)
+PY
+  done;;
 bench)
   timeout 1200 python bench.py > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?"; tail -c 3000 $OUT/bench.json;;
 launches)
