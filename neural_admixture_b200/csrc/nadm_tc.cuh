@@ -69,6 +69,7 @@ NADM_DEF_MMA_SS(mma_f16_ss, "f16")
             "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)                                                 \
             : "memory");                                                                                         \
     }
+NADM_DEF_MMA_TS(mma_i8_ts, "i8")
 NADM_DEF_MMA_TS(mma_tf32_ts, "tf32")
 NADM_DEF_MMA_TS(mma_f16_ts, "f16")
 #undef NADM_DEF_MMA_TS

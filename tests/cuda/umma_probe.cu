@@ -62,7 +62,8 @@ __global__ void __launch_bounds__(128) probe_kernel(const uint8_t* a_img, const 
             const uint64_t bd = smem_desc(smem_u32(sb) + k * p.b_step, p.b_lbo, p.b_sbo);
             if (p.a_from_tmem) {
                 const uint32_t at = tbase + a_col0 + k * p.a_step;
-                if (p.kind == 1) mma_tf32_ts(tbase, at, bd, p.idesc, k > 0);
+                if (p.kind == 0) mma_i8_ts(tbase, at, bd, p.idesc, k > 0);
+                else if (p.kind == 1) mma_tf32_ts(tbase, at, bd, p.idesc, k > 0);
                 else mma_f16_ts(tbase, at, bd, p.idesc, k > 0);
             } else {
                 const uint64_t ad = smem_desc(smem_u32(sa) + k * p.a_step, p.a_lbo, p.a_sbo);
@@ -263,6 +264,33 @@ int main() {
         }
         printf("case bf16 SS, A MN-major M=64 N=24, B MN-major: rel err %.3e -> %s\n", sqrt(err / nrm), sqrt(err / nrm) < 1e-5 ? "PASS" : "FAIL");
         fails += !(sqrt(err / nrm) < 1e-5);
+    }
+    // ---------------------------------------------------------------- case 6: i8, A (u8) from TMEM (TS), B MN-major
+    // (not used by the library yet: the layout a forward encoder with its genotype operand in tensor memory would need)
+    {
+        const int M = 128, N = 32, K = 96;   // 3 instructions of K = 32; A image: 4 consecutive k bytes per 32-bit column
+        std::vector<int> A(M * K), B(N * K);
+        for (auto& x : A) x = rand() % 3;
+        for (auto& x : B) x = rand() % 256 - 128;
+        std::vector<uint32_t> atm(M * (K / 4), 0);
+        for (int r = 0; r < M; ++r) for (int k = 0; k < K; ++k)
+            atm[r * (K / 4) + k / 4] |= (uint32_t)A[r * K + k] << (8 * (k % 4));
+        std::vector<uint8_t> b(N * K, 0);
+        for (int n = 0; n < N; ++n) for (int k = 0; k < K; ++k)
+            b[(n % 16) + (n / 16) * 128 + (k % 8) * 16 + (k / 8) * 256] = (uint8_t)(int8_t)B[n * K + k];
+        Params p{};
+        p.kind = 0; p.a_from_tmem = 1; p.nk = K / 32; p.d_cols = N; p.a_tmem_cols = K / 4; p.a_step = 8;
+        p.b_sbo = 128; p.b_lbo = 256; p.b_step = 4 * 256;
+        p.idesc = instr_desc(kAccS32, kFmtU8, kFmtS8, false, true, M, N);
+        auto d = run({}, b, atm, p);
+        long bad = 0;
+        for (int r = 0; r < M; ++r) for (int n = 0; n < N; ++n) {
+            int ref = 0;
+            for (int k = 0; k < K; ++k) ref += A[r * K + k] * B[n * K + k];
+            if ((int)d[r * N + n] != ref) ++bad;
+        }
+        printf("case i8 TS (A u8 in TMEM, 4 k per column), B MN-major: %s (%ld mismatches)\n", bad ? "FAIL" : "PASS", bad);
+        fails += bad != 0;
     }
     printf(fails ? "PROBE FAILED (%d)\n" : "PROBE OK\n", fails);
     return fails ? 1 : 0;
