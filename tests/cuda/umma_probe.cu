@@ -87,6 +87,62 @@ __global__ void __launch_bounds__(128) probe_kernel(const uint8_t* a_img, const 
     if (warp == 0) tmem_dealloc<512>(tbase);
 }
 
+// Two threads of DIFFERENT warps issue interleaved K steps into the SAME accumulator (zero-initialised with tcgen05.st,
+// every MMA accumulates).  Integer adds commute, so any ordering is fine; what the probe looks for is a lost update
+// when read-modify-writes of one accumulator come from two instruction streams.
+__global__ void __launch_bounds__(128) probe2_kernel(const uint8_t* a_img, const uint8_t* b_img, uint32_t* d_out, Params p,
+                                                     int reps) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(8) uint64_t bar;
+    uint8_t* sa = smem;
+    uint8_t* sb = smem + ((p.a_bytes + 127) / 128) * 128;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < p.a_bytes; i += 128) sa[i] = a_img[i];
+    for (int i = tid; i < p.b_bytes; i += 128) sb[i] = b_img[i];
+    if (warp == 0) tmem_alloc<512>(&tmem_base_s);
+    if (tid == 0) {
+        mbar_init(&bar, 2);
+        mbar_init_fence();
+    }
+    fence_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tbase = tmem_base_s;
+    const uint32_t lane_base = tbase + ((uint32_t)(warp * 32) << 16);
+    {
+        uint32_t z[16];
+        for (int j = 0; j < 16; ++j) z[j] = 0u;
+        for (int c0 = 0; c0 < p.d_cols; c0 += 16) tmem_st16(lane_base + c0, z);
+        tmem_wait_st();
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    if (tid == 0 || tid == 32) {
+        const int me = tid >> 5;
+        for (int rep = 0; rep < reps; ++rep)
+            for (int k = me; k < p.nk; k += 2) {
+                const uint64_t ad = smem_desc(smem_u32(sa) + k * p.a_step, p.a_lbo, p.a_sbo);
+                const uint64_t bd = smem_desc(smem_u32(sb) + k * p.b_step, p.b_lbo, p.b_sbo);
+                mma_i8_ss(tbase, ad, bd, p.idesc, 1u);
+            }
+        mma_commit(&bar);
+    }
+    mbar_wait(&bar, 0);
+    tc_fence_after_sync();
+    for (int c0 = 0; c0 < p.d_cols; c0 += 8) {
+        uint32_t v[8];
+        tmem_ld8(lane_base + c0, v);
+        tmem_wait_ld();
+        for (int j = 0; j < 8; ++j) d_out[tid * p.d_cols + c0 + j] = v[j];
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tbase);
+}
+
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(2); } } while (0)
 
 static std::vector<uint32_t> run(const std::vector<uint8_t>& a, const std::vector<uint8_t>& b,
@@ -291,6 +347,46 @@ int main() {
         }
         printf("case i8 TS (A u8 in TMEM, 4 k per column), B MN-major: %s (%ld mismatches)\n", bad ? "FAIL" : "PASS", bad);
         fails += bad != 0;
+    }
+    // ---------------------------------------------------------------- case 7: i8 SS, two issuing threads, one accumulator
+    {
+        const int M = 128, N = 32, K = 512, REPS = 40;   // 16 K steps x 40 repetitions, alternating between two warps
+        std::vector<int> A(M * K), B(N * K);
+        for (auto& x : A) x = rand() % 3;
+        for (auto& x : B) x = rand() % 256 - 128;
+        const uint32_t LBO_t = 128, SBO_t = 128 * (K / 16);
+        std::vector<uint8_t> a(M * K, 0), b(N * K, 0);
+        for (int r = 0; r < M; ++r) for (int k = 0; k < K; ++k)
+            a[(r % 8) * 16 + (r / 8) * SBO_t + (k / 16) * LBO_t + (k % 16)] = (uint8_t)A[r * K + k];
+        for (int n = 0; n < N; ++n) for (int k = 0; k < K; ++k)
+            b[(n % 16) + (n / 16) * 128 + (k % 8) * 16 + (k / 8) * 256] = (uint8_t)(int8_t)B[n * K + k];
+        Params p{};
+        p.kind = 0; p.nk = K / 32; p.d_cols = N;
+        p.a_lbo = LBO_t; p.a_sbo = SBO_t; p.a_step = 2 * LBO_t;
+        p.b_sbo = 128; p.b_lbo = 256; p.b_step = 4 * 256;
+        p.idesc = instr_desc(kAccS32, kFmtU8, kFmtS8, false, true, M, N);
+        p.a_bytes = (int)a.size(); p.b_bytes = (int)b.size();
+        uint8_t *da, *db; uint32_t* dd;
+        CK(cudaMalloc(&da, a.size())); CK(cudaMalloc(&db, b.size())); CK(cudaMalloc(&dd, 128 * N * 4));
+        CK(cudaMemcpy(da, a.data(), a.size(), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(db, b.data(), b.size(), cudaMemcpyHostToDevice));
+        CK(cudaFuncSetAttribute(probe2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        long bad = 0;
+        for (int launch = 0; launch < 20; ++launch) {
+            probe2_kernel<<<1, 128, a.size() + b.size() + 256>>>(da, db, dd, p, REPS);
+            CK(cudaDeviceSynchronize());
+            std::vector<uint32_t> d(128 * N);
+            CK(cudaMemcpy(d.data(), dd, d.size() * 4, cudaMemcpyDeviceToHost));
+            for (int r = 0; r < M; ++r) for (int n = 0; n < N; ++n) {
+                int ref = 0;
+                for (int k = 0; k < K; ++k) ref += A[r * K + k] * B[n * K + k];
+                if ((int)d[r * N + n] != ref * REPS) ++bad;
+            }
+        }
+        cudaFree(da); cudaFree(db); cudaFree(dd);
+        // informational (the library does not rely on it yet): does not count as a probe failure
+        printf("info i8 SS, two issuer threads into ONE accumulator (20 launches x 640 MMAs): %s (%ld mismatches)\n",
+               bad ? "LOST UPDATES" : "exact", bad);
     }
     printf(fails ? "PROBE FAILED (%d)\n" : "PROBE OK\n", fails);
     return fails ? 1 : 0;
