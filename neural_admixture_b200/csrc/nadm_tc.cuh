@@ -95,14 +95,18 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
 NADM_DEF_MMA_SS_P(mma_i8_ss_p, "i8")
 NADM_DEF_MMA_SS_P(mma_f16_ss_p, "f16")
 #undef NADM_DEF_MMA_SS_P
-__device__ __forceinline__ void mma_f16_ts_p(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
-                                             uint32_t accumulate, uint32_t issue) {
-    asm volatile(
-        "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
-        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
-        "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(issue)
-        : "memory");
-}
+#define NADM_DEF_MMA_TS_P(NAME, KIND)                                                                            \
+    __device__ __forceinline__ void NAME(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,      \
+                                         uint32_t accumulate, uint32_t issue) {                                  \
+        asm volatile(                                                                                            \
+            "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"                      \
+            "@q tcgen05.mma.cta_group::1.kind::" KIND " [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),            \
+            "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(issue)                                     \
+            : "memory");                                                                                         \
+    }
+NADM_DEF_MMA_TS_P(mma_f16_ts_p, "f16")
+NADM_DEF_MMA_TS_P(mma_i8_ts_p, "i8")
+#undef NADM_DEF_MMA_TS_P
 __device__ __forceinline__ void mma_commit_p(uint64_t* bar, uint32_t issue) {
     asm volatile(
         "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"

@@ -70,6 +70,25 @@ __device__ __forceinline__ void widen_store(uint8_t* dst, uint32_t w, uint32_t m
     *reinterpret_cast<uint4*>(dst) = o;
 }
 
+// the same widening into registers (tensor-memory operand path): o[0..3] = byte positions 0-3, 4-7, 8-11, 12-15
+template <bool RAW>
+__device__ __forceinline__ void widen_regs(uint32_t w, uint32_t mvx, uint32_t* o) {
+    if (!RAW) {
+        const uint32_t c = clear_missing(w);
+        o[0] = c & 0x03030303u;
+        o[1] = (c >> 2) & 0x03030303u;
+        o[2] = (c >> 4) & 0x03030303u;
+        o[3] = (c >> 6) & 0x03030303u;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t v = (w >> (2 * k)) & 0x03030303u;
+            const uint32_t m3 = v & (v >> 1) & 0x01010101u;          // bytes equal to 3
+            o[k] = v ^ (m3 * mvx);
+        }
+    }
+}
+
 // power-of-two fixed-point scale for values with absolute maximum `mx`: q = rint(v * inv) fits in [-2^30, 2^30]
 struct FixScale {
     float inv;      // 2^(30 - e)
@@ -180,6 +199,33 @@ __device__ __forceinline__ void feed_store(uint8_t* tile, int wl, int lane, cons
     }
 }
 
+// ---- tensor-memory operand path of the forward kernel (TSA): thread = tensor-memory lane = batch row ----------------
+// Thread `lane` of producer warp wl takes the four 16-byte pieces of row wl*32 + lane of the block (they were copied by
+// four different lanes of this warp: piece q of row r + 8 it by lane 8 q + r into plane `it`), widens them in registers
+// and stores them with tcgen05.st: 4 K positions per 32-bit column, 64 columns per 128 x 256 tile (K order = the byte
+// order of the shared-memory tile, so the digit operand is unchanged).
+__device__ __forceinline__ void feed_load_rows(const Feed& f, int slot, int wl, int lane, uint4 (&w)[4]) {
+    cp_async_wait<kStDepth - 1>();
+    __syncwarp();                                                // the other lanes' copies of my row have landed
+    const uint8_t* st = f.stage + slot * kStTile + (wl * 32 + (lane & 7)) * 16 + (lane >> 3) * 2048;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) w[q] = *reinterpret_cast<const uint4*>(st + q * 128);
+    __syncwarp();                                                // every lane has read before any lane refills the slot
+}
+template <bool RAW>
+__device__ __forceinline__ void feed_store_tmem(uint32_t taddr, const uint4 (&w)[4], uint32_t mvx) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        uint32_t v[16];
+        widen_regs<RAW>(w[q].x, mvx, v);
+        widen_regs<RAW>(w[q].y, mvx, v + 4);
+        widen_regs<RAW>(w[q].z, mvx, v + 8);
+        widen_regs<RAW>(w[q].w, mvx, v + 12);
+        tmem_st16(taddr + q * 16, v);
+    }
+}
+constexpr int kColA = 256;   // TSA: tensor-memory columns [256, 512) = 4 genotype tiles of 64 columns; [0, 256) accumulators
+
 // =================================================================================================================
 // forward
 // =================================================================================================================
@@ -210,7 +256,11 @@ struct EncSmem {
 // With 1 issuer, fewer than 3 or more than 8 row blocks: one accumulator set.
 constexpr int kFwdDigWarps = 2, kFwdIssueWarp = kProdWarps + kFwdDigWarps, kFwdThreads = (kFwdIssueWarp + 2) * 32;
 
-template <int NISS, bool RAW>   // NISS: MMA issuer warps in use (2, or 1: the second then idles); RAW: see widen_store
+// TSA: the genotype operand lives in TENSOR memory (tcgen05.mma TS form) instead of shared memory: the 32 KB widened
+// tile is then neither written to nor read from shared memory (the kernel's measured bound).  Both issuers accumulate
+// into ONE accumulator set (zero-initialised, every MMA accumulates; integer adds commute; tests/cuda/umma_probe.cu
+// case 7): 8 x 32 accumulator columns + 4 x 64 tile columns = 512.
+template <int NISS, bool RAW, bool TSA>   // NISS: MMA issuer warps in use (2, or 1: the second then idles); RAW: see widen_store
 __global__ void __launch_bounds__(kFwdThreads, 1)
 enc_fwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* __restrict__ row_idx, int64_t row0,
                   int B, int64_t M, const float* __restrict__ V, int C, float* __restrict__ cta_vmax,
@@ -268,6 +318,18 @@ enc_fwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
     float vmax = 0.f;
     for (int w = 0; w < kFwdThreads / 32; ++w) vmax = fmaxf(vmax, S->red[w]);
     if (tid == 0) cta_vmax[blockIdx.x] = vmax;
+    if (TSA) {
+        if (warp < 4) {                                                 // warps 0..3 = lane quadrants 0..3
+            uint32_t z[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) z[j] = 0u;
+            for (int c0 = 0; c0 < nblk * 32; c0 += 16) tmem_st16(tbase + ((uint32_t)(warp * 32) << 16) + c0, z);
+            tmem_wait_st();
+        }
+        tc_fence_before_sync();
+        __syncthreads();
+        tc_fence_after_sync();
+    }
     if (tid == 0) TLE(2, 1);                                            // setup done
 
     if (warp < kProdWarps) {
@@ -279,14 +341,22 @@ enc_fwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
         for (int i = g; i < ntile; i += 4) {
             uint4 w[4];
             if (tid == 0) TLE(0, i);
-            feed_load(f, slot, wl, lane, w);
+            if (TSA) feed_load_rows(f, slot, wl, lane, w);
+            else feed_load(f, slot, wl, lane, w);
             feed_issue(f, wl, lane);                                 // refill the staging slot just read
             if (tid == 0) TLE(5, i);
             mbar_wait(&S->emptyA[g], phase);
             if (tid == 0) TLE(1, i);
-            feed_store<RAW>(tilesA + g * kATile, wl, lane, w, mvx);
+            if (TSA) {
+                tc_fence_after_sync();                               // the MMAs that read this stage have completed
+                feed_store_tmem<RAW>(tbase + ((uint32_t)(wl * 32) << 16) + kColA + g * 64, w, mvx);
+                tmem_wait_st();
+                tc_fence_before_sync();
+            } else {
+                feed_store<RAW>(tilesA + g * kATile, wl, lane, w, mvx);
+                fence_async_smem();
+            }
             if (tid == 0) TLE(3, i);
-            fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&S->fullA[g]);                // one arrival per warp of the group
             if (tid == 0) TLE(4, i);
@@ -307,11 +377,11 @@ enc_fwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
             uint32_t v[32];
             tmem_ld32(tbase + ((uint32_t)(q * 32) << 16) + blk * 32, v);
             tmem_wait_ld();
-            if (!((init0 >> blk) & 1u)) {
+            if (!TSA && !((init0 >> blk) & 1u)) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = 0u;
             }
-            if (NISS == 2 && ((init1 >> blk) & 1u)) {
+            if (!TSA && NISS == 2 && ((init1 >> blk) & 1u)) {
                 uint32_t v1[32];
                 tmem_ld32(tbase + ((uint32_t)(q * 32) << 16) + (nblk + blk) * 32, v1);
                 tmem_wait_ld();
@@ -388,10 +458,17 @@ enc_fwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
                     tc_fence_after_sync();
                     if (lane == 0) TLE(6, i);
                     const uint64_t a = A0 + (uint64_t)(s * (kATile >> 4)), b = B0 + (uint64_t)(vs * (kDigTile >> 4));
-                    const uint32_t d = tbase + (par * nblk + blk) * 32, acc0 = (inited >> blk) & 1u;
+                    const uint32_t d = tbase + ((TSA ? 0 : par * nblk) + blk) * 32, acc0 = (inited >> blk) & 1u;
+                    if (TSA) {
+                        const uint32_t at = tbase + kColA + s * 64;
 #pragma unroll
-                    for (int ks = 0; ks < kSub / 32; ++ks)
-                        mma_i8_ss_p(d, a + (uint64_t)(ks * 16), b + (uint64_t)(ks * 64), kIdescFwd, ks ? 1u : acc0, leader);
+                        for (int ks = 0; ks < kSub / 32; ++ks)
+                            mma_i8_ts_p(d, at + ks * 8, b + (uint64_t)(ks * 64), kIdescFwd, 1u, leader);
+                    } else {
+#pragma unroll
+                        for (int ks = 0; ks < kSub / 32; ++ks)
+                            mma_i8_ss_p(d, a + (uint64_t)(ks * 16), b + (uint64_t)(ks * 64), kIdescFwd, ks ? 1u : acc0, leader);
+                    }
                     inited |= 1u << blk;
                     mma_commit_p(&S->emptyA[s], leader);
                     if (lane == 0) TLE(7, i);
@@ -654,6 +731,16 @@ enc_bwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
 // host launchers (called from the C ABI in nadm_stream.cu)
 // =================================================================================================================
 // MMA issuer warps per encoder kernel: NADM_ENC_ISSUERS=1|2 (A/B measurements; default below)
+// NADM_ENC_TS=1: forward encoder with its genotype operand in tensor memory (TSA).  Off by default until it has been
+// through the full parity suite on the device.
+static bool enc_fwd_tmem_operand() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("NADM_ENC_TS");
+        v = (e != nullptr && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
 static int enc_issuers() {
     static int n = 0;
     if (n == 0) {
@@ -684,21 +771,29 @@ int launch_enc_fwd_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_i
                         sizeof(EncSmem) + 64;
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(enc_fwd_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(enc_fwd_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(enc_fwd_tc_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(enc_fwd_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+        cudaError_t e = cudaSuccess;
+#define NADM_FWD_ATTR(N_, R_, T_)                                                                                      \
+    if (e == cudaSuccess)                                                                                              \
+        e = cudaFuncSetAttribute(enc_fwd_tc_kernel<N_, R_, T_>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)
+        NADM_FWD_ATTR(1, false, false); NADM_FWD_ATTR(2, false, false); NADM_FWD_ATTR(1, true, false); NADM_FWD_ATTR(2, true, false);
+        NADM_FWD_ATTR(1, false, true); NADM_FWD_ATTR(2, false, true); NADM_FWD_ATTR(1, true, true); NADM_FWD_ATTR(2, true, true);
+#undef NADM_FWD_ATTR
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(enc_fwd_tc)");
         attr = true;
     }
     const int nblk_ = (B + 127) / 128;
     const bool two = enc_issuers() == 2 && nblk_ >= 3 && nblk_ <= 8;   // two accumulator sets: 2 x 32 columns per row block
     const uint32_t mvx = raw_mv >= 0 ? (3u ^ (uint32_t)(raw_mv & 0xFF)) : 0u;
-#define NADM_FWD_GO(N_, R_) \
-    launch_pdl(enc_fwd_tc_kernel<N_, R_>, dim3(ncta), dim3(kFwdThreads), smem, st, packed, pitch, row_idx, row0, B, M, V, C, vmax, part, T, mvx)
+    const bool tsa = enc_fwd_tmem_operand() && nblk_ <= 8;           // accumulators + 4 tiles must fit 512 columns
+#define NADM_FWD_GO(N_, R_)                                                                                            \
+    do {                                                                                                               \
+        if (tsa)                                                                                                       \
+            launch_pdl(enc_fwd_tc_kernel<N_, R_, true>, dim3(ncta), dim3(kFwdThreads), smem, st, packed, pitch, row_idx, \
+                       row0, B, M, V, C, vmax, part, T, mvx);                                                          \
+        else                                                                                                           \
+            launch_pdl(enc_fwd_tc_kernel<N_, R_, false>, dim3(ncta), dim3(kFwdThreads), smem, st, packed, pitch, row_idx, \
+                       row0, B, M, V, C, vmax, part, T, mvx);                                                          \
+    } while (0)
     if (raw_mv >= 0) { if (two) NADM_FWD_GO(2, true); else NADM_FWD_GO(1, true); }
     else { if (two) NADM_FWD_GO(2, false); else NADM_FWD_GO(1, false); }
 #undef NADM_FWD_GO

@@ -46,6 +46,15 @@ except Exception as e:
     print("NADM_NO_PDL=$nopdl failed", e)
 PY
   done;;
+encts)
+  NADM_ENC_TS=1 timeout 60 python -c 'import __graft_entry__ as g; g.smoke()' > $OUT/encts_smoke.txt 2>&1; rc=$?; tail -2 $OUT/encts_smoke.txt; echo "encts smoke rc=$rc"
+  if [ $rc -eq 0 ]; then
+    for ts in 0 1 0 1; do
+      NADM_ENC_TS=$ts timeout 100 python bench.py --rows 20000 --steps 100 --warmup 5 --no-cpu --no-e2e > $OUT/ab_encts$ts.json 2> $OUT/ab_encts$ts.err
+      python -c "import json;d=json.loads(open('$OUT/ab_encts$ts.json').read().strip().splitlines()[-1]);print('NADM_ENC_TS=$ts ms/step',round(d['ms_per_step'],4),'infer',round(d['infer']['value']))" || echo "NADM_ENC_TS=$ts failed"
+    done
+    NADM_ENC_TS=1 timeout 200 python -m pytest tests -m gpu -x -q --timeout 40 > $OUT/encts_pytest.log 2>&1; echo "encts pytest rc=$?"; tail -3 $OUT/encts_pytest.log
+  fi;;
 bench)
   timeout 1200 python bench.py > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?"; tail -c 3000 $OUT/bench.json;;
 launches)
