@@ -31,6 +31,11 @@ constexpr int kProdWarps = 16;             // 4 producer groups of 4 warps; a gr
 constexpr int kProdThreads = kProdWarps * 32;
 constexpr int kStTile = 128 * 64;          // packed bytes of one tile in the staging ring
 constexpr int kStDepth = 2;                // tiles in flight from HBM per producer group (cp.async commit groups)
+#ifndef NADM_ENC_TS_DEPTH
+#define NADM_ENC_TS_DEPTH 2
+#endif
+constexpr int kStDepthTS = NADM_ENC_TS_DEPTH;   // the same for the tensor-memory operand variant (no widened tiles in
+                                                // shared memory: room for a deeper ring)
 constexpr int kMaxBlkTc = 16;              // 16 blocks of 128 rows per launch (16 x 32 tensor-memory columns)
 constexpr uint32_t kIdescFwd = instr_desc(kAccS32, kFmtU8, kFmtS8, /*A MN*/ false, /*B MN*/ true, 128, 32);
 constexpr uint32_t kIdescBwd = instr_desc(kAccS32, kFmtU8, kFmtS8, /*A MN*/ true, /*B MN*/ true, 128, 32);
@@ -74,11 +79,23 @@ __device__ __forceinline__ void widen_store(uint8_t* dst, uint32_t w, uint32_t m
 template <bool RAW>
 __device__ __forceinline__ void widen_regs(uint32_t w, uint32_t mvx, uint32_t* o) {
     if (!RAW) {
+#ifdef NADM_ENC_TS_SCALED
+        // fields left in place: byte positions 4j..4j+3 hold 4^j x code (<= 128, still a u8), one LOP3 per output word
+        // and no shifts (integer/logic instructions issue at one per 2 clocks); the digit operand of those K positions
+        // is built from V / 4^j (store_digits_scaled), i.e. they carry 2j fewer fixed-point bits (>= 2^-25 of max|V|)
+        const uint32_t m = w & (w >> 1) & 0x55555555u;
+        const uint32_t keep = ~(m * 3u);
+        o[0] = w & 0x03030303u & keep;
+        o[1] = w & 0x0C0C0C0Cu & keep;
+        o[2] = w & 0x30303030u & keep;
+        o[3] = w & 0xC0C0C0C0u & keep;
+#else
         const uint32_t c = clear_missing(w);
         o[0] = c & 0x03030303u;
         o[1] = (c >> 2) & 0x03030303u;
         o[2] = (c >> 4) & 0x03030303u;
         o[3] = (c >> 6) & 0x03030303u;
+#endif
     } else {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -145,6 +162,7 @@ struct Feed {
     uint8_t* stage;          // this group's ring: kStDepth x kStTile; thread (wl, lane) owns 4 pieces of 16 bytes per slot
     int c_blk, c_tt, c_i;    // next tile of this group to copy (tile index c_i = g + 4 n)
     int c_slot;
+    int depth;               // slots of the ring
 };
 // every thread of the group: start the asynchronous copy of its four 16-byte pieces of the group's next tile.
 // Pieces of rows past the batch (or past the row pitch) are zeroed with a plain shared-memory store instead of a
@@ -171,7 +189,7 @@ __device__ __forceinline__ void feed_issue(Feed& f, int wl, int lane) {
         f.c_blk += 4;
         while (f.c_blk >= f.nblk) { f.c_blk -= f.nblk; ++f.c_tt; }
     }
-    f.c_slot = (f.c_slot + 1 == kStDepth) ? 0 : f.c_slot + 1;
+    f.c_slot = (f.c_slot + 1 == f.depth) ? 0 : f.c_slot + 1;
     cp_async_commit();       // always one group per call: keeps wait_group counting aligned at the tail
 }
 // load this thread's four staged pieces of the tile in staging slot `slot` into registers (they have landed once at most
@@ -204,8 +222,9 @@ __device__ __forceinline__ void feed_store(uint8_t* tile, int wl, int lane, cons
 // four different lanes of this warp: piece q of row r + 8 it by lane 8 q + r into plane `it`), widens them in registers
 // and stores them with tcgen05.st: 4 K positions per 32-bit column, 64 columns per 128 x 256 tile (K order = the byte
 // order of the shared-memory tile, so the digit operand is unchanged).
+template <int DEPTH>
 __device__ __forceinline__ void feed_load_rows(const Feed& f, int slot, int wl, int lane, uint4 (&w)[4]) {
-    cp_async_wait<kStDepth - 1>();
+    cp_async_wait<DEPTH - 1>();
     __syncwarp();                                                // the other lanes' copies of my row have landed
     const uint8_t* st = f.stage + slot * kStTile + (wl * 32 + (lane & 7)) * 16 + (lane >> 3) * 2048;
 #pragma unroll
@@ -267,10 +286,11 @@ enc_fwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
                   long long* __restrict__ part, int T, uint32_t mvx) {
     pdl_prologue();
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint8_t* tilesA = smem;                                         // kAStages x 32 KB
-    uint8_t* tilesV = tilesA + kAStages * kATile;                   // 2 x 8 KB
-    uint8_t* stage = tilesV + 2 * kDigTile;                         // kStDepth x 10 KB packed rows
-    uint32_t* rowoff = reinterpret_cast<uint32_t*>(stage + 4 * kStDepth * kStTile);
+    constexpr int kDepth = TSA ? kStDepthTS : kStDepth;
+    uint8_t* tilesA = smem;                                         // kAStages x 32 KB (not allocated with TSA)
+    uint8_t* tilesV = TSA ? smem : tilesA + kAStages * kATile;      // 2 x 8 KB
+    uint8_t* stage = tilesV + 2 * kDigTile;                         // 4 groups x kDepth x 8 KB packed rows
+    uint32_t* rowoff = reinterpret_cast<uint32_t*>(stage + 4 * kDepth * kStTile);
     EncSmem* S = reinterpret_cast<EncSmem*>(rowoff + ((B + 3) & ~3));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nblk = (B + 127) / 128;
@@ -335,13 +355,13 @@ enc_fwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
     if (warp < kProdWarps) {
         // ---------------- producers: widened genotype tiles (group g = warp / 4 handles tiles g, g + 4, ...) ----------------
         const int g = warp >> 2, wl = warp & 3;
-        Feed f{packed, pitch, rowoff, B, nblk, t0, ntile, stage + g * (kStDepth * kStTile), g % nblk, g / nblk, g, 0};
-        for (int p = 0; p < kStDepth; ++p) feed_issue(f, wl, lane);
+        Feed f{packed, pitch, rowoff, B, nblk, t0, ntile, stage + g * (kDepth * kStTile), g % nblk, g / nblk, g, 0, kDepth};
+        for (int p = 0; p < kDepth; ++p) feed_issue(f, wl, lane);
         int blk = g % nblk, slot = 0, phase = 1;
         for (int i = g; i < ntile; i += 4) {
             uint4 w[4];
             if (tid == 0) TLE(0, i);
-            if (TSA) feed_load_rows(f, slot, wl, lane, w);
+            if (TSA) feed_load_rows<kDepth>(f, slot, wl, lane, w);
             else feed_load(f, slot, wl, lane, w);
             feed_issue(f, wl, lane);                                 // refill the staging slot just read
             if (tid == 0) TLE(5, i);
@@ -361,7 +381,7 @@ enc_fwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
             if (lane == 0) mbar_arrive(&S->fullA[g]);                // one arrival per warp of the group
             if (tid == 0) TLE(4, i);
             phase ^= 1;
-            slot = (slot + 1 == kStDepth) ? 0 : slot + 1;
+            slot = (slot + 1 == kDepth) ? 0 : slot + 1;
             blk += 4;
             while (blk >= nblk) blk -= nblk;
         }
@@ -433,7 +453,12 @@ enc_fwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int pos = dt + 64 * e;
-                store_digits(tilesV + vs * kDigTile + (pos & 7) * 16 + (pos >> 3) * 256, v[e], fs.inv);
+#ifdef NADM_ENC_TS_SCALED
+                const float inv_pos = (TSA && !RAW) ? fs.inv * __uint_as_float((uint32_t)(127 - 2 * ((pos & 15) >> 2)) << 23) : fs.inv;
+#else
+                const float inv_pos = fs.inv;
+#endif
+                store_digits(tilesV + vs * kDigTile + (pos & 7) * 16 + (pos >> 3) * 256, v[e], inv_pos);
             }
             fence_async_smem();
             __syncwarp();
@@ -587,7 +612,7 @@ enc_bwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
     if (warp < kProdWarps) {
         // ---------------- producers: widened genotype tiles, order (sub-tile, block) ----------------
         const int g = warp >> 2, wl = warp & 3;
-        Feed f{packed, pitch, rowoff, B, nblk, t0, ntile, stage + g * (kStDepth * kStTile), g % nblk, g / nblk, g, 0};
+        Feed f{packed, pitch, rowoff, B, nblk, t0, ntile, stage + g * (kStDepth * kStTile), g % nblk, g / nblk, g, 0, kStDepth};
         for (int p = 0; p < kStDepth; ++p) feed_issue(f, wl, lane);
         int blk = g % nblk, slot = 0, phase = 1;
         for (int i = g; i < ntile; i += 4) {
@@ -767,8 +792,10 @@ int launch_enc_fwd_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_i
     NADM_REQUIRE(need <= ws_bytes, "workspace too small for encoder_fwd (%zu > %zu)", need, ws_bytes);
     float* vmax = reinterpret_cast<float*>(ws);                     // per-CTA |max| of its slice of V (ncta floats)
     long long* part = reinterpret_cast<long long*>(reinterpret_cast<uint8_t*>(ws) + kEncWsHeader);
-    const size_t smem = (size_t)kAStages * kATile + 2 * kDigTile + (size_t)4 * kStDepth * kStTile + (size_t)((B + 3) & ~3) * 4 +
-                        sizeof(EncSmem) + 64;
+    const int nblk_ = (B + 127) / 128;
+    const bool tsa = enc_fwd_tmem_operand() && nblk_ <= 8;           // accumulators + 4 tiles must fit 512 columns
+    const size_t smem = (tsa ? (size_t)4 * kStDepthTS * kStTile : (size_t)kAStages * kATile + (size_t)4 * kStDepth * kStTile) +
+                        2 * kDigTile + (size_t)((B + 3) & ~3) * 4 + sizeof(EncSmem) + 64;
     static bool attr = false;
     if (!attr) {
         cudaError_t e = cudaSuccess;
@@ -781,10 +808,8 @@ int launch_enc_fwd_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_i
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(enc_fwd_tc)");
         attr = true;
     }
-    const int nblk_ = (B + 127) / 128;
     const bool two = enc_issuers() == 2 && nblk_ >= 3 && nblk_ <= 8;   // two accumulator sets: 2 x 32 columns per row block
     const uint32_t mvx = raw_mv >= 0 ? (3u ^ (uint32_t)(raw_mv & 0xFF)) : 0u;
-    const bool tsa = enc_fwd_tmem_operand() && nblk_ <= 8;           // accumulators + 4 tiles must fit 512 columns
 #define NADM_FWD_GO(N_, R_)                                                                                            \
     do {                                                                                                               \
         if (tsa)                                                                                                       \
