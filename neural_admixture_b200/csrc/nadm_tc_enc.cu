@@ -231,10 +231,10 @@ __device__ __forceinline__ void feed_load_rows(const Feed& f, int slot, int wl, 
     for (int q = 0; q < 4; ++q) w[q] = *reinterpret_cast<const uint4*>(st + q * 128);
     __syncwarp();                                                // every lane has read before any lane refills the slot
 }
-template <bool RAW>
+template <bool RAW, int Q0 = 0, int Q1 = 4>   // pieces [Q0, Q1) of the row: 64 SNPs = 16 columns each
 __device__ __forceinline__ void feed_store_tmem(uint32_t taddr, const uint4 (&w)[4], uint32_t mvx) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = Q0; q < Q1; ++q) {
         uint32_t v[16];
         widen_regs<RAW>(w[q].x, mvx, v);
         widen_regs<RAW>(w[q].y, mvx, v + 4);
@@ -260,6 +260,9 @@ extern "C" int nadm_debug_enc_timeline(long long* host_out) {
 
 struct EncSmem {
     uint64_t fullA[kAStages], emptyA[kAStages], fullV[2], emptyV[2], done, fdone;
+#ifdef NADM_ENC_TS_HALF
+    uint64_t fullA2[kAStages], emptyA2[kAStages];   // the second half (SNPs 128..255) of every stage
+#endif
     uint32_t tmem_base;
     uint32_t finit[2];   // per issuer: bit blk set = its accumulator of row block blk has been written
     float red[32];       // per-warp |max| of this CTA's slice of V
@@ -302,6 +305,9 @@ enc_fwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
         rowoff[b] = (uint32_t)((((row_idx != nullptr) ? row_idx[b] : (row0 + b)) * pitch) >> 4);
     if (tid == 0) {
         for (int s = 0; s < kAStages; ++s) { mbar_init(&S->fullA[s], 4); mbar_init(&S->emptyA[s], 1); }
+#ifdef NADM_ENC_TS_HALF
+        for (int s = 0; s < kAStages; ++s) { mbar_init(&S->fullA2[s], 4); mbar_init(&S->emptyA2[s], 1); }
+#endif
         for (int s = 0; s < 2; ++s) { mbar_init(&S->fullV[s], kFwdDigWarps); mbar_init(&S->emptyV[s], NISS); }
         mbar_init(&S->done, NISS);
         mbar_init(&S->fdone, NISS);
@@ -368,17 +374,38 @@ enc_fwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
             mbar_wait(&S->emptyA[g], phase);
             if (tid == 0) TLE(1, i);
             if (TSA) {
+                const uint32_t ta = tbase + ((uint32_t)(wl * 32) << 16) + kColA + g * 64;
                 tc_fence_after_sync();                               // the MMAs that read this stage have completed
-                feed_store_tmem<RAW>(tbase + ((uint32_t)(wl * 32) << 16) + kColA + g * 64, w, mvx);
+#ifdef NADM_ENC_TS_HALF
+                // (untested on the device: prepared for the next round)  The stage is handed over in
+                // two halves with their own full / empty barriers: while the issuer multiplies SNPs 128..255 of tile t
+                // (and the commit -> mbarrier -> poll hop runs), this group already widens SNPs 0..127 of its next tile.
+                feed_store_tmem<RAW, 0, 2>(ta, w, mvx);
                 tmem_wait_st();
                 tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&S->fullA[g]);
+                mbar_wait(&S->emptyA2[g], phase);
+                tc_fence_after_sync();
+                feed_store_tmem<RAW, 2, 4>(ta, w, mvx);
+                tmem_wait_st();
+                tc_fence_before_sync();
+#else
+                feed_store_tmem<RAW>(ta, w, mvx);
+                tmem_wait_st();
+                tc_fence_before_sync();
+#endif
             } else {
                 feed_store<RAW>(tilesA + g * kATile, wl, lane, w, mvx);
                 fence_async_smem();
             }
             if (tid == 0) TLE(3, i);
             __syncwarp();
+#ifdef NADM_ENC_TS_HALF
+            if (lane == 0) mbar_arrive(TSA ? &S->fullA2[g] : &S->fullA[g]);
+#else
             if (lane == 0) mbar_arrive(&S->fullA[g]);                // one arrival per warp of the group
+#endif
             if (tid == 0) TLE(4, i);
             phase ^= 1;
             slot = (slot + 1 == kDepth) ? 0 : slot + 1;
@@ -486,16 +513,32 @@ enc_fwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
                     const uint32_t d = tbase + ((TSA ? 0 : par * nblk) + blk) * 32, acc0 = (inited >> blk) & 1u;
                     if (TSA) {
                         const uint32_t at = tbase + kColA + s * 64;
+#ifdef NADM_ENC_TS_HALF
+#pragma unroll
+                        for (int ks = 0; ks < kSub / 64; ++ks)
+                            mma_i8_ts_p(d, at + ks * 8, b + (uint64_t)(ks * 64), kIdescFwd, 1u, leader);
+                        mma_commit_p(&S->emptyA[s], leader);             // first half of the stage may be refilled
+                        mbar_wait(&S->fullA2[s], (i >> 2) & 1);
+                        tc_fence_after_sync();
+#pragma unroll
+                        for (int ks = kSub / 64; ks < kSub / 32; ++ks)
+                            mma_i8_ts_p(d, at + ks * 8, b + (uint64_t)(ks * 64), kIdescFwd, 1u, leader);
+#else
 #pragma unroll
                         for (int ks = 0; ks < kSub / 32; ++ks)
                             mma_i8_ts_p(d, at + ks * 8, b + (uint64_t)(ks * 64), kIdescFwd, 1u, leader);
+#endif
                     } else {
 #pragma unroll
                         for (int ks = 0; ks < kSub / 32; ++ks)
                             mma_i8_ss_p(d, a + (uint64_t)(ks * 16), b + (uint64_t)(ks * 64), kIdescFwd, ks ? 1u : acc0, leader);
                     }
                     inited |= 1u << blk;
+#ifdef NADM_ENC_TS_HALF
+                    mma_commit_p(TSA ? &S->emptyA2[s] : &S->emptyA[s], leader);
+#else
                     mma_commit_p(&S->emptyA[s], leader);
+#endif
                     if (lane == 0) TLE(7, i);
                 }
                 mma_commit_p(&S->emptyV[vs], leader);
