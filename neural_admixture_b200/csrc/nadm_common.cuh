@@ -33,15 +33,15 @@ int sm_count();
         nadm::count_launch();                                    \
     } while (0)
 
-// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------------
-// Every kernel of the step is launched with cudaLaunchAttributeProgrammaticStreamSerialization and begins with
-// pdl_prologue(): `launch_dependents` lets the NEXT kernel of the stream (or of the captured graph) be scheduled as soon
-// as all CTAs of this one have started, `wait` then blocks until the PREVIOUS kernel has completed and its memory is
-// visible.  Nothing before the wait touches global memory, so the semantics are those of plain stream order; what is
-// gained is the launch / CTA-scheduling latency at each kernel boundary of EAGERLY launched sequences (the forward-only
-// Q pass: +3.5 %).  Inside a captured CUDA graph the programmatic edges were measured to be slower than the graph's
-// ordinary kernel-to-kernel edges (0.451 vs 0.441 ms per step), so launches made while the stream is capturing do not
-// set the attribute.  NADM_NO_PDL=1 turns it off everywhere (the two instructions are then no-ops).
+// ---- programmatic dependent launch (PDL), opt-in with NADM_PDL=1 --------------------------------------------------
+// Every kernel of the step begins with pdl_prologue(): `launch_dependents` lets the NEXT kernel of the stream be
+// scheduled as soon as all CTAs of this one have started, `wait` then blocks until the PREVIOUS kernel has completed and
+// its memory is visible.  Nothing before the wait touches global memory, so the semantics are those of plain stream
+// order.  Without the launch attribute (the default) the two instructions are no-ops.  With NADM_PDL=1 eager launches
+// set cudaLaunchAttributeProgrammaticStreamSerialization: measured +3.5 % on the forward-only Q pass (launch and
+// CTA-scheduling latency of each kernel boundary hidden); inside a captured CUDA graph the programmatic edges were
+// slower than the graph's ordinary edges (0.451 vs 0.441 ms per step), so capturing launches never set it.  It stays
+// opt-in until the host-fed loop (two streams, events) has been through the device tests with it.
 bool pdl_enabled();
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_prologue() {

@@ -40,11 +40,11 @@ int sm_count() {
     return cached[dev];
 }
 
-bool pdl_enabled() {
+bool pdl_enabled() {   // opt-in (NADM_PDL=1): see nadm_common.cuh
     static int v = -1;
     if (v < 0) {
-        const char* e = getenv("NADM_NO_PDL");
-        v = (e != nullptr && e[0] == '1') ? 0 : 1;
+        const char* e = getenv("NADM_PDL");
+        v = (e != nullptr && e[0] == '1') ? 1 : 0;
     }
     return v == 1;
 }

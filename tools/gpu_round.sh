@@ -35,15 +35,15 @@ except Exception as e:
 PY
   done;;
 abpdl)
-  for nopdl in 1 0 1 0; do
-    NADM_NO_PDL=$nopdl timeout 150 python bench.py --rows 20000 --steps 100 --warmup 5 --no-cpu --no-e2e > $OUT/ab_nopdl$nopdl.json 2> $OUT/ab_nopdl$nopdl.err
+  for pdl in 0 1 0 1; do
+    NADM_PDL=$pdl timeout 150 python bench.py --rows 20000 --steps 100 --warmup 5 --no-cpu --no-e2e > $OUT/ab_pdl$pdl.json 2> $OUT/ab_pdl$pdl.err
     python - <<PY
 import json
 try:
-    d=json.loads(open("$OUT/ab_nopdl$nopdl.json").read().strip().splitlines()[-1])
-    print("NADM_NO_PDL=$nopdl ms/step", round(d["ms_per_step"],4), "dec ms", round(d["roofline"]["ms_per_launch"],4), "grad_only ms", round(d["grad_only"]["ms_per_step"],4), "infer", round(d["infer"]["value"]))
+    d=json.loads(open("$OUT/ab_pdl$pdl.json").read().strip().splitlines()[-1])
+    print("NADM_PDL=$pdl ms/step", round(d["ms_per_step"],4), "dec ms", round(d["roofline"]["ms_per_launch"],4), "grad_only ms", round(d["grad_only"]["ms_per_step"],4), "infer", round(d["infer"]["value"]))
 except Exception as e:
-    print("NADM_NO_PDL=$nopdl failed", e)
+    print("NADM_PDL=$pdl failed", e)
 PY
   done;;
 encts)
