@@ -557,6 +557,40 @@ def test_graph_replayed_steps_match_eager(dev, monkeypatch):
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# host-fed steps (train_from_host: two streams, staged batches; what bench.py's e2e leg times) == resident-matrix steps
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.xfail(strict=False, reason="written after this round's GPU budget was spent: not yet seen on the device; "
+                                        "drop the marker once it has passed (also run it with NADM_PDL=1)")
+def test_host_fed_steps_match_resident_steps(dev, monkeypatch):
+    from neural_admixture_b200 import ops
+    from neural_admixture_b200.model.neural_admixture import NeuralAdmixture
+    rng = np.random.default_rng(11)
+    N, M, K, C, H, B, S = 300, 2051, 4, 8, 64, 100, 3
+    G = rand_genotypes(rng, N, M)
+    V = np.linalg.qr(rng.standard_normal((M, C)))[0].astype(np.float32)
+    P0 = rng.uniform(0.05, 0.95, size=(K, M)).astype(np.float32)
+    order = torch.as_tensor(rng.permutation(N)[: S * B].astype(np.int64))
+    monkeypatch.setattr(NeuralAdmixture, "use_graph", False)      # eager resident steps: the same five calls per step
+    res = []
+    for host_fed in (False, True):
+        torch.manual_seed(5)
+        na = NeuralAdmixture(K, 1, B, 2e-3, dev, 7, 0, True, "nadm_b200", None, None)
+        pg = packed_from(ops, G, dev)
+        na.prepare(torch.as_tensor(P0, device=dev), pg, H, C, torch.as_tensor(V, device=dev), M, N)
+        if host_fed:
+            rows = pg.storage.cpu()                                  # N x pitch, the PackedGenotypes row layout
+            batches = [rows[order[s * B:(s + 1) * B]].contiguous().pin_memory() for s in range(S)]
+            losses = np.array(na.train_from_host(batches))
+        else:
+            losses = na.train_steps(order.to(dev), S, True).cpu().numpy()
+        torch.cuda.synchronize()
+        res.append((na.raw_model.V.detach().cpu().numpy().copy(),
+                    na.raw_model.decoders.decoders[0].weight.detach().cpu().numpy().copy(), losses))
+    assert relF(res[1][0], res[0][0]) < 1e-6 and relF(res[1][1], res[0][1]) < 1e-6
+    np.testing.assert_allclose(res[1][2], res[0][2], rtol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------------------------
 # full-size properties (config 2: 10k x 100k, K = 8; B = 800) — no oracle needed
 # ---------------------------------------------------------------------------------------------------------------
 def test_fullsize_properties(ops, dev):
