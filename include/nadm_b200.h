@@ -63,6 +63,10 @@ const char* nadm_last_error(void);
 
 /* Number of kernels this library has launched from the calling process so far (bench.py's gpu_launches). */
 int64_t nadm_launch_count(void);
+/* How many of those were the first-generation CUDA-core kernels, which serve the shapes the tensor-core kernels do not
+ * take (C > 8, B above the tensor-memory budget, misaligned parameter pointers) and are several times slower: a caller
+ * that sees this number move should know it left the fast path (the Python mirror warns once, bench.py reports it). */
+int64_t nadm_generic_launch_count(void);
 
 /* ---- 2-bit pack / unpack: device -> device.  Replaces pack2bit_kernel (pack2bit.cu:10-36; the host wrapper
  * pack2bit_cpu_to_gpu :65-117 stages <=1024 unpacked rows to the device and calls it) and unpack2bit_kernel /

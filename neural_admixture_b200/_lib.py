@@ -35,6 +35,7 @@ SIGNATURES = {
     "nadm_version": (C.c_int, []),
     "nadm_last_error": (C.c_char_p, []),
     "nadm_launch_count": (C.c_int64, []),
+    "nadm_generic_launch_count": (C.c_int64, []),
     "nadm_pack2bit": (C.c_int, [c_u8p, C.c_int64, C.c_int64, C.c_int64, c_u8p, C.c_int64, C.c_void_p]),
     "nadm_unpack2bit": (C.c_int, [c_u8p, C.c_int64, C.c_int64, C.c_int64, c_u8p, C.c_int64, C.c_void_p]),
     "nadm_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32]),

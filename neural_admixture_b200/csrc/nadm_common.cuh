@@ -16,7 +16,18 @@ namespace nadm {
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
 void count_launch(int n = 1);
+void count_generic(int n = 1);   // launches of the first-generation CUDA-core kernels (shapes outside the tensor-core path)
 int sm_count();
+
+// cudaFuncSetAttribute is a per-DEVICE setting: remember per device whether a kernel's shared-memory opt-in is done
+struct PerDeviceOnce {
+    bool done_[64] = {};
+    bool* slot() {
+        int d = 0;
+        if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return nullptr;
+        return &done_[d];
+    }
+};
 
 #define NADM_REQUIRE(cond, ...)            \
     do {                                   \

@@ -15,7 +15,7 @@ namespace nadm {
 
 // ---- error / bookkeeping (shared by all translation units) -------------------------------------------------------
 static thread_local char g_err[512] = "";
-static int64_t g_launches = 0;
+static int64_t g_launches = 0, g_generic = 0;
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -28,6 +28,7 @@ int cuda_fail(cudaError_t e, const char* what) {
     return NADM_ECUDA;
 }
 void count_launch(int n) { __atomic_fetch_add(&g_launches, (int64_t)n, __ATOMIC_RELAXED); }
+void count_generic(int n) { __atomic_fetch_add(&g_generic, (int64_t)n, __ATOMIC_RELAXED); }
 int sm_count() {
     static int cached[64] = {0};
     int dev = 0;
@@ -413,6 +414,7 @@ static int make_heads(const int32_t* ks, int nheads, Heads* hd) {
 extern "C" int nadm_version(void) { return 100; }
 extern "C" const char* nadm_last_error(void) { return g_err; }
 extern "C" int64_t nadm_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+extern "C" int64_t nadm_generic_launch_count(void) { return __atomic_load_n(&g_generic, __ATOMIC_RELAXED); }
 
 extern "C" int nadm_mlp_fwd(const float* Z, int32_t B, int32_t C, int32_t H, const float* w_rms, const float* W1,
                             const float* b1, const float* W2, const float* b2, const int32_t* ks, int32_t nheads,
@@ -424,11 +426,12 @@ extern "C" int nadm_mlp_fwd(const float* Z, int32_t B, int32_t C, int32_t H, con
     NADM_REQUIRE(Z && w_rms && W1 && b1 && W2 && b2 && rinv && Hh && Q, "NULL pointer");
     const size_t smem = ((size_t)kMlpRows * NADM_MAX_C + (size_t)kMlpRows * H + (size_t)kMlpRows * hd.sumK) * sizeof(float);
     NADM_REQUIRE(smem <= 200 * 1024, "hidden_size H=%d too large", H);
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce once;
+    bool* attr = once.slot();
+    if (attr == nullptr || !*attr) {
         cudaError_t e = cudaFuncSetAttribute(mlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(mlp_fwd)");
-        attr = true;
+        if (attr) *attr = true;
     }
     launch_pdl(mlp_fwd_kernel, dim3((B + kMlpRows - 1) / kMlpRows), dim3(kMlpThreads), smem, (cudaStream_t)stream, Z, B, C, H,
                w_rms, W1, b1, W2, b2, hd, rinv, Hh, Q);

@@ -619,14 +619,16 @@ static int launch_enc_fwd(const uint8_t* packed, int64_t pitch, const int64_t* r
     nslab = std::min(std::min(nslab, ntiles), kMaxParts);
     NADM_REQUIRE((size_t)nslab * B * CP * sizeof(float) <= ws_bytes, "workspace too small for encoder_fwd");
     const size_t smem = ((RB * 8 + 15) / 16) * 16 + 2 * ((size_t)RB * kEncRowStride + kEncTileSnps * CP * 4);
-    static bool attr_done[2] = {false, false};
-    if (!attr_done[CP == 16]) {
+    static PerDeviceOnce once;                       // (one instance per template instantiation)
+    bool* attr = once.slot();
+    if (attr == nullptr || !*attr) {
         cudaError_t e = cudaFuncSetAttribute(enc_fwd_kernel<CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(enc_fwd)");
-        attr_done[CP == 16] = true;
+        if (attr) *attr = true;
     }
     enc_fwd_kernel<CP><<<dim3(nslab, ngroups), RB, smem, st>>>(packed, pitch, row_idx, row0, B, M, V, C, ws, ntiles, nslab);
     NADM_CHECK_LAUNCH("enc_fwd_kernel");
+    count_generic();
     const int64_t n = (int64_t)B * CP;
     reduce_parts_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(ws, nslab, B, CP, C, Z, C, 0, 0.5f, nullptr, nullptr);
     NADM_CHECK_LAUNCH("reduce_parts_kernel");
@@ -640,6 +642,7 @@ extern "C" int nadm_encoder_fwd(const uint8_t* packed, int64_t pitch, const int6
     NADM_REQUIRE(B > 0 && M > 0, "empty batch or no SNPs (B=%d, M=%lld)", B, (long long)M);
     NADM_REQUIRE(C >= 1 && C <= NADM_MAX_C, "n_components C=%d unsupported (1..%d)", C, NADM_MAX_C);
     NADM_REQUIRE(V && Z && ws, "NULL pointer");
+    NADM_REQUIRE(row0 >= 0 && row0 + B <= (1ll << 32), "row numbers must fit 32 bits (row0=%lld)", (long long)row0);
     if (C <= 8 && !use_generic_kernels() && (reinterpret_cast<uintptr_t>(V) & 15) == 0) {
         // tensor-core path: at most 2048 rows (16 blocks of 128) per launch
         for (int r0 = 0; r0 < B; r0 += 2048) {
@@ -666,18 +669,19 @@ static int launch_dec(const uint8_t* packed, int64_t pitch, const int64_t* row_i
     const int per_sm = std::max(1, (int)((227 * 1024) / (smem + 2048)));
     int ncta = std::min(std::min(ntiles, sm_count() * std::min(per_sm, 3)), kMaxParts);
     NADM_REQUIRE((size_t)ncta * ((size_t)B * KP + 1) * sizeof(float) <= ws_bytes, "workspace too small for decoder_step");
-    static bool attr_done[3] = {false, false, false};
-    const int ai = KP == 4 ? 0 : (KP == 8 ? 1 : 2);
-    if (!attr_done[ai]) {
+    static PerDeviceOnce once;
+    bool* attr = once.slot();
+    if (attr == nullptr || !*attr) {
         cudaError_t e = cudaFuncSetAttribute(dec_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(dec)");
-        attr_done[ai] = true;
+        if (attr) *attr = true;
     }
     float* dQpart = ws;
     float* loss_part = ws + (size_t)ncta * B * KP;
     dec_kernel<KP><<<ncta, kStreamWarps * 32, smem, st>>>(packed, pitch, row_idx, row0, B, M, Q, q_ld, q_off, k, P, Pm, Pv,
                                                          make_adam(adam), dP_out, dQpart, loss_part, ntiles);
     NADM_CHECK_LAUNCH("dec_kernel");
+    count_generic();
     const int64_t n = (int64_t)B * KP;
     reduce_parts_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(dQpart, ncta, B, KP, k, dQ, q_ld, q_off, 1.0f, loss_part, loss);
     NADM_CHECK_LAUNCH("reduce_parts_kernel");
@@ -718,15 +722,17 @@ static int launch_enc_bwd(const uint8_t* packed, int64_t pitch, const int64_t* r
     NADM_REQUIRE(smem <= (size_t)kMaxDynSmem, "batch B=%d too large for encoder_bwd (needs %zu bytes of shared memory)", B, smem);
     const int per_sm = std::max(1, (int)((227 * 1024) / (smem + 2048)));
     const int ncta = std::min(ntiles, sm_count() * std::min(per_sm, 3));
-    static bool attr_done[2] = {false, false};
-    if (!attr_done[CP == 16]) {
+    static PerDeviceOnce once;
+    bool* attr = once.slot();
+    if (attr == nullptr || !*attr) {
         cudaError_t e = cudaFuncSetAttribute(enc_bwd_kernel<CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(enc_bwd)");
-        attr_done[CP == 16] = true;
+        if (attr) *attr = true;
     }
     enc_bwd_kernel<CP><<<ncta, kStreamWarps * 32, smem, st>>>(packed, pitch, row_idx, row0, B, M, dZ, C, V, Vm, Vv,
                                                              make_adam(adam), dV_out, ntiles);
     NADM_CHECK_LAUNCH("enc_bwd_kernel");
+    count_generic();
     return NADM_OK;
 }
 
@@ -740,6 +746,7 @@ extern "C" int nadm_encoder_bwd(const uint8_t* packed, int64_t pitch, const int6
     NADM_REQUIRE(dZ && V, "NULL pointer");
     NADM_REQUIRE(adam == nullptr || (Vm && Vv), "Adam moments are NULL");
     NADM_REQUIRE(adam != nullptr || dV_out != nullptr, "nothing to do: neither Adam nor dV_out requested");
+    NADM_REQUIRE(row0 >= 0 && row0 + B <= (1ll << 32), "row numbers must fit 32 bits (row0=%lld)", (long long)row0);
     if (C <= 8 && enc_bwd_tc_supported(B) && !use_generic_kernels() && (reinterpret_cast<uintptr_t>(V) & 15) == 0 &&
         (dV_out == nullptr || (reinterpret_cast<uintptr_t>(dV_out) & 15) == 0))
         return launch_enc_bwd_tc(packed, pitch, row_idx, row0, B, M, dZ, C, V, Vm, Vv, adam, dV_out, (cudaStream_t)stream);

@@ -80,6 +80,13 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
                  : "memory");
 }
 
+// knock-out measurement build (-DNADM_KO_MMA): the predicated MMA issue below never fires (issue flag compared with 2),
+// commits still arrive: shows what the rest of a kernel costs without its tensor-core work.  Garbage results by design.
+#ifdef NADM_KO_MMA
+#define NADM_KO_MMA_EXTRA "setp.eq.b32 q, %5, 2;\n\t"
+#else
+#define NADM_KO_MMA_EXTRA
+#endif
 // ---- predicated issue: the WHOLE warp executes the (convergent) descriptor arithmetic, only the lane whose `issue`
 // flag is set executes the MMA / commit.  Keeping the issuing code free of a divergent `if (elected)` region lets the
 // compiler hold descriptors and counters in uniform registers instead of moving them there (R2UR) per instruction.
@@ -87,7 +94,7 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     __device__ __forceinline__ void NAME(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,       \
                                          uint32_t accumulate, uint32_t issue) {                                  \
         asm volatile(                                                                                            \
-            "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"                      \
+            "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t" NADM_KO_MMA_EXTRA             \
             "@q tcgen05.mma.cta_group::1.kind::" KIND " [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),              \
             "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(issue)                                      \
             : "memory");                                                                                         \
@@ -99,7 +106,7 @@ NADM_DEF_MMA_SS_P(mma_f16_ss_p, "f16")
     __device__ __forceinline__ void NAME(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,      \
                                          uint32_t accumulate, uint32_t issue) {                                  \
         asm volatile(                                                                                            \
-            "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"                      \
+            "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t" NADM_KO_MMA_EXTRA             \
             "@q tcgen05.mma.cta_group::1.kind::" KIND " [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),            \
             "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(issue)                                     \
             : "memory");                                                                                         \
@@ -190,16 +197,29 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// Hang watchdog: every wait of the pipelines below is bounded.  A failed try_wait suspends the thread for >= 25 ns, so
+// 2^26 failed polls are > 1.5 s on a barrier that is normally reached within microseconds: the kernel then traps
+// (the launch fails with a CUDA error that the C ABI reports) instead of spinning forever and taking the GPU with it.
+// One predicated add per FAILED poll; nothing on the success path.  -DNADM_NO_WATCHDOG removes it.
+#ifndef NADM_NO_WATCHDOG
+#define NADM_WATCHDOG_POLL(n) do { if (++(n) > (1u << 26)) __trap(); } while (0)
+#else
+#define NADM_WATCHDOG_POLL(n) do { } while (0)
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) {
-    }
+    uint32_t polls = 0;
+    while (!mbar_try_wait(bar, parity)) NADM_WATCHDOG_POLL(polls);
 }
 // Wait of a warp that is NOT on the kernel's critical path (epilogues, operand producers running ahead): failed polls
 // are spaced by nanosleep so that the polling loop does not compete for issue slots with the warps of its SM
 // sub-partition (back-to-back try_wait polls were measured to be 10-20 % of all instructions issued; the try_wait
 // suspend-time hint does not space them: the hardware wakes the thread after ~25 ns regardless).
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, uint32_t ns) {
-    while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
+    uint32_t polls = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(ns);
+        NADM_WATCHDOG_POLL(polls);
+    }
 }
 // named barrier among `nthreads` threads (whole warps) of the CTA; id 1..15 (0 is __syncthreads)
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {

@@ -16,9 +16,9 @@
 // dQ accumulates in tensor memory over all SNP sub-tiles of the CTA (one 128 x 16 accumulator per row block), dP over
 // the row blocks of one sub-tile, after which four epilogue warps apply Adam + clamp to the 64 x k slice of P.
 //
-// Warp roles (640 threads): 0-11 three compute warpgroups (unit u -> warpgroup u % 3, raw / G slot u % SLOTS), 12 tensor
-// memory allocation only, 13 MMA issuer A (MMA2 of a unit, then MMA1 of the unit that takes over its slot), 14 MMA
-// issuer B (MMA3), 15 P-tile producer, 16-19 dP/Adam epilogue.  Pipelines are mbarrier based; tcgen05.commit frees
+// Warp roles (WGS = 3: 640 threads; WGS = 4: 768): 0 .. 4 WGS - 1 the compute warpgroups (unit u -> warpgroup u % WGS,
+// raw / G slot u % SLOTS), then: tensor memory allocation only, MMA issuer A (MMA2 of a unit, then MMA1 of the unit that
+// takes over its slot), MMA issuer B (MMA3), P-tile producer, and four dP/Adam epilogue warps.  Pipelines are mbarrier based; tcgen05.commit frees
 // operand buffers.
 #include "nadm_common.cuh"
 #include "nadm_tc.cuh"
@@ -39,9 +39,10 @@ constexpr int kPStages = 3;
 // Tensor-memory columns: [0, 64 SLOTS) slots, then the dP accumulator(s) (32 each: one for SLOTS = 4, two for 3),
 // then one 32-column dQ accumulator per row block:  SLOTS = 4: 256 + 32 + 32 nblk (nblk <= 7, B <= 896);
 // SLOTS = 3: 192 + 64 + 32 nblk (nblk <= 8).
-constexpr int kWGs = 3, kMaxSlots = 4;
-constexpr int kWarpIssueA1 = 4 * kWGs, kWarpIssueA2 = kWarpIssueA1 + 1, kWarpIssueB = kWarpIssueA1 + 2,
-              kWarpProd = kWarpIssueA1 + 3, kDecThreads = (4 * kWGs + 4 + 4) * 32;
+// WGS compute warpgroups (template parameter: 3, or 4 = one more warp per SM sub-partition to fill the issue slots the
+// others leave while they wait for their slot's turn-around; 768 threads, 80 registers each)
+constexpr int kMaxSlots = 4;
+__host__ __device__ constexpr int dec_threads(int WGS) { return (4 * WGS + 4 + 4) * 32; }
 __host__ __device__ constexpr int dec_nd3(int SLOTS) { return SLOTS == 3 ? 2 : 1; }
 constexpr uint32_t kIdesc1 = instr_desc(kAccF32, kFmtBF16, kFmtBF16, false, false, 128, kMS);
 constexpr uint32_t kIdesc2 = instr_desc(kAccF32, kFmtBF16, kFmtBF16, false, true, 128, 32);
@@ -190,13 +191,15 @@ __device__ __forceinline__ void decode16_fast(const uint32_t (&v)[16], const flo
     }
 }
 
-template <bool kLoss, int SLOTS>
-__global__ void __launch_bounds__(kDecThreads, 1)
+template <bool kLoss, int SLOTS, int WGS>
+__global__ void __launch_bounds__(dec_threads(WGS), 1)
 dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* __restrict__ row_idx, int64_t row0, int B,
               int64_t M, const float* __restrict__ Q, int q_ld, int q_off, int k, float* __restrict__ P,
               float* __restrict__ Pm, float* __restrict__ Pv, AdamCoef adam_in, float* __restrict__ dP_out,
               float* __restrict__ dQpart, float* __restrict__ loss_part, int TS) {
     pdl_prologue();
+    constexpr int kWGs = WGS, kWarpIssueA1 = 4 * WGS, kWarpIssueA2 = kWarpIssueA1 + 1, kWarpIssueB = kWarpIssueA1 + 2,
+                  kWarpProd = kWarpIssueA1 + 3;
     constexpr int kSlots = SLOTS, kWarpIssue = kWarpIssueA1;
     const AdamCoef adam = adam_resolve(adam_in);
     constexpr int ngt = SLOTS;   // one G^T tile per slot (see the issuer warps for why not more)
@@ -245,6 +248,18 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tbase = S->tmem_base;
+#ifdef NADM_KO_MMA   // knock-out measurement build: no tensor-core work; every raw value is 0.5 (decode-only timing)
+    if (warp < 4) {
+        uint32_t h[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) h[j] = 0x3F000000u;
+        for (int c0 = 0; c0 < 64 * SLOTS; c0 += 16) tmem_st16(tbase + ((uint32_t)(warp * 32) << 16) + c0, h);
+        tmem_wait_st();
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+#endif
 
     if (warp < kWarpIssue) {
         // =============================== compute warpgroups ===============================
@@ -307,8 +322,10 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
                     const float mn = fminf(fminf(fminf(t0, t1), t2), fminf(fminf(t3, t4), prod[7].y));
                     if (mn >= kProdFast) decode16_fast<kLoss>(v, prod, w, magic, magic21, hi, lo, acc_hom, acc_het);
                     else decode16_general<kLoss>(v, w, magic, hi, lo, acc_hom, acc_het);
+#ifndef NADM_KO_MMA   // (knock-out build: raw stays the constant written at setup, so that the decode keeps its fast path)
                     tmem_st8(tlane + slot * 64 + c * 16, hi);          // G hi / lo overwrite their own raw columns
                     tmem_st8(tlane + slot * 64 + c * 16 + 8, lo);
+#endif
                     *reinterpret_cast<uint4*>(gt + (2 * c) * 128) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                     *reinterpret_cast<uint4*>(gt + (2 * c + 1) * 128) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
                     *reinterpret_cast<uint4*>(gt + 16384 + (2 * c) * 128) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -584,19 +601,20 @@ extern "C" int nadm_debug_timeline(long long* host_out) {
 }
 #endif
 
-template <bool kLoss, int SLOTS>
+template <bool kLoss, int SLOTS, int WGS>
 static int dec_launch_one(int ncta, size_t smem, cudaStream_t st, const uint8_t* packed, int64_t pitch,
                           const int64_t* row_idx, int64_t row0, int B, int64_t M, const float* Q, int q_ld, int q_off,
                           int k, float* P, float* Pm, float* Pv, const AdamCoef& adam, float* dP_out, float* dQpart,
                           float* loss_part, int TS) {
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(dec_tc_kernel<kLoss, SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    static PerDeviceOnce once;                       // one per template instantiation
+    bool* attr = once.slot();
+    if (attr == nullptr || !*attr) {
+        cudaError_t e = cudaFuncSetAttribute(dec_tc_kernel<kLoss, SLOTS, WGS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              kMaxDynSmem);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(dec_tc)");
-        attr = true;
+        if (attr) *attr = true;
     }
-    launch_pdl(dec_tc_kernel<kLoss, SLOTS>, dim3(ncta), dim3(kDecThreads), smem, st, packed, pitch, row_idx, row0, B, M, Q, q_ld,
+    launch_pdl(dec_tc_kernel<kLoss, SLOTS, WGS>, dim3(ncta), dim3(dec_threads(WGS)), smem, st, packed, pitch, row_idx, row0, B, M, Q, q_ld,
                q_off, k, P, Pm, Pv, adam, dP_out, dQpart, loss_part, TS);
     NADM_CHECK_LAUNCH("dec_tc_kernel");
     return NADM_OK;
@@ -615,6 +633,16 @@ static int dec_pick_slots(int nblk, size_t fixed) {
     return slots;
 }
 
+// compute warpgroups: NADM_DEC_WGS=3|4 (A/B measurements; default below)
+static int dec_pick_wgs() {
+    static int n = 0;
+    if (n == 0) {
+        const char* e = getenv("NADM_DEC_WGS");
+        n = (e != nullptr && (e[0] == '3' || e[0] == '4')) ? e[0] - '0' : 4;
+    }
+    return n;
+}
+
 int launch_dec_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_idx, int64_t row0, int B, int64_t M,
                   const float* Q, float* dQ, int q_ld, int q_off, int k, float* P, float* Pm, float* Pv,
                   const nadm_adam_t* adam, float* dP_out, float* loss, float* ws, size_t ws_bytes, cudaStream_t st) {
@@ -630,14 +658,18 @@ int launch_dec_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_idx, 
     float* loss_part = ws + (size_t)ncta * B * 8;
     const AdamCoef ac = make_adam(adam);
     int rc;
-#define NADM_DEC_GO(L, W)                                                                                              \
-    rc = dec_launch_one<L, W>(ncta, smem, st, packed, pitch, row_idx, row0, B, M, Q, q_ld, q_off, k, P, Pm, Pv, ac, dP_out, \
-                              dQpart, loss_part, TS)
+    const int wgs = dec_pick_wgs();
+#define NADM_DEC_GO(L, W, G)                                                                                           \
+    rc = dec_launch_one<L, W, G>(ncta, smem, st, packed, pitch, row_idx, row0, B, M, Q, q_ld, q_off, k, P, Pm, Pv, ac,   \
+                                 dP_out, dQpart, loss_part, TS)
+#define NADM_DEC_GO_WG(L, W)                                                                                           \
+    do { if (wgs == 4) NADM_DEC_GO(L, W, 4); else NADM_DEC_GO(L, W, 3); } while (0)
     if (slots == 4) {
-        if (want_loss) NADM_DEC_GO(true, 4); else NADM_DEC_GO(false, 4);
+        if (want_loss) NADM_DEC_GO_WG(true, 4); else NADM_DEC_GO_WG(false, 4);
     } else {
-        if (want_loss) NADM_DEC_GO(true, 3); else NADM_DEC_GO(false, 3);
+        if (want_loss) NADM_DEC_GO_WG(true, 3); else NADM_DEC_GO_WG(false, 3);
     }
+#undef NADM_DEC_GO_WG
 #undef NADM_DEC_GO
     if (rc != NADM_OK) return rc;
     return launch_reduce_parts(dQpart, ncta, B, 8, k, dQ, q_ld, q_off, 1.0f, want_loss ? loss_part : nullptr, loss, st);

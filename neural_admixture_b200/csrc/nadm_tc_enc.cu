@@ -56,6 +56,10 @@ __device__ __forceinline__ uint4 ldg_nc(const uint8_t* p) {
 template <bool RAW>
 __device__ __forceinline__ void widen_store(uint8_t* dst, uint32_t w, uint32_t mvx) {
     uint4 o;
+#ifdef NADM_KO_WIDEN   // knock-out measurement build: no widening arithmetic (results are garbage by design)
+    *reinterpret_cast<uint4*>(dst) = make_uint4(w, w, w, w);
+    return;
+#endif
     if (!RAW) {
         const uint32_t c = clear_missing(w);
         o.x = c & 0x03030303u;
@@ -78,6 +82,10 @@ __device__ __forceinline__ void widen_store(uint8_t* dst, uint32_t w, uint32_t m
 // the same widening into registers (tensor-memory operand path): o[0..3] = byte positions 0-3, 4-7, 8-11, 12-15
 template <bool RAW>
 __device__ __forceinline__ void widen_regs(uint32_t w, uint32_t mvx, uint32_t* o) {
+#ifdef NADM_KO_WIDEN   // knock-out measurement build: no widening arithmetic (results are garbage by design)
+    o[0] = w; o[1] = w; o[2] = w; o[3] = w;
+    return;
+#endif
     if (!RAW) {
 #ifdef NADM_ENC_TS_SCALED
         // fields left in place: byte positions 4j..4j+3 hold 4^j x code (<= 128, still a u8), one LOP3 per output word
@@ -114,11 +122,27 @@ struct FixScale {
 __device__ __forceinline__ FixScale fix_scale(float mx) {
     FixScale s;
     const int E = (int)((__float_as_uint(mx) >> 23) & 0xFF);       // biased exponent: mx < 2^(E - 126)
+    if (E == 255) {   // Inf or NaN among the values: the result is NaN, as a floating-point matmul would give
+        s.inv = 0.f;
+        s.back = __longlong_as_double(0x7FF8000000000000ll);
+        return s;
+    }
     if (mx == 0.f || E == 0) { s.inv = 0.f; s.back = 0.0; return s; }
     const int e = max(E - 126, -96);                                // keep 2^(30-e) a finite float
     s.inv = __uint_as_float((uint32_t)(127 + 30 - e) << 23);
     s.back = __longlong_as_double((long long)(1023 + e - 30) << 52);
     return s;
+}
+// |max| over floats as the maximum of their sign-cleared BIT PATTERNS: same order as the values for finite numbers, and
+// Inf / NaN (which fmaxf would drop) come out on top, so that fix_scale sees them
+__device__ __forceinline__ uint32_t absbits(float x) { return __float_as_uint(x) & 0x7FFFFFFFu; }
+__device__ __forceinline__ uint32_t absbits_max4(uint32_t m, const float4& x) {
+    return max(max(m, max(absbits(x.x), absbits(x.y))), max(absbits(x.z), absbits(x.w)));
+}
+__device__ __forceinline__ uint32_t warp_max_u32(uint32_t m) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    return m;
 }
 // four signed base-256 digits of q, most significant first: q = ((d0*256 + d1)*256 + d2)*256 + d3
 __device__ __forceinline__ void digits4(int q, int (&d)[4]) {
@@ -157,7 +181,7 @@ __device__ __forceinline__ void store_digits(uint8_t* tile_pos, const float (&v)
 struct Feed {
     const uint8_t* packed;
     int64_t pitch;
-    const uint32_t* rowoff;  // byte offset / 16 (row number x pitch / 16; pitch % 16 == 0) of every batch row
+    const uint32_t* rowoff;  // row NUMBER of every batch row (< 2^32; the byte offset row x pitch is formed in 64 bits)
     int B, nblk, t0, ntile;
     uint8_t* stage;          // this group's ring: kStDepth x kStTile; thread (wl, lane) owns 4 pieces of 16 bytes per slot
     int c_blk, c_tt, c_i;    // next tile of this group to copy (tile index c_i = g + 4 n)
@@ -182,8 +206,12 @@ __device__ __forceinline__ void feed_issue(Feed& f, int wl, int lane) {
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
             const int b = b0 + it * 8;
-            if (b < nrows) cp_async16_full(dst + it * 2048, base + ((uint64_t)f.rowoff[b] << 4));
+#ifdef NADM_KO_LOAD     // knock-out measurement build: no global loads
+            if (b >= nrows) *reinterpret_cast<uint4*>(dst + it * 2048) = make_uint4(0u, 0u, 0u, 0u);
+#else
+            if (b < nrows) cp_async16_full(dst + it * 2048, base + (uint64_t)f.rowoff[b] * (uint64_t)f.pitch);
             else *reinterpret_cast<uint4*>(dst + it * 2048) = make_uint4(0u, 0u, 0u, 0u);
+#endif
         }
         f.c_i += 4;
         f.c_blk += 4;
@@ -302,7 +330,7 @@ enc_fwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
     if (tid == 0) TLE(2, 0);                                            // kernel entry
 
     for (int b = tid; b < B; b += blockDim.x)
-        rowoff[b] = (uint32_t)((((row_idx != nullptr) ? row_idx[b] : (row0 + b)) * pitch) >> 4);
+        rowoff[b] = (uint32_t)((row_idx != nullptr) ? row_idx[b] : (row0 + b));
     if (tid == 0) {
         for (int s = 0; s < kAStages; ++s) { mbar_init(&S->fullA[s], 4); mbar_init(&S->emptyA[s], 1); }
 #ifdef NADM_ENC_TS_HALF
@@ -321,28 +349,28 @@ enc_fwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
         const int64_t m0 = (int64_t)t0 * kSub, m1 = min((int64_t)t1 * kSub, M);
         const int64_t n = (m1 > m0) ? (m1 - m0) * C : 0;
         const float* v0 = V + m0 * C;
-        float mx = 0.f;
+        uint32_t mx = 0u;
         if ((reinterpret_cast<uintptr_t>(v0) & 15) == 0) {
             const int64_t n4 = n / 4;
 #pragma unroll 8
-            for (int64_t i = tid; i < n4; i += blockDim.x) {
-                const float4 x = reinterpret_cast<const float4*>(v0)[i];
-                mx = fmaxf(fmaxf(mx, fmaxf(fabsf(x.x), fabsf(x.y))), fmaxf(fabsf(x.z), fabsf(x.w)));
-            }
-            for (int64_t i = n4 * 4 + tid; i < n; i += blockDim.x) mx = fmaxf(mx, fabsf(v0[i]));
+            for (int64_t i = tid; i < n4; i += blockDim.x) mx = absbits_max4(mx, reinterpret_cast<const float4*>(v0)[i]);
+            for (int64_t i = n4 * 4 + tid; i < n; i += blockDim.x) mx = max(mx, absbits(v0[i]));
         } else {
-            for (int64_t i = tid; i < n; i += blockDim.x) mx = fmaxf(mx, fabsf(v0[i]));
+            for (int64_t i = tid; i < n; i += blockDim.x) mx = max(mx, absbits(v0[i]));
         }
-#pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        if (lane == 0) S->red[warp] = mx;
+        mx = warp_max_u32(mx);
+        if (lane == 0) S->red[warp] = __uint_as_float(mx);
     }
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tbase = S->tmem_base;
-    float vmax = 0.f;
-    for (int w = 0; w < kFwdThreads / 32; ++w) vmax = fmaxf(vmax, S->red[w]);
+    float vmax;
+    {
+        uint32_t m = 0u;
+        for (int w = 0; w < kFwdThreads / 32; ++w) m = max(m, __float_as_uint(S->red[w]));
+        vmax = __uint_as_float(m);
+    }
     if (tid == 0) cta_vmax[blockIdx.x] = vmax;
     if (TSA) {
         if (warp < 4) {                                                 // warps 0..3 = lane quadrants 0..3
@@ -615,7 +643,7 @@ enc_bwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
     const int ntile = (t1 - t0) * nblk;
 
     for (int b = tid; b < B; b += blockDim.x)
-        rowoff[b] = (uint32_t)((((row_idx != nullptr) ? row_idx[b] : (row0 + b)) * pitch) >> 4);
+        rowoff[b] = (uint32_t)((row_idx != nullptr) ? row_idx[b] : (row0 + b));
     if (tid == 0) {
         for (int s = 0; s < kAStages; ++s) { mbar_init(&S->fullA[s], 4); mbar_init(&S->emptyA[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&S->dfull[s], NISS); mbar_init(&S->dempty[s], 4); }
@@ -623,25 +651,21 @@ enc_bwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
     }
     if (warp == kProdWarps) tmem_alloc<256>(&S->tmem_base);
     // |max| of dZ over the batch (every CTA computes the same value)
-    float mx = 0.f;
+    uint32_t mxb = 0u;
     if ((reinterpret_cast<uintptr_t>(dZ) & 15) == 0 && ((B * C) & 3) == 0) {
 #pragma unroll 4
-        for (int i = tid; i < (B * C) / 4; i += blockDim.x) {
-            const float4 x = reinterpret_cast<const float4*>(dZ)[i];
-            mx = fmaxf(fmaxf(mx, fmaxf(fabsf(x.x), fabsf(x.y))), fmaxf(fabsf(x.z), fabsf(x.w)));
-        }
+        for (int i = tid; i < (B * C) / 4; i += blockDim.x) mxb = absbits_max4(mxb, reinterpret_cast<const float4*>(dZ)[i]);
     } else {
-        for (int i = tid; i < B * C; i += blockDim.x) mx = fmaxf(mx, fabsf(dZ[i]));
+        for (int i = tid; i < B * C; i += blockDim.x) mxb = max(mxb, absbits(dZ[i]));
     }
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if (lane == 0) S->red[warp] = mx;
+    mxb = warp_max_u32(mxb);
+    if (lane == 0) S->red[warp] = __uint_as_float(mxb);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
-    mx = 0.f;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) mx = fmaxf(mx, S->red[w]);
-    const FixScale fs = fix_scale(mx);
+    mxb = 0u;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) mxb = max(mxb, __float_as_uint(S->red[w]));
+    const FixScale fs = fix_scale(__uint_as_float(mxb));
     for (int b = tid; b < nblk * 128; b += blockDim.x) {
         float v[8];
 #pragma unroll
@@ -839,8 +863,9 @@ int launch_enc_fwd_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_i
     const bool tsa = enc_fwd_tmem_operand() && nblk_ <= 8;           // accumulators + 4 tiles must fit 512 columns
     const size_t smem = (tsa ? (size_t)4 * kStDepthTS * kStTile : (size_t)kAStages * kATile + (size_t)4 * kStDepth * kStTile) +
                         2 * kDigTile + (size_t)((B + 3) & ~3) * 4 + sizeof(EncSmem) + 64;
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce once;
+    bool* attr = once.slot();
+    if (attr == nullptr || !*attr) {
         cudaError_t e = cudaSuccess;
 #define NADM_FWD_ATTR(N_, R_, T_)                                                                                      \
     if (e == cudaSuccess)                                                                                              \
@@ -849,7 +874,7 @@ int launch_enc_fwd_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_i
         NADM_FWD_ATTR(1, false, true); NADM_FWD_ATTR(2, false, true); NADM_FWD_ATTR(1, true, true); NADM_FWD_ATTR(2, true, true);
 #undef NADM_FWD_ATTR
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(enc_fwd_tc)");
-        attr = true;
+        if (attr) *attr = true;
     }
     const bool two = enc_issuers() == 2 && nblk_ >= 3 && nblk_ <= 8;   // two accumulator sets: 2 x 32 columns per row block
     const uint32_t mvx = raw_mv >= 0 ? (3u ^ (uint32_t)(raw_mv & 0xFF)) : 0u;
@@ -880,8 +905,9 @@ int launch_enc_bwd_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_i
     const size_t smem = (size_t)kAStages * kATile + (size_t)nblk * 4096 + (size_t)4 * kStDepth * kStTile + (size_t)((B + 3) & ~3) * 4 +
                         sizeof(EncBwdSmem) + 64;
     NADM_REQUIRE(smem <= (size_t)kMaxDynSmem, "batch B=%d too large for encoder_bwd", B);
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce once;
+    bool* attr = once.slot();
+    if (attr == nullptr || !*attr) {
         cudaError_t e = cudaFuncSetAttribute(enc_bwd_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(enc_bwd_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
@@ -890,7 +916,7 @@ int launch_enc_bwd_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_i
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(enc_bwd_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(enc_bwd_tc)");
-        attr = true;
+        if (attr) *attr = true;
     }
     const bool two = enc_issuers() == 2 && nblk >= 3;       // both issuers then have tiles in every sub-tile
     const uint32_t mvx = raw_mv >= 0 ? (3u ^ (uint32_t)(raw_mv & 0xFF)) : 0u;

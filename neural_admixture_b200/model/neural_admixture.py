@@ -19,6 +19,7 @@ import json
 import logging
 import os
 import sys
+import warnings
 from pathlib import Path
 from typing import Dict, List, Optional, Tuple
 
@@ -107,6 +108,7 @@ class Q_P(torch.nn.Module):
         self.W2cat = None
         self.b2cat = None
         self._bufs: Dict[int, dict] = {}
+        self.bind_epoch = 0        # bumped whenever bind() re-allocates the flat buffers (captured graphs key on it)
 
     # ---- binding: flat device buffers the kernels read; the per-head nn.Parameters become views of them ----------
     def bind(self) -> None:
@@ -129,6 +131,7 @@ class Q_P(torch.nn.Module):
         if self.V is not None:
             self.V.data = self.V.data.contiguous()
         self._bufs = {}
+        self.bind_epoch += 1
 
     def _fwd_buffers(self, B: int) -> dict:
         buf = self._bufs.get(B)
@@ -213,6 +216,26 @@ class Q_P(torch.nn.Module):
         with open(Path(save_dir) / f"{name}_config.json", "w") as fb:
             json.dump(cfg, fb)
         log.info("    Configuration file saved.")
+
+
+def gather_rows(t: torch.Tensor, group=None) -> torch.Tensor:
+    """Concatenate, in rank order, the row blocks ``t`` (rows x cols, row counts may differ between ranks) that the
+    ranks of ``group`` hold: the full M x k matrix out of the SNP shards.  Every rank receives the result.  Works on
+    any backend (NCCL on the device, gloo in the CPU tests)."""
+    if not (torch.distributed.is_available() and torch.distributed.is_initialized()):
+        return t
+    world = torch.distributed.get_world_size(group)
+    if world == 1:
+        return t
+    rows = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+    sizes = [torch.zeros_like(rows) for _ in range(world)]
+    torch.distributed.all_gather(sizes, rows, group=group)
+    sizes = [int(x.item()) for x in sizes]
+    pad = torch.zeros((max(sizes),) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    pad[:t.shape[0]] = t
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    torch.distributed.all_gather(parts, pad, group=group)
+    return torch.cat([p_[:n] for p_, n in zip(parts, sizes)], dim=0)
 
 
 class NeuralAdmixture:
@@ -321,7 +344,9 @@ class NeuralAdmixture:
 
     # ---- CUDA-graph replayed steps ------------------------------------------------------------------------------------
     use_graph = os.environ.get("NADM_NO_GRAPH", "0") != "1"
+    graph_fallback: Optional[str] = None   # why this instance stopped replaying graphs (None: it has not)
     graph_kernel_launches = 0     # library kernels executed through graph replays (they bypass nadm_launch_count)
+    generic_kernel_launches = 0   # of which first-generation CUDA-core kernels (shapes outside the tensor-core path)
 
     def _graph_state(self, order_len: int) -> dict:
         gs = getattr(self, "_gs", None)
@@ -332,7 +357,7 @@ class NeuralAdmixture:
                   "coef": torch.zeros(8, dtype=torch.float32, device=dev),
                   "loss1": torch.zeros(1, dtype=torch.float32, device=dev),
                   "losses": torch.zeros(order_len, dtype=torch.float32, device=dev), "idx": {}, "graphs": {},
-                  "pops": None}
+                  "pops": None}   # "pops": persistent device copy of the labels (its ADDRESS is baked into the graphs)
             self._gs = gs
         return gs
 
@@ -341,7 +366,7 @@ class NeuralAdmixture:
         minibatch out of the device-resident permutation + this step's Adam coefficients, both indexed by a device
         counter), the five hot-path calls (and, sharded, their two all-reduces), ``nadm_step_end``.  Nothing in the
         graph depends on host state, so an epoch is ``nsteps`` graph launches."""
-        key = (Bs, want_loss, sup)
+        key = (Bs, want_loss, sup, self.batch_size, self.raw_model.bind_epoch)
         g = gs["graphs"].get(key)
         if g is not None:
             return g
@@ -354,13 +379,15 @@ class NeuralAdmixture:
         h_dev = ops.adam_hyper(o.lr, 0, o.betas[0], o.betas[1], o.eps, device_coef=gs["coef"])
         torch.cuda.synchronize(self.device)
         g = torch.cuda.CUDAGraph()
-        before = ops.launch_count()
+        before, gen_before = ops.launch_count(), ops.generic_launch_count()
         with torch.cuda.graph(g):
             ops.step_begin(gs["order"], gs["counters"], self.batch_size, Bs, idx, h_host, gs["coef"], loss_acc)
             labels = gs["pops"][idx] if sup else None
             self._train_step(idx, labels, loss_acc if want_loss else None, hyper=h_dev, managed_loss=True)
             ops.step_end(gs["counters"], loss_acc if want_loss else None, gs["losses"] if want_loss else None)
         g.nadm_kernels = ops.launch_count() - before          # library kernels per replay (bench.py's gpu_launches)
+        g.nadm_generic = ops.generic_launch_count() - gen_before
+        self._warn_generic(g.nadm_generic)
         gs["graphs"][key] = g
         return g
 
@@ -383,26 +410,50 @@ class NeuralAdmixture:
                 gs = self._graph_state(n)
                 if gs["order"].data_ptr() != order_dev.data_ptr():
                     gs["order"][:n].copy_(order_dev)
-                gs["pops"] = pops
+                if pops is not None:
+                    # the graphs read the labels through THIS buffer: copy, never rebind (a rebound tensor would leave
+                    # the captured gather pointing at freed memory)
+                    if gs["pops"] is None or gs["pops"].shape != pops.shape:
+                        gs["pops"] = torch.empty_like(pops)
+                        gs["graphs"] = {k_: g_ for k_, g_ in gs["graphs"].items() if not k_[2]}
+                    gs["pops"].copy_(pops)
                 gs["counters"].copy_(torch.tensor([first, o.step_count], dtype=torch.int64))
                 graphs = [self._get_graph(gs, min(Bfull, n - (first + s) * Bfull), want_loss, pops is not None)
                           for s in range(nsteps)]
             except Exception as e:  # capture not possible (e.g. a collective that cannot be captured): eager steps
-                log.info(f"    CUDA-graph capture unavailable ({type(e).__name__}: {e}); running eager steps.")
-                type(self).use_graph = False
+                self.graph_fallback = f"{type(e).__name__}: {e}"
+                warnings.warn(f"nadm_b200: CUDA-graph capture of the training step failed ({self.graph_fallback}); "
+                              "this engine falls back to eager launches (about 0.16 ms more host time per step)",
+                              RuntimeWarning, stacklevel=2)
+                self.use_graph = False           # this instance only
                 graphs = None
             if graphs is not None:
                 for g in graphs:
                     g.replay()
                     self.graph_kernel_launches += g.nadm_kernels
+                    self.generic_kernel_launches += g.nadm_generic
                 o.step_count += nsteps
                 return gs["losses"][first:first + nsteps] if want_loss else None
         losses = torch.zeros(nsteps, dtype=torch.float32, device=self.device) if want_loss else None
+        gen_before = ops.generic_launch_count()
         for s in range(nsteps):
             idx = order_dev[(first + s) * Bfull:(first + s + 1) * Bfull]
             labels = pops[idx].contiguous() if pops is not None else None
             self._train_step(idx, labels, losses[s:s + 1] if want_loss else None)
+        gen = ops.generic_launch_count() - gen_before
+        self.generic_kernel_launches += gen
+        self._warn_generic(gen)
         return losses
+
+    _warned_generic = False
+
+    def _warn_generic(self, n: int) -> None:
+        if n > 0 and not self._warned_generic:
+            self._warned_generic = True
+            warnings.warn(f"nadm_b200: this configuration (heads K={self.ks_list}, C={self.raw_model.num_features}, "
+                          f"batch {self.batch_size}) leaves the tensor-core kernels for {n} launch(es) per step and runs "
+                          "the first-generation CUDA-core kernels instead (several times slower; see DESIGN.md)",
+                          RuntimeWarning, stacklevel=3)
 
     def epoch_order(self, N: int) -> torch.Tensor:
         """Row order of one epoch: exactly what the reference's ``RandomSampler(dataset, generator=self.generator)``
@@ -465,6 +516,7 @@ class NeuralAdmixture:
 
         # inference of Q for every sample, sequential batches of min(N, 1024) (reference :368-383)
         Qs = self.infer_Q(min(N, 1024))
+        self.last_Q = Qs                     # device tensors, full N x k on every rank
         self.release_graphs()
         if self.master:
             log.info("")
@@ -522,20 +574,12 @@ class NeuralAdmixture:
     def gather_P(self) -> List[torch.Tensor]:
         """Full M x k P per head on every rank (concatenating the SNP shards in rank order)."""
         Ps = [d.weight.data for d in self.raw_model.decoders.decoders]
-        if not self.sharded:
-            return Ps
-        world = torch.distributed.get_world_size()
-        out = []
-        for P in Ps:
-            sizes = [torch.zeros(1, dtype=torch.int64, device=self.device) for _ in range(world)]
-            torch.distributed.all_gather(sizes, torch.tensor([P.shape[0]], dtype=torch.int64, device=self.device))
-            mx = int(max(s.item() for s in sizes))
-            pad = torch.zeros((mx, P.shape[1]), dtype=P.dtype, device=self.device)
-            pad[:P.shape[0]] = P
-            parts = [torch.empty_like(pad) for _ in range(world)]
-            torch.distributed.all_gather(parts, pad)
-            out.append(torch.cat([p[:int(s.item())] for p, s in zip(parts, sizes)], dim=0))
-        return out
+        return [gather_rows(P) for P in Ps] if self.sharded else Ps
+
+    def gather_V(self) -> torch.Tensor:
+        """Full M x C projection matrix on every rank (the ranks' row slices in rank order)."""
+        V = self.raw_model.V.data
+        return gather_rows(V) if self.sharded else V
 
     def display_divergences(self, k) -> None:
         """Hudson's Fst between estimated populations (reference :476-509)."""
@@ -557,8 +601,15 @@ class NeuralAdmixture:
             log.info("\n")
 
     def process_results(self, Qs: List[torch.Tensor]):
-        """Reference :511-530."""
+        """Reference :511-530.  Sharded runs: the returned model carries the FULL M x C ``V`` (every rank trained only
+        its row slice), so that ``state_dict()`` minus the decoders — what the reference saves, src/main.py:41 — is the
+        same checkpoint a single-GPU run writes and ``src.inference.load_model`` can read it.  Training is over at
+        this point: the per-shard optimizer state is not gathered."""
         Ps = self.gather_P()
+        if self.sharded:
+            self.shard_V = self.raw_model.V.data                 # this rank's trained slice (kept for inspection)
+            self.raw_model.V = torch.nn.Parameter(self.gather_V().contiguous(), requires_grad=False)
+            self.raw_model._bufs = {}
         if self.master:
             return [Q.cpu().numpy() for Q in Qs], [P.detach().cpu().numpy() for P in Ps], self.raw_model
         return [], [], self.raw_model

@@ -109,14 +109,20 @@ def train(epochs: int, batch_size: int, learning_rate: float, K: int, seed: int,
                             max_k)
     Qs, Ps, raw = model.launch_training(P_init, packed, hidden_size, V_dev.shape[1], V_dev, c1 - c0, N, y)
 
-    if master:
-        ws = torch.empty(ops.workspace_bytes(min(N, 1024), M, V_dev.shape[1], hidden_size, sumK), dtype=torch.uint8,
-                         device=device)
-        full = packed if not sharded else ops.PackedGenotypes.from_unpacked_host(data, device)
-        ks = [K] if K is not None else list(range(min_k, max_k + 1))
-        for i, k in enumerate(ks):
-            logl = ops.loglikelihood(full, torch.as_tensor(Qs[i], device=device).contiguous(),
-                                     torch.as_tensor(Ps[i], device=device).contiguous(), ws)
+    # log-likelihood (reference :134-146, utils.pyx:17-40) on the resident packed data: every rank evaluates its own SNP
+    # slice against the full Q and its slice of P, the fp64 partial sums are all-reduced (the reference evaluates it on
+    # the host matrix; nothing is re-uploaded here)
+    ws = torch.empty(ops.workspace_bytes(min(N, 1024), c1 - c0, V_dev.shape[1], hidden_size, sumK), dtype=torch.uint8,
+                     device=device)
+    ks = [K] if K is not None else list(range(min_k, max_k + 1))
+    for i, k in enumerate(ks):
+        ll = torch.tensor([ops.loglikelihood(packed, model.last_Q[i].contiguous(),
+                                             raw.decoders.decoders[i].weight.data.contiguous(), ws)],
+                          dtype=torch.float64, device=device)
+        if sharded:
+            dist.all_reduce(ll, op=dist.ReduceOp.SUM)
+        if master:
+            logl = float(ll.item())
             log.info(f"    Log-likelihood: {logl:2f}." if K is not None else f"    Log-likelihood for K={k}: {logl:2f}.")
     return Ps, Qs, raw
 

@@ -17,8 +17,28 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
-def _stream() -> C.c_void_p:
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(t: Optional[torch.Tensor] = None) -> C.c_void_p:
+    """The current stream of the device that holds ``t`` (not of whatever device happens to be current)."""
+    return C.c_void_p(torch.cuda.current_stream(None if t is None else t.device).cuda_stream)
+
+
+class _on:
+    """Make the tensor's device current for the duration of a library call: the library launches on the current device
+    (cudaFuncSetAttribute, SM count and the launch itself), the pointers live on the tensor's device."""
+
+    def __init__(self, t: torch.Tensor):
+        self.idx = t.device.index if t.is_cuda else None
+        self.prev = None
+
+    def __enter__(self):
+        if self.idx is not None and self.idx != torch.cuda.current_device():
+            self.prev = torch.cuda.current_device()
+            torch.cuda.set_device(self.idx)
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            torch.cuda.set_device(self.prev)
+        return False
 
 
 def _need_cuda(*ts):
@@ -36,6 +56,11 @@ def launch_count() -> int:
     return int(_lib.load().nadm_launch_count())
 
 
+def generic_launch_count() -> int:
+    """Launches of the slow first-generation kernels so far (shapes outside the tensor-core path)."""
+    return int(_lib.load().nadm_generic_launch_count())
+
+
 def pack2bit(src: torch.Tensor, dst: torch.Tensor, M: Optional[int] = None) -> None:
     """src: rows x M uint8 codes (cuda), dst: rows x >=ceil(M/4) uint8 (cuda); row strides are honoured."""
     _need_cuda(src, dst)
@@ -47,7 +72,7 @@ def pack2bit(src: torch.Tensor, dst: torch.Tensor, M: Optional[int] = None) -> N
     src_pitch = src.stride(0) if rows > 1 else max(src.shape[1], 1)
     if rows > 1 and dst.stride(0) != dst.shape[1]:
         raise NadmError("pack2bit: destination rows must be contiguous (the kernel zero-fills each row's tail)")
-    check(_lib.load().nadm_pack2bit(_ptr(src), rows, M, src_pitch, _ptr(dst), dst.shape[1], _stream()))
+    with _on(src): check(_lib.load().nadm_pack2bit(_ptr(src), rows, M, src_pitch, _ptr(dst), dst.shape[1], _stream(src)))
 
 
 def unpack2bit(src: torch.Tensor, dst: torch.Tensor) -> None:
@@ -59,7 +84,7 @@ def unpack2bit(src: torch.Tensor, dst: torch.Tensor) -> None:
     assert src.shape[0] == rows
     src_pitch = src.stride(0) if rows > 1 else src.shape[1]
     dst_pitch = dst.stride(0) if rows > 1 else max(M, 1)
-    check(_lib.load().nadm_unpack2bit(_ptr(src), rows, M, src_pitch, _ptr(dst), dst_pitch, _stream()))
+    with _on(src): check(_lib.load().nadm_unpack2bit(_ptr(src), rows, M, src_pitch, _ptr(dst), dst_pitch, _stream(src)))
 
 
 def workspace_bytes(B: int, M: int, C_: int, H: int, sumK: int) -> int:
@@ -83,8 +108,8 @@ class PackedGenotypes:
     def __init__(self, storage: torch.Tensor, N: int, M: int):
         assert storage.dtype == torch.uint8 and storage.dim() == 2 and storage.is_cuda and storage.is_contiguous()
         assert storage.shape[0] == N and storage.shape[1] % 16 == 0 and storage.shape[1] >= (M + 3) // 4
-        # the tensor-core encoder kernels keep row offsets as 32-bit counts of 16 bytes
-        assert N * storage.shape[1] < 2 ** 36, "packed matrix must be smaller than 64 GiB per device"
+        if N >= 2 ** 32:
+            raise NadmError("at most 2^32 - 1 sample rows per device (the kernels keep row numbers in 32 bits)")
         self.storage, self.N, self.M = storage, N, M
 
     @property
@@ -132,8 +157,8 @@ def encoder_fwd(pg: PackedGenotypes, V: torch.Tensor, Z: torch.Tensor, ws: torch
     assert V.dtype == torch.float32 and V.is_contiguous() and V.shape[0] == pg.M
     assert Z.dtype == torch.float32 and Z.is_contiguous() and Z.shape == (B, V.shape[1])
     assert row_idx is None or (row_idx.dtype == torch.int64 and row_idx.is_contiguous())
-    check(_lib.load().nadm_encoder_fwd(_ptr(pg.storage), pg.pitch, _ptr(row_idx), row0, B, pg.M, _ptr(V), V.shape[1],
-                                       _ptr(Z), _ptr(ws), ws.numel() * ws.element_size(), _stream()))
+    with _on(pg.storage): check(_lib.load().nadm_encoder_fwd(_ptr(pg.storage), pg.pitch, _ptr(row_idx), row0, B, pg.M, _ptr(V), V.shape[1],
+                                       _ptr(Z), _ptr(ws), ws.numel() * ws.element_size(), _stream(pg.storage)))
 
 
 def mlp_fwd(Z, w_rms, W1, b1, W2, b2, ks, rinv, Hh, Q) -> None:
@@ -143,8 +168,8 @@ def mlp_fwd(Z, w_rms, W1, b1, W2, b2, ks, rinv, Hh, Q) -> None:
     for t in (Z, w_rms, W1, b1, W2, b2, rinv, Hh, Q):
         assert t.dtype == torch.float32 and t.is_contiguous()
     assert W2.shape == (sum(ks), H) and Q.shape == (B, sum(ks)) and Hh.shape == (B, H)
-    check(_lib.load().nadm_mlp_fwd(_ptr(Z), B, C_, H, _ptr(w_rms), _ptr(W1), _ptr(b1), _ptr(W2), _ptr(b2),
-                                   _ks_array(ks), len(ks), _ptr(rinv), _ptr(Hh), _ptr(Q), _stream()))
+    with _on(Z): check(_lib.load().nadm_mlp_fwd(_ptr(Z), B, C_, H, _ptr(w_rms), _ptr(W1), _ptr(b1), _ptr(W2), _ptr(b2),
+                                   _ks_array(ks), len(ks), _ptr(rinv), _ptr(Hh), _ptr(Q), _stream(Z)))
 
 
 def decoder_step(pg: PackedGenotypes, Q, dQ, q_off: int, k: int, P, Pm, Pv, adam: Optional[AdamHyper], loss, ws, *,
@@ -154,10 +179,10 @@ def decoder_step(pg: PackedGenotypes, Q, dQ, q_off: int, k: int, P, Pm, Pv, adam
     assert P.shape == (pg.M, k) and P.is_contiguous() and P.dtype == torch.float32
     assert Q.is_contiguous() and dQ.is_contiguous() and dQ.shape == Q.shape
     assert row_idx is None or (row_idx.dtype == torch.int64 and row_idx.is_contiguous() and row_idx.numel() == B)
-    check(_lib.load().nadm_decoder_step(_ptr(pg.storage), pg.pitch, _ptr(row_idx), row0, B, pg.M, _ptr(Q), _ptr(dQ),
+    with _on(pg.storage): check(_lib.load().nadm_decoder_step(_ptr(pg.storage), pg.pitch, _ptr(row_idx), row0, B, pg.M, _ptr(Q), _ptr(dQ),
                                         q_ld, q_off, k, _ptr(P), _ptr(Pm), _ptr(Pv),
                                         None if adam is None else C.byref(adam), _ptr(dP_out), _ptr(loss), _ptr(ws),
-                                        ws.numel() * ws.element_size(), _stream()))
+                                        ws.numel() * ws.element_size(), _stream(pg.storage)))
 
 
 def mlp_bwd(dQ, Q, Hh, Z, rinv, ks, params: MlpParams, adam: Optional[AdamHyper], dZ, loss, ws, *, labels=None,
@@ -166,10 +191,10 @@ def mlp_bwd(dQ, Q, Hh, Z, rinv, ks, params: MlpParams, adam: Optional[AdamHyper]
     B, C_ = Z.shape
     H = Hh.shape[1]
     assert labels is None or (labels.dtype == torch.int64 and labels.is_contiguous() and labels.numel() == B)
-    check(_lib.load().nadm_mlp_bwd(_ptr(dQ), _ptr(Q), _ptr(Hh), _ptr(Z), _ptr(rinv), B, C_, H, _ks_array(ks), len(ks),
+    with _on(dQ): check(_lib.load().nadm_mlp_bwd(_ptr(dQ), _ptr(Q), _ptr(Hh), _ptr(Z), _ptr(rinv), B, C_, H, _ks_array(ks), len(ks),
                                    _ptr(labels), float(sup_weight), C.byref(params),
                                    None if adam is None else C.byref(adam), _ptr(dZ), _ptr(loss), _ptr(ws),
-                                   ws.numel() * ws.element_size(), _stream()))
+                                   ws.numel() * ws.element_size(), _stream(dQ)))
 
 
 def encoder_bwd(pg: PackedGenotypes, dZ, V, Vm, Vv, adam: Optional[AdamHyper], ws, *, row_idx=None, row0: int = 0,
@@ -177,9 +202,9 @@ def encoder_bwd(pg: PackedGenotypes, dZ, V, Vm, Vv, adam: Optional[AdamHyper], w
     _need_cuda(dZ, V, Vm, Vv, ws, row_idx, dV_out)
     B, C_ = dZ.shape
     assert V.shape == (pg.M, C_) and V.is_contiguous() and dZ.is_contiguous()
-    check(_lib.load().nadm_encoder_bwd(_ptr(pg.storage), pg.pitch, _ptr(row_idx), row0, B, pg.M, _ptr(dZ), C_, _ptr(V),
+    with _on(pg.storage): check(_lib.load().nadm_encoder_bwd(_ptr(pg.storage), pg.pitch, _ptr(row_idx), row0, B, pg.M, _ptr(dZ), C_, _ptr(V),
                                        _ptr(Vm), _ptr(Vv), None if adam is None else C.byref(adam), _ptr(dV_out),
-                                       _ptr(ws), ws.numel() * ws.element_size(), _stream()))
+                                       _ptr(ws), ws.numel() * ws.element_size(), _stream(pg.storage)))
 
 
 def loglikelihood(pg: PackedGenotypes, Q: torch.Tensor, P: torch.Tensor, ws: torch.Tensor, eps: float = 1e-6) -> float:
@@ -187,8 +212,8 @@ def loglikelihood(pg: PackedGenotypes, Q: torch.Tensor, P: torch.Tensor, ws: tor
     k = P.shape[1]
     assert Q.shape == (pg.N, k) and P.shape == (pg.M, k) and Q.is_contiguous() and P.is_contiguous()
     out = torch.zeros(1, dtype=torch.float64, device=Q.device)
-    check(_lib.load().nadm_loglikelihood(_ptr(pg.storage), pg.pitch, pg.N, pg.M, _ptr(Q), _ptr(P), k, eps, _ptr(out),
-                                         _ptr(ws), ws.numel() * ws.element_size(), _stream()))
+    with _on(pg.storage): check(_lib.load().nadm_loglikelihood(_ptr(pg.storage), pg.pitch, pg.N, pg.M, _ptr(Q), _ptr(P), k, eps, _ptr(out),
+                                         _ptr(ws), ws.numel() * ws.element_size(), _stream(pg.storage)))
     return float(out.item())
 
 
@@ -200,13 +225,13 @@ def bed_to_packed(bed: torch.Tensor, N: int, dst: PackedGenotypes, snp0: int = 0
     assert bed.dtype == torch.uint8 and bed.dim() == 2 and bed.stride(1) == 1
     assert counts is None or (counts.dtype == torch.int64 and counts.numel() == 4 and counts.is_contiguous())
     Mc = bed.shape[0]
-    check(_lib.load().nadm_bed_to_packed(_ptr(bed), bed.stride(0) if Mc > 1 else bed.shape[1], N, Mc, snp0, int(flip),
-                                         _ptr(dst.storage), dst.pitch, _ptr(counts), _stream()))
+    with _on(bed): check(_lib.load().nadm_bed_to_packed(_ptr(bed), bed.stride(0) if Mc > 1 else bed.shape[1], N, Mc, snp0, int(flip),
+                                         _ptr(dst.storage), dst.pitch, _ptr(counts), _stream(bed)))
 
 
 def flip_packed(pg: PackedGenotypes) -> None:
     """In place g -> 2 - g (missing unchanged): the reference's minor-allele orientation (snp_reader.py:110)."""
-    check(_lib.load().nadm_flip_packed(_ptr(pg.storage), pg.pitch, pg.N, pg.M, _stream()))
+    with _on(pg.storage): check(_lib.load().nadm_flip_packed(_ptr(pg.storage), pg.pitch, pg.N, pg.M, _stream(pg.storage)))
 
 
 def step_begin(order: torch.Tensor, counters: torch.Tensor, stride: int, B: int, row_idx_out: torch.Tensor,
@@ -216,12 +241,12 @@ def step_begin(order: torch.Tensor, counters: torch.Tensor, stride: int, B: int,
     _need_cuda(order, counters, row_idx_out, coef_out)
     assert order.dtype == torch.int64 and counters.dtype == torch.int64 and counters.numel() == 2
     assert row_idx_out.dtype == torch.int64 and row_idx_out.numel() >= B and coef_out.numel() * coef_out.element_size() >= 32
-    check(_lib.load().nadm_step_begin(_ptr(order), order.numel(), _ptr(counters), stride, B, _ptr(row_idx_out),
-                                      C.byref(hyper), _ptr(coef_out), _ptr(loss_accum), _stream()))
+    with _on(order): check(_lib.load().nadm_step_begin(_ptr(order), order.numel(), _ptr(counters), stride, B, _ptr(row_idx_out),
+                                      C.byref(hyper), _ptr(coef_out), _ptr(loss_accum), _stream(order)))
 
 
 def step_end(counters: torch.Tensor, loss: Optional[torch.Tensor], losses_out: Optional[torch.Tensor]) -> None:
-    check(_lib.load().nadm_step_end(_ptr(counters), _ptr(loss), _ptr(losses_out), _stream()))
+    with _on(counters): check(_lib.load().nadm_step_end(_ptr(counters), _ptr(loss), _ptr(losses_out), _stream(counters)))
 
 
 def geno_matmul(pg: PackedGenotypes, Omega: torch.Tensor, ws: torch.Tensor, missing_value: int = 3) -> torch.Tensor:
@@ -235,8 +260,8 @@ def geno_matmul(pg: PackedGenotypes, Omega: torch.Tensor, ws: torch.Tensor, miss
         c1 = min(K, c0 + 8)
         om = Omega[:, c0:c1].contiguous()
         y = torch.empty((pg.N, c1 - c0), dtype=torch.float32, device=Omega.device)
-        check(_lib.load().nadm_geno_matmul(_ptr(pg.storage), pg.pitch, pg.N, pg.M, _ptr(om), c1 - c0, missing_value,
-                                           _ptr(y), _ptr(ws), ws.numel() * ws.element_size(), _stream()))
+        with _on(pg.storage): check(_lib.load().nadm_geno_matmul(_ptr(pg.storage), pg.pitch, pg.N, pg.M, _ptr(om), c1 - c0, missing_value,
+                                           _ptr(y), _ptr(ws), ws.numel() * ws.element_size(), _stream(pg.storage)))
         Y[:, c0:c1] = y
     return Y
 
@@ -252,7 +277,7 @@ def geno_matmul_t(pg: PackedGenotypes, QT: torch.Tensor, ws: torch.Tensor, missi
         c1 = min(K, c0 + 8)
         q = QT[c0:c1].T.contiguous()                                  # N x k
         bt = torch.empty((pg.M, c1 - c0), dtype=torch.float32, device=QT.device)
-        check(_lib.load().nadm_geno_matmul_t(_ptr(pg.storage), pg.pitch, pg.N, pg.M, _ptr(q), c1 - c0, missing_value,
-                                             _ptr(bt), _ptr(ws), ws.numel() * ws.element_size(), _stream()))
+        with _on(pg.storage): check(_lib.load().nadm_geno_matmul_t(_ptr(pg.storage), pg.pitch, pg.N, pg.M, _ptr(q), c1 - c0, missing_value,
+                                             _ptr(bt), _ptr(ws), ws.numel() * ws.element_size(), _stream(pg.storage)))
         Bm[c0:c1] = bt.T
     return Bm

@@ -23,11 +23,11 @@ log = logging.getLogger(__name__)
 
 
 def svd_flip(V: np.ndarray, U: np.ndarray) -> np.ndarray:
-    """Sign convention of the reference (:16-37): make the largest-magnitude entry of every column of U positive."""
-    k_components = U.shape[1]
-    max_abs_val_row_indices = np.argmax(np.abs(U), axis=0)
-    elements_for_sign = U[max_abs_val_row_indices, np.arange(k_components)]
-    return V * np.sign(elements_for_sign)[:, np.newaxis]
+    """Sign convention of the reference (:16-37): row j of V is multiplied by the sign of the entry of column j of U
+    that is largest in magnitude, which makes the decomposition deterministic."""
+    pivot = np.abs(U).argmax(axis=0)
+    signs = np.sign(U[pivot, np.arange(U.shape[1])])
+    return V * signs[:, None]
 
 
 def RSVD(pg: ops.PackedGenotypes, N: int, M: int, k: int = 8, seed: int = 42, oversampling: int = 10,
@@ -48,19 +48,18 @@ def RSVD(pg: ops.PackedGenotypes, N: int, M: int, k: int = 8, seed: int = 42, ov
     def qt_a(qt: np.ndarray) -> np.ndarray:             # (k', N) -> (k', M)
         return ops.geno_matmul_t(pg, torch.as_tensor(qt, dtype=torch.float32, device=dev), ws, missing_value).cpu().numpy()
 
-    log.info("    1) Generating Ω y Y = A @ Ω...")
+    log.info("    RSVD 1/4: random test matrix and Y = A @ Omega")
     Omega = rng.standard_normal(size=(M, k_prime), dtype=np.float32)
     Y = a_omega(Omega)
     for _ in range(power_iterations):
-        Q_y, _ = np.linalg.qr(Y, mode="reduced")
-        B_tmp = qt_a(np.ascontiguousarray(Q_y.T))
-        Y = a_omega(np.ascontiguousarray(B_tmp.T))
-    log.info("    2) QR of Y...")
+        basis, _ = np.linalg.qr(Y, mode="reduced")
+        Y = a_omega(np.ascontiguousarray(qt_a(np.ascontiguousarray(basis.T)).T))
+    log.info("    RSVD 2/4: thin QR of Y")
     Q, _ = np.linalg.qr(Y, mode="reduced")
-    log.info("    3) B = Qᵀ @ A...")
+    log.info("    RSVD 3/4: B = Q^T @ A")
     B = qt_a(np.ascontiguousarray(Q.T))
-    log.info("    4) SVD of B...")
+    log.info("    RSVD 4/4: SVD of the k' x M factor")
     Ut, St, Vt = np.linalg.svd(B, full_matrices=False)
     Vt = svd_flip(Vt, Ut)
-    log.info(f"    Total time SVD: {time.time() - t0:.4f}s")
+    log.info(f"    RSVD done in {time.time() - t0:.2f} s")
     return Vt[:k, :]

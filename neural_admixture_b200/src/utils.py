@@ -1,9 +1,11 @@
-"""Output writers with the reference's file names and formats (src/utils.py:36-67)."""
+"""Writers of the ``.Q`` / ``.P`` text outputs (file names and number format of the reference's ``write_outputs``,
+src/utils.py:36-67: ``{run_name}.{K}.Q`` is N x K, ``{run_name}.{K}.P`` is M x K, space-delimited ``%.18e``)."""
 from __future__ import annotations
 
 import logging
 import sys
 from pathlib import Path
+from typing import Optional, Sequence
 
 import numpy as np
 
@@ -11,21 +13,19 @@ logging.basicConfig(stream=sys.stdout, level=logging.INFO, format="%(message)s")
 log = logging.getLogger(__name__)
 
 
+def _heads(K, min_k, max_k) -> Sequence[int]:
+    return [K] if K is not None else list(range(min_k, max_k + 1))
+
+
 def write_outputs(Qs, run_name: str, K, min_k, max_k, out_path, Ps=None) -> None:
-    """``{run_name}.{K}.Q`` (N x K) and, when given, ``{run_name}.{K}.P`` (M x K), space-delimited ``np.savetxt``
-    (reference src/utils.py:36-67)."""
-    out_path = Path(out_path)
-    out_path.mkdir(parents=True, exist_ok=True)
-    if K is not None:
-        np.savetxt(out_path / f"{run_name}.{K}.Q", Qs[0], delimiter=" ")
-        if Ps is not None:
-            np.savetxt(out_path / f"{run_name}.{K}.P", Ps[0], delimiter=" ")
-            log.info("    Q and P matrices saved.")
-        else:
-            log.info("    Q matrix saved.")
-    else:
-        for i, k in enumerate(range(min_k, max_k + 1)):
-            np.savetxt(out_path / f"{run_name}.{k}.Q", Qs[i], delimiter=" ")
-            if Ps is not None:
-                np.savetxt(out_path / f"{run_name}.{k}.P", Ps[i], delimiter=" ")
-        log.info("    Q and P matrices saved for all K." if Ps is not None else "    Q matrices saved for all K.")
+    """One ``.Q`` (and, when ``Ps`` is given, one ``.P``) file per head; ``K`` selects single-head naming, otherwise the
+    heads are ``min_k..max_k`` in order.  Same call signature as the reference's writer."""
+    folder = Path(out_path)
+    folder.mkdir(parents=True, exist_ok=True)
+    ks = _heads(K, min_k, max_k)
+    for i, k in enumerate(ks):
+        for ext, mats in (("Q", Qs), ("P", Ps)):
+            if mats is not None:
+                np.savetxt(folder / f"{run_name}.{k}.{ext}", np.asarray(mats[i]), delimiter=" ")
+    what = "Q and P matrices" if Ps is not None else ("Q matrix" if len(ks) == 1 else "Q matrices")
+    log.info(f"    {what} saved{'' if len(ks) == 1 else ' for all K'}.")

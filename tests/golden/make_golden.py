@@ -24,6 +24,9 @@ Fixtures (all small npz):
                      fields exchanged, each with the N x M uint8 matrix SNPReader.read_data returns (flip in case b)
   rsvd_demo_slices.npz  the reference's rsvd.multiply_A_omega / multiply_QT_A / RSVD on the two matrices of
                      bed_demo_slices.npz (missing = 3 and, flipped, 255)
+  train_k4to12.npz   multi-head K=4..12 (sum K = 72: BASELINE configs[3]'s head range), 2 epochs
+  loglik.npz         utils_c.loglikelihood (utils.pyx:17-40) on fp64 Q / P with missing codes, exact 0/1 entries of P
+                     and reconstructions outside [eps, 1 - eps]: values for K = 3 and K = 8
   demo_k7.npz        the shipped demo BED through read_bed -> RSVD -> GMM init -> 5 epochs (K=7, seed 42), plus the
                      shipped demo_run.7.{Q,P}.expected for reference
 """
@@ -195,6 +198,39 @@ def make_trainings(ref_model):
                   epochs=3, H=32, seed=5, data=G, V=V, P=P3, pops=pops)
 
 
+def make_k4to12(ref_model):
+    """The head range of BASELINE.json configs[3] (multi-head K=4..12) at a size the reference finishes in seconds."""
+    rng = np.random.default_rng(21)
+    N, M, C = 160, 515, 8
+    G = _synthetic(rng, N, M, 6)
+    V = np.linalg.qr(rng.standard_normal((M, C)))[0].astype(np.float32)
+    ks = list(range(4, 13))
+    P = rng.uniform(0.05, 0.95, size=(sum(ks), M)).astype(np.float32)
+    _run_training(ref_model, HERE / "train_k4to12.npz", N=N, M=M, ks=ks, k=None, min_k=4, max_k=12, batch=64,
+                  epochs=2, H=32, seed=13, data=G, V=V, P=P)
+
+
+def make_loglik(out: Path):
+    """The reference's Cython log-likelihood (src/utils_c/utils.pyx:17-40, called at model/train.py:139,145)."""
+    from neural_admixture.src.utils_c import utils as ref_utils_c
+    rng = np.random.default_rng(33)
+    N, M = 97, 1013
+    res = {}
+    G = rng.integers(0, 3, size=(N, M), dtype=np.uint8)
+    G[rng.random((N, M)) < 0.04] = 3
+    res["G"] = G
+    for K in (3, 8):
+        Q = rng.dirichlet(0.3 * np.ones(K), size=N)
+        P = rng.uniform(0.0, 1.0, size=(M, K))
+        P[rng.random((M, K)) < 0.15] = 0.0          # reconstructions at / below eps
+        P[rng.random((M, K)) < 0.15] = 1.0          # ... and at / above 1 - eps
+        Q32, P32 = Q.astype(np.float32), P.astype(np.float32)    # what the engine holds; the reference gets them as fp64
+        ll = ref_utils_c.loglikelihood(np.ascontiguousarray(G), np.ascontiguousarray(P32.astype(np.float64)),
+                                       np.ascontiguousarray(Q32.astype(np.float64)), K)
+        res[f"Q{K}"], res[f"P{K}"], res[f"ll{K}"] = Q32, P32, np.float64(ll)
+    np.savez_compressed(out, **res, meta="reference utils_c.loglikelihood (Cython, fp64), eps = 1e-6")
+
+
 def make_demo(ref_model, ref_root: str):
     """The reference's only integration test (demo/run_demo.sh:4 + demo/run_diagnostics.py:9-26): K=7, 5 epochs,
     seed 42, through the reference's own read_bed, RSVD and GMM initialisation (model/train.py:47-69)."""
@@ -308,7 +344,10 @@ def make_rsvd(ref_root: str, out: Path):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("ref_root", help="built scratch copy of /root/reference (see module docstring)")
+    ap.add_argument("--only", default="", help="comma-separated subset: step,train,k4to12,loglik,demo,bed,rsvd")
     args = ap.parse_args()
+    want = set(filter(None, args.only.split(",")))
+    todo = lambda name: not want or name in want
     ref_model = _import_reference(args.ref_root)
     # numpy pack restatement without importing the oracle package path twice
     sys.path.insert(0, str(HERE.parent.parent / "oracle"))
@@ -316,11 +355,20 @@ def main():
     import nadm_oracle
     mod.pack2bit = nadm_oracle.pack2bit
     sys.modules["oracle_pack"] = mod
-    make_step(ref_model, HERE / "step_k5.npz")
-    make_trainings(ref_model)
-    make_demo(ref_model, args.ref_root)
-    make_bed(args.ref_root, HERE / "bed_demo_slices.npz")
-    make_rsvd(args.ref_root, HERE / "rsvd_demo_slices.npz")
+    if todo("step"):
+        make_step(ref_model, HERE / "step_k5.npz")
+    if todo("train"):
+        make_trainings(ref_model)
+    if todo("k4to12"):
+        make_k4to12(ref_model)
+    if todo("loglik"):
+        make_loglik(HERE / "loglik.npz")
+    if todo("demo"):
+        make_demo(ref_model, args.ref_root)
+    if todo("bed"):
+        make_bed(args.ref_root, HERE / "bed_demo_slices.npz")
+    if todo("rsvd"):
+        make_rsvd(args.ref_root, HERE / "rsvd_demo_slices.npz")
     for f in sorted(HERE.glob("*.npz")):
         print(f.name, f.stat().st_size)
 

@@ -2,7 +2,7 @@ import sys, ctypes, numpy as np
 sys.path.insert(0, '/root/repo')
 import neural_admixture_b200._lib as L
 from pathlib import Path
-L.LIB_PATH = Path('/root/repo/neural_admixture_b200/csrc/libnadm_b200_tl.so')
+L.LIB_PATH = Path('/root/repo/neural_admixture_b200/csrc') / (sys.argv[1] if len(sys.argv) > 1 else 'libnadm_b200_tl.so')
 import torch
 from neural_admixture_b200 import ops
 dev = torch.device('cuda:0')
