@@ -88,12 +88,40 @@ size_t nadm_workspace_bytes(int32_t B, int64_t M, int32_t C, int32_t H, int32_t 
 int nadm_encoder_fwd(const uint8_t* packed, int64_t pitch, const int64_t* row_idx, int64_t row0, int32_t B,
                      int64_t M, const float* V, int32_t C, float* Z, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- SNP-sharded runs: the exchange of the two small per-step messages, fused into the kernels that consume them.
+ * Rank r owns a contiguous slice of the SNP axis; the B x C partial projection (after nadm_encoder_fwd) and the
+ * B x sumK partial dQ plus the partial loss (after nadm_decoder_step) must be summed over the ranks — the role of DDP's
+ * gradient all-reduce in the reference (model/neural_admixture.py:315-319), 25.6 KB instead of 32-96 MB.  Instead of
+ * two NCCL all-reduce kernels per step, nadm_mlp_fwd / nadm_mlp_bwd do the exchange themselves when given a
+ * nadm_xchg_t: every CTA stores its rows' partial values into all peers' exchange areas over NVLink (peer-mapped device
+ * memory), publishes a sequence number, waits for the peers' numbers for the same rows, and sums the slots in rank
+ * order (so every rank obtains bit-identical sums).  One area per rank, allocated with nadm_ipc_alloc and opened by the
+ * peers with nadm_ipc_open (CUDA IPC: one process per GPU on one node).  `seq` is LOCAL device memory of
+ * NADM_XCHG_SEQ_WORDS uint32, zero-initialised, private to the rank.  xchg == NULL: no exchange (single GPU, or the
+ * caller all-reduces itself, e.g. with NCCL). */
+#define NADM_MAX_RANKS 8
+#define NADM_XCHG_MAX_CTAS 1024
+#define NADM_XCHG_SEQ_WORDS (2 * NADM_XCHG_MAX_CTAS)
+typedef struct nadm_xchg {
+    int32_t world, rank;
+    void* area[NADM_MAX_RANKS];   /* exchange area of every rank, as mapped into THIS process (area[rank] = own) */
+    uint32_t* seq;                /* this rank's private exchange counters */
+    int64_t slot_floats;          /* capacity of one slot: >= max(B * C, B * sumK + 1) over all calls */
+} nadm_xchg_t;
+size_t nadm_xchg_area_bytes(int64_t slot_floats);
+/* cudaMalloc + zero + cudaIpcGetMemHandle (handle_out: 64 bytes [host]); open / close a peer's area; free one's own. */
+int nadm_ipc_alloc(size_t bytes, void** dev_ptr, void* handle_out);
+int nadm_ipc_open(const void* handle, void** dev_ptr);
+int nadm_ipc_close(void* dev_ptr);
+int nadm_ipc_free(void* dev_ptr);
+
 /* ---- the small replicated network: RMSNorm(C, eps 1e-8) -> Linear(C,H)+ReLU -> per-head Linear(H,k) -> softmax
  * (neural_admixture.py:135-144 construction, :173-176 forward).  ks [host]: nheads head sizes; Q: B x sumK
- * (heads side by side); Hh: B x H post-ReLU activations and rinv: B (kept for the backward). */
-int nadm_mlp_fwd(const float* Z, int32_t B, int32_t C, int32_t H, const float* w_rms, const float* W1,
+ * (heads side by side); Hh: B x H post-ReLU activations and rinv: B (kept for the backward).
+ * xchg != NULL: Z holds this rank's PARTIAL projection on entry and the sum over the ranks on return. */
+int nadm_mlp_fwd(float* Z, int32_t B, int32_t C, int32_t H, const float* w_rms, const float* W1,
                  const float* b1, const float* W2, const float* b2, const int32_t* ks, int32_t nheads,
-                 float* rinv, float* Hh, float* Q, void* stream);
+                 float* rinv, float* Hh, float* Q, const nadm_xchg_t* xchg /*[host], may be NULL*/, void* stream);
 
 /* ---- fused decoder for ONE head: R = clamp(Q_k P_k^T, 0, 1); loss += BCE_sum(R, X); G = dLoss/dR through the
  * clamp mask; dQ[:, q_off:q_off+k] = G P_k; dP = G^T Q_k; then Adam on P_k and clamp to [0,1].
@@ -113,7 +141,8 @@ int nadm_decoder_step(const uint8_t* packed, int64_t pitch, const int64_t* row_i
 /* ---- backward of the small network + Adam on its parameters.  dQ: B x sumK (sum of the decoder's and, when
  * labels != NULL, of supervised_loss_weight * CrossEntropyLoss(sum)(Q_0, labels) — neural_admixture.py:293,:473 —
  * which this call adds itself, also adding that loss term to *loss).  Outputs dZ: B x C.  Updates w_rms, W1, b1,
- * W2, b2 and their moments in place when adam != NULL; raw gradients go to the optional g_* buffers. */
+ * W2, b2 and their moments in place when adam != NULL; raw gradients go to the optional g_* buffers.
+ * xchg != NULL: dQ and *loss hold this rank's PARTIAL sums on entry and the sums over the ranks on return. */
 typedef struct nadm_mlp_params {
     float* w_rms; float* W1; float* b1; float* W2; float* b2;          /* parameters             */
     float* m_w_rms; float* m_W1; float* m_b1; float* m_W2; float* m_b2; /* Adam first moments     */
@@ -121,11 +150,12 @@ typedef struct nadm_mlp_params {
     float* g_w_rms; float* g_W1; float* g_b1; float* g_W2; float* g_b2; /* optional raw gradients */
 } nadm_mlp_params_t;
 
-int nadm_mlp_bwd(const float* dQ, const float* Q, const float* Hh, const float* Z, const float* rinv,
+int nadm_mlp_bwd(float* dQ, const float* Q, const float* Hh, const float* Z, const float* rinv,
                  int32_t B, int32_t C, int32_t H, const int32_t* ks /*[host]*/, int32_t nheads,
                  const int64_t* labels /*B, or NULL*/, float sup_weight,
                  const nadm_mlp_params_t* params /*[host]*/, const nadm_adam_t* adam /*[host]*/,
-                 float* dZ, float* loss, void* ws, size_t ws_bytes, void* stream);
+                 float* dZ, float* loss, void* ws, size_t ws_bytes, const nadm_xchg_t* xchg /*[host], may be NULL*/,
+                 void* stream);
 
 /* ---- encoder backward: dV = X^T dZ, then Adam on V.  Replaces the autograd of `X @ self.V`
  * (neural_admixture.py:172,:410) and the V part of optimizer.step() (:411).  dV_out optional. */

@@ -24,6 +24,12 @@ class AdamHyper(C.Structure):
                 ("step", C.c_int32), ("reserved", C.c_int32), ("device_coef", C.c_void_p)]
 
 
+class Xchg(C.Structure):
+    """nadm_xchg_t"""
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("area", C.c_void_p * 8), ("seq", C.c_void_p),
+                ("slot_floats", C.c_int64)]
+
+
 class MlpParams(C.Structure):
     """nadm_mlp_params_t"""
     _names = ["w_rms", "W1", "b1", "W2", "b2"]
@@ -42,13 +48,19 @@ SIGNATURES = {
     "nadm_encoder_fwd": (C.c_int, [c_u8p, C.c_int64, c_i64p, C.c_int64, C.c_int32, C.c_int64, c_f32p, C.c_int32,
                                    c_f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "nadm_mlp_fwd": (C.c_int, [c_f32p, C.c_int32, C.c_int32, C.c_int32, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p,
-                               C.POINTER(C.c_int32), C.c_int32, c_f32p, c_f32p, c_f32p, C.c_void_p]),
+                               C.POINTER(C.c_int32), C.c_int32, c_f32p, c_f32p, c_f32p, C.POINTER(Xchg), C.c_void_p]),
     "nadm_decoder_step": (C.c_int, [c_u8p, C.c_int64, c_i64p, C.c_int64, C.c_int32, C.c_int64, c_f32p, c_f32p,
                                     C.c_int32, C.c_int32, C.c_int32, c_f32p, c_f32p, c_f32p, C.POINTER(AdamHyper),
                                     c_f32p, c_f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "nadm_mlp_bwd": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int32, C.c_int32, C.c_int32,
                                C.POINTER(C.c_int32), C.c_int32, c_i64p, C.c_float, C.POINTER(MlpParams),
-                               C.POINTER(AdamHyper), c_f32p, c_f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
+                               C.POINTER(AdamHyper), c_f32p, c_f32p, C.c_void_p, C.c_size_t, C.POINTER(Xchg),
+                               C.c_void_p]),
+    "nadm_xchg_area_bytes": (C.c_size_t, [C.c_int64]),
+    "nadm_ipc_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p), C.c_void_p]),
+    "nadm_ipc_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "nadm_ipc_close": (C.c_int, [C.c_void_p]),
+    "nadm_ipc_free": (C.c_int, [C.c_void_p]),
     "nadm_encoder_bwd": (C.c_int, [c_u8p, C.c_int64, c_i64p, C.c_int64, C.c_int32, C.c_int64, c_f32p, C.c_int32,
                                    c_f32p, c_f32p, c_f32p, C.POINTER(AdamHyper), c_f32p, C.c_void_p, C.c_size_t,
                                    C.c_void_p]),

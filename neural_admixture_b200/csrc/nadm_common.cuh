@@ -121,6 +121,8 @@ int launch_enc_bwd_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_i
 size_t enc_tc_workspace_bytes(int B);
 size_t mlp_bwd_workspace_bytes(int B, int C, int H, int sumK);   // nadm_mlp.cu
 bool enc_bwd_tc_supported(int B);
+bool enc_fwd_slab();                   // NADM_ENC_FWD_SLAB=1 (measurement switch, nadm_tc_enc.cu)
+bool enc_bwd_slab_supported(int B);   // the slab-fed backward kernel (256-byte runs per row): B <= 896
 // tensor-core fused decoder, nadm_tc_dec.cu
 bool dec_tc_supported(int B, int k);
 int launch_dec_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_idx, int64_t row0, int B, int64_t M,
@@ -159,6 +161,7 @@ __device__ __forceinline__ void cp_async4(void* smem, const void* gmem, int src_
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {

@@ -10,6 +10,7 @@
 #include "nadm_common.cuh"
 
 #include <mutex>
+#include <string.h>
 
 namespace nadm {
 
@@ -71,14 +72,110 @@ struct Heads {
 };
 
 // =================================================================================================================
+// fused peer exchange (SNP-sharded runs): see nadm_xchg_t in nadm_b200.h
+// =================================================================================================================
+// Layout of one rank's exchange area: flags [2 phases][NADM_XCHG_MAX_CTAS][NADM_MAX_RANKS] uint32, then slots
+// [2 phases][2 parities][NADM_MAX_RANKS][slot_floats] float.  Phase 0 = partial projection Z (nadm_mlp_fwd), phase 1 =
+// partial dQ | loss (nadm_mlp_bwd).  A CTA's exchange number `seq` counts the exchanges that CTA index has done in that
+// phase; slots are double-buffered by its parity: a peer can be at most one exchange ahead (it cannot finish exchange
+// seq + 1 without this rank's contribution to it, which this rank sends only after it has consumed exchange seq).
+struct Xchg {
+    int world, rank;
+    uint8_t* area[NADM_MAX_RANKS];
+    uint32_t* seq;
+    long long slot_floats;
+};
+constexpr size_t kXchgFlagBytes = (size_t)2 * NADM_XCHG_MAX_CTAS * NADM_MAX_RANKS * sizeof(uint32_t);
+__host__ __device__ inline size_t xchg_area_bytes(long long slot_floats) {
+    return kXchgFlagBytes + (size_t)2 * 2 * NADM_MAX_RANKS * (size_t)slot_floats * sizeof(float);
+}
+__device__ __forceinline__ uint32_t* xchg_flag(uint8_t* area, int phase, int cta, int src) {
+    return reinterpret_cast<uint32_t*>(area) + ((size_t)phase * NADM_XCHG_MAX_CTAS + cta) * NADM_MAX_RANKS + src;
+}
+__device__ __forceinline__ float* xchg_slot(uint8_t* area, long long slot_floats, int phase, int parity, int src) {
+    return reinterpret_cast<float*>(area + kXchgFlagBytes) + ((size_t)(phase * 2 + parity) * NADM_MAX_RANKS + src) * (size_t)slot_floats;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// All threads of the CTA call this.  vals[off .. off + n) are this CTA's floats of the rank's partial result (global
+// memory, written by an earlier kernel); on return they hold the sum over the ranks, visible to the whole CTA.
+// `extra` (CTA 0 only, may be NULL): one more scalar exchanged through slot element extra_off (the partial loss).
+__device__ void xchg_allreduce_cta(const Xchg& x, int phase, float* vals, long long off, int n, float* extra,
+                                   long long extra_off) {
+    const int tid = threadIdx.x, cta = blockIdx.x;
+    const uint32_t seq = x.seq[phase * NADM_XCHG_MAX_CTAS + cta] + 1u;
+    const int parity = (int)(seq & 1u);
+    // push: my values into slot [rank] of every rank's area (own included)
+    for (int idx = tid; idx < x.world * n; idx += blockDim.x) {
+        const int r = idx / n, i = idx - r * n;
+        xchg_slot(x.area[r], x.slot_floats, phase, parity, x.rank)[off + i] = vals[off + i];
+    }
+    if (extra != nullptr && tid < x.world) xchg_slot(x.area[tid], x.slot_floats, phase, parity, x.rank)[extra_off] = *extra;
+    __threadfence_system();
+    __syncthreads();
+    if (tid < x.world) {
+        st_release_sys(xchg_flag(x.area[tid], phase, cta, x.rank), seq);
+        // pull: wait until rank `tid` has published this exchange of this CTA index into MY area
+        const uint32_t* f = xchg_flag(x.area[x.rank], phase, cta, tid);
+        uint32_t polls = 0;
+        while ((int32_t)(ld_acquire_sys(f) - seq) < 0) {
+            __nanosleep(32);
+            if (++polls > (1u << 25)) __trap();      // a peer never arrived: fail the launch instead of hanging
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += blockDim.x) {
+        float acc = 0.f;
+        for (int r = 0; r < x.world; ++r) acc += __ldcg(xchg_slot(x.area[x.rank], x.slot_floats, phase, parity, r) + off + i);
+        vals[off + i] = acc;
+    }
+    if (extra != nullptr && tid == 0) {
+        float acc = 0.f;
+        for (int r = 0; r < x.world; ++r) acc += __ldcg(xchg_slot(x.area[x.rank], x.slot_floats, phase, parity, r) + extra_off);
+        *extra = acc;
+    }
+    if (tid == 0) x.seq[phase * NADM_XCHG_MAX_CTAS + cta] = seq;
+    __syncthreads();
+}
+static int make_xchg(const nadm_xchg_t* in, long long need_floats, int nctas, Xchg* out) {
+    out->world = 1;
+    if (in == nullptr) return NADM_OK;
+    NADM_REQUIRE(in->world >= 1 && in->world <= NADM_MAX_RANKS && in->rank >= 0 && in->rank < in->world,
+                 "exchange: world=%d rank=%d unsupported (at most %d ranks)", in->world, in->rank, NADM_MAX_RANKS);
+    NADM_REQUIRE(in->seq != nullptr, "exchange: seq is NULL");
+    NADM_REQUIRE(need_floats <= in->slot_floats, "exchange: slot of %lld floats too small (%lld needed)",
+                 (long long)in->slot_floats, need_floats);
+    NADM_REQUIRE(nctas <= NADM_XCHG_MAX_CTAS, "exchange: batch too large (%d CTAs > %d)", nctas, NADM_XCHG_MAX_CTAS);
+    out->world = in->world;
+    out->rank = in->rank;
+    for (int r = 0; r < in->world; ++r) {
+        NADM_REQUIRE(in->area[r] != nullptr, "exchange: area[%d] is NULL", r);
+        out->area[r] = reinterpret_cast<uint8_t*>(in->area[r]);
+    }
+    out->seq = in->seq;
+    out->slot_floats = in->slot_floats;
+    return NADM_OK;
+}
+
+// =================================================================================================================
 // forward
 // =================================================================================================================
 __global__ void __launch_bounds__(kMlpThreads)
-mlp_fwd_kernel(const float* __restrict__ Z, int B, int C, int H, const float* __restrict__ w_rms,
+mlp_fwd_kernel(float* Z, int B, int C, int H, const float* __restrict__ w_rms,
                const float* __restrict__ W1, const float* __restrict__ b1, const float* __restrict__ W2,
                const float* __restrict__ b2, Heads hd, float* __restrict__ rinv_out, float* __restrict__ Hh,
-               float* __restrict__ Q) {
+               float* __restrict__ Q, Xchg xc) {
     pdl_prologue();
+    if (xc.world > 1) {   // sum the ranks' partial projections of this CTA's rows (in place)
+        const int r0 = blockIdx.x * kMlpRows;
+        xchg_allreduce_cta(xc, 0, Z, (long long)r0 * C, min(kMlpRows, B - r0) * C, nullptr, 0);
+    }
     extern __shared__ __align__(16) float sm[];
     float* Zn = sm;                         // kMlpRows x C
     float* Hs = Zn + kMlpRows * NADM_MAX_C;  // kMlpRows x H
@@ -177,12 +274,17 @@ __host__ __device__ inline size_t mlp_slab_floats(int C, int H, int sumK) {
 
 template <int CP>   // components padded to 8 or 16
 __global__ void __launch_bounds__(kMlpThreads)
-mlp_bwd_rows_kernel(const float* __restrict__ dQ, const float* __restrict__ Q, const float* __restrict__ Hh,
+mlp_bwd_rows_kernel(float* dQ, const float* __restrict__ Q, const float* __restrict__ Hh,
                     const float* __restrict__ Z, const float* __restrict__ rinv, int B, int C, int H, Heads hd,
                     const int64_t* __restrict__ labels, float sup_weight, const float* __restrict__ w_rms,
                     const float* __restrict__ W1, const float* __restrict__ W2, float* __restrict__ part,
-                    float* __restrict__ dZ) {
+                    float* __restrict__ dZ, float* loss, Xchg xc) {
     pdl_prologue();
+    if (xc.world > 1) {   // sum the ranks' partial dQ of this CTA's rows (in place); CTA 0 also sums the partial losses
+        const int r0 = blockIdx.x * kBwdRows;
+        xchg_allreduce_cta(xc, 1, dQ, (long long)r0 * hd.sumK, min(kBwdRows, B - r0) * hd.sumK,
+                           blockIdx.x == 0 ? loss : nullptr, (long long)B * hd.sumK);
+    }
     extern __shared__ __align__(16) float sm[];
     float* dLs = sm;                                         // kBwdRows x sumK
     float* Zn = dLs + (size_t)kBwdRows * hd.sumK;             // kBwdRows x MAX_C   (normalised inputs, recomputed)
@@ -416,11 +518,47 @@ extern "C" const char* nadm_last_error(void) { return g_err; }
 extern "C" int64_t nadm_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 extern "C" int64_t nadm_generic_launch_count(void) { return __atomic_load_n(&g_generic, __ATOMIC_RELAXED); }
 
-extern "C" int nadm_mlp_fwd(const float* Z, int32_t B, int32_t C, int32_t H, const float* w_rms, const float* W1,
+extern "C" size_t nadm_xchg_area_bytes(int64_t slot_floats) { return nadm::xchg_area_bytes(slot_floats); }
+
+extern "C" int nadm_ipc_alloc(size_t bytes, void** dev_ptr, void* handle_out) {
+    NADM_REQUIRE(dev_ptr != nullptr && handle_out != nullptr && bytes > 0, "nadm_ipc_alloc: bad argument");
+    cudaError_t e = cudaMalloc(dev_ptr, bytes);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(exchange area)");
+    e = cudaMemset(*dev_ptr, 0, bytes);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, *dev_ptr);
+    if (e != cudaSuccess) { cudaFree(*dev_ptr); *dev_ptr = nullptr; return cuda_fail(e, "cudaIpcGetMemHandle"); }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    memcpy(handle_out, &h, sizeof(h));
+    return NADM_OK;
+}
+extern "C" int nadm_ipc_open(const void* handle, void** dev_ptr) {
+    NADM_REQUIRE(handle != nullptr && dev_ptr != nullptr, "nadm_ipc_open: NULL pointer");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    cudaError_t e = cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaIpcOpenMemHandle");
+    return NADM_OK;
+}
+extern "C" int nadm_ipc_close(void* dev_ptr) {
+    cudaError_t e = cudaIpcCloseMemHandle(dev_ptr);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaIpcCloseMemHandle");
+    return NADM_OK;
+}
+extern "C" int nadm_ipc_free(void* dev_ptr) {
+    cudaError_t e = cudaFree(dev_ptr);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFree(exchange area)");
+    return NADM_OK;
+}
+
+extern "C" int nadm_mlp_fwd(float* Z, int32_t B, int32_t C, int32_t H, const float* w_rms, const float* W1,
                             const float* b1, const float* W2, const float* b2, const int32_t* ks, int32_t nheads,
-                            float* rinv, float* Hh, float* Q, void* stream) {
+                            float* rinv, float* Hh, float* Q, const nadm_xchg_t* xchg, void* stream) {
     Heads hd;
     if (int rc = make_heads(ks, nheads, &hd)) return rc;
+    Xchg xc;
+    if (int rc = make_xchg(xchg, (long long)B * C, (B + kMlpRows - 1) / kMlpRows, &xc)) return rc;
     NADM_REQUIRE(B > 0 && H > 0, "empty batch or hidden layer");
     NADM_REQUIRE(C >= 1 && C <= NADM_MAX_C, "n_components C=%d unsupported (1..%d)", C, NADM_MAX_C);
     NADM_REQUIRE(Z && w_rms && W1 && b1 && W2 && b2 && rinv && Hh && Q, "NULL pointer");
@@ -434,17 +572,19 @@ extern "C" int nadm_mlp_fwd(const float* Z, int32_t B, int32_t C, int32_t H, con
         if (attr) *attr = true;
     }
     launch_pdl(mlp_fwd_kernel, dim3((B + kMlpRows - 1) / kMlpRows), dim3(kMlpThreads), smem, (cudaStream_t)stream, Z, B, C, H,
-               w_rms, W1, b1, W2, b2, hd, rinv, Hh, Q);
+               w_rms, W1, b1, W2, b2, hd, rinv, Hh, Q, xc);
     NADM_CHECK_LAUNCH("mlp_fwd_kernel");
     return NADM_OK;
 }
 
-extern "C" int nadm_mlp_bwd(const float* dQ, const float* Q, const float* Hh, const float* Z, const float* rinv,
+extern "C" int nadm_mlp_bwd(float* dQ, const float* Q, const float* Hh, const float* Z, const float* rinv,
                             int32_t B, int32_t C, int32_t H, const int32_t* ks, int32_t nheads, const int64_t* labels,
                             float sup_weight, const nadm_mlp_params_t* params, const nadm_adam_t* adam, float* dZ,
-                            float* loss, void* ws, size_t ws_bytes, void* stream) {
+                            float* loss, void* ws, size_t ws_bytes, const nadm_xchg_t* xchg, void* stream) {
     Heads hd;
     if (int rc = make_heads(ks, nheads, &hd)) return rc;
+    Xchg xc;
+    if (int rc = make_xchg(xchg, (long long)B * hd.sumK + 1, (B + kBwdRows - 1) / kBwdRows, &xc)) return rc;
     NADM_REQUIRE(B > 0 && H > 0, "empty batch or hidden layer");
     NADM_REQUIRE(C >= 1 && C <= NADM_MAX_C, "n_components C=%d unsupported (1..%d)", C, NADM_MAX_C);
     NADM_REQUIRE(dQ && Q && Hh && Z && rinv && params && dZ && loss && ws, "NULL pointer");
@@ -463,10 +603,10 @@ extern "C" int nadm_mlp_bwd(const float* dQ, const float* Q, const float* Hh, co
                          (size_t)(kMlpThreads / 32) * kBwdRows * CP + kBwdRows) * sizeof(float);
     if (CP == 8)
         launch_pdl(mlp_bwd_rows_kernel<8>, dim3(nslab), dim3(kMlpThreads), smem, st, dQ, Q, Hh, Z, rinv, B, C, H, hd, labels,
-                   sup_weight, p.w_rms, p.W1, p.W2, gpart, dZ);
+                   sup_weight, p.w_rms, p.W1, p.W2, gpart, dZ, loss, xc);
     else
         launch_pdl(mlp_bwd_rows_kernel<16>, dim3(nslab), dim3(kMlpThreads), smem, st, dQ, Q, Hh, Z, rinv, B, C, H, hd, labels,
-                   sup_weight, p.w_rms, p.W1, p.W2, gpart, dZ);
+                   sup_weight, p.w_rms, p.W1, p.W2, gpart, dZ, loss, xc);
     NADM_CHECK_LAUNCH("mlp_bwd_rows_kernel");
     const AdamCoef ac = make_adam(adam);
     const size_t nparam = mlp_slab_floats(C, H, hd.sumK);

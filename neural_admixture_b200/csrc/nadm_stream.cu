@@ -644,9 +644,10 @@ extern "C" int nadm_encoder_fwd(const uint8_t* packed, int64_t pitch, const int6
     NADM_REQUIRE(V && Z && ws, "NULL pointer");
     NADM_REQUIRE(row0 >= 0 && row0 + B <= (1ll << 32), "row numbers must fit 32 bits (row0=%lld)", (long long)row0);
     if (C <= 8 && !use_generic_kernels() && (reinterpret_cast<uintptr_t>(V) & 15) == 0) {
-        // tensor-core path: at most 2048 rows (16 blocks of 128) per launch
-        for (int r0 = 0; r0 < B; r0 += 2048) {
-            const int nb = std::min(2048, B - r0);
+        // tensor-core path: at most 2048 rows (16 blocks of 128) per launch (1024 for the slab-fed variant)
+        const int chunk = enc_fwd_slab() ? 1024 : 2048;
+        for (int r0 = 0; r0 < B; r0 += chunk) {
+            const int nb = std::min(chunk, B - r0);
             if (int rc = launch_enc_fwd_tc(packed, pitch, row_idx ? row_idx + r0 : nullptr, row0 + r0, nb, M, V, C,
                                            Z + (int64_t)r0 * C, ws, ws_bytes, (cudaStream_t)stream))
                 return rc;

@@ -125,9 +125,10 @@ __device__ __forceinline__ void decode16_general(const uint32_t (&v)[16], uint32
             g[e] = (raw <= 1.0f) ? num * inv : 0.0f;                    // clamp backward mask (raw >= 0 always)
             if (kLoss) {
                 // BCE with torch's log clamp; X in {0, .5, 1}: a single log per element.
-                // x = 0: 1 - R = 1 - |R - x| ;  x = 1: R = 1 - |R - x| ;  x = .5: weight .5 on log(R (1 - R))
-                const bool het = (wsrc >> sh) & 1u;
-                const float arg = het ? prod : (1.0f - fabsf(num));
+                // x = 0: log(1 - R) ;  x = 1: log R (taken from R itself: 1 - |R - 1| would lose an R below 2^-24) ;
+                // x = .5: weight .5 on log(R (1 - R))
+                const bool het = (wsrc >> sh) & 1u, one = (wsrc >> sh) & 2u;
+                const float arg = het ? prod : (one ? Rs : 1.0f - Rs);
                 const float l = fmaxf(lg2_approx(arg), kLog2Clamp);
                 acc_hom += het ? 0.0f : l;
                 acc_het += het ? l : 0.0f;
@@ -146,10 +147,17 @@ __device__ __forceinline__ void decode16_general(const uint32_t (&v)[16], uint32
 // per product (<= 2^120: no overflow), so 16 elements cost 4 logs and one multiply each instead of 16 logs:
 // sum_j log t_j = -log prod_j (1 / t_j).
 constexpr float kProdFast = 3.0517578125e-05f;
+// Between the two: every R (1 - R) >= kProdMid = 1e-12 (the floor of BCELoss' backward).  Then still 0 < raw < 1 (no
+// clamp, mask 1) and the floor does not bind, so the GRADIENT is exactly the fast path's num * rcp(prod) (rcp <= 1e12,
+// no overflow); only the product-accumulated loss would overflow (factors up to 1e12), so the loss takes one log per
+// element here (t >= 1e-12 > e^-100: torch's log clamp cannot bind either).  This is the path of late training, where
+// restrict_P has pinned many allele frequencies at exactly 0 / 1 and Q is concentrated: R gets very small or very close
+// to 1 for many elements without being exactly 0 or 1 (bench.py's late_training leg).
+constexpr float kProdMid = 1e-12f;
 // The fp32 arithmetic of the fast path is issued as PACKED pairs (sm_100 FFMA2 / FADD2 / FMUL2 via __ffma2_rn & co.:
 // one issue slot per two elements, results bit-identical to the scalar .rn instructions; negation / |.| fold into
 // operand modifiers).  The kernel is bound by instruction issue, not by the fp32 pipe.
-template <bool kLoss>
+template <bool kLoss, bool kLogPerElement = false>
 __device__ __forceinline__ void decode16_fast(const uint32_t (&v)[16], const float2 (&prod)[8], uint32_t w,
                                               uint32_t magic, uint32_t magic21, uint32_t (&hi)[8], uint32_t (&lo)[8],
                                               float& acc_hom, float& acc_het) {
@@ -171,18 +179,29 @@ __device__ __forceinline__ void decode16_fast(const uint32_t (&v)[16], const flo
         const float cs = -0.5f / (float)(1 << sh);
         const float2 num = __ffma2_rn(f, make_float2(cs, cs), raw);      // R - x
         const float2 g = __fmul2_rn(num, inv);
-        if (kLoss) {
+        if (kLoss && !kLogPerElement) {
             // x in {0,1}: |G| = 1 / (1 - |R - x|), the reciprocal of the BCE argument;  x = 1/2: inv = 1 / (R (1 - R))
             if ((wsrc >> sh) & 1u) p_het *= inv.x;
             else p_hom *= fabsf(g.x);
             if ((wsrc >> sh) & 4u) p_het *= inv.y;
             else p_hom *= fabsf(g.y);
         }
+        if (kLoss && kLogPerElement) {
+            // one log per element (arguments down to 1e-12): x = 0: t = 1 - R;  x = 1: t = R;  x = 1/2: t = R (1 - R)
+            const bool het0 = (wsrc >> sh) & 1u, het1 = (wsrc >> sh) & 4u;
+            const bool one0 = (wsrc >> sh) & 2u, one1 = (wsrc >> sh) & 8u;
+            const float l0 = lg2_approx(het0 ? prod[j2].x : (one0 ? raw.x : 1.0f - raw.x));
+            const float l1 = lg2_approx(het1 ? prod[j2].y : (one1 ? raw.y : 1.0f - raw.y));
+            acc_hom += het0 ? 0.0f : l0;
+            acc_het += het0 ? l0 : 0.0f;
+            acc_hom += het1 ? 0.0f : l1;
+            acc_het += het1 ? l1 : 0.0f;
+        }
         const uint32_t h = pack_bf16x2(g.x, g.y);
         hi[j2] = h;
         const float2 l = __fadd2_rn(g, make_float2(-__uint_as_float(h << 16), -__uint_as_float(h & 0xFFFF0000u)));
         lo[j2] = pack_bf16x2(l.x, l.y);
-        if (kLoss && (j2 & 3) == 3) {
+        if (kLoss && !kLogPerElement && (j2 & 3) == 3) {
             acc_hom -= lg2_approx(p_hom);
             acc_het -= lg2_approx(p_het);
             p_hom = 1.0f;
@@ -320,7 +339,13 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
                     const float t2 = fminf(fminf(prod[3].x, prod[3].y), prod[4].x), t3 = fminf(fminf(prod[4].y, prod[5].x), prod[5].y);
                     const float t4 = fminf(fminf(prod[6].x, prod[6].y), prod[7].x);
                     const float mn = fminf(fminf(fminf(t0, t1), t2), fminf(fminf(t3, t4), prod[7].y));
-                    if (mn >= kProdFast) decode16_fast<kLoss>(v, prod, w, magic, magic21, hi, lo, acc_hom, acc_het);
+                    // Path per WARP, not per lane (thread = row: in late training nearly every warp holds rows of both
+                    // kinds, and a divergent warp pays for every path any of its lanes takes): all lanes fast -> fast;
+                    // otherwise every lane whose products clear the 1e-12 floor takes the mid path (it is valid on the
+                    // fast range too) and only the lanes below it the general one.
+                    const bool all_fast = __all_sync(0xffffffffu, mn >= kProdFast);
+                    if (all_fast) decode16_fast<kLoss>(v, prod, w, magic, magic21, hi, lo, acc_hom, acc_het);
+                    else if (mn >= kProdMid) decode16_fast<kLoss, true>(v, prod, w, magic, magic21, hi, lo, acc_hom, acc_het);
                     else decode16_general<kLoss>(v, w, magic, hi, lo, acc_hom, acc_het);
 #ifndef NADM_KO_MMA   // (knock-out build: raw stays the constant written at setup, so that the decode keeps its fast path)
                     tmem_st8(tlane + slot * 64 + c * 16, hi);          // G hi / lo overwrite their own raw columns

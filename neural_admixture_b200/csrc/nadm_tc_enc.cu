@@ -162,14 +162,23 @@ __device__ __forceinline__ long long combine4(const uint32_t* v, int c) {
     return z;
 }
 // write the digits of 8 components (one K position) into an MN-major digit tile: 2 chunks of 16 bytes, 128 B apart
+// The signed base-256 digits of q = sum_i d_i 256^i, d_i in [-128, 127], are the bytes of (q + 0x80808080) with their
+// top bits flipped back: adding 128 to every digit makes all of them non-negative, so the carries of the ordinary
+// binary addition do the borrowing.  A 4 x 4 byte transpose (8 PRMT) then turns four components' words into the four
+// digit planes: 24 instructions per 4 components instead of ~65 with shifts.
 __device__ __forceinline__ void store_digits(uint8_t* tile_pos, const float (&v)[8], float inv) {
-    uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // w[2*p + h]: plane p, components 4h..4h+3
+    uint32_t w[8];  // w[2*p + h]: plane p (0 = most significant digit), components 4h..4h+3
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        int d[4];
-        digits4(__float2int_rn(v[c] * inv), d);
+    for (int h = 0; h < 2; ++h) {
+        uint32_t t[4];
 #pragma unroll
-        for (int p = 0; p < 4; ++p) w[2 * p + (c >> 2)] |= (uint32_t)(d[p] & 0xFF) << (8 * (c & 3));
+        for (int c = 0; c < 4; ++c) t[c] = ((uint32_t)__float2int_rn(v[4 * h + c] * inv) + 0x80808080u) ^ 0x80808080u;
+        const uint32_t lo01 = __byte_perm(t[0], t[1], 0x5140), hi01 = __byte_perm(t[0], t[1], 0x7362);
+        const uint32_t lo23 = __byte_perm(t[2], t[3], 0x5140), hi23 = __byte_perm(t[2], t[3], 0x7362);
+        w[6 + h] = __byte_perm(lo01, lo23, 0x5410);     // least significant digits of the four components
+        w[4 + h] = __byte_perm(lo01, lo23, 0x7632);
+        w[2 + h] = __byte_perm(hi01, hi23, 0x5410);
+        w[0 + h] = __byte_perm(hi01, hi23, 0x7632);     // most significant
     }
     *reinterpret_cast<uint4*>(tile_pos) = make_uint4(w[0], w[1], w[2], w[3]);
     *reinterpret_cast<uint4*>(tile_pos + 128) = make_uint4(w[4], w[5], w[6], w[7]);
@@ -288,9 +297,6 @@ extern "C" int nadm_debug_enc_timeline(long long* host_out) {
 
 struct EncSmem {
     uint64_t fullA[kAStages], emptyA[kAStages], fullV[2], emptyV[2], done, fdone;
-#ifdef NADM_ENC_TS_HALF
-    uint64_t fullA2[kAStages], emptyA2[kAStages];   // the second half (SNPs 128..255) of every stage
-#endif
     uint32_t tmem_base;
     uint32_t finit[2];   // per issuer: bit blk set = its accumulator of row block blk has been written
     float red[32];       // per-warp |max| of this CTA's slice of V
@@ -333,9 +339,6 @@ enc_fwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
         rowoff[b] = (uint32_t)((row_idx != nullptr) ? row_idx[b] : (row0 + b));
     if (tid == 0) {
         for (int s = 0; s < kAStages; ++s) { mbar_init(&S->fullA[s], 4); mbar_init(&S->emptyA[s], 1); }
-#ifdef NADM_ENC_TS_HALF
-        for (int s = 0; s < kAStages; ++s) { mbar_init(&S->fullA2[s], 4); mbar_init(&S->emptyA2[s], 1); }
-#endif
         for (int s = 0; s < 2; ++s) { mbar_init(&S->fullV[s], kFwdDigWarps); mbar_init(&S->emptyV[s], NISS); }
         mbar_init(&S->done, NISS);
         mbar_init(&S->fdone, NISS);
@@ -404,36 +407,16 @@ enc_fwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
             if (TSA) {
                 const uint32_t ta = tbase + ((uint32_t)(wl * 32) << 16) + kColA + g * 64;
                 tc_fence_after_sync();                               // the MMAs that read this stage have completed
-#ifdef NADM_ENC_TS_HALF
-                // (untested on the device: prepared for the next round)  The stage is handed over in
-                // two halves with their own full / empty barriers: while the issuer multiplies SNPs 128..255 of tile t
-                // (and the commit -> mbarrier -> poll hop runs), this group already widens SNPs 0..127 of its next tile.
-                feed_store_tmem<RAW, 0, 2>(ta, w, mvx);
-                tmem_wait_st();
-                tc_fence_before_sync();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&S->fullA[g]);
-                mbar_wait(&S->emptyA2[g], phase);
-                tc_fence_after_sync();
-                feed_store_tmem<RAW, 2, 4>(ta, w, mvx);
-                tmem_wait_st();
-                tc_fence_before_sync();
-#else
                 feed_store_tmem<RAW>(ta, w, mvx);
                 tmem_wait_st();
                 tc_fence_before_sync();
-#endif
             } else {
                 feed_store<RAW>(tilesA + g * kATile, wl, lane, w, mvx);
                 fence_async_smem();
             }
             if (tid == 0) TLE(3, i);
             __syncwarp();
-#ifdef NADM_ENC_TS_HALF
-            if (lane == 0) mbar_arrive(TSA ? &S->fullA2[g] : &S->fullA[g]);
-#else
             if (lane == 0) mbar_arrive(&S->fullA[g]);                // one arrival per warp of the group
-#endif
             if (tid == 0) TLE(4, i);
             phase ^= 1;
             slot = (slot + 1 == kDepth) ? 0 : slot + 1;
@@ -541,32 +524,16 @@ enc_fwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
                     const uint32_t d = tbase + ((TSA ? 0 : par * nblk) + blk) * 32, acc0 = (inited >> blk) & 1u;
                     if (TSA) {
                         const uint32_t at = tbase + kColA + s * 64;
-#ifdef NADM_ENC_TS_HALF
-#pragma unroll
-                        for (int ks = 0; ks < kSub / 64; ++ks)
-                            mma_i8_ts_p(d, at + ks * 8, b + (uint64_t)(ks * 64), kIdescFwd, 1u, leader);
-                        mma_commit_p(&S->emptyA[s], leader);             // first half of the stage may be refilled
-                        mbar_wait(&S->fullA2[s], (i >> 2) & 1);
-                        tc_fence_after_sync();
-#pragma unroll
-                        for (int ks = kSub / 64; ks < kSub / 32; ++ks)
-                            mma_i8_ts_p(d, at + ks * 8, b + (uint64_t)(ks * 64), kIdescFwd, 1u, leader);
-#else
 #pragma unroll
                         for (int ks = 0; ks < kSub / 32; ++ks)
                             mma_i8_ts_p(d, at + ks * 8, b + (uint64_t)(ks * 64), kIdescFwd, 1u, leader);
-#endif
                     } else {
 #pragma unroll
                         for (int ks = 0; ks < kSub / 32; ++ks)
                             mma_i8_ss_p(d, a + (uint64_t)(ks * 16), b + (uint64_t)(ks * 64), kIdescFwd, ks ? 1u : acc0, leader);
                     }
                     inited |= 1u << blk;
-#ifdef NADM_ENC_TS_HALF
-                    mma_commit_p(TSA ? &S->emptyA2[s] : &S->emptyA[s], leader);
-#else
                     mma_commit_p(&S->emptyA[s], leader);
-#endif
                     if (lane == 0) TLE(7, i);
                 }
                 mma_commit_p(&S->emptyV[vs], leader);
@@ -584,6 +551,324 @@ enc_fwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
     __syncthreads();
     if (tid == 0) TLE(2, 4);                                            // epilogue done
     if (warp == kFwdIssueWarp) tmem_dealloc<512>(tbase);
+}
+
+// =================================================================================================================
+// forward, slab feed (the default): the same contraction as above, but the rows are streamed in 256-BYTE runs.
+//
+// Why: profiles/r2_gather_probe.txt.  Gathering B random sample rows out of HBM at 64 contiguous bytes per row and
+// request (one 256-SNP tile) reaches 2.1 TB/s whatever the depth, the tile order, the engine (cp.async, 1-D bulk copies,
+// TMA gather4) or an L2 prefetch hint; 128-byte runs reach 3.8 TB/s and 256-byte runs 4.5 TB/s (the same rows out of L2:
+// 5.2 TB/s).  The round-1 kernel's loads alone took 50 of its 64 us.  So a producer group now copies a SLAB = one row
+// block (128 rows) x 4 consecutive sub-tiles (1024 SNPs = 256 bytes per row) with one burst of cp.async instructions
+// whose lanes cover 2 rows x 256 contiguous bytes each, and then widens its four 256-SNP tiles out of it.
+// Tile order: slab column (4 sub-tiles) outer, row block, sub-tile inner; the accumulators of all row blocks stay in
+// tensor memory as before, four digit tiles (one slab column) are live and the next four are produced ahead.
+// The genotype operand lives in tensor memory (TS form); widening leaves the 2-bit fields in place (4^j x code, j =
+// field index) and the digit operand of those K positions is built from V / 4^j, which removes the shifts.
+// =================================================================================================================
+#ifndef NADM_SLAB_SUB
+#define NADM_SLAB_SUB 2
+#endif
+#ifndef NADM_SLAB_DEPTH
+#define NADM_SLAB_DEPTH 2
+#endif
+// A slab of kSlabSub sub-tiles = 64 kSlabSub contiguous bytes of every row; kSlabDepth slabs per producer group are in
+// flight / being widened.  Measured on one box (profiles/r2_*): 4 sub-tiles x depth 1 (256-byte runs, but nothing in
+// flight while a group widens its four tiles) was SLOWER than the round-1 kernel; 2 x 2 (128-byte runs, the next slab
+// lands while this one is widened) is the default.  Both use 32 KB of staging per group.
+constexpr int kSlabSub = NADM_SLAB_SUB;            // sub-tiles per slab (2 or 4)
+constexpr int kSlabDepth = NADM_SLAB_DEPTH;        // slabs per producer group
+constexpr int kSlabBytes = 128 * 64 * kSlabSub;    // 16 KB (32 KB)
+constexpr int kSlabPieces = 4 * kSlabSub;          // 16-byte pieces per row
+constexpr int kSlabRowsPerInstr = 32 / kSlabPieces, kSlabIters = 32 / kSlabRowsPerInstr;
+enum : int { kModeTrain = 0, kModeRaw3 = 1, kModeRawAny = 2 };   // what a 2-bit code means (see widen_fields)
+
+// one packed word (16 SNPs) -> 4 words of 4 bytes; byte b of o[k] belongs to SNP 4 b + k of the word (= sigma16(4 k + b)).
+//   kModeTrain : 4^k x code, code 3 (missing) -> 0          (x = code / 2, missing trained as 0)
+//   kModeRaw3  : 4^k x code, code 3 stays 3                  (randomized-SVD products when the reader's missing value is 3)
+//   kModeRawAny: the byte VALUE, code 3 -> any uint8 value   (unscaled: 255 x 64 would not fit a byte)
+template <int MODE>
+__device__ __forceinline__ void widen_fields(uint32_t w, uint32_t mvx, uint32_t* o) {
+#ifdef NADM_KO_WIDEN
+    o[0] = w; o[1] = w; o[2] = w; o[3] = w;
+    return;
+#endif
+    if (MODE == kModeRawAny) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t v = (w >> (2 * k)) & 0x03030303u;
+            const uint32_t m3 = v & (v >> 1) & 0x01010101u;
+            o[k] = v ^ (m3 * mvx);
+        }
+    } else {
+        uint32_t keep = 0xFFFFFFFFu;
+        if (MODE == kModeTrain) keep = ~((w & (w >> 1) & 0x55555555u) * 3u);
+        o[0] = w & 0x03030303u & keep;
+        o[1] = w & 0x0C0C0C0Cu & keep;
+        o[2] = w & 0x30303030u & keep;
+        o[3] = w & 0xC0C0C0C0u & keep;
+    }
+}
+
+struct EncSlabSmem {
+    uint64_t fullA[4], emptyA[4], fullV[2][kSlabSub], emptyV[2], done;
+    uint32_t tmem_base;
+    float red[32];
+};
+constexpr int kSlabThreads = (kProdWarps + 2 + 2) * 32;    // 16 producer warps, 2 digit warps, 2 MMA issuers
+
+// staging address of piece p (16 bytes) of row r inside a slab: piece-major planes, rows XOR-ed with the piece number so
+// that both the copy (a quarter warp writes 8 consecutive pieces of one row) and the read-back (a quarter warp reads one
+// piece of 8 consecutive rows) touch 8 different 16-byte bank groups
+__device__ __forceinline__ uint32_t slab_unit(int r, int p) { return (uint32_t)(p * 128 + (r ^ (p & 7))) << 4; }
+
+template <int NISS, int MODE>
+__global__ void __launch_bounds__(kSlabThreads, 1)
+enc_fwd_slab_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* __restrict__ row_idx, int64_t row0,
+                    int B, int64_t M, const float* __restrict__ V, int C, float* __restrict__ cta_vmax,
+                    long long* __restrict__ part, int T, uint32_t mvx) {
+    pdl_prologue();
+    constexpr bool kScaled = MODE != kModeRawAny;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* tilesV = smem;                                          // 2 sets x kSlabSub digit tiles x 8 KB
+    uint8_t* slabs = tilesV + 2 * kSlabSub * kDigTile;               // 4 groups x kSlabDepth slabs
+    uint32_t* rowoff = reinterpret_cast<uint32_t*>(slabs + 4 * kSlabDepth * kSlabBytes);
+    EncSlabSmem* S = reinterpret_cast<EncSlabSmem*>(rowoff + ((B + 3) & ~3));
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nblk = (B + 127) / 128;
+    const int t0 = (int)(((int64_t)T * blockIdx.x) / gridDim.x), t1 = (int)(((int64_t)T * (blockIdx.x + 1)) / gridDim.x);
+    const int ntt = t1 - t0, ncol = (ntt + kSlabSub - 1) / kSlabSub, nslab = ncol * nblk;
+
+    for (int b = tid; b < B; b += blockDim.x)
+        rowoff[b] = (uint32_t)((row_idx != nullptr) ? row_idx[b] : (row0 + b));
+    if (tid == 0) {
+        for (int s = 0; s < 4; ++s) { mbar_init(&S->fullA[s], 4); mbar_init(&S->emptyA[s], 1); }
+        for (int s = 0; s < 2; ++s) {
+            for (int j = 0; j < kSlabSub; ++j) mbar_init(&S->fullV[s][j], 2);
+            mbar_init(&S->emptyV[s], NISS);
+        }
+        mbar_init(&S->done, NISS);
+        mbar_init_fence();
+    }
+    if (warp == kProdWarps + 2) tmem_alloc<512>(&S->tmem_base);
+    __syncthreads();                                                 // row numbers are in shared memory
+
+    // ---- producer side of the feed ----
+    const int g = warp >> 2, wl = warp & 3;                          // (producer warps only)
+    uint8_t* ring = slabs + (g & 3) * (kSlabDepth * kSlabBytes);
+    auto issue_slab = [&](int sl, int slot) {
+        if (sl < nslab) {
+            const int col = sl / nblk, blk = sl - col * nblk;
+            const int npiece = 4 * min(kSlabSub, ntt - kSlabSub * col);
+            const int p = lane & (kSlabPieces - 1);
+            const int64_t off = (int64_t)(t0 + kSlabSub * col) * (kSub / 4) + p * 16;
+            if (p < npiece) {
+                const uint8_t* base = packed + off;
+                const bool inrow = off + 16 <= pitch;
+                uint8_t* slab = ring + slot * kSlabBytes;
+#pragma unroll 4
+                for (int it = 0; it < kSlabIters; ++it) {
+                    const int r = wl * 32 + lane / kSlabPieces + kSlabRowsPerInstr * it, b = blk * 128 + r;
+                    if (b < B) {
+                        uint8_t* dst = slab + slab_unit(r, p);
+#ifndef NADM_KO_LOAD
+                        if (inrow) cp_async16_full(dst, base + (uint64_t)rowoff[b] * (uint64_t)pitch);
+                        else
+#endif
+                            *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+                    }
+                }
+            }
+        }
+        cp_async_commit();
+    };
+    if (warp < kProdWarps)                                           // in flight while the scale of V is computed
+        for (int d = 0; d < kSlabDepth; ++d) issue_slab(g + 4 * d, d);
+
+    // ---- |max| of this CTA's rows of V (fixed-point scale per CTA), accumulators zeroed ----
+    {
+        const int64_t m0 = (int64_t)t0 * kSub, m1 = min((int64_t)t1 * kSub, M);
+        const int64_t n = (m1 > m0) ? (m1 - m0) * C : 0;
+        const float* v0 = V + m0 * C;
+        uint32_t mx = 0u;
+        if ((reinterpret_cast<uintptr_t>(v0) & 15) == 0) {
+            const int64_t n4 = n / 4;
+#pragma unroll 8
+            for (int64_t i = tid; i < n4; i += blockDim.x) mx = absbits_max4(mx, reinterpret_cast<const float4*>(v0)[i]);
+            for (int64_t i = n4 * 4 + tid; i < n; i += blockDim.x) mx = max(mx, absbits(v0[i]));
+        } else {
+            for (int64_t i = tid; i < n; i += blockDim.x) mx = max(mx, absbits(v0[i]));
+        }
+        mx = warp_max_u32(mx);
+        if (lane == 0) S->red[warp] = __uint_as_float(mx);
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tbase = S->tmem_base;
+    float vmax;
+    {
+        uint32_t m = 0u;
+        for (int w = 0; w < kSlabThreads / 32; ++w) m = max(m, __float_as_uint(S->red[w]));
+        vmax = __uint_as_float(m);
+    }
+    if (tid == 0) cta_vmax[blockIdx.x] = vmax;
+    if (warp < 4) {                                                  // warps 0..3 = lane quadrants 0..3
+        uint32_t z[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) z[j] = 0u;
+        for (int c0 = 0; c0 < nblk * 32; c0 += 16) tmem_st16(tbase + ((uint32_t)(warp * 32) << 16) + c0, z);
+        tmem_wait_st();
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+
+    if (warp < kProdWarps) {
+        // ---------------- producers: group g widens the four tiles of slabs g, g + 4, ... ----------------
+        const int r = wl * 32 + lane;                                // my row of the block = my tensor-memory lane
+        const uint32_t ta = tbase + ((uint32_t)(wl * 32) << 16) + kColA + g * 64;
+        uint32_t phase = 1;
+        int slot = 0;
+        for (int sl = g; sl < nslab; sl += 4) {
+            const int col = sl / nblk, blk = sl - col * nblk;
+            const int nj = min(kSlabSub, ntt - kSlabSub * col);
+            const bool active = blk * 128 + wl * 32 < B;             // warp-uniform: any real row in this warp
+            const uint8_t* slab = ring + slot * kSlabBytes;
+            cp_async_wait<kSlabDepth - 1>();
+            __syncwarp();                                            // the other lanes' copies of my row have landed
+#pragma unroll
+            for (int j = 0; j < kSlabSub; ++j) {
+                if (j < nj) {
+                    uint4 w[4];
+                    if (active) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) w[q] = *reinterpret_cast<const uint4*>(slab + slab_unit(r, 4 * j + q));
+                    }
+                    if (j == nj - 1) {
+                        __syncwarp();                                // every lane has read the slab: refill it
+                        issue_slab(sl + 4 * kSlabDepth, slot);
+                        slot = (slot + 1 == kSlabDepth) ? 0 : slot + 1;
+                    }
+                    mbar_wait(&S->emptyA[g], phase);
+                    if (active) {
+                        tc_fence_after_sync();                       // the MMAs that read this stage have completed
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            uint32_t v[16];
+                            widen_fields<MODE>(w[q].x, mvx, v);
+                            widen_fields<MODE>(w[q].y, mvx, v + 4);
+                            widen_fields<MODE>(w[q].z, mvx, v + 8);
+                            widen_fields<MODE>(w[q].w, mvx, v + 12);
+                            tmem_st16(ta + q * 16, v);
+                        }
+                        tmem_wait_st();
+                        tc_fence_before_sync();
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&S->fullA[g]);        // one arrival per warp of the group
+                    phase ^= 1;
+                }
+            }
+        }
+        // ---------------- epilogue: recombine the digit planes, write this CTA's exact partial sums ----------------
+        mbar_wait(&S->done, 0);
+        tc_fence_after_sync();
+        const int q = warp & 3;
+        for (int blk = warp >> 2; blk < nblk; blk += kProdWarps / 4) {
+            uint32_t v[32];
+            tmem_ld32(tbase + ((uint32_t)(q * 32) << 16) + blk * 32, v);
+            tmem_wait_ld();
+            const int b = blk * 128 + q * 32 + lane;
+            if (b < B) {
+                long long* out = part + ((int64_t)blockIdx.x * B + b) * 8;
+#pragma unroll
+                for (int c = 0; c < 8; c += 2) {
+                    longlong2 z;
+                    z.x = combine4(v, c);
+                    z.y = combine4(v, c + 1);
+                    *reinterpret_cast<longlong2*>(out + c) = z;
+                }
+            }
+        }
+    } else if (warp < kProdWarps + 2) {
+        // ---------------- digit warps: int8 digit planes of V, one slab column (4 sub-tiles) ahead of the MMAs ----------------
+        const FixScale fs = fix_scale(vmax);
+        const int dt = tid - kProdThreads;                              // 0..63: K positions dt, dt+64, dt+128, dt+192
+        auto load_v = [&](int tt, float (&v)[4][8]) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int pos = dt + 64 * e;
+                const int64_t m = (int64_t)(t0 + tt) * kSub + (pos & ~15) + sigma16(pos & 15);
+                if (m < M && C == 8) {
+                    const float4 a = reinterpret_cast<const float4*>(V + m * 8)[0], b4 = reinterpret_cast<const float4*>(V + m * 8)[1];
+                    v[e][0] = a.x; v[e][1] = a.y; v[e][2] = a.z; v[e][3] = a.w;
+                    v[e][4] = b4.x; v[e][5] = b4.y; v[e][6] = b4.z; v[e][7] = b4.w;
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) v[e][c] = (m < M && c < C) ? V[m * C + c] : 0.f;
+                }
+            }
+        };
+        float vnext[4][8];
+        load_v(0, vnext);
+        for (int tt = 0; tt < ntt; ++tt) {
+            const int col = tt / kSlabSub, j = tt % kSlabSub, set = col & 1;
+            float v[4][8];
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+#pragma unroll
+                for (int c = 0; c < 8; ++c) v[e][c] = vnext[e][c];
+            if (tt + 1 < ntt) load_v(tt + 1, vnext);
+            if (j == 0) mbar_wait_relaxed(&S->emptyV[set], ((col >> 1) & 1) ^ 1, 128);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int pos = dt + 64 * e;
+                // scaled widening: K positions 4 k .. 4 k + 3 of every 16 hold 4^k x code -> digits of V / 4^k
+                const float inv_pos = kScaled ? fs.inv * __uint_as_float((uint32_t)(127 - 2 * ((pos & 15) >> 2)) << 23) : fs.inv;
+                store_digits(tilesV + (set * kSlabSub + j) * kDigTile + (pos & 7) * 16 + (pos >> 3) * 256, v[e], inv_pos);
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S->fullV[set][j]);
+        }
+    } else {
+        // ---------------- MMA issuers: issuer `par` takes the slabs of producer groups 2 par, 2 par + 1 ----------------
+        const int par = warp - (kProdWarps + 2);
+        if (par < NISS) {
+            const uint64_t B0 = smem_desc(smem_u32(tilesV), 256, 128);
+            const uint32_t leader = elect_one() ? 1u : 0u;
+            uint32_t phbits = 0u;                                        // phase of fullA[g], bit g
+            for (int col = 0; col < ncol; ++col) {
+                const int set = col & 1, nj = min(kSlabSub, ntt - kSlabSub * col);
+                const uint32_t vph = (uint32_t)((col >> 1) & 1);
+                for (int blk = 0; blk < nblk; ++blk) {
+                    const int sl = col * nblk + blk;
+                    if (NISS == 2 && ((sl >> 1) & 1) != par) continue;
+                    const int gg = sl & 3;
+                    const uint32_t d = tbase + blk * 32, at = tbase + kColA + gg * 64;
+                    for (int j = 0; j < nj; ++j) {
+                        mbar_wait(&S->fullV[set][j], vph);
+                        mbar_wait(&S->fullA[gg], (phbits >> gg) & 1u);
+                        tc_fence_after_sync();
+                        const uint64_t b = B0 + (uint64_t)((set * kSlabSub + j) * (kDigTile >> 4));
+#pragma unroll
+                        for (int ks = 0; ks < kSub / 32; ++ks)
+                            mma_i8_ts_p(d, at + ks * 8, b + (uint64_t)(ks * 64), kIdescFwd, 1u, leader);
+                        mma_commit_p(&S->emptyA[gg], leader);
+                        phbits ^= 1u << gg;
+                    }
+                }
+                mma_commit_p(&S->emptyV[set], leader);
+            }
+            mma_commit_p(&S->done, leader);
+        }
+        __syncwarp();
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == kProdWarps + 2) tmem_dealloc<512>(tbase);
 }
 
 // Z[b, c] = 0.5 * sum over CTAs p of part_p[b, c] * 2^(e_p - 30): every CTA's partial is an exact integer at the CTA's own
@@ -742,6 +1027,21 @@ enc_bwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
         const int q = warp & 3;             // tensor-memory lane quadrant this warp may access (warp id % 4)
         for (int tt = 0; tt < t1 - t0; ++tt) {
             const int buf = tt & 1;
+            // The 128 epilogue threads move all of V / m / v (96 MB per launch) with 12 loads of 16 bytes in flight each:
+            // latency-bound, and the epilogue then paces the whole kernel (85 us with Adam against 60 without).  So the
+            // lines of the sub-tile TWO iterations ahead are pulled into L2 here (no registers held; requesting the current
+            // sub-tile's lines at this point came too late to matter: 88 us; loading them into registers spilled: 128 us).
+            if (adam.enabled && C == 8) {
+                const int tp = tt + (tt == 0 ? 0 : 2);               // iteration 0 also covers sub-tiles 0 and 1
+                for (int ta = tp; ta <= tt + 2 && ta < t1 - t0; ++ta) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int pos = q * 32 + lane;
+                        const int64_t m = (int64_t)(t0 + ta) * kSub + h * 128 + (pos & ~15) + sigma16(pos & 15);
+                        if (m < M) { prefetch_l2(V + m * 8); prefetch_l2(Vm + m * 8); prefetch_l2(Vv + m * 8); }
+                    }
+                }
+            }
             if (warp == kProdWarps + 2) mbar_wait_relaxed(&S->dfull[buf], (tt >> 1) & 1, 64);   // one warp polls
             named_bar_sync(1, 128);
             tc_fence_after_sync();
@@ -820,6 +1120,302 @@ enc_bwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
 }
 
 // =================================================================================================================
+// backward, slab feed (the default): dV = X^T dZ + Adam with the rows streamed in 256-byte runs (see the forward slab
+// kernel for why).  The operand X^T must come from shared memory (SNPs on the M axis), so the widened stages stay
+// there — but as HALF tiles (128 rows x 128 SNPs, 16 KB) so that four 32 KB slabs fit beside them.  Order: slab column
+// (4 sub-tiles) outer, row block, sub-tile, half inner; the 4 x 2 accumulators (128 SNPs x 32 digit columns) of a
+// column are shared by both issuers (zero-initialised by the epilogue, every MMA accumulates: integer adds commute)
+// and double-buffered against the epilogue: 2 x 8 x 32 = 512 tensor-memory columns.
+// =================================================================================================================
+constexpr int kHalfTile = 128 * 128;               // bytes of one widened half tile
+struct EncBwdSlabSmem {
+    uint64_t fullA[4], emptyA[4], dfull[2], dempty[2];
+    uint32_t tmem_base;
+    float red[32];
+};
+constexpr int kBwdSlabThreads = kProdThreads + 64 + 128;
+
+template <int NISS, int MODE>
+__global__ void __launch_bounds__(kBwdSlabThreads, 1)
+enc_bwd_slab_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* __restrict__ row_idx, int64_t row0,
+                    int B, int64_t M, const float* __restrict__ dZ, int C, float* __restrict__ V, float* __restrict__ Vm,
+                    float* __restrict__ Vv, AdamCoef adam_in, float* __restrict__ dV_out, int T, uint32_t mvx,
+                    double out_scale, int accumulate) {
+    pdl_prologue();
+    constexpr bool kScaled = MODE != kModeRawAny;
+    const AdamCoef adam = adam_resolve(adam_in);
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int nblk = (B + 127) / 128;
+    uint8_t* tilesA = smem;                                          // 4 stages x 16 KB (one per producer group)
+    uint8_t* digZ = tilesA + 4 * kHalfTile;                          // nblk x 4 KB: dZ digits, K position = batch row
+    uint8_t* slabs = digZ + nblk * 4096;                             // 4 groups x kSlabDepth slabs of packed rows
+    uint32_t* rowoff = reinterpret_cast<uint32_t*>(slabs + 4 * kSlabDepth * kSlabBytes);
+    EncBwdSlabSmem* S = reinterpret_cast<EncBwdSlabSmem*>(rowoff + ((B + 3) & ~3));
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int t0 = (int)(((int64_t)T * blockIdx.x) / gridDim.x), t1 = (int)(((int64_t)T * (blockIdx.x + 1)) / gridDim.x);
+    const int ntt = t1 - t0, ncol = (ntt + kSlabSub - 1) / kSlabSub, nslab = ncol * nblk;
+
+    for (int b = tid; b < B; b += blockDim.x)
+        rowoff[b] = (uint32_t)((row_idx != nullptr) ? row_idx[b] : (row0 + b));
+    if (tid == 0) {
+        for (int s = 0; s < 4; ++s) { mbar_init(&S->fullA[s], 4); mbar_init(&S->emptyA[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&S->dfull[s], NISS); mbar_init(&S->dempty[s], 4); }
+        mbar_init_fence();
+    }
+    if (warp == kProdWarps) tmem_alloc<512>(&S->tmem_base);
+    __syncthreads();                                                 // row numbers are in shared memory
+
+    const int g = warp >> 2, wl = warp & 3;                          // (producer warps only)
+    uint8_t* ring = slabs + (g & 3) * (kSlabDepth * kSlabBytes);
+    auto issue_slab = [&](int sl, int slot) {
+        if (sl < nslab) {
+            const int col = sl / nblk, blk = sl - col * nblk;
+            const int npiece = 4 * min(kSlabSub, ntt - kSlabSub * col);
+            const int p = lane & (kSlabPieces - 1);
+            const int64_t off = (int64_t)(t0 + kSlabSub * col) * (kSub / 4) + p * 16;
+            if (p < npiece) {
+                const uint8_t* base = packed + off;
+                const bool inrow = off + 16 <= pitch;
+                uint8_t* slab = ring + slot * kSlabBytes;
+#pragma unroll 4
+                for (int it = 0; it < kSlabIters; ++it) {
+                    const int r = wl * 32 + lane / kSlabPieces + kSlabRowsPerInstr * it, b = blk * 128 + r;
+                    if (b < B) {
+                        uint8_t* dst = slab + slab_unit(r, p);
+#ifndef NADM_KO_LOAD
+                        if (inrow) cp_async16_full(dst, base + (uint64_t)rowoff[b] * (uint64_t)pitch);
+                        else
+#endif
+                            *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+                    }
+                }
+            }
+        }
+        cp_async_commit();
+    };
+    if (warp < kProdWarps)                                           // in flight during the set-up below
+        for (int d = 0; d < kSlabDepth; ++d) issue_slab(g + 4 * d, d);
+
+    // |max| of dZ over the batch (every CTA computes the same value), digits of dZ
+    uint32_t mxb = 0u;
+    if ((reinterpret_cast<uintptr_t>(dZ) & 15) == 0 && ((B * C) & 3) == 0) {
+#pragma unroll 4
+        for (int i = tid; i < (B * C) / 4; i += blockDim.x) mxb = absbits_max4(mxb, reinterpret_cast<const float4*>(dZ)[i]);
+    } else {
+        for (int i = tid; i < B * C; i += blockDim.x) mxb = max(mxb, absbits(dZ[i]));
+    }
+    mxb = warp_max_u32(mxb);
+    if (lane == 0) S->red[warp] = __uint_as_float(mxb);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    mxb = 0u;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) mxb = max(mxb, __float_as_uint(S->red[w]));
+    const FixScale fs = fix_scale(__uint_as_float(mxb));
+    for (int b = tid; b < nblk * 128; b += blockDim.x) {
+        float v[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[c] = (b < B && c < C) ? dZ[(int64_t)b * C + c] : 0.f;
+        store_digits(digZ + (b & 7) * 16 + (b >> 3) * 256, v, fs.inv);
+    }
+    const uint32_t tbase = S->tmem_base;
+    if (warp < 4) {                                                  // zero both accumulator buffers (512 columns)
+        uint32_t z[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) z[j] = 0u;
+        for (int c0 = 0; c0 < 512; c0 += 16) tmem_st16(tbase + ((uint32_t)(warp * 32) << 16) + c0, z);
+        tmem_wait_st();
+    }
+    fence_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+
+    if (warp < kProdWarps) {
+        // ---------------- producers: group g widens the eight half tiles of slabs g, g + 4, ... ----------------
+        const int r8 = lane & 7, qq = (lane >> 3) & 1, gsel = lane >> 4;
+        uint8_t* tile = tilesA + g * kHalfTile;
+        uint32_t phase = 1;
+        int slot = 0;
+        for (int sl = g; sl < nslab; sl += 4) {
+            const int col = sl / nblk, blk = sl - col * nblk;
+            const int nj = min(kSlabSub, ntt - kSlabSub * col);
+            const bool active = blk * 128 + wl * 32 < B;             // warp-uniform: any real row in this warp
+            const uint8_t* slab = ring + slot * kSlabBytes;
+            cp_async_wait<kSlabDepth - 1>();
+            __syncwarp();                                            // this warp's copies of its 32 rows have landed
+#pragma unroll
+            for (int j = 0; j < kSlabSub; ++j) {
+                if (j < nj) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        uint4 w[2];
+                        if (active) {
+#pragma unroll
+                            for (int it = 0; it < 2; ++it)
+                                w[it] = *reinterpret_cast<const uint4*>(
+                                    slab + slab_unit((wl * 4 + gsel * 2 + it) * 8 + r8, 4 * j + 2 * h + qq));
+                        }
+                        if (j == nj - 1 && h == 1) {
+                            __syncwarp();                            // every lane has read the slab: refill it
+                            issue_slab(sl + 4 * kSlabDepth, slot);
+                            slot = (slot + 1 == kSlabDepth) ? 0 : slot + 1;
+                        }
+                        mbar_wait(&S->emptyA[g], phase);
+                        if (active) {
+#pragma unroll
+                            for (int it = 0; it < 2; ++it) {
+                                const int g8 = wl * 4 + gsel * 2 + it;                       // 8-row group of the block
+                                uint8_t* dst = tile + r8 * 16 + g8 * 1024 + (qq * 4) * 128;
+                                uint32_t o[4];
+                                widen_fields<MODE>(w[it].x, mvx, o);
+                                *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
+                                widen_fields<MODE>(w[it].y, mvx, o);
+                                *reinterpret_cast<uint4*>(dst + 128) = make_uint4(o[0], o[1], o[2], o[3]);
+                                widen_fields<MODE>(w[it].z, mvx, o);
+                                *reinterpret_cast<uint4*>(dst + 256) = make_uint4(o[0], o[1], o[2], o[3]);
+                                widen_fields<MODE>(w[it].w, mvx, o);
+                                *reinterpret_cast<uint4*>(dst + 384) = make_uint4(o[0], o[1], o[2], o[3]);
+                            }
+                            fence_async_smem();
+                        }
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&S->fullA[g]);
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp <= kProdWarps + 1) {
+        // ---------------- MMA issuers: issuer p takes the slabs of producer groups 2 p, 2 p + 1 ----------------
+        const int par = warp - kProdWarps;
+        if (par < NISS) {
+            const uint64_t A0 = smem_desc(smem_u32(tilesA), 1024, 128), B0 = smem_desc(smem_u32(digZ), 256, 128);
+            const int nks_last = min(4, (B - (nblk - 1) * 128 + 31) / 32);  // K steps holding real batch rows
+            const uint32_t leader = elect_one() ? 1u : 0u;
+            uint32_t phbits = 0u;
+            for (int col = 0; col < ncol; ++col) {
+                const int buf = col & 1, nj = min(kSlabSub, ntt - kSlabSub * col);
+                mbar_wait(&S->dempty[buf], ((col >> 1) & 1) ^ 1);
+                tc_fence_after_sync();
+                for (int blk = 0; blk < nblk; ++blk) {
+                    const int sl = col * nblk + blk;
+                    if (NISS == 2 && ((sl >> 1) & 1) != par) continue;
+                    const int gg = sl & 3;
+                    const uint64_t a = A0 + (uint64_t)(gg * (kHalfTile >> 4)), b = B0 + (uint64_t)(blk * 256);
+                    const int nks = (blk == nblk - 1) ? nks_last : 4;
+                    for (int j = 0; j < nj; ++j) {
+                        for (int h = 0; h < 2; ++h) {
+                            mbar_wait(&S->fullA[gg], (phbits >> gg) & 1u);
+                            tc_fence_after_sync();
+                            const uint32_t d = tbase + ((buf * kSlabSub + j) * 2 + h) * 32;
+                            if (nks == 4) {
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks)
+                                    mma_i8_ss_p(d, a + (uint64_t)(ks * 256), b + (uint64_t)(ks * 64), kIdescBwd, 1u, leader);
+                            } else {
+                                for (int ks = 0; ks < nks; ++ks)
+                                    mma_i8_ss_p(d, a + (uint64_t)(ks * 256), b + (uint64_t)(ks * 64), kIdescBwd, 1u, leader);
+                            }
+                            mma_commit_p(&S->emptyA[gg], leader);
+                            phbits ^= 1u << gg;
+                        }
+                    }
+                }
+                mma_commit_p(&S->dfull[buf], leader);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ---------------- epilogue: digit planes -> dV -> Adam on V, one SNP per thread and half tile ----------------
+        const int q = warp & 3;             // tensor-memory lane quadrant this warp may access (warp id % 4)
+        for (int col = 0; col < ncol; ++col) {
+            const int buf = col & 1, nj = min(kSlabSub, ntt - kSlabSub * col);
+            if (warp == kProdWarps + 2) mbar_wait_relaxed(&S->dfull[buf], (col >> 1) & 1, 64);   // one warp polls
+            named_bar_sync(1, 128);
+            tc_fence_after_sync();
+            for (int j = 0; j < nj; ++j) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t v[32];
+                    tmem_ld32(tbase + ((uint32_t)(q * 32) << 16) + ((buf * kSlabSub + j) * 2 + h) * 32, v);
+                    tmem_wait_ld();
+                    const int pos = q * 32 + lane;
+                    const int64_t m = (int64_t)(t0 + kSlabSub * col + j) * kSub + h * 128 + (pos & ~15) + sigma16(pos & 15);
+                    if (m >= M) continue;
+                    // scaled widening: this SNP's bytes were 4^k x code, k = its field index inside the packed byte
+                    const double sc = fs.back * out_scale *
+                        (kScaled ? __longlong_as_double((long long)(1023 - 2 * ((pos & 15) >> 2)) << 52) : 1.0);
+                    float gr[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) gr[c] = (float)((double)combine4(v, c) * sc);
+                    if (C == 8) {
+                        float4* gv = reinterpret_cast<float4*>(gr);
+                        if (dV_out != nullptr) {
+                            if (accumulate) {                              // += over successive row batches (nadm_geno_matmul_t)
+                                const float4 a0 = reinterpret_cast<float4*>(dV_out + m * 8)[0];
+                                const float4 a1 = reinterpret_cast<float4*>(dV_out + m * 8)[1];
+                                gv[0] = make_float4(gv[0].x + a0.x, gv[0].y + a0.y, gv[0].z + a0.z, gv[0].w + a0.w);
+                                gv[1] = make_float4(gv[1].x + a1.x, gv[1].y + a1.y, gv[1].z + a1.z, gv[1].w + a1.w);
+                            }
+                            reinterpret_cast<float4*>(dV_out + m * 8)[0] = gv[0];
+                            reinterpret_cast<float4*>(dV_out + m * 8)[1] = gv[1];
+                        }
+                        if (adam.enabled) {
+#pragma unroll
+                            for (int hh = 0; hh < 2; ++hh) {
+                                float4 p4 = reinterpret_cast<float4*>(V + m * 8)[hh];
+                                float4 m4 = reinterpret_cast<float4*>(Vm + m * 8)[hh];
+                                float4 v4 = reinterpret_cast<float4*>(Vv + m * 8)[hh];
+                                p4.x = adam_apply(p4.x, gr[hh * 4 + 0], m4.x, v4.x, adam);
+                                p4.y = adam_apply(p4.y, gr[hh * 4 + 1], m4.y, v4.y, adam);
+                                p4.z = adam_apply(p4.z, gr[hh * 4 + 2], m4.z, v4.z, adam);
+                                p4.w = adam_apply(p4.w, gr[hh * 4 + 3], m4.w, v4.w, adam);
+                                reinterpret_cast<float4*>(V + m * 8)[hh] = p4;
+                                reinterpret_cast<float4*>(Vm + m * 8)[hh] = m4;
+                                reinterpret_cast<float4*>(Vv + m * 8)[hh] = v4;
+                            }
+                        }
+                    } else {
+                        for (int c = 0; c < C; ++c) {
+                            const int64_t vi = m * C + c;
+                            if (dV_out != nullptr) dV_out[vi] = accumulate ? dV_out[vi] + gr[c] : gr[c];
+                            if (adam.enabled) {
+                                float mm = Vm[vi], vv = Vv[vi];
+                                V[vi] = adam_apply(V[vi], gr[c], mm, vv, adam);
+                                Vm[vi] = mm;
+                                Vv[vi] = vv;
+                            }
+                        }
+                    }
+                }
+            }
+            // hand the buffer back zeroed: both issuers accumulate into it from the first MMA on
+            {
+                uint32_t z[16];
+#pragma unroll
+                for (int jj = 0; jj < 16; ++jj) z[jj] = 0u;
+                for (int c0 = 0; c0 < kSlabSub * 64; c0 += 16)
+                    tmem_st16(tbase + ((uint32_t)(q * 32) << 16) + buf * (kSlabSub * 64) + c0, z);
+                tmem_wait_st();
+            }
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S->dempty[buf]);
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == kProdWarps) tmem_dealloc<512>(tbase);
+}
+
+bool enc_bwd_slab_supported(int B) {
+    const int nblk = (B + 127) / 128;
+    return (size_t)4 * kHalfTile + (size_t)nblk * 4096 + (size_t)4 * kSlabDepth * kSlabBytes + (size_t)((B + 3) & ~3) * 4 +
+               sizeof(EncBwdSlabSmem) + 64 <= (size_t)kMaxDynSmem;
+}
+
+// =================================================================================================================
 // host launchers (called from the C ABI in nadm_stream.cu)
 // =================================================================================================================
 // MMA issuer warps per encoder kernel: NADM_ENC_ISSUERS=1|2 (A/B measurements; default below)
@@ -829,6 +1425,29 @@ static bool enc_fwd_tmem_operand() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("NADM_ENC_TS");
+        v = (e != nullptr && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
+// NADM_ENC_FWD_SLAB=1: the slab-fed forward kernel (128-byte runs per row, operand in tensor memory, scaled widening).
+// Same-box A/B inside the training step (profiles/r2_*): 0.4428 vs 0.4425 ms per step — no gain where it matters (every
+// step gathers rows that are not in L2), and the forward-only Q pass loses (1024 instead of 2048 rows per launch), so it
+// stays opt-in for measurements.
+bool enc_fwd_slab() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("NADM_ENC_FWD_SLAB");
+        v = (e != nullptr && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
+// NADM_ENC_BWD_SLAB=1: the slab-fed backward kernel.  Measured SLOWER than the round-1 backward kernel (82 vs 60 us at
+// cfg3, profiles/r2_encoder_slab_variants.txt: its half-tile stages double the producer / issuer hand-overs, and that
+// costs more than the 128-byte runs gain), so it stays opt-in for measurements.
+static bool enc_bwd_slab() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("NADM_ENC_BWD_SLAB");
         v = (e != nullptr && e[0] == '1') ? 1 : 0;
     }
     return v == 1;
@@ -860,6 +1479,40 @@ int launch_enc_fwd_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_i
     float* vmax = reinterpret_cast<float*>(ws);                     // per-CTA |max| of its slice of V (ncta floats)
     long long* part = reinterpret_cast<long long*>(reinterpret_cast<uint8_t*>(ws) + kEncWsHeader);
     const int nblk_ = (B + 127) / 128;
+    if (enc_fwd_slab() && nblk_ <= 8) {
+        // ---- slab-fed kernel (default): 256-byte runs per row, genotype operand in tensor memory ----
+        NADM_REQUIRE((M + ncta - 1) / ncta <= 65536, "M=%lld: more than 65536 SNPs per CTA would overflow the int32 accumulators",
+                     (long long)M);
+        const size_t smem_s = (size_t)2 * kSlabSub * kDigTile + (size_t)4 * kSlabDepth * kSlabBytes + (size_t)((B + 3) & ~3) * 4 +
+                              sizeof(EncSlabSmem) + 64;
+        static PerDeviceOnce once_s;
+        bool* as = once_s.slot();
+        if (as == nullptr || !*as) {
+            cudaError_t e = cudaSuccess;
+#define NADM_SLAB_ATTR(N_, M_)                                                                                         \
+    if (e == cudaSuccess)                                                                                              \
+        e = cudaFuncSetAttribute(enc_fwd_slab_kernel<N_, M_>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)
+            NADM_SLAB_ATTR(1, kModeTrain); NADM_SLAB_ATTR(2, kModeTrain); NADM_SLAB_ATTR(1, kModeRaw3);
+            NADM_SLAB_ATTR(2, kModeRaw3); NADM_SLAB_ATTR(1, kModeRawAny); NADM_SLAB_ATTR(2, kModeRawAny);
+#undef NADM_SLAB_ATTR
+            if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(enc_fwd_slab)");
+            if (as) *as = true;
+        }
+        const bool two_s = enc_issuers() == 2 && nblk_ >= 3;
+        const uint32_t mvx_s = raw_mv >= 0 ? (3u ^ (uint32_t)(raw_mv & 0xFF)) : 0u;
+        const int mode = raw_mv < 0 ? kModeTrain : (raw_mv == 3 ? kModeRaw3 : kModeRawAny);
+#define NADM_SLAB_GO(N_, M_)                                                                                           \
+    launch_pdl(enc_fwd_slab_kernel<N_, M_>, dim3(ncta), dim3(kSlabThreads), smem_s, st, packed, pitch, row_idx, row0, B, \
+               M, V, C, vmax, part, T, mvx_s)
+        if (mode == kModeTrain) { if (two_s) NADM_SLAB_GO(2, kModeTrain); else NADM_SLAB_GO(1, kModeTrain); }
+        else if (mode == kModeRaw3) { if (two_s) NADM_SLAB_GO(2, kModeRaw3); else NADM_SLAB_GO(1, kModeRaw3); }
+        else { if (two_s) NADM_SLAB_GO(2, kModeRawAny); else NADM_SLAB_GO(1, kModeRawAny); }
+#undef NADM_SLAB_GO
+        NADM_CHECK_LAUNCH("enc_fwd_slab_kernel");
+        launch_pdl(enc_fwd_reduce_kernel, dim3(B), dim3(256), 0, st, part, ncta, B, C, vmax, Z, raw_mv >= 0 ? 1.0 : 0.5);
+        NADM_CHECK_LAUNCH("enc_fwd_reduce_kernel");
+        return NADM_OK;
+    }
     const bool tsa = enc_fwd_tmem_operand() && nblk_ <= 8;           // accumulators + 4 tiles must fit 512 columns
     const size_t smem = (tsa ? (size_t)4 * kStDepthTS * kStTile : (size_t)kAStages * kATile + (size_t)4 * kStDepth * kStTile) +
                         2 * kDigTile + (size_t)((B + 3) & ~3) * 4 + sizeof(EncSmem) + 64;
@@ -902,6 +1555,37 @@ int launch_enc_bwd_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_i
     const int T = (int)((M + kSub - 1) / kSub);
     const int ncta = std::min(T, sm_count());
     const int nblk = (B + 127) / 128;
+    if (enc_bwd_slab() && enc_bwd_slab_supported(B)) {
+        // ---- slab-fed kernel (default): 256-byte runs per row, half-tile stages ----
+        const size_t smem_s = (size_t)4 * kHalfTile + (size_t)nblk * 4096 + (size_t)4 * kSlabDepth * kSlabBytes +
+                              (size_t)((B + 3) & ~3) * 4 + sizeof(EncBwdSlabSmem) + 64;
+        static PerDeviceOnce once_s;
+        bool* as = once_s.slot();
+        if (as == nullptr || !*as) {
+            cudaError_t e = cudaSuccess;
+#define NADM_BSLAB_ATTR(N_, M_)                                                                                        \
+    if (e == cudaSuccess)                                                                                              \
+        e = cudaFuncSetAttribute(enc_bwd_slab_kernel<N_, M_>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)
+            NADM_BSLAB_ATTR(1, kModeTrain); NADM_BSLAB_ATTR(2, kModeTrain); NADM_BSLAB_ATTR(1, kModeRaw3);
+            NADM_BSLAB_ATTR(2, kModeRaw3); NADM_BSLAB_ATTR(1, kModeRawAny); NADM_BSLAB_ATTR(2, kModeRawAny);
+#undef NADM_BSLAB_ATTR
+            if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(enc_bwd_slab)");
+            if (as) *as = true;
+        }
+        const bool two_s = enc_issuers() == 2 && nblk >= 3;
+        const uint32_t mvx_s = raw_mv >= 0 ? (3u ^ (uint32_t)(raw_mv & 0xFF)) : 0u;
+        const double scale_s = raw_mv >= 0 ? 1.0 : 0.5;
+        const int mode = raw_mv < 0 ? kModeTrain : (raw_mv == 3 ? kModeRaw3 : kModeRawAny);
+#define NADM_BSLAB_GO(N_, M_)                                                                                          \
+    launch_pdl(enc_bwd_slab_kernel<N_, M_>, dim3(ncta), dim3(kBwdSlabThreads), smem_s, st, packed, pitch, row_idx, row0, B, M, \
+               dZ, C, V, Vm, Vv, make_adam(adam), dV_out, T, mvx_s, scale_s, accumulate)
+        if (mode == kModeTrain) { if (two_s) NADM_BSLAB_GO(2, kModeTrain); else NADM_BSLAB_GO(1, kModeTrain); }
+        else if (mode == kModeRaw3) { if (two_s) NADM_BSLAB_GO(2, kModeRaw3); else NADM_BSLAB_GO(1, kModeRaw3); }
+        else { if (two_s) NADM_BSLAB_GO(2, kModeRawAny); else NADM_BSLAB_GO(1, kModeRawAny); }
+#undef NADM_BSLAB_GO
+        NADM_CHECK_LAUNCH("enc_bwd_slab_kernel");
+        return NADM_OK;
+    }
     const size_t smem = (size_t)kAStages * kATile + (size_t)nblk * 4096 + (size_t)4 * kStDepth * kStTile + (size_t)((B + 3) & ~3) * 4 +
                         sizeof(EncBwdSmem) + 64;
     NADM_REQUIRE(smem <= (size_t)kMaxDynSmem, "batch B=%d too large for encoder_bwd", B);

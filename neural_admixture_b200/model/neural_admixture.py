@@ -146,25 +146,28 @@ class Q_P(torch.nn.Module):
         return buf
 
     def encode_packed(self, pg: ops.PackedGenotypes, *, row_idx: Optional[torch.Tensor] = None, row0: int = 0,
-                      B: Optional[int] = None, allreduce=None) -> Tuple[List[torch.Tensor], dict]:
+                      B: Optional[int] = None, allreduce=None, xchg=None) -> Tuple[List[torch.Tensor], dict]:
         """Forward of the encoder on rows of a packed matrix: Z = X V -> RMSNorm -> MLP -> per-head softmax
-        (reference :169-176).  ``allreduce`` (callable on a tensor) sums the partial projection over SNP shards."""
+        (reference :169-176).  SNP-sharded runs sum the partial projection over the ranks either inside the MLP kernel
+        (``xchg``: an ``ops.PeerExchange.xchg``, stores over NVLink into the peers' exchange areas) or with
+        ``allreduce`` (a callable on the tensor, e.g. NCCL)."""
         self.bind()
         B = row_idx.numel() if row_idx is not None else B
         buf = self._fwd_buffers(B)
         ops.encoder_fwd(pg, self.V.data, buf["Z"], buf["ws"], row_idx=row_idx, row0=row0, B=B)
-        if allreduce is not None:
+        if allreduce is not None and xchg is None:
             allreduce(buf["Z"])
         ks = self.multihead_encoder.ks
         ops.mlp_fwd(buf["Z"], self.batch_norm.weight.data, self.common_encoder[0].weight.data,
-                    self.common_encoder[0].bias.data, self.W2cat, self.b2cat, ks, buf["rinv"], buf["Hh"], buf["Q"])
+                    self.common_encoder[0].bias.data, self.W2cat, self.b2cat, ks, buf["rinv"], buf["Hh"], buf["Q"],
+                    xchg=xchg)
         probs, off = [], 0
         for k in ks:
             probs.append(buf["Q"][:, off:off + k])
             off += k
         return probs, buf
 
-    def infer_packed(self, pg: ops.PackedGenotypes, batch: int = 2048, allreduce=None) -> List[torch.Tensor]:
+    def infer_packed(self, pg: ops.PackedGenotypes, batch: int = 2048, allreduce=None, xchg=None) -> List[torch.Tensor]:
         """Q for every row of a packed matrix, sequential row batches, outputs preallocated (the reference's
         inference loop, src/inference.py:71-77, and post-training Q pass, :369-383, grow Q with ``torch.cat`` per
         batch).  The batch size does not change any row's result.  ``allreduce`` sums the partial projections of the
@@ -174,7 +177,7 @@ class Q_P(torch.nn.Module):
         outs = [torch.empty((pg.N, k), dtype=torch.float32, device=pg.storage.device) for k in ks]
         for r0 in range(0, pg.N, batch):
             nb = min(batch, pg.N - r0)
-            probs, _ = self.encode_packed(pg, row0=r0, B=nb, allreduce=allreduce)
+            probs, _ = self.encode_packed(pg, row0=r0, B=nb, allreduce=allreduce, xchg=xchg)
             for o, p in zip(outs, probs):
                 o[r0:r0 + nb].copy_(p)
         return outs
@@ -262,6 +265,7 @@ class NeuralAdmixture:
         self.pack2bit = pack2bit
         self.sharded = bool(num_gpus > 1 and torch.distributed.is_available() and torch.distributed.is_initialized())
         self.loss_history: List[float] = []
+        self.exchange: Optional[ops.PeerExchange] = None    # fused peer exchange of the sharded step (else NCCL)
 
     # ---- model ---------------------------------------------------------------------------------------------------
     def initialize_model(self, P: torch.Tensor, hidden_size: int, num_features: int, V: torch.Tensor,
@@ -279,6 +283,36 @@ class NeuralAdmixture:
 
     def _allreduce(self, t: torch.Tensor) -> None:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM)
+
+    def open_exchange(self, max_rows: int = 2048) -> None:
+        """Sharded runs: set up the peer-mapped exchange areas (collective).  ``NADM_XCHG=nccl`` keeps the two NCCL
+        all-reduces per step instead (the baseline the fused exchange is measured against); so does a node where CUDA
+        IPC between the ranks' devices is not possible."""
+        if not self.sharded or self.exchange is not None or os.environ.get("NADM_XCHG", "peer") == "nccl":
+            return
+        if torch.distributed.get_world_size() > 8:
+            return
+        width = max(self.raw_model.num_features, sum(self.ks_list))
+        ex = ops.PeerExchange(max(max_rows, self.batch_size) * width + 1, self.device)
+        if ex.ok:
+            self.exchange = ex
+        else:
+            warnings.warn("nadm_b200: CUDA IPC between the ranks' devices is not available; the sharded step uses NCCL "
+                          "all-reduces instead of the fused peer exchange", RuntimeWarning, stacklevel=2)
+            ex.close()
+
+    def close_exchange(self) -> None:
+        """Collective: drop the step graphs that reference the exchange areas, then unmap / free them."""
+        if self.exchange is not None:
+            self.release_graphs()
+            self.exchange.close()
+            self.exchange = None
+
+    def comm(self) -> dict:
+        """Keyword arguments that make ``Q_P.encode_packed`` / ``infer_packed`` sum over the SNP shards."""
+        if not self.sharded:
+            return {}
+        return {"xchg": self.exchange.xchg} if self.exchange is not None else {"allreduce": self._allreduce}
 
     def _step_buffers(self, B: int) -> dict:
         buf = self._train_bufs.get(B)
@@ -320,8 +354,8 @@ class NeuralAdmixture:
             B = row_idx.numel()
         else:
             row_idx, B = None, pg.N
-        probs, fb = m.encode_packed(pg, row_idx=row_idx, row0=0, B=B,
-                                    allreduce=self._allreduce if self.sharded else None)
+        xc = self.exchange.xchg if self.exchange is not None else None
+        probs, fb = m.encode_packed(pg, row_idx=row_idx, row0=0, B=B, **self.comm())
         sb = self._step_buffers(B)
         if not managed_loss:
             sb["loss"].zero_()
@@ -333,11 +367,11 @@ class NeuralAdmixture:
             ops.decoder_step(pg, fb["Q"], sb["dQ"], off, k, m.decoders.decoders[i].weight.data, o.m["P"][i], o.v["P"][i],
                              hyper, sb["loss"] if loss_out is not None else None, fb["ws"], row_idx=row_idx)
             off += k
-        if self.sharded:
+        if self.sharded and xc is None:
             self._allreduce(sb["dq_loss"])
         ops.mlp_bwd(sb["dQ"], fb["Q"], fb["Hh"], fb["Z"], fb["rinv"], m.multihead_encoder.ks, self._mlp_params(), hyper,
                     sb["dZ"], sb["loss"], fb["ws"], labels=labels,
-                    sup_weight=float(self.supervised_loss_weight) if labels is not None else 0.0)
+                    sup_weight=float(self.supervised_loss_weight) if labels is not None else 0.0, xchg=xc)
         ops.encoder_bwd(pg, sb["dZ"], m.V.data, o.m["V"], o.v["V"], hyper, fb["ws"], row_idx=row_idx)
         if loss_out is not None and not managed_loss:
             loss_out.copy_(sb["loss"])
@@ -394,9 +428,10 @@ class NeuralAdmixture:
     def release_graphs(self) -> None:
         """Drop the captured step graphs (they hold the sharded step's NCCL kernels: release them before the process
         group is destroyed)."""
-        if getattr(self, "_gs", None) is not None:
+        if getattr(self, "_gs", None) is not None or getattr(self, "_host_stage", None) is not None:
             torch.cuda.synchronize(self.device)
             self._gs = None
+            self._host_stage = None
 
     def train_steps(self, order_dev: torch.Tensor, nsteps: int, want_loss: bool = True,
                     pops: Optional[torch.Tensor] = None, first: int = 0) -> Optional[torch.Tensor]:
@@ -493,6 +528,7 @@ class NeuralAdmixture:
         self.initialize_model(P.to(self.device, torch.float32), hidden_size, num_features,
                               V.to(self.device, torch.float32), self.ks_list)
         self.optimizer = self.raw_model.create_custom_adam(device=self.device, lr=self.lr)
+        self.open_exchange()
 
     def launch_training(self, P: torch.Tensor, data, hidden_size: int, num_features: int, V: torch.Tensor, M: int,
                         N: int, pops: Optional[torch.Tensor] = None):
@@ -518,6 +554,7 @@ class NeuralAdmixture:
         Qs = self.infer_Q(min(N, 1024))
         self.last_Q = Qs                     # device tensors, full N x k on every rank
         self.release_graphs()
+        self.close_exchange()
         if self.master:
             log.info("")
             log.info("    Training finished!")
@@ -529,47 +566,117 @@ class NeuralAdmixture:
         """Out-of-core feed: train on minibatches whose 2-bit packed rows live in (pinned) HOST memory — each element
         of ``host_batches`` is a uint8 B x pitch tensor in the ``PackedGenotypes`` row layout.  Per step: the batch is
         copied host->device on a side stream into one of two staging buffers (overlapping the previous step's
-        kernels), the fused step runs on it, and the step's loss is read back to the host (the reference's
-        ``loss.item()``, :414).  Returns the per-step losses.  Requires ``prepare`` (or ``launch_training``) first."""
+        kernels), the fused step runs on it, and the step's loss is copied back to the host (the reference's
+        ``loss.item()``, :414).  Returns the per-step losses.  Requires ``prepare`` (or ``launch_training``) first.
+
+        With uniform batch shapes and no labels the step on each staging buffer is ONE replayed CUDA graph and nothing
+        on the host waits for the device until the last step: the copies, the steps and the 4-byte loss read-backs are
+        ordered by events only.  Otherwise (supervised labels, ragged shapes, ``NADM_NO_GRAPH=1``) every step is issued
+        eagerly and its loss is read synchronously."""
+        n = len(host_batches)
+        if n == 0:
+            return []
         main = torch.cuda.current_stream(self.device)
         copy = getattr(self, "_copy_stream", None)
         if copy is None:
             copy = self._copy_stream = torch.cuda.Stream(self.device)
-        stage, ready, free = [None, None], [torch.cuda.Event(), torch.cuda.Event()], [None, None]
+        shape = tuple(host_batches[0].shape)
+        uniform = all(tuple(hb.shape) == shape for hb in host_batches)
+        hs = getattr(self, "_host_stage", None)
+        if hs is None or hs["shape"] != shape:
+            hs = self._host_stage = {
+                "shape": shape, "graphs": {},
+                "stage": [ops.PackedGenotypes(torch.empty(shape, dtype=torch.uint8, device=self.device), shape[0], self.M)
+                          for _ in range(2)]}
+        stage = hs["stage"]
+        ready, free = [torch.cuda.Event(), torch.cuda.Event()], [None, None]
+
+        def prefetch(i):
+            hb, s_ = host_batches[i], i & 1
+            st = stage[s_] if tuple(hb.shape) == shape else \
+                ops.PackedGenotypes(torch.empty(hb.shape, dtype=torch.uint8, device=self.device), hb.shape[0], self.M)
+            with torch.cuda.stream(copy):
+                if free[s_] is not None:
+                    copy.wait_event(free[s_])
+                st.storage.copy_(hb, non_blocking=True)
+                ready[s_].record(copy)
+            return st
+
+        if self.use_graph and uniform and labels is None:
+            o = self.optimizer
+            gs = self._graph_state(max(n, 1024))
+            gs["counters"].copy_(torch.tensor([0, o.step_count], dtype=torch.int64))
+            try:
+                graphs = [self._get_host_graph(gs, hs, s_) for s_ in range(min(2, n))]
+            except Exception as e:
+                self.graph_fallback = f"{type(e).__name__}: {e}"
+                warnings.warn(f"nadm_b200: CUDA-graph capture of the host-fed step failed ({self.graph_fallback}); "
+                              "falling back to eager launches", RuntimeWarning, stacklevel=2)
+                self.use_graph = False
+                graphs = None
+            if graphs is not None:
+                loss_host = torch.zeros(n, dtype=torch.float32).pin_memory()
+                prefetch(0)
+                for i in range(n):
+                    s_ = i & 1
+                    if i + 1 < n:
+                        prefetch(i + 1)
+                    main.wait_event(ready[s_])
+                    graphs[s_].replay()
+                    self.graph_kernel_launches += graphs[s_].nadm_kernels
+                    free[s_] = torch.cuda.Event()
+                    free[s_].record(main)
+                    loss_host[i:i + 1].copy_(gs["losses"][i:i + 1], non_blocking=True)   # this step's loss -> host
+                main.synchronize()
+                o.step_count += n
+                return loss_host.tolist()
+
         loss_dev = torch.zeros(1, dtype=torch.float32, device=self.device)
         loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
         out: List[float] = []
-
-        def prefetch(i):
-            hb = host_batches[i]
-            s = i & 1
-            if stage[s] is None or stage[s].storage.shape != hb.shape:
-                stage[s] = ops.PackedGenotypes(torch.empty(hb.shape, dtype=torch.uint8, device=self.device),
-                                               hb.shape[0], self.M)
-            with torch.cuda.stream(copy):
-                if free[s] is not None:
-                    copy.wait_event(free[s])
-                stage[s].storage.copy_(hb, non_blocking=True)
-                ready[s].record(copy)
-
-        n = len(host_batches)
-        if n:
-            prefetch(0)
+        nxt = prefetch(0)
         for i in range(n):
-            s = i & 1
+            s_, cur = i & 1, nxt
             if i + 1 < n:
-                prefetch(i + 1)
-            main.wait_event(ready[s])
-            self._train_step(None, None if labels is None else labels[i], loss_dev, pg=stage[s])
-            free[s] = torch.cuda.Event()
-            free[s].record(main)
+                nxt = prefetch(i + 1)
+            main.wait_event(ready[s_])
+            self._train_step(None, None if labels is None else labels[i], loss_dev, pg=cur)
+            free[s_] = torch.cuda.Event()
+            free[s_].record(main)
             loss_host.copy_(loss_dev, non_blocking=True)
             main.synchronize()
             out.append(float(loss_host[0]))
         return out
 
+    def _get_host_graph(self, gs: dict, hs: dict, s_: int):
+        """The host-fed step on staging buffer ``s_`` as one replayable graph (see ``_get_graph``; the minibatch is all
+        rows of the staging buffer, so ``nadm_step_begin`` only provides the step's Adam coefficients and zeroes the
+        loss accumulator)."""
+        pg = hs["stage"][s_]
+        key = (s_, pg.N, self.raw_model.bind_epoch, gs["counters"].data_ptr())
+        g = hs["graphs"].get(key)
+        if g is not None:
+            return g
+        o = self.optimizer
+        self.raw_model.bind()
+        self.raw_model._fwd_buffers(pg.N)
+        loss_acc = self._step_buffers(pg.N)["loss"]
+        idx = gs["idx"].setdefault(pg.N, torch.zeros(pg.N, dtype=torch.int64, device=self.device))
+        h_host = ops.adam_hyper(o.lr, 0, o.betas[0], o.betas[1], o.eps)
+        h_dev = ops.adam_hyper(o.lr, 0, o.betas[0], o.betas[1], o.eps, device_coef=gs["coef"])
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        before = ops.launch_count()
+        with torch.cuda.graph(g):
+            ops.step_begin(gs["order"], gs["counters"], pg.N, pg.N, idx, h_host, gs["coef"], loss_acc)
+            self._train_step(None, None, loss_acc, pg=pg, hyper=h_dev, managed_loss=True)
+            ops.step_end(gs["counters"], loss_acc, gs["losses"])
+        g.nadm_kernels = ops.launch_count() - before
+        hs["graphs"][key] = g
+        return g
+
     def infer_Q(self, batch: int) -> List[torch.Tensor]:
-        return self.raw_model.infer_packed(self.packed, batch, allreduce=self._allreduce if self.sharded else None)
+        return self.raw_model.infer_packed(self.packed, batch, **self.comm())
 
     def gather_P(self) -> List[torch.Tensor]:
         """Full M x k P per head on every rank (concatenating the SNP shards in rank order)."""

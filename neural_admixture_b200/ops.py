@@ -8,7 +8,7 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import AdamHyper, MlpParams, NadmError, check
+from ._lib import AdamHyper, MlpParams, NadmError, Xchg, check
 
 PITCH_ALIGN = 128  # bytes; rows of the packed matrix start on 128-byte lines
 
@@ -161,7 +161,7 @@ def encoder_fwd(pg: PackedGenotypes, V: torch.Tensor, Z: torch.Tensor, ws: torch
                                        _ptr(Z), _ptr(ws), ws.numel() * ws.element_size(), _stream(pg.storage)))
 
 
-def mlp_fwd(Z, w_rms, W1, b1, W2, b2, ks, rinv, Hh, Q) -> None:
+def mlp_fwd(Z, w_rms, W1, b1, W2, b2, ks, rinv, Hh, Q, xchg: Optional[Xchg] = None) -> None:
     _need_cuda(Z, w_rms, W1, b1, W2, b2, rinv, Hh, Q)
     B, C_ = Z.shape
     H = W1.shape[0]
@@ -169,7 +169,8 @@ def mlp_fwd(Z, w_rms, W1, b1, W2, b2, ks, rinv, Hh, Q) -> None:
         assert t.dtype == torch.float32 and t.is_contiguous()
     assert W2.shape == (sum(ks), H) and Q.shape == (B, sum(ks)) and Hh.shape == (B, H)
     with _on(Z): check(_lib.load().nadm_mlp_fwd(_ptr(Z), B, C_, H, _ptr(w_rms), _ptr(W1), _ptr(b1), _ptr(W2), _ptr(b2),
-                                   _ks_array(ks), len(ks), _ptr(rinv), _ptr(Hh), _ptr(Q), _stream(Z)))
+                                   _ks_array(ks), len(ks), _ptr(rinv), _ptr(Hh), _ptr(Q),
+                                   None if xchg is None else C.byref(xchg), _stream(Z)))
 
 
 def decoder_step(pg: PackedGenotypes, Q, dQ, q_off: int, k: int, P, Pm, Pv, adam: Optional[AdamHyper], loss, ws, *,
@@ -186,7 +187,7 @@ def decoder_step(pg: PackedGenotypes, Q, dQ, q_off: int, k: int, P, Pm, Pv, adam
 
 
 def mlp_bwd(dQ, Q, Hh, Z, rinv, ks, params: MlpParams, adam: Optional[AdamHyper], dZ, loss, ws, *, labels=None,
-            sup_weight: float = 0.0) -> None:
+            sup_weight: float = 0.0, xchg: Optional[Xchg] = None) -> None:
     _need_cuda(dQ, Q, Hh, Z, rinv, dZ, loss, ws, labels)
     B, C_ = Z.shape
     H = Hh.shape[1]
@@ -194,7 +195,7 @@ def mlp_bwd(dQ, Q, Hh, Z, rinv, ks, params: MlpParams, adam: Optional[AdamHyper]
     with _on(dQ): check(_lib.load().nadm_mlp_bwd(_ptr(dQ), _ptr(Q), _ptr(Hh), _ptr(Z), _ptr(rinv), B, C_, H, _ks_array(ks), len(ks),
                                    _ptr(labels), float(sup_weight), C.byref(params),
                                    None if adam is None else C.byref(adam), _ptr(dZ), _ptr(loss), _ptr(ws),
-                                   ws.numel() * ws.element_size(), _stream(dQ)))
+                                   ws.numel() * ws.element_size(), None if xchg is None else C.byref(xchg), _stream(dQ)))
 
 
 def encoder_bwd(pg: PackedGenotypes, dZ, V, Vm, Vv, adam: Optional[AdamHyper], ws, *, row_idx=None, row0: int = 0,
@@ -281,3 +282,62 @@ def geno_matmul_t(pg: PackedGenotypes, QT: torch.Tensor, ws: torch.Tensor, missi
                                              _ptr(bt), _ptr(ws), ws.numel() * ws.element_size(), _stream(pg.storage)))
         Bm[c0:c1] = bt.T
     return Bm
+
+
+class PeerExchange:
+    """The peer-mapped exchange areas of an SNP-sharded run (nadm_xchg_t): one area per rank (CUDA IPC, one process per
+    GPU on one node), opened by every other rank.  ``xchg`` is what ``mlp_fwd`` / ``mlp_bwd`` take.  Collective: every
+    rank of ``group`` must construct it at the same point."""
+
+    def __init__(self, slot_floats: int, device: torch.device, group=None):
+        import torch.distributed as dist
+        lib = _lib.load()
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > 8:
+            raise NadmError("the fused peer exchange supports at most 8 ranks")
+        self.device, self.lib, self.peers = device, lib, []
+        nbytes = int(lib.nadm_xchg_area_bytes(slot_floats))
+        own, handle = C.c_void_p(), (C.c_ubyte * 64)()
+        with torch.cuda.device(device):
+            check(lib.nadm_ipc_alloc(nbytes, C.byref(own), handle))
+        self.own = own
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle), group=group)
+        self.xchg = Xchg()
+        self.xchg.world, self.xchg.rank, self.xchg.slot_floats = self.world, self.rank, int(slot_floats)
+        ok = True
+        for r in range(self.world):
+            if r == self.rank:
+                self.xchg.area[r] = own.value
+                continue
+            p = C.c_void_p()
+            buf = (C.c_ubyte * 64).from_buffer_copy(handles[r])
+            with torch.cuda.device(device):
+                rc = lib.nadm_ipc_open(buf, C.byref(p))
+            if rc != 0:
+                ok = False
+                self.err = lib.nadm_last_error().decode(errors="replace")
+                break
+            self.peers.append(p)
+            self.xchg.area[r] = p.value
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        self.seq = torch.zeros(2 * 1024, dtype=torch.int32, device=device)
+        self.xchg.seq = self.seq.data_ptr()
+        self.ok = bool(flag.item())
+        dist.barrier(group=group)
+
+    def close(self) -> None:
+        """Collective: unmap the peers' areas, then (after a barrier, when nobody can touch it any more) free one's own."""
+        import torch.distributed as dist
+        if self.own is None:
+            return
+        torch.cuda.synchronize(self.device)
+        with torch.cuda.device(self.device):
+            for p in self.peers:
+                self.lib.nadm_ipc_close(p)
+            self.peers = []
+            if dist.is_initialized():
+                dist.barrier()
+            self.lib.nadm_ipc_free(self.own)
+        self.own = None

@@ -42,7 +42,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
         if (!ok && ++polls > (1u << 24)) __trap();
     }
 }
-__device__ __forceinline__ void cp_async16(void* s, const void* g) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(s)), "l"(g)); }
+template <int HINT = 0>   // HINT: L2 prefetch size qualifier (.L2::128B / .L2::256B) of the copy
+__device__ __forceinline__ void cp_async16(void* s, const void* g) {
+    if (HINT == 256) asm volatile("cp.async.cg.shared.global.L2::256B [%0], [%1], 16;" ::"r"(smem_u32(s)), "l"(g));
+    else if (HINT == 128) asm volatile("cp.async.cg.shared.global.L2::128B [%0], [%1], 16;" ::"r"(smem_u32(s)), "l"(g));
+    else asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(s)), "l"(g));
+}
 __device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;"); }
 template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
 __device__ __forceinline__ uint32_t x4(uint4 v) { return v.x ^ v.y ^ v.z ^ v.w; }
@@ -95,11 +100,41 @@ __global__ void __launch_bounds__(512) k_ldg(Geo g) {
     if ((tid & 31) == 0) atomicXor(&g.checksum[blockIdx.x], acc);
 }
 
+// the fused decoder's pattern: thread = row, ONE 16-byte load per (row, 64-SNP unit), row block inner; HINT as above
+template <int HINT>
+__global__ void __launch_bounds__(384) k_ldg16(Geo g) {
+    const int tid = threadIdx.x, grp = tid >> 7, r = tid & 127;
+    const int nunit = g.nblk * g.ntt * 4;
+    const long long c0 = (long long)blockIdx.x * g.ntt * 64;
+    uint32_t acc = 0;
+    auto load = [&](int u) {
+        const int sub = u / g.nblk, blk = u - sub * g.nblk, b = blk * 128 + r;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (b < g.B) {
+            const uint8_t* p = g.mat + (long long)g.rows[b] * g.pitch + c0 + sub * 16;
+            if (HINT == 256) asm volatile("ld.global.nc.L2::256B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+            else if (HINT == 128) asm volatile("ld.global.nc.L2::128B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+            else asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+        }
+        return v;
+    };
+    uint4 cur = make_uint4(0, 0, 0, 0);
+    if (grp < nunit) cur = load(grp);
+    for (int u = grp; u < nunit; u += 3) {
+        uint4 nxt = make_uint4(0, 0, 0, 0);
+        if (u + 3 < nunit) nxt = load(u + 3);
+        acc ^= x4(cur);
+        cur = nxt;
+    }
+    for (int o = 16; o; o >>= 1) acc ^= __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((tid & 31) == 0) atomicXor(&g.checksum[blockIdx.x], acc);
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // cp.async ring: NG groups of 4 warps, each group owns tiles grp, grp + NG, ...; DEPTH tiles in flight per group;
 // tile = 128 rows x TB bytes (TB = 64: lane covers 8 rows x 4 pieces per instruction; TB = 256: 2 rows x 16 pieces)
 // ---------------------------------------------------------------------------------------------------------------------
-template <bool BLK_OUTER, int TB, int NG, int DEPTH>
+template <bool BLK_OUTER, int TB, int NG, int DEPTH, int HINT = 0>
 __global__ void __launch_bounds__(NG * 128) k_cpasync(Geo g) {
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr int PIECES = TB / 16;                  // 16-byte pieces per row and tile
@@ -119,7 +154,7 @@ __global__ void __launch_bounds__(NG * 128) k_cpasync(Geo g) {
 #pragma unroll
             for (int it = 0; it < PER_THREAD; ++it) {
                 const int b = blk * 128 + wl * 32 + r0 + it * ROWS_PER_INSTR;
-                if (b < g.B) cp_async16(dst + it * 2048, g.mat + (long long)g.rows[b] * g.pitch + c0 + (long long)tt * TB + q * 16);
+                if (b < g.B) cp_async16<HINT>(dst + it * 2048, g.mat + (long long)g.rows[b] * g.pitch + c0 + (long long)tt * TB + q * 16);
                 else *reinterpret_cast<uint4*>(dst + it * 2048) = make_uint4(0, 0, 0, 0);
             }
         }
@@ -246,6 +281,11 @@ typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, v
                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 static std::vector<unsigned> g_ref;
+static int g_nsets = 1, g_launch = 0;      // row sets; run() rotates through them so that no launch finds its rows in L2
+static const int* g_rows_base = nullptr;
+static Geo* g_geo = nullptr;
+static int g_B = 0;
+static void next_rows() { g_geo->rows = g_rows_base + (size_t)(g_launch++ % g_nsets) * g_B; }
 static unsigned* d_sum;
 static int g_ncta;
 static double g_bytes;
@@ -253,6 +293,8 @@ static double g_bytes;
 template <typename F>
 static void run(const char* name, F launch) {
     CK(cudaMemset(d_sum, 0, g_ncta * sizeof(unsigned)));
+    g_launch = 0;
+    next_rows();
     launch();
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("%-46s FAILED: %s\n", name, cudaGetErrorString(e)); exit(2); }
@@ -261,11 +303,12 @@ static void run(const char* name, F launch) {
     const char* verdict = "checksum = reference";
     if (g_ref.empty()) { g_ref = got; verdict = "(reference)"; }
     else if (got != g_ref) verdict = "CHECKSUM MISMATCH";
-    for (int i = 0; i < 3; ++i) launch();
+    for (int i = 0; i < 3; ++i) { next_rows(); launch(); }
     cudaEvent_t a, b;
     CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
     float best = 1e30f, tot = 0.f;
     for (int i = 0; i < 10; ++i) {
+        next_rows();
         CK(cudaEventRecord(a)); launch(); CK(cudaEventRecord(b)); CK(cudaEventSynchronize(b));
         float ms; CK(cudaEventElapsedTime(&ms, a, b));
         best = std::min(best, ms); tot += ms;
@@ -285,26 +328,45 @@ int main(int argc, char** argv) {
     std::vector<int> rows(N);
     for (int i = 0; i < N; ++i) rows[i] = i;
     uint64_t s = 88172645463325252ull;
-    for (int i = 0; i < B; ++i) {                          // partial Fisher-Yates: B distinct random rows
+    const int nsets = std::max(1, std::min(16, N / B));    // disjoint sets of B random rows, one per launch in turn
+    for (int i = 0; i < nsets * B; ++i) {                  // partial Fisher-Yates
         s ^= s << 13; s ^= s >> 7; s ^= s << 17;
         std::swap(rows[i], rows[i + (int)(s % (uint64_t)(N - i))]);
     }
     int* d_rows;
-    CK(cudaMalloc(&d_rows, B * sizeof(int)));
-    CK(cudaMemcpy(d_rows, rows.data(), B * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&d_rows, (size_t)nsets * B * sizeof(int)));
+    CK(cudaMemcpy(d_rows, rows.data(), (size_t)nsets * B * sizeof(int), cudaMemcpyHostToDevice));
+    g_nsets = nsets; g_rows_base = d_rows; g_B = B;
     CK(cudaMalloc(&d_sum, ncta * sizeof(unsigned)));
     Geo g{mat, pitch, d_rows, B, (B + 127) / 128, ntt, d_sum};
-    printf("gather probe: %d x %lld byte matrix (%.2f GB), B = %d random rows, %d CTAs x %d B per row = %.1f MB per launch\n",
-           N, pitch, (double)N * pitch / 1e9, B, ncta, ntt * 64, g_bytes / 1e6);
+    g_geo = &g;
+    printf("gather probe: %d x %lld byte matrix (%.2f GB), B = %d random rows, %d CTAs x %d B per row = %.1f MB per launch, "
+           "%d disjoint row sets used in turn (%s)\n",
+           N, pitch, (double)N * pitch / 1e9, B, ncta, ntt * 64, g_bytes / 1e6, nsets,
+           nsets > 1 ? "every launch gathers rows that are not in L2, like a training step" : "the same rows every launch: L2-resident");
 
     run("ldg 64B/row, row block inner", [&] { k_ldg<false><<<ncta, 512>>>(g); });
     run("ldg 64B/row, row block outer", [&] { k_ldg<true><<<ncta, 512>>>(g); });
+    run("ldg 16B/row per unit (decoder pattern)", [&] { k_ldg16<0><<<ncta, 384>>>(g); });
+    run("ldg 16B/row per unit, .L2::128B hint", [&] { k_ldg16<128><<<ncta, 384>>>(g); });
+    run("ldg 16B/row per unit, .L2::256B hint", [&] { k_ldg16<256><<<ncta, 384>>>(g); });
 #define CPA(BO, TB, NG, D, label)                                                                                      \
     {                                                                                                                  \
         const size_t sm = (size_t)NG * D * 128 * TB;                                                                   \
         CK(cudaFuncSetAttribute(k_cpasync<BO, TB, NG, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));     \
         run(label, [&] { k_cpasync<BO, TB, NG, D><<<ncta, NG * 128, sm>>>(g); });                                      \
     }
+#define CPAH(BO, TB, NG, D, H, label)                                                                                  \
+    {                                                                                                                  \
+        const size_t sm = (size_t)NG * D * 128 * TB;                                                                   \
+        CK(cudaFuncSetAttribute(k_cpasync<BO, TB, NG, D, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));  \
+        run(label, [&] { k_cpasync<BO, TB, NG, D, H><<<ncta, NG * 128, sm>>>(g); });                                   \
+    }
+    CPAH(false, 64, 4, 2, 128, "cp.async 64B/row inner, 4x2, .L2::128B hint")
+    CPAH(false, 64, 4, 2, 256, "cp.async 64B/row inner, 4x2, .L2::256B hint")
+    CPAH(true, 64, 4, 2, 256, "cp.async 64B/row outer, 4x2, .L2::256B hint")
+    CPAH(false, 64, 4, 6, 256, "cp.async 64B/row inner, 4x6, .L2::256B hint")
+    CPAH(true, 128, 4, 3, 256, "cp.async 128B/row outer, 4x3, .L2::256B hint")
     CPA(false, 64, 4, 2, "cp.async 64B/row inner, 4 groups x 2 deep")
     CPA(false, 64, 4, 6, "cp.async 64B/row inner, 4 groups x 6 deep")
     CPA(true, 64, 4, 2, "cp.async 64B/row outer, 4 groups x 2 deep")

@@ -210,6 +210,45 @@ def test_decoder_step_grads(ops, dev, N, M, k, B, edge):
         assert np.abs(dP_ref).max() > 1e10
 
 
+@pytest.mark.parametrize("with_loss", [True, False])
+def test_decoder_step_late_training_ranges(ops, dev, with_loss):
+    """Late-training inputs: concentrated Q, allele frequencies at exactly 0 / 1 and very close to them, so that many
+    reconstructions have R (1 - R) between the 1e-12 floor of BCELoss' backward and 2^-15 (the kernel's mid path: fast
+    gradient formula, one log per element), some below the floor or at raw >= 1 (general path), the rest in the fast
+    range.  Gradients and loss against the fp64 oracle."""
+    rng = np.random.default_rng(77)
+    N, M, k, B = 900, 12_007, 8, 800
+    G = rand_genotypes(rng, N, M)
+    P = rng.uniform(0.05, 0.95, size=(M, k))
+    u = rng.random((M, k))
+    P[u < 0.15] = 0.0
+    P[(u >= 0.15) & (u < 0.30)] = 1.0
+    P[(u >= 0.30) & (u < 0.45)] = 10.0 ** rng.uniform(-9, -4, size=int(((u >= 0.30) & (u < 0.45)).sum()))
+    P[(u >= 0.45) & (u < 0.55)] = 1.0 - 10.0 ** rng.uniform(-7, -4, size=int(((u >= 0.45) & (u < 0.55)).sum()))
+    P = P.astype(np.float32)
+    Q = rng.dirichlet(0.05 * np.ones(k), size=B).astype(np.float32)
+    idx = rng.permutation(N)[:B]
+    pg = packed_from(ops, G, dev)
+    dQ = torch.zeros((B, k), device=dev)
+    dP = torch.empty((M, k), device=dev)
+    loss = torch.zeros(1, device=dev)
+    ws = ws_for(ops, B, M, 8, 64, k, dev)
+    ops.decoder_step(pg, t(Q, dev), dQ, 0, k, t(P, dev), None, None, None, loss if with_loss else None, ws,
+                     row_idx=t(idx, dev, torch.int64), dP_out=dP)
+    x = orc.genotype_to_x(G[idx])
+    Q64, P64 = Q.astype(np.float64), P.astype(np.float64)
+    l_ref, dQ_ref, dP_ref = orc.decoder_loss_grads(x, Q64, P64)
+    R = np.clip(Q64 @ P64.T, 0, 1)
+    prod = R * (1 - R)
+    mid = ((prod >= 1e-12) & (prod < 2.0 ** -15)).mean()
+    assert mid > 0.02 and (prod < 1e-12).mean() > 0.001 and (prod >= 2.0 ** -15).mean() > 0.2   # all three paths are hit
+    _, dQ_r32, dP_r32 = decoder_grads_with_fp32_raw(x, Q64, P64)
+    if with_loss:
+        assert abs(loss.item() - l_ref) < 1e-5 * abs(l_ref)
+    assert relF(dQ.cpu().numpy(), dQ_ref) < KERNEL_TOL + 8 * relF(dQ_r32, dQ_ref)
+    assert relF(dP.cpu().numpy(), dP_ref) < KERNEL_TOL + 8 * relF(dP_r32, dP_ref)
+
+
 def test_decoder_step_without_loss_is_the_same_update(ops, dev):
     """loss = NULL (gradients only: the schedule used on epochs whose loss the reference does not print) must give
     bit-identical dQ and P updates."""
@@ -389,8 +428,6 @@ def test_training_fixtures(dev, fixture):
     assert relF(raw.V.detach().cpu().numpy(), final["V"]) < QP_TOL
     # the sampler stream is the reference's (loaders.py:29-30)
     from neural_admixture_b200.model.neural_admixture import NeuralAdmixture
-    if fixture == "train_k4to12.npz":
-        assert na.generic_kernel_launches == 0          # every head K=4..12 stays on the tensor-core decoder
     fresh = NeuralAdmixture(3, 1, 8, 1e-3, dev, int(g["seed"]), 0, True, None, 3, 5)
     for e in range(g["orders"].shape[0]):
         assert np.array_equal(fresh.epoch_order(g["G"].shape[0]).numpy(), g["orders"][e])
@@ -570,7 +607,8 @@ def test_graph_replayed_steps_match_eager(dev, monkeypatch):
 # ---------------------------------------------------------------------------------------------------------------
 # host-fed steps (train_from_host: two streams, staged batches; what bench.py's e2e leg times) == resident-matrix steps
 # ---------------------------------------------------------------------------------------------------------------
-def test_host_fed_steps_match_resident_steps(dev, monkeypatch):
+@pytest.mark.parametrize("graph", [False, True])
+def test_host_fed_steps_match_resident_steps(dev, monkeypatch, graph):
     from neural_admixture_b200 import ops
     from neural_admixture_b200.model.neural_admixture import NeuralAdmixture
     rng = np.random.default_rng(11)
@@ -579,7 +617,10 @@ def test_host_fed_steps_match_resident_steps(dev, monkeypatch):
     V = np.linalg.qr(rng.standard_normal((M, C)))[0].astype(np.float32)
     P0 = rng.uniform(0.05, 0.95, size=(K, M)).astype(np.float32)
     order = torch.as_tensor(rng.permutation(N)[: S * B].astype(np.int64))
-    monkeypatch.setattr(NeuralAdmixture, "use_graph", False)      # eager resident steps: the same five calls per step
+    # graph = False: eager steps on both sides (the same five calls per step); True: replayed CUDA graphs on both sides
+    # (the host-fed loop then never waits for the device between steps: copies, steps and loss read-backs are ordered
+    # by events only)
+    monkeypatch.setattr(NeuralAdmixture, "use_graph", graph)
     res = []
     for host_fed in (False, True):
         torch.manual_seed(5)
@@ -593,6 +634,7 @@ def test_host_fed_steps_match_resident_steps(dev, monkeypatch):
         else:
             losses = na.train_steps(order.to(dev), S, True).cpu().numpy()
         torch.cuda.synchronize()
+        assert na.use_graph == graph and (na.graph_kernel_launches > 0) == graph
         res.append((na.raw_model.V.detach().cpu().numpy().copy(),
                     na.raw_model.decoders.decoders[0].weight.detach().cpu().numpy().copy(), losses))
     assert relF(res[1][0], res[0][0]) < 1e-6 and relF(res[1][1], res[0][1]) < 1e-6
@@ -716,11 +758,14 @@ def test_inference_main_end_to_end(ops, dev, tmp_path):
     torch.save(saved, tmp_path / "run.pt")
     H, C = final["common_encoder.0.weight"].shape
     Q_P(H, C, ks_list=ks, V=torch.as_tensor(final["V"]), is_train=False).save_config("run", str(tmp_path))
-    G = g["G"]                                                    # N x M codes; mean < 1: the reader does not flip
+    G = g["G"]                                                    # N x M codes the fixture's Q belongs to
     N, M = G.shape
-    assert G[G != 3].mean() < 1
+    # the reader keeps the matrix when its mean (missing counted as 3) is < 1 and maps g -> 2 - g otherwise
+    # (snp_reader.py:110): store the orientation that reads back as G
+    Gfile = G if G.mean() < 1 else np.where(G == 3, 3, 2 - G).astype(np.uint8)
+    assert (Gfile.mean() < 1) == (Gfile is G)
     # write it as a .bed: SNP-major, 4 samples per byte, fields 00 -> 2, 01 -> missing, 10 -> 1, 11 -> 0 (utils.pyx:43-68)
-    field = np.array([3, 2, 0, 1], dtype=np.uint8)[G.T]           # code -> bed field
+    field = np.array([3, 2, 0, 1], dtype=np.uint8)[Gfile.T]       # code -> bed field
     pad = np.zeros((M, (-N) % 4), dtype=np.uint8)
     f4 = np.concatenate([field, pad], axis=1).reshape(M, -1, 4)
     payload = (f4[:, :, 0] | (f4[:, :, 1] << 2) | (f4[:, :, 2] << 4) | (f4[:, :, 3] << 6)).astype(np.uint8)

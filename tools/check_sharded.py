@@ -37,6 +37,7 @@ def main():
     V = np.linalg.qr(rng.standard_normal((M, C)))[0].astype(np.float32)
     P0 = rng.uniform(0.05, 0.95, size=(sum(ks), M)).astype(np.float32)
     init = {}
+    exch = ["?"]
 
     def run(sharded):
         c0, c1 = snp_slice(M, rank, world) if sharded else (0, M)
@@ -52,11 +53,19 @@ def main():
 
         na.initialize_model = init_and_capture
         packed = ops.PackedGenotypes.from_unpacked_host(torch.as_tensor(G), dev, c0, c1)
+        orig_open = na.open_exchange
+
+        def open_and_note(*a, **kw):
+            orig_open(*a, **kw)
+            exch[0] = "fused peer exchange" if na.exchange is not None else "NCCL all-reduce"
+
+        na.open_exchange = open_and_note
         Qs, Ps, raw = na.launch_training(torch.as_tensor(P0[:, c0:c1].copy(), device=dev), packed, H, C,
                                          torch.as_tensor(V[c0:c1].copy(), device=dev), c1 - c0, N)
         if rank == 0:
             print(f"  {'sharded' if sharded else 'single '} run: cuda-graph steps = {na.use_graph}, "
-                  f"graph-replayed kernels = {na.graph_kernel_launches}, generic kernels = {na.generic_kernel_launches}")
+                  f"graph-replayed kernels = {na.graph_kernel_launches}, generic kernels = {na.generic_kernel_launches}, "
+                  f"exchange = {exch[0] if sharded else 'none'}")
         return Qs, Ps, na.loss_history, raw
 
     Qs_s, Ps_s, loss_s, raw_s = run(True)

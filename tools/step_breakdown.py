@@ -23,13 +23,15 @@ ap.add_argument("--steps", type=int, default=60)
 ap.add_argument("--workload", default="cfg3")
 ap.add_argument("--batch", type=int, default=None)
 ap.add_argument("--out", default=None)
+ap.add_argument("--snps", type=int, default=None, help="override M (e.g. 62500 = one rank's shard of cfg3 at 8 GPUs)")
 a = ap.parse_args()
 N, M, ks, B = bench.WORKLOADS[a.workload]
 N = a.rows or N
+M = a.snps or M
 B = a.batch or B
 dev = torch.device("cuda:0")
-pg = bench.synth_packed(ops, N, M, bench.SEED, 0, dev)
-V, P = bench.synth_init(M, ks, bench.SEED, 0, dev)
+pg = bench.synth_packed(ops, N, M, 0, M, bench.SEED, dev)
+V, P = bench.synth_init(M, 0, M, ks, bench.SEED, dev)
 torch.manual_seed(bench.SEED)
 k = ks[0] if len(ks) == 1 else None
 na = NeuralAdmixture(k, 1, B, bench.LR, dev, bench.SEED, 1, True, "nadm_b200", None if k else min(ks), None if k else max(ks))
