@@ -199,7 +199,6 @@ def cpu_reference(wl, ks, M, B, steps, warmup, budget_s, as_line=False, n_gpus=1
     """EXACTLY `steps` timed steps after `warmup` untimed ones; what is bounded is the SNP width of each step (a
     subsample of the workload's columns, step time scaled by M / Ms: the op sequence is linear in M)."""
     import torch
-    from nadm_torch_port import TorchPort  # noqa: F401  (path set by _port_problem)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     gen_dev = torch.device("cuda:0") if torch.cuda.is_available() else torch.device("cpu")

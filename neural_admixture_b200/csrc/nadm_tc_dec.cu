@@ -1,4 +1,5 @@
-// Fused decoder step on the 5th-generation tensor cores (tcgen05), sm_100a.  One head, k <= 8.
+// Fused decoder step on the 5th-generation tensor cores (tcgen05), sm_100a.  One head, k <= 16 (KH = 1: k <= 8; KH = 2:
+// two halves of 8 components each, see "two component halves" below).
 //
 //   raw = Q P^T ; R = clamp(raw, 0, 1) ; loss += BCE_sum(R, X) ; G = dLoss/draw (BCELoss backward, 1e-12 floor,
 //   inclusive clamp mask) ; dQ = G P ; dP = G^T Q ; Adam(P) ; P <- clamp(P, 0, 1)
@@ -30,8 +31,17 @@ using namespace tc;
 
 constexpr int kMS = 64;                       // SNPs per sub-tile
 constexpr int kGtBytes = 2 * 128 * kMS * 2;   // G^T tile: two bf16 terms x 128 rows x 64 SNPs = 32 KB
-constexpr int kPTileBytes = 4096;             // P sub-tile: 64 SNPs x 4 bf16 chunks [h | l | m | h] of 8 components
-constexpr int kQBlkBytes = 16 * 384;          // Q block: 128 rows x 3 bf16 chunks [h | m | l]
+// Operand tiles hold, per 8-row (8-SNP) group, the 16-byte chunks (8 components as bf16) of ONE component half after the
+// other.  Q: [h | m | l] per half.  P: KH = 1: [h | l | m | h]; KH = 2: [h | l | m | h | m'] per half, m' = the middle
+// term ROUNDED to nearest (not truncated), read only by MMA2.
+// Two component halves (KH = 2, heads with 9 <= k <= 16): raw = Q_a P_a^T + Q_b P_b^T (MMA1 accumulates the second half
+// onto the first), dP_a | dP_b are two accumulators of MMA3, and dQ = G . [P_h | P_m'] per half with N = 16 instead of
+// N = 32 — the exact three-term form would need 2 x 32 tensor-memory columns per row block, which 512 columns do not
+// hold beside the raw / G slots; h + m' carries P to 2^-17 (unbiased), and dQ is a sum over all the SNPs of the CTA.
+__host__ __device__ constexpr int dec_pchunks(int KH) { return KH == 1 ? 4 : 5; }          // chunks per half in a P tile
+__host__ __device__ constexpr int dec_ptile_bytes(int KH) { return 8 * 128 * dec_pchunks(KH) * KH; }   // 64 SNPs
+__host__ __device__ constexpr int dec_qblk_bytes(int KH) { return 16 * 384 * KH; }                    // 128 rows
+__host__ __device__ constexpr int dec_dq_cols(int KH) { return KH == 1 ? 32 : 16; }        // dQ accumulator columns per half
 constexpr int kPStages = 3;
 // Three compute warpgroups (4 warps each) work on units round-robin; a unit lives in one of SLOTS raw / G slots of 64
 // tensor-memory columns (+ one G^T tile in shared memory per slot).  SLOTS = 4 > 3 warpgroups lets a warpgroup start
@@ -46,6 +56,7 @@ __host__ __device__ constexpr int dec_threads(int WGS) { return (4 * WGS + 4 + 4
 __host__ __device__ constexpr int dec_nd3(int SLOTS) { return SLOTS == 3 ? 2 : 1; }
 constexpr uint32_t kIdesc1 = instr_desc(kAccF32, kFmtBF16, kFmtBF16, false, false, 128, kMS);
 constexpr uint32_t kIdesc2 = instr_desc(kAccF32, kFmtBF16, kFmtBF16, false, true, 128, 32);
+constexpr uint32_t kIdesc2h = instr_desc(kAccF32, kFmtBF16, kFmtBF16, false, true, 128, 16);
 constexpr uint32_t kIdesc3 = instr_desc(kAccF32, kFmtBF16, kFmtBF16, true, true, 64, 24);
 constexpr float kLog2Clamp = -144.26950408889634f;   // -100 / ln 2: torch clamps log at -100 (BCELoss)
 
@@ -101,45 +112,6 @@ __device__ __forceinline__ void split3_row(const float (&x)[8], uint4& H, uint4&
 // w: the 16 2-bit codes (missing cleared).  Loss accumulators in log2 units, kept apart for x in {0, 1} (acc_hom) and
 // x = 1/2 (acc_het, weight 1/2); kLoss = false: gradients only.
 //
-// General path: raw may exceed 1 by rounding (clamp + inclusive mask of the clamp backward), R (1 - R) may fall
-// below the 1e-12 floor of BCELoss' backward, log may hit torch's -100 clamp.  One log per element.
-template <bool kLoss>
-__device__ __forceinline__ void decode16_general(const uint32_t (&v)[16], uint32_t w, uint32_t magic, uint32_t (&hi)[8],
-                                                 uint32_t (&lo)[8], float& acc_hom, float& acc_het) {
-    const uint32_t wh = w >> 16;
-#pragma unroll
-    for (int j2 = 0; j2 < 8; ++j2) {
-        float g[2];
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const int j = 2 * j2 + e;
-            const uint32_t wsrc = (j < 8) ? w : wh;
-            const int sh = 2 * (j & 7);
-            const float raw = __uint_as_float(v[j]);
-            // code * 4^(j&7) as an exact float via the 2^23 magic constant (kept in a register: one LOP3); x = code / 2
-            const float f = __uint_as_float((wsrc & (3u << sh)) | magic) - 8388608.0f;
-            const float Rs = fminf(raw, 1.0f);
-            const float prod = fmaf(-Rs, Rs, Rs);                       // R (1 - R)
-            const float inv = rcp_approx(fmaxf(prod, 1e-12f));
-            const float num = fmaf(f, -0.5f / (float)(1 << sh), Rs);     // R - x
-            g[e] = (raw <= 1.0f) ? num * inv : 0.0f;                    // clamp backward mask (raw >= 0 always)
-            if (kLoss) {
-                // BCE with torch's log clamp; X in {0, .5, 1}: a single log per element.
-                // x = 0: log(1 - R) ;  x = 1: log R (taken from R itself: 1 - |R - 1| would lose an R below 2^-24) ;
-                // x = .5: weight .5 on log(R (1 - R))
-                const bool het = (wsrc >> sh) & 1u, one = (wsrc >> sh) & 2u;
-                const float arg = het ? prod : (one ? Rs : 1.0f - Rs);
-                const float l = fmaxf(lg2_approx(arg), kLog2Clamp);
-                acc_hom += het ? 0.0f : l;
-                acc_het += het ? l : 0.0f;
-            }
-        }
-        const uint32_t h = pack_bf16x2(g[0], g[1]);
-        hi[j2] = h;
-        lo[j2] = pack_bf16x2(g[0] - __uint_as_float(h << 16), g[1] - __uint_as_float(h & 0xFFFF0000u));
-    }
-}
-
 // Fast path, taken when every R (1 - R) of the 16 values (prod[], computed by the caller from the unclamped raw) is at
 // least kProdFast = 2^-15: then 0 < raw < 1 (no clamp, mask = 1), the 1e-12 floor and the -100 log clamp cannot bind,
 // and each BCE argument t (R, 1 - R or R (1 - R)) lies in [2^-15, 1].  The loss is accumulated as PRODUCTS of the
@@ -147,18 +119,17 @@ __device__ __forceinline__ void decode16_general(const uint32_t (&v)[16], uint32
 // per product (<= 2^120: no overflow), so 16 elements cost 4 logs and one multiply each instead of 16 logs:
 // sum_j log t_j = -log prod_j (1 / t_j).
 constexpr float kProdFast = 3.0517578125e-05f;
-// Between the two: every R (1 - R) >= kProdMid = 1e-12 (the floor of BCELoss' backward).  Then still 0 < raw < 1 (no
-// clamp, mask 1) and the floor does not bind, so the GRADIENT is exactly the fast path's num * rcp(prod) (rcp <= 1e12,
-// no overflow); only the product-accumulated loss would overflow (factors up to 1e12), so the loss takes one log per
-// element here (t >= 1e-12 > e^-100: torch's log clamp cannot bind either).  This is the path of late training, where
-// restrict_P has pinned many allele frequencies at exactly 0 / 1 and Q is concentrated: R gets very small or very close
-// to 1 for many elements without being exactly 0 or 1 (bench.py's late_training leg).
-constexpr float kProdMid = 1e-12f;
+// General path (kGeneral): any value — raw may exceed 1 by rounding (clamp + inclusive mask of the clamp backward),
+// R (1 - R) may fall below the 1e-12 floor of BCELoss' backward, the log may hit torch's -100 clamp — with torch's
+// formulas evaluated literally and one log per element, in the SAME packed form as the fast path (+ ~6 instructions
+// per element).  It is chosen per WARP, not per lane (thread = row: in late training, when restrict_P has pinned many
+// allele frequencies at exactly 0 / 1 and Q is concentrated, nearly every warp holds a row that needs it, and a
+// divergent warp pays for every path any of its lanes takes): bench.py's late_training leg measures that regime.
 // The fp32 arithmetic of the fast path is issued as PACKED pairs (sm_100 FFMA2 / FADD2 / FMUL2 via __ffma2_rn & co.:
 // one issue slot per two elements, results bit-identical to the scalar .rn instructions; negation / |.| fold into
 // operand modifiers).  The kernel is bound by instruction issue, not by the fp32 pipe.
-template <bool kLoss, bool kLogPerElement = false>
-__device__ __forceinline__ void decode16_fast(const uint32_t (&v)[16], const float2 (&prod)[8], uint32_t w,
+template <bool kLoss, bool kGeneral = false>
+__device__ __forceinline__ void decode16_fast(const uint32_t (&v)[16], const float2 (&prod_in)[8], uint32_t w,
                                               uint32_t magic, uint32_t magic21, uint32_t (&hi)[8], uint32_t (&lo)[8],
                                               float& acc_hom, float& acc_het) {
     const uint32_t wh = w >> 16;
@@ -168,8 +139,12 @@ __device__ __forceinline__ void decode16_fast(const uint32_t (&v)[16], const flo
         const int j = 2 * j2;
         const uint32_t wsrc = (j < 8) ? w : wh;
         const int sh = 2 * (j & 7);                                      // element j: bits sh, sh+1; j+1: sh+2, sh+3
-        const float2 raw = make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));
-        const float2 inv = make_float2(rcp_approx(prod[j2].x), rcp_approx(prod[j2].y));
+        const float2 raw_u = make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+        // general: R = clamp(raw, 0, 1) (raw >= 0 always: every term of the split Q, P is), floor under R (1 - R)
+        const float2 raw = kGeneral ? make_float2(fminf(raw_u.x, 1.0f), fminf(raw_u.y, 1.0f)) : raw_u;
+        const float2 prod = kGeneral ? __ffma2_rn(make_float2(-raw.x, -raw.y), raw, raw) : prod_in[j2];
+        const float2 inv = kGeneral ? make_float2(rcp_approx(fmaxf(prod.x, 1e-12f)), rcp_approx(fmaxf(prod.y, 1e-12f)))
+                                    : make_float2(rcp_approx(prod.x), rcp_approx(prod.y));
         // code * 4^(j&7) as an exact float via the 2^23 magic constant (kept in a register: one LOP3 per element).  The
         // odd element's field sits two bits higher: OR-ing it into 2^21 (ulp 1/4) instead of 2^23 (ulp 1) gives it the
         // SAME scale as the even element, so the pair shares one multiplier (an immediate of the packed FFMA2).
@@ -178,20 +153,25 @@ __device__ __forceinline__ void decode16_fast(const uint32_t (&v)[16], const flo
         const float2 f = __fadd2_rn(fm, make_float2(-8388608.0f, -2097152.0f));
         const float cs = -0.5f / (float)(1 << sh);
         const float2 num = __ffma2_rn(f, make_float2(cs, cs), raw);      // R - x
-        const float2 g = __fmul2_rn(num, inv);
-        if (kLoss && !kLogPerElement) {
+        float2 g = __fmul2_rn(num, inv);
+        if (kGeneral) {                                               // clamp backward: inclusive mask 0 <= raw <= 1
+            g.x = (raw_u.x <= 1.0f) ? g.x : 0.0f;
+            g.y = (raw_u.y <= 1.0f) ? g.y : 0.0f;
+        }
+        if (kLoss && !kGeneral) {
             // x in {0,1}: |G| = 1 / (1 - |R - x|), the reciprocal of the BCE argument;  x = 1/2: inv = 1 / (R (1 - R))
             if ((wsrc >> sh) & 1u) p_het *= inv.x;
             else p_hom *= fabsf(g.x);
             if ((wsrc >> sh) & 4u) p_het *= inv.y;
             else p_hom *= fabsf(g.y);
         }
-        if (kLoss && kLogPerElement) {
-            // one log per element (arguments down to 1e-12): x = 0: t = 1 - R;  x = 1: t = R;  x = 1/2: t = R (1 - R)
+        if (kLoss && kGeneral) {
+            // one log per element with torch's -100 clamp: x = 0: log(1 - R);  x = 1: log R (from R itself: 1 - |R - 1|
+            // would lose an R below 2^-24);  x = 1/2: weight 1/2 on log(R (1 - R))
             const bool het0 = (wsrc >> sh) & 1u, het1 = (wsrc >> sh) & 4u;
             const bool one0 = (wsrc >> sh) & 2u, one1 = (wsrc >> sh) & 8u;
-            const float l0 = lg2_approx(het0 ? prod[j2].x : (one0 ? raw.x : 1.0f - raw.x));
-            const float l1 = lg2_approx(het1 ? prod[j2].y : (one1 ? raw.y : 1.0f - raw.y));
+            const float l0 = fmaxf(lg2_approx(het0 ? prod.x : (one0 ? raw.x : 1.0f - raw.x)), kLog2Clamp);
+            const float l1 = fmaxf(lg2_approx(het1 ? prod.y : (one1 ? raw.y : 1.0f - raw.y)), kLog2Clamp);
             acc_hom += het0 ? 0.0f : l0;
             acc_het += het0 ? l0 : 0.0f;
             acc_hom += het1 ? 0.0f : l1;
@@ -201,7 +181,7 @@ __device__ __forceinline__ void decode16_fast(const uint32_t (&v)[16], const flo
         hi[j2] = h;
         const float2 l = __fadd2_rn(g, make_float2(-__uint_as_float(h << 16), -__uint_as_float(h & 0xFFFF0000u)));
         lo[j2] = pack_bf16x2(l.x, l.y);
-        if (kLoss && !kLogPerElement && (j2 & 3) == 3) {
+        if (kLoss && !kGeneral && (j2 & 3) == 3) {
             acc_hom -= lg2_approx(p_hom);
             acc_het -= lg2_approx(p_het);
             p_hom = 1.0f;
@@ -210,7 +190,7 @@ __device__ __forceinline__ void decode16_fast(const uint32_t (&v)[16], const flo
     }
 }
 
-template <bool kLoss, int SLOTS, int WGS>
+template <bool kLoss, int SLOTS, int WGS, int KH>
 __global__ void __launch_bounds__(dec_threads(WGS), 1)
 dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* __restrict__ row_idx, int64_t row0, int B,
               int64_t M, const float* __restrict__ Q, int q_ld, int q_off, int k, float* __restrict__ P,
@@ -222,11 +202,14 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
     constexpr int kSlots = SLOTS, kWarpIssue = kWarpIssueA1;
     const AdamCoef adam = adam_resolve(adam_in);
     constexpr int ngt = SLOTS;   // one G^T tile per slot (see the issuer warps for why not more)
-    constexpr int kND3 = dec_nd3(SLOTS), kColD3 = 64 * SLOTS, kColD2 = kColD3 + 32 * kND3;
+    constexpr int kND3 = (KH == 2) ? 1 : dec_nd3(SLOTS), kColD3 = 64 * SLOTS, kColD2 = kColD3 + 32 * kND3 * KH;
+    constexpr int kPTileBytes = dec_ptile_bytes(KH), kQBlkBytes = dec_qblk_bytes(KH), kDQ = dec_dq_cols(KH);
+    constexpr int kQGrp = 384 * KH, kPGrp = 128 * dec_pchunks(KH) * KH;   // bytes of one 8-row (8-SNP) group of a Q / P tile
+    constexpr int kPHalf = 128 * dec_pchunks(KH);                          // bytes between the two halves inside a P group
     extern __shared__ __align__(1024) uint8_t smem[];
     const int nblk = (B + 127) / 128;
-    uint8_t* QA = smem;                                   // nblk x 6 KB : bf16 h/m/l of Q (MMA1 A K-major, MMA3 B MN-major)
-    uint8_t* PT = QA + nblk * kQBlkBytes;                 // kPStages x 4 KB : P sub-tiles (MMA1 B K-major, MMA2 B MN-major)
+    uint8_t* QA = smem;                                   // nblk x 6 KB x KH : bf16 h/m/l of Q (MMA1 A K-major, MMA3 B MN-major)
+    uint8_t* PT = QA + nblk * kQBlkBytes;                 // kPStages P sub-tiles (MMA1 B K-major, MMA2 B MN-major)
     uint8_t* GT = PT + kPStages * kPTileBytes;            // ngt x 32 KB : G^T tiles
     int64_t* rowoff = reinterpret_cast<int64_t*>(GT + ngt * kGtBytes);
     DecSmem* S = reinterpret_cast<DecSmem*>(rowoff + nblk * 128);
@@ -238,15 +221,18 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
     for (int b = tid; b < nblk * 128; b += blockDim.x)
         rowoff[b] = (b < B) ? ((row_idx != nullptr) ? row_idx[b] : (row0 + b)) * pitch : -1;
     for (int b = tid; b < nblk * 128; b += blockDim.x) {
-        float q[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) q[c] = (b < B && c < k) ? Q[(int64_t)b * q_ld + q_off + c] : 0.f;
-        uint4 H, Mm, L;
-        split3_row(q, H, Mm, L);
-        uint8_t* a = QA + (b & 7) * 16 + (b >> 3) * 384;
-        *reinterpret_cast<uint4*>(a) = H;
-        *reinterpret_cast<uint4*>(a + 128) = Mm;
-        *reinterpret_cast<uint4*>(a + 256) = L;
+        for (int hf = 0; hf < KH; ++hf) {
+            float q[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) q[c] = (b < B && 8 * hf + c < k) ? Q[(int64_t)b * q_ld + q_off + 8 * hf + c] : 0.f;
+            uint4 H, Mm, L;
+            split3_row(q, H, Mm, L);
+            uint8_t* a = QA + (b & 7) * 16 + (b >> 3) * kQGrp + hf * 384;
+            *reinterpret_cast<uint4*>(a) = H;
+            *reinterpret_cast<uint4*>(a + 128) = Mm;
+            *reinterpret_cast<uint4*>(a + 256) = L;
+        }
     }
     if (tid == 0) {
         for (int i = 0; i < kMaxSlots; ++i) {
@@ -339,14 +325,11 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
                     const float t2 = fminf(fminf(prod[3].x, prod[3].y), prod[4].x), t3 = fminf(fminf(prod[4].y, prod[5].x), prod[5].y);
                     const float t4 = fminf(fminf(prod[6].x, prod[6].y), prod[7].x);
                     const float mn = fminf(fminf(fminf(t0, t1), t2), fminf(fminf(t3, t4), prod[7].y));
-                    // Path per WARP, not per lane (thread = row: in late training nearly every warp holds rows of both
-                    // kinds, and a divergent warp pays for every path any of its lanes takes): all lanes fast -> fast;
-                    // otherwise every lane whose products clear the 1e-12 floor takes the mid path (it is valid on the
-                    // fast range too) and only the lanes below it the general one.
-                    const bool all_fast = __all_sync(0xffffffffu, mn >= kProdFast);
-                    if (all_fast) decode16_fast<kLoss>(v, prod, w, magic, magic21, hi, lo, acc_hom, acc_het);
-                    else if (mn >= kProdMid) decode16_fast<kLoss, true>(v, prod, w, magic, magic21, hi, lo, acc_hom, acc_het);
-                    else decode16_general<kLoss>(v, w, magic, hi, lo, acc_hom, acc_het);
+                    // one path per warp: all 32 rows in the fast range -> fast, else the general form for all of them
+                    if (__all_sync(0xffffffffu, mn >= kProdFast))
+                        decode16_fast<kLoss, false>(v, prod, w, magic, magic21, hi, lo, acc_hom, acc_het);
+                    else
+                        decode16_fast<kLoss, true>(v, prod, w, magic, magic21, hi, lo, acc_hom, acc_het);
 #ifndef NADM_KO_MMA   // (knock-out build: raw stays the constant written at setup, so that the decode keeps its fast path)
                     tmem_st8(tlane + slot * 64 + c * 16, hi);          // G hi / lo overwrite their own raw columns
                     tmem_st8(tlane + slot * 64 + c * 16 + 8, lo);
@@ -383,18 +366,24 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
         tc_fence_after_sync();
         for (int blk = wg; blk < nblk; blk += kWGs) {
             uint32_t v[32];
-            tmem_ld32(tlane + kColD2 + blk * 32, v);
+            tmem_ld32(tlane + kColD2 + blk * 32, v);      // KH = 1: one 32-column accumulator; KH = 2: two of 16 columns
             tmem_wait_ld();
             const int b = blk * 128 + rb;
             if (b < B) {
-                float* out = dQpart + ((int64_t)blockIdx.x * B + b) * 8;
-                float o[8];
+                float* out = dQpart + ((int64_t)blockIdx.x * B + b) * (8 * KH);
 #pragma unroll
-                for (int c = 0; c < 8; ++c)   // columns: G.P_h | G.P_l | G.P_m | G.P_h (duplicate, unused)
-                    o[c] = (U > 0) ? (__uint_as_float(v[c]) + __uint_as_float(v[16 + c])) + __uint_as_float(v[8 + c]) : 0.f;
-                const float4 o0 = make_float4(o[0], o[1], o[2], o[3]), o1 = make_float4(o[4], o[5], o[6], o[7]);
-                reinterpret_cast<float4*>(out)[0] = o0;
-                reinterpret_cast<float4*>(out)[1] = o1;
+                for (int hf = 0; hf < KH; ++hf) {
+                    float o[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        // KH = 1 columns: G.P_h | G.P_l | G.P_m | G.P_h (duplicate, unused);  KH = 2, per half: G.P_h | G.P_m'
+                        const float sum = (KH == 1) ? (__uint_as_float(v[c]) + __uint_as_float(v[16 + c])) + __uint_as_float(v[8 + c])
+                                                    : __uint_as_float(v[16 * hf + c]) + __uint_as_float(v[16 * hf + 8 + c]);
+                        o[c] = (U > 0) ? sum : 0.f;
+                    }
+                    reinterpret_cast<float4*>(out + 8 * hf)[0] = make_float4(o[0], o[1], o[2], o[3]);
+                    reinterpret_cast<float4*>(out + 8 * hf)[1] = make_float4(o[4], o[5], o[6], o[7]);
+                }
             }
         }
     } else if (warp == kWarpIssueA1) {
@@ -411,10 +400,11 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
         const uint32_t qa = smem_u32(QA), pt = smem_u32(PT);
         // Q chunks [h m l] (128 B apart, 8-row groups 384 B apart); P chunks [h l m h] (8-row groups 512 B apart).
         // A K=16 instruction multiplies two chunk pairs: start address = first chunk, LBO = distance to the second.
-        const uint64_t A_hm = smem_desc(qa, 128, 384), A_hl = smem_desc(qa, 256, 384), A_ml = smem_desc(qa + 128, 128, 384);
-        const uint64_t B_hm = smem_desc(pt, 256, 512), B_mh = smem_desc(pt + 256, 128, 512);
-        const uint64_t B_lh = smem_desc(pt + 128, 256, 512), B_lm = smem_desc(pt + 128, 128, 512);
-        const uint64_t B2 = smem_desc(pt, 512, 128);
+        const uint64_t A_hm = smem_desc(qa, 128, kQGrp), A_hl = smem_desc(qa, 256, kQGrp), A_ml = smem_desc(qa + 128, 128, kQGrp);
+        const uint64_t B_hm = smem_desc(pt, 256, kPGrp), B_mh = smem_desc(pt + 256, 128, kPGrp);
+        const uint64_t B_lh = smem_desc(pt + 128, 256, kPGrp), B_lm = smem_desc(pt + 128, 128, kPGrp);
+        // MMA2's B operand, MN-major: KH = 1: all four chunks [h l m h] (N = 32); KH = 2: chunks [h m'] of a half (N = 16)
+        const uint64_t B2 = smem_desc(pt + (KH == 1 ? 0 : 384), kPGrp, 128);
         const uint32_t leader = elect_one() ? 1u : 0u;                  // the one lane that executes the MMAs / commits
         int l_blk = 0, l_stage = 0, l_phase = 0, l_slot = 0;
         auto issue_mma1 = [&]() {
@@ -422,10 +412,14 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
             tc_fence_after_sync();
             const uint32_t ao = (uint32_t)(l_blk * (kQBlkBytes >> 4)), bo = (uint32_t)(l_stage * (kPTileBytes >> 4));
             const uint32_t d = tbase + l_slot * 64;
-            mma_f16_ss_p(d, desc_add(A_hm, ao), desc_add(B_hm, bo), kIdesc1, 0u, leader);   // h.h + m.m
-            mma_f16_ss_p(d, desc_add(A_hm, ao), desc_add(B_mh, bo), kIdesc1, 1u, leader);   // h.m + m.h
-            mma_f16_ss_p(d, desc_add(A_hl, ao), desc_add(B_lh, bo), kIdesc1, 1u, leader);   // h.l + l.h
-            mma_f16_ss_p(d, desc_add(A_ml, ao), desc_add(B_lm, bo), kIdesc1, 1u, leader);   // m.l + l.m
+#pragma unroll
+            for (int hf = 0; hf < KH; ++hf) {                            // the second component half accumulates onto the first
+                const uint32_t ah = ao + (uint32_t)(hf * (384 >> 4)), bh = bo + (uint32_t)(hf * (kPHalf >> 4));
+                mma_f16_ss_p(d, desc_add(A_hm, ah), desc_add(B_hm, bh), kIdesc1, hf ? 1u : 0u, leader);   // h.h + m.m
+                mma_f16_ss_p(d, desc_add(A_hm, ah), desc_add(B_mh, bh), kIdesc1, 1u, leader);             // h.m + m.h
+                mma_f16_ss_p(d, desc_add(A_hl, ah), desc_add(B_lh, bh), kIdesc1, 1u, leader);             // h.l + l.h
+                mma_f16_ss_p(d, desc_add(A_ml, ah), desc_add(B_lm, bh), kIdesc1, 1u, leader);             // m.l + l.m
+            }
             mma_commit_p(&S->d1full[l_slot], leader);
             if (l_blk == nblk - 1) mma_commit_p(&S->pempty[l_stage], leader); // MMA1's reads of the P stage are issued
             if (++l_slot == kSlots) l_slot = 0;
@@ -442,14 +436,19 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
             tc_fence_after_sync();
             if (lane == 0) TL(4, u);                                    // issuer saw G(u)
             const uint64_t b2 = desc_add(B2, (uint32_t)(stage * (kPTileBytes >> 4)));
-            const uint32_t d2 = tbase + kColD2 + blk * 32, a2 = tbase + slot * 64;
+            const uint32_t a2 = tbase + slot * 64;
             const uint32_t acc2 = sub > 0 ? 1u : 0u;
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
+            for (int hf = 0; hf < KH; ++hf) {
+                const uint32_t d2 = tbase + kColD2 + (blk * KH + hf) * kDQ;
 #pragma unroll
-                for (int t = 0; t < 2; ++t)
-                    mma_f16_ts_p(d2, a2 + c * 16 + t * 8, desc_add(b2, (uint32_t)(c * 2 * 32)), kIdesc2, (c + t) ? 1u : acc2,
-                                 leader);
+                for (int c = 0; c < 4; ++c)
+#pragma unroll
+                    for (int t = 0; t < 2; ++t)
+                        mma_f16_ts_p(d2, a2 + c * 16 + t * 8,
+                                     desc_add(b2, (uint32_t)(c * 2 * (kPGrp >> 4) + hf * (kPHalf >> 4))),
+                                     KH == 1 ? kIdesc2 : kIdesc2h, (c + t) ? 1u : acc2, leader);
+            }
             if (blk == nblk - 1) mma_commit_p(&S->pempty[stage], leader); // MMA2's reads of the P stage are issued
             if (u + kSlots < U) issue_mma1();                           // raw of unit u + SLOTS into the slot just consumed
             if (lane == 0) TL(5, u);                                    // issuer done with unit u
@@ -466,7 +465,7 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
         // =============================== MMA issuer B: dP_sub += G^T . [Q_h | Q_m | Q_l] (MMA3) ===============================
         // A = the shared G^T tile of the unit's slot, MN-major; B = the Q block re-read MN-major; only K steps holding
         // real rows are issued for the last row block.
-        const uint64_t A3 = smem_desc(smem_u32(GT), 1024, 128), B3 = smem_desc(smem_u32(QA), 384, 128);
+        const uint64_t A3 = smem_desc(smem_u32(GT), 1024, 128), B3 = smem_desc(smem_u32(QA), kQGrp, 128);
         const int nks_last = min(8, (B - (nblk - 1) * 128 + 15) / 16);
         const uint32_t leader = elect_one() ? 1u : 0u;
         int blk = 0, slot = 0, slot_phase = 0, dbuf = 0, d3_phase = 1;
@@ -477,20 +476,24 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
             {
                 const uint64_t a3 = desc_add(A3, (uint32_t)(slot * (kGtBytes >> 4))),
                                b3 = desc_add(B3, (uint32_t)(blk * (kQBlkBytes >> 4)));
-                const uint32_t d3 = tbase + kColD3 + dbuf * 32;
                 const uint32_t acc3 = blk > 0 ? 1u : 0u;
-                if (blk != nblk - 1 || nks_last == 8) {
 #pragma unroll
-                    for (int t = 0; t < 2; ++t)
+                for (int hf = 0; hf < KH; ++hf) {
+                    const uint32_t d3 = tbase + kColD3 + (dbuf * KH + hf) * 32;
+                    const uint64_t b3h = desc_add(b3, (uint32_t)(hf * (384 >> 4)));
+                    if (blk != nblk - 1 || nks_last == 8) {
 #pragma unroll
-                        for (int ks = 0; ks < 8; ++ks)
-                            mma_f16_ss_p(d3, desc_add(a3, (uint32_t)(t * 1024 + ks * 128)), desc_add(b3, (uint32_t)(ks * 48)),
-                                         kIdesc3, (t + ks) ? 1u : acc3, leader);
-                } else {
-                    for (int t = 0; t < 2; ++t)
-                        for (int ks = 0; ks < nks_last; ++ks)
-                            mma_f16_ss_p(d3, desc_add(a3, (uint32_t)(t * 1024 + ks * 128)), desc_add(b3, (uint32_t)(ks * 48)),
-                                         kIdesc3, (t + ks) ? 1u : acc3, leader);
+                        for (int t = 0; t < 2; ++t)
+#pragma unroll
+                            for (int ks = 0; ks < 8; ++ks)
+                                mma_f16_ss_p(d3, desc_add(a3, (uint32_t)(t * 1024 + ks * 128)),
+                                             desc_add(b3h, (uint32_t)(ks * 2 * (kQGrp >> 4))), kIdesc3, (t + ks) ? 1u : acc3, leader);
+                    } else {
+                        for (int t = 0; t < 2; ++t)
+                            for (int ks = 0; ks < nks_last; ++ks)
+                                mma_f16_ss_p(d3, desc_add(a3, (uint32_t)(t * 1024 + ks * 128)),
+                                             desc_add(b3h, (uint32_t)(ks * 2 * (kQGrp >> 4))), kIdesc3, (t + ks) ? 1u : acc3, leader);
+                    }
                 }
                 mma_commit_p(&S->gtfree[slot], leader);
                 if (blk == nblk - 1) mma_commit_p(&S->d3full[dbuf], leader);
@@ -506,20 +509,23 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
         // =============================== P sub-tile producer ===============================
         for (int sub = 0; sub < nsub; ++sub) {
             const int st = sub % kPStages;
-            float p[2][8];
+            float p[2][8 * KH];
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int64_t m = (int64_t)(s0 + sub) * kMS + lane + 32 * e;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) p[e][c] = 0.f;
+                for (int c = 0; c < 8 * KH; ++c) p[e][c] = 0.f;
                 if (m < M) {
-                    if (k == 8) {
-                        const float4 a = reinterpret_cast<const float4*>(P + m * 8)[0];
-                        const float4 b = reinterpret_cast<const float4*>(P + m * 8)[1];
-                        p[e][0] = a.x; p[e][1] = a.y; p[e][2] = a.z; p[e][3] = a.w;
-                        p[e][4] = b.x; p[e][5] = b.y; p[e][6] = b.z; p[e][7] = b.w;
+                    if (k == 8 * KH) {
+#pragma unroll
+                        for (int c4 = 0; c4 < 2 * KH; ++c4) {
+                            const float4 a = reinterpret_cast<const float4*>(P + m * (8 * KH))[c4];
+                            p[e][4 * c4] = a.x; p[e][4 * c4 + 1] = a.y; p[e][4 * c4 + 2] = a.z; p[e][4 * c4 + 3] = a.w;
+                        }
                     } else {
-                        for (int c = 0; c < k; ++c) p[e][c] = P[m * k + c];
+#pragma unroll
+                        for (int c = 0; c < 8 * KH; ++c)
+                            if (c < k) p[e][c] = P[m * k + c];
                     }
                 }
             }
@@ -528,13 +534,30 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int ml = lane + 32 * e;
-                uint8_t* t1 = tile + (ml & 7) * 16 + (ml >> 3) * 512;
-                uint4 H, Mm, L;
-                split3_row(p[e], H, Mm, L);
-                *reinterpret_cast<uint4*>(t1) = H;
-                *reinterpret_cast<uint4*>(t1 + 128) = L;
-                *reinterpret_cast<uint4*>(t1 + 256) = Mm;
-                *reinterpret_cast<uint4*>(t1 + 384) = H;
+#pragma unroll
+                for (int hf = 0; hf < KH; ++hf) {
+                    uint8_t* t1 = tile + (ml & 7) * 16 + (ml >> 3) * kPGrp + hf * kPHalf;
+                    float ph[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) ph[c] = p[e][8 * hf + c];
+                    uint4 H, Mm, L;
+                    split3_row(ph, H, Mm, L);
+                    *reinterpret_cast<uint4*>(t1) = H;
+                    *reinterpret_cast<uint4*>(t1 + 128) = L;
+                    *reinterpret_cast<uint4*>(t1 + 256) = Mm;
+                    *reinterpret_cast<uint4*>(t1 + 384) = H;
+                    if (KH == 2) {   // m' = bf16_rn(p - h): with h, carries p to 2^-17 (MMA2's two-term operand)
+                        uint32_t mr[8];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const float hfl = __uint_as_float(__float_as_uint(ph[c]) & 0xFFFF0000u);
+                            const __nv_bfloat16 r = __float2bfloat16_rn(ph[c] - hfl);
+                            mr[c] = (uint32_t)(*reinterpret_cast<const unsigned short*>(&r));
+                        }
+                        *reinterpret_cast<uint4*>(t1 + 512) = make_uint4(mr[0] | (mr[1] << 16), mr[2] | (mr[3] << 16),
+                                                                         mr[4] | (mr[5] << 16), mr[6] | (mr[7] << 16));
+                    }
+                }
             }
             fence_async_smem();
             __syncwarp();
@@ -553,19 +576,22 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
             if (warp == kPoller) mbar_wait_relaxed(&S->d3full[dbuf], (sub / kND3) & 1, 64);
             named_bar_sync(1, 128);
             tc_fence_after_sync();
-            uint32_t v[32];
-            tmem_ld32(tbase + ((uint32_t)(q * 32) << 16) + kColD3 + dbuf * 32, v);
-            tmem_wait_ld();
+            float g[8 * KH];
+#pragma unroll
+            for (int hf = 0; hf < KH; ++hf) {
+                uint32_t v[32];
+                tmem_ld32(tbase + ((uint32_t)(q * 32) << 16) + kColD3 + (dbuf * KH + hf) * 32, v);
+                tmem_wait_ld();
+#pragma unroll
+                for (int c = 0; c < 8; ++c)   // columns: G^T.Q_h | G^T.Q_m | G^T.Q_l
+                    g[8 * hf + c] = (__uint_as_float(v[c]) + __uint_as_float(v[8 + c])) + __uint_as_float(v[16 + c]);
+            }
             tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&S->d3empty[dbuf]);
             const int64_t m = (int64_t)(s0 + sub) * kMS + q * 16 + lane;       // M = 64 accumulator: lanes 32q + (0..15)
             if (lane < 16 && m < M) {
-                float g[8];
-#pragma unroll
-                for (int c = 0; c < 8; ++c)   // columns: G^T.Q_h | G^T.Q_m | G^T.Q_l
-                    g[c] = (__uint_as_float(v[c]) + __uint_as_float(v[8 + c])) + __uint_as_float(v[16 + c]);
-                if (k == 8) {
+                if (KH == 1 && k == 8) {
                     if (dP_out != nullptr) {
                         reinterpret_cast<float4*>(dP_out + m * 8)[0] = make_float4(g[0], g[1], g[2], g[3]);
                         reinterpret_cast<float4*>(dP_out + m * 8)[1] = make_float4(g[4], g[5], g[6], g[7]);
@@ -586,15 +612,18 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
                         }
                     }
                 } else {
-                    for (int c = 0; c < k; ++c) {
-                        const int64_t pi = m * k + c;
-                        if (dP_out != nullptr) dP_out[pi] = g[c];
-                        if (adam.enabled) {
-                            float mm = Pm[pi], vv = Pv[pi];
-                            const float pn = adam_apply(P[pi], g[c], mm, vv, adam);
-                            P[pi] = fminf(fmaxf(pn, 0.f), 1.f);
-                            Pm[pi] = mm;
-                            Pv[pi] = vv;
+#pragma unroll
+                    for (int c = 0; c < 8 * KH; ++c) {
+                        if (c < k) {
+                            const int64_t pi = m * k + c;
+                            if (dP_out != nullptr) dP_out[pi] = g[c];
+                            if (adam.enabled) {
+                                float mm = Pm[pi], vv = Pv[pi];
+                                const float pn = adam_apply(P[pi], g[c], mm, vv, adam);
+                                P[pi] = fminf(fmaxf(pn, 0.f), 1.f);
+                                Pm[pi] = mm;
+                                Pv[pi] = vv;
+                            }
                         }
                     }
                 }
@@ -614,10 +643,13 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
 // =================================================================================================================
 // host launcher
 // =================================================================================================================
+static size_t dec_fixed_smem(int nblk, int KH) {
+    return (size_t)nblk * (dec_qblk_bytes(KH) + 1024) + (size_t)kPStages * dec_ptile_bytes(KH) + sizeof(DecSmem) + 128;
+}
 bool dec_tc_supported(int B, int k) {
-    const int nblk = (B + 127) / 128;
-    const size_t fixed = (size_t)nblk * (kQBlkBytes + 1024) + kPStages * kPTileBytes + sizeof(DecSmem) + 128;
-    return k <= 8 && nblk <= 8 && fixed + 3 * (size_t)kGtBytes <= (size_t)kMaxDynSmem;
+    const int nblk = (B + 127) / 128, KH = k <= 8 ? 1 : 2;
+    // tensor memory with 3 slots: 192 + dP (KH = 1: 2 x 32; KH = 2: 2 x 32) + dQ (32 nblk either way) <= 512
+    return k <= 16 && nblk <= 8 && dec_fixed_smem(nblk, KH) + 3 * (size_t)kGtBytes <= (size_t)kMaxDynSmem;
 }
 
 #ifdef NADM_TIMELINE
@@ -626,7 +658,7 @@ extern "C" int nadm_debug_timeline(long long* host_out) {
 }
 #endif
 
-template <bool kLoss, int SLOTS, int WGS>
+template <bool kLoss, int SLOTS, int WGS, int KH>
 static int dec_launch_one(int ncta, size_t smem, cudaStream_t st, const uint8_t* packed, int64_t pitch,
                           const int64_t* row_idx, int64_t row0, int B, int64_t M, const float* Q, int q_ld, int q_off,
                           int k, float* P, float* Pm, float* Pv, const AdamCoef& adam, float* dP_out, float* dQpart,
@@ -634,12 +666,12 @@ static int dec_launch_one(int ncta, size_t smem, cudaStream_t st, const uint8_t*
     static PerDeviceOnce once;                       // one per template instantiation
     bool* attr = once.slot();
     if (attr == nullptr || !*attr) {
-        cudaError_t e = cudaFuncSetAttribute(dec_tc_kernel<kLoss, SLOTS, WGS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(dec_tc_kernel<kLoss, SLOTS, WGS, KH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              kMaxDynSmem);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(dec_tc)");
         if (attr) *attr = true;
     }
-    launch_pdl(dec_tc_kernel<kLoss, SLOTS, WGS>, dim3(ncta), dim3(dec_threads(WGS)), smem, st, packed, pitch, row_idx, row0, B, M, Q, q_ld,
+    launch_pdl(dec_tc_kernel<kLoss, SLOTS, WGS, KH>, dim3(ncta), dim3(dec_threads(WGS)), smem, st, packed, pitch, row_idx, row0, B, M, Q, q_ld,
                q_off, k, P, Pm, Pv, adam, dP_out, dQpart, loss_part, TS);
     NADM_CHECK_LAUNCH("dec_tc_kernel");
     return NADM_OK;
@@ -658,14 +690,17 @@ static int dec_pick_slots(int nblk, size_t fixed) {
     return slots;
 }
 
-// compute warpgroups: NADM_DEC_WGS=3|4 (A/B measurements; default below)
-static int dec_pick_wgs() {
-    static int n = 0;
-    if (n == 0) {
+// compute warpgroups: NADM_DEC_WGS=3|4 forces one (A/B measurements).  Default, measured on one box
+// (profiles/r2_decoder_wgs.txt): gradients only -> 4 (243 vs 248 us: a fourth warp per sub-partition fills issue slots
+// the others leave while they wait for their slot's turn-around); with the loss value -> 3 (275 vs 282 us: at the 80
+// registers per thread that 768 threads allow, the loss-evaluating decode loop is allocated worse).
+static int dec_pick_wgs(bool want_loss) {
+    static int forced = -1;
+    if (forced < 0) {
         const char* e = getenv("NADM_DEC_WGS");
-        n = (e != nullptr && (e[0] == '3' || e[0] == '4')) ? e[0] - '0' : 4;
+        forced = (e != nullptr && (e[0] == '3' || e[0] == '4')) ? e[0] - '0' : 0;
     }
-    return n;
+    return forced ? forced : (want_loss ? 3 : 4);
 }
 
 int launch_dec_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_idx, int64_t row0, int B, int64_t M,
@@ -675,29 +710,32 @@ int launch_dec_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_idx, 
     const int nblk = (B + 127) / 128;
     const int TS = (int)((M + kMS - 1) / kMS);
     const int ncta = std::min(TS, sm_count());
-    const size_t fixed = (size_t)nblk * (kQBlkBytes + 1024) + kPStages * kPTileBytes + sizeof(DecSmem) + 128;
-    const int slots = dec_pick_slots(nblk, fixed);
+    const int KH = k <= 8 ? 1 : 2;                                   // component halves (9 <= k <= 16: two)
+    const size_t fixed = dec_fixed_smem(nblk, KH);
+    const int slots = KH == 2 ? 3 : dec_pick_slots(nblk, fixed);
     const size_t smem = fixed + (size_t)slots * kGtBytes;             // one G^T tile per slot
-    NADM_REQUIRE((size_t)ncta * ((size_t)B * 8 + 1) * sizeof(float) <= ws_bytes, "workspace too small for decoder_step");
+    NADM_REQUIRE((size_t)ncta * ((size_t)B * 8 * KH + 1) * sizeof(float) <= ws_bytes, "workspace too small for decoder_step");
     float* dQpart = ws;
-    float* loss_part = ws + (size_t)ncta * B * 8;
+    float* loss_part = ws + (size_t)ncta * B * 8 * KH;
     const AdamCoef ac = make_adam(adam);
     int rc;
-    const int wgs = dec_pick_wgs();
-#define NADM_DEC_GO(L, W, G)                                                                                           \
-    rc = dec_launch_one<L, W, G>(ncta, smem, st, packed, pitch, row_idx, row0, B, M, Q, q_ld, q_off, k, P, Pm, Pv, ac,   \
-                                 dP_out, dQpart, loss_part, TS)
-#define NADM_DEC_GO_WG(L, W)                                                                                           \
-    do { if (wgs == 4) NADM_DEC_GO(L, W, 4); else NADM_DEC_GO(L, W, 3); } while (0)
-    if (slots == 4) {
-        if (want_loss) NADM_DEC_GO_WG(true, 4); else NADM_DEC_GO_WG(false, 4);
+    const int wgs = dec_pick_wgs(want_loss);
+#define NADM_DEC_GO(L, W, G, H)                                                                                        \
+    rc = dec_launch_one<L, W, G, H>(ncta, smem, st, packed, pitch, row_idx, row0, B, M, Q, q_ld, q_off, k, P, Pm, Pv, ac, \
+                                    dP_out, dQpart, loss_part, TS)
+#define NADM_DEC_GO_WG(L, W, H)                                                                                        \
+    do { if (wgs == 4) NADM_DEC_GO(L, W, 4, H); else NADM_DEC_GO(L, W, 3, H); } while (0)
+    if (KH == 2) {
+        if (want_loss) NADM_DEC_GO_WG(true, 3, 2); else NADM_DEC_GO_WG(false, 3, 2);
+    } else if (slots == 4) {
+        if (want_loss) NADM_DEC_GO_WG(true, 4, 1); else NADM_DEC_GO_WG(false, 4, 1);
     } else {
-        if (want_loss) NADM_DEC_GO_WG(true, 3); else NADM_DEC_GO_WG(false, 3);
+        if (want_loss) NADM_DEC_GO_WG(true, 3, 1); else NADM_DEC_GO_WG(false, 3, 1);
     }
 #undef NADM_DEC_GO_WG
 #undef NADM_DEC_GO
     if (rc != NADM_OK) return rc;
-    return launch_reduce_parts(dQpart, ncta, B, 8, k, dQ, q_ld, q_off, 1.0f, want_loss ? loss_part : nullptr, loss, st);
+    return launch_reduce_parts(dQpart, ncta, B, 8 * KH, k, dQ, q_ld, q_off, 1.0f, want_loss ? loss_part : nullptr, loss, st);
 }
 
 }  // namespace nadm

@@ -346,6 +346,12 @@ enc_fwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
         mbar_init_fence();
     }
     if (warp == kFwdIssueWarp) tmem_alloc<512>(&S->tmem_base);
+    __syncthreads();                                                // row numbers are in shared memory
+    // the producers' first copies are in flight while the scale of V is computed (they need the row numbers only)
+    Feed f{packed, pitch, rowoff, B, nblk, t0, ntile, stage + (warp >> 2 & 3) * (kDepth * kStTile), (warp >> 2) % nblk,
+           (warp >> 2) / nblk, warp >> 2, 0, kDepth};
+    if (warp < kProdWarps)
+        for (int p = 0; p < kDepth; ++p) feed_issue(f, warp & 3, lane);
     // |max| of THIS CTA's rows of V: the fixed-point scale is per CTA (its partial sums are exact integers at that scale;
     // the reduction kernel converts each CTA's partial with the CTA's own power-of-two scale).  No grid-wide pass over V.
     {
@@ -392,8 +398,6 @@ enc_fwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
     if (warp < kProdWarps) {
         // ---------------- producers: widened genotype tiles (group g = warp / 4 handles tiles g, g + 4, ...) ----------------
         const int g = warp >> 2, wl = warp & 3;
-        Feed f{packed, pitch, rowoff, B, nblk, t0, ntile, stage + g * (kDepth * kStTile), g % nblk, g / nblk, g, 0, kDepth};
-        for (int p = 0; p < kDepth; ++p) feed_issue(f, wl, lane);
         int blk = g % nblk, slot = 0, phase = 1;
         for (int i = g; i < ntile; i += 4) {
             uint4 w[4];
@@ -907,9 +911,11 @@ struct EncBwdSmem {
 };
 
 // warps: 16 producers, 2 MMA issuers (issuer p owns stages 2p, 2p+1 and its own accumulator set, as in the forward), 4 epilogue
-constexpr int kBwdThreads = kProdThreads + 64 + 128;
-template <int NISS, bool RAW>   // NISS: MMA issuer warps in use (2, or 1: issuer 0 then issues both halves)
-__global__ void __launch_bounds__(kBwdThreads, 1)
+__host__ __device__ constexpr int bwd_threads(int EPW) { return kProdThreads + 64 + EPW * 32; }
+// NISS: MMA issuer warps in use (2, or 1: issuer 0 then issues both halves).  EPW: epilogue warps, 4 (one thread does both
+// 128-SNP halves of a sub-tile) or 8 (one half each: twice the loads of V / m / v in flight)
+template <int NISS, bool RAW, int EPW>
+__global__ void __launch_bounds__(bwd_threads(EPW), 1)
 enc_bwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* __restrict__ row_idx, int64_t row0,
                   int B, int64_t M, const float* __restrict__ dZ, int C, float* __restrict__ V, float* __restrict__ Vm,
                   float* __restrict__ Vv, AdamCoef adam_in, float* __restrict__ dV_out, int T, uint32_t mvx,
@@ -931,10 +937,16 @@ enc_bwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
         rowoff[b] = (uint32_t)((row_idx != nullptr) ? row_idx[b] : (row0 + b));
     if (tid == 0) {
         for (int s = 0; s < kAStages; ++s) { mbar_init(&S->fullA[s], 4); mbar_init(&S->emptyA[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&S->dfull[s], NISS); mbar_init(&S->dempty[s], 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&S->dfull[s], NISS); mbar_init(&S->dempty[s], EPW); }
         mbar_init_fence();
     }
     if (warp == kProdWarps) tmem_alloc<256>(&S->tmem_base);
+    __syncthreads();                                                // row numbers are in shared memory
+    // the producers' first copies are in flight while the digits of dZ are set up (they need the row numbers only)
+    Feed f{packed, pitch, rowoff, B, nblk, t0, ntile, stage + (warp >> 2 & 3) * (kStDepth * kStTile), (warp >> 2) % nblk,
+           (warp >> 2) / nblk, warp >> 2, 0, kStDepth};
+    if (warp < kProdWarps)
+        for (int p = 0; p < kStDepth; ++p) feed_issue(f, warp & 3, lane);
     // |max| of dZ over the batch (every CTA computes the same value)
     uint32_t mxb = 0u;
     if ((reinterpret_cast<uintptr_t>(dZ) & 15) == 0 && ((B * C) & 3) == 0) {
@@ -964,8 +976,6 @@ enc_bwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
     if (warp < kProdWarps) {
         // ---------------- producers: widened genotype tiles, order (sub-tile, block) ----------------
         const int g = warp >> 2, wl = warp & 3;
-        Feed f{packed, pitch, rowoff, B, nblk, t0, ntile, stage + g * (kStDepth * kStTile), g % nblk, g / nblk, g, 0, kStDepth};
-        for (int p = 0; p < kStDepth; ++p) feed_issue(f, wl, lane);
         int blk = g % nblk, slot = 0, phase = 1;
         for (int i = g; i < ntile; i += 4) {
             uint4 w[4];
@@ -1025,53 +1035,45 @@ enc_bwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
     } else {
         // ---------------- epilogue: digit planes -> dV -> Adam on V, one SNP per thread ----------------
         const int q = warp & 3;             // tensor-memory lane quadrant this warp may access (warp id % 4)
+        constexpr int kHalves = (EPW == 8) ? 1 : 2;                   // 128-SNP halves of a sub-tile per thread
+        const int hsel = (EPW == 8) ? ((warp - (kProdWarps + 2)) >> 2) : 0;
         for (int tt = 0; tt < t1 - t0; ++tt) {
             const int buf = tt & 1;
-            // The 128 epilogue threads move all of V / m / v (96 MB per launch) with 12 loads of 16 bytes in flight each:
-            // latency-bound, and the epilogue then paces the whole kernel (85 us with Adam against 60 without).  So the
-            // lines of the sub-tile TWO iterations ahead are pulled into L2 here (no registers held; requesting the current
-            // sub-tile's lines at this point came too late to matter: 88 us; loading them into registers spilled: 128 us).
-            if (adam.enabled && C == 8) {
-                const int tp = tt + (tt == 0 ? 0 : 2);               // iteration 0 also covers sub-tiles 0 and 1
-                for (int ta = tp; ta <= tt + 2 && ta < t1 - t0; ++ta) {
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int pos = q * 32 + lane;
-                        const int64_t m = (int64_t)(t0 + ta) * kSub + h * 128 + (pos & ~15) + sigma16(pos & 15);
-                        if (m < M) { prefetch_l2(V + m * 8); prefetch_l2(Vm + m * 8); prefetch_l2(Vv + m * 8); }
-                    }
-                }
-            }
+            // (measured and kept out, profiles/r2_*: with Adam this kernel takes 85 us against 60 without.  Requesting the
+            //  sub-tile's V / m / v ahead of the wait for its accumulators did not help — into registers: 128 us, the 48
+            //  extra live registers spill in this 704-thread kernel; as L2 prefetches, this or two sub-tiles ahead: 88 us.)
             if (warp == kProdWarps + 2) mbar_wait_relaxed(&S->dfull[buf], (tt >> 1) & 1, 64);   // one warp polls
-            named_bar_sync(1, 128);
+            named_bar_sync(1, EPW * 32);
             tc_fence_after_sync();
             // recombine the digit planes of each accumulator set right after loading it (int64, exact) and add the sets:
             // 32 live accumulator registers at a time instead of 96
-            long long z[2][8];
+            long long z[kHalves][8];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
+            for (int hi_ = 0; hi_ < kHalves; ++hi_) {
+                const int h = hsel + hi_;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) z[h][c] = 0;
+                for (int c = 0; c < 8; ++c) z[hi_][c] = 0;
 #pragma unroll
                 for (int set = 0; set < NISS; ++set) {
                     uint32_t v[32];
                     tmem_ld32(tbase + ((uint32_t)(q * 32) << 16) + (buf * NISS + set) * 64 + h * 32, v);
                     tmem_wait_ld();
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) z[h][c] += combine4(v, c);
+                    for (int c = 0; c < 8; ++c) z[hi_][c] += combine4(v, c);
                 }
             }
             tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&S->dempty[buf]);
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
+            for (int hi_ = 0; hi_ < kHalves; ++hi_) {
+                const int h = hsel + hi_;
                 const int pos = q * 32 + lane;
                 const int64_t m = (int64_t)(t0 + tt) * kSub + h * 128 + (pos & ~15) + sigma16(pos & 15);
                 if (m >= M) continue;
                 float g[8];
 #pragma unroll
-                for (int c = 0; c < 8; ++c) g[c] = (float)((double)z[h][c] * fs.back * out_scale);
+                for (int c = 0; c < 8; ++c) g[c] = (float)((double)z[hi_][c] * fs.back * out_scale);
                 if (C == 8) {
                     float4* gv = reinterpret_cast<float4*>(g);
                     if (dV_out != nullptr) {
@@ -1592,24 +1594,31 @@ int launch_enc_bwd_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_i
     static PerDeviceOnce once;
     bool* attr = once.slot();
     if (attr == nullptr || !*attr) {
-        cudaError_t e = cudaFuncSetAttribute(enc_bwd_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(enc_bwd_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(enc_bwd_tc_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(enc_bwd_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+        cudaError_t e = cudaSuccess;
+#define NADM_BWD_ATTR(N_, R_, E_)                                                                                      \
+    if (e == cudaSuccess)                                                                                              \
+        e = cudaFuncSetAttribute(enc_bwd_tc_kernel<N_, R_, E_>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)
+        NADM_BWD_ATTR(1, false, 4); NADM_BWD_ATTR(2, false, 4); NADM_BWD_ATTR(1, true, 4); NADM_BWD_ATTR(2, true, 4);
+        NADM_BWD_ATTR(1, false, 8); NADM_BWD_ATTR(2, false, 8); NADM_BWD_ATTR(1, true, 8); NADM_BWD_ATTR(2, true, 8);
+#undef NADM_BWD_ATTR
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(enc_bwd_tc)");
         if (attr) *attr = true;
     }
     const bool two = enc_issuers() == 2 && nblk >= 3;       // both issuers then have tiles in every sub-tile
     const uint32_t mvx = raw_mv >= 0 ? (3u ^ (uint32_t)(raw_mv & 0xFF)) : 0u;
     const double scale = raw_mv >= 0 ? 1.0 : 0.5;
-#define NADM_BWD_GO(N_, R_)                                                                                            \
-    launch_pdl(enc_bwd_tc_kernel<N_, R_>, dim3(ncta), dim3(kBwdThreads), smem, st, packed, pitch, row_idx, row0, B, M, dZ, C, \
-               V, Vm, Vv, make_adam(adam), dV_out, T, mvx, scale, accumulate)
-    if (raw_mv >= 0) { if (two) NADM_BWD_GO(2, true); else NADM_BWD_GO(1, true); }
-    else { if (two) NADM_BWD_GO(2, false); else NADM_BWD_GO(1, false); }
+    static int epw = 0;                                     // NADM_ENC_BWD_EPW=4|8: epilogue warps (A/B measurements)
+    if (epw == 0) {
+        const char* e = getenv("NADM_ENC_BWD_EPW");
+        epw = (e != nullptr && e[0] == '4') ? 4 : 8;      // default 8: 73 instead of 84 us with Adam (profiles/r2_*)
+    }
+#define NADM_BWD_GO(N_, R_, E_)                                                                                        \
+    launch_pdl(enc_bwd_tc_kernel<N_, R_, E_>, dim3(ncta), dim3(bwd_threads(E_)), smem, st, packed, pitch, row_idx, row0, B, M, \
+               dZ, C, V, Vm, Vv, make_adam(adam), dV_out, T, mvx, scale, accumulate)
+#define NADM_BWD_GO_E(N_, R_) do { if (epw == 8) NADM_BWD_GO(N_, R_, 8); else NADM_BWD_GO(N_, R_, 4); } while (0)
+    if (raw_mv >= 0) { if (two) NADM_BWD_GO_E(2, true); else NADM_BWD_GO_E(1, true); }
+    else { if (two) NADM_BWD_GO_E(2, false); else NADM_BWD_GO_E(1, false); }
+#undef NADM_BWD_GO_E
 #undef NADM_BWD_GO
     NADM_CHECK_LAUNCH("enc_bwd_tc_kernel");
     return NADM_OK;

