@@ -200,6 +200,11 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
     constexpr int kWGs = WGS, kWarpIssueA1 = 4 * WGS, kWarpIssueA2 = kWarpIssueA1 + 1, kWarpIssueB = kWarpIssueA1 + 2,
                   kWarpProd = kWarpIssueA1 + 3;
     constexpr int kSlots = SLOTS, kWarpIssue = kWarpIssueA1;
+    // unit u is decoded by warpgroup u % WGS in slot u % SLOTS; its wait for raw(u) tests the parity of the slot's phase
+    // u / SLOTS, which is only unambiguous if raw(u - SLOTS) is known to be complete: the warpgroup has seen raw(u - WGS),
+    // MMA1s complete in unit order, so WGS <= SLOTS is required (4 warpgroups over 3 slots: the fourth's first wait
+    // passes on the fresh barrier and it decodes the slot together with the first).
+    static_assert(WGS <= SLOTS, "compute warpgroups must not outnumber the raw / G slots");
     const AdamCoef adam = adam_resolve(adam_in);
     constexpr int ngt = SLOTS;   // one G^T tile per slot (see the issuer warps for why not more)
     constexpr int kND3 = (KH == 2) ? 1 : dec_nd3(SLOTS), kColD3 = 64 * SLOTS, kColD2 = kColD3 + 32 * kND3 * KH;
@@ -216,6 +221,7 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int s0 = (int)(((int64_t)TS * blockIdx.x) / gridDim.x), s1 = (int)(((int64_t)TS * (blockIdx.x + 1)) / gridDim.x);
     const int nsub = s1 - s0, U = nsub * nblk;
+    if (tid == 0) TL(0, 500);                                           // (timeline builds) kernel entry
 
     // ---------------- one-time setup: row offsets, Q operands, barriers, tensor memory ----------------
     for (int b = tid; b < nblk * 128; b += blockDim.x)
@@ -253,6 +259,7 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tbase = S->tmem_base;
+    if (tid == 0) TL(0, 501);                                           // setup done
 #ifdef NADM_KO_MMA   // knock-out measurement build: no tensor-core work; every raw value is 0.5 (decode-only timing)
     if (warp < 4) {
         uint32_t h[16];
@@ -356,14 +363,16 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
             blk = nblk_;
             sub = nsub_;
             slot += kWGs;
-            if (slot >= kSlots) { slot -= kSlots; ++uq; }
+            if (slot >= kSlots) { slot -= kSlots; ++uq; }              // (kWGs <= kSlots: wraps at most once)
         }
         // ---- loss partial of this CTA (log2 units -> nats), dQ partial from tensor memory ----
         float l = -(acc_hom + 0.5f * acc_het) * 0.6931471805599453f;
         l = warp_sum(l);
         if (lane == 0) S->lossred[warp] = l;
+        if (tid == 0) TL(0, 502);                                       // this warpgroup's units done
         mbar_wait(&S->alldone, 0);
         tc_fence_after_sync();
+        if (tid == 0) TL(0, 503);                                       // all MMA2s complete
         for (int blk = wg; blk < nblk; blk += kWGs) {
             uint32_t v[32];
             tmem_ld32(tlane + kColD2 + blk * 32, v);      // KH = 1: one 32-column accumulator; KH = 2: two of 16 columns
@@ -630,12 +639,14 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
             }
         }
     }
+    if (tid == 0) TL(0, 504);                                           // this warp's dQ partial written
     tc_fence_before_sync();
     __syncthreads();
     if (tid == 0) {
         float s = 0.f;
         for (int w = 0; w < kWarpIssue; ++w) s += S->lossred[w];
         loss_part[blockIdx.x] = s;
+        TL(0, 505);                                                     // every role done (incl. the last dP epilogue)
     }
     if (warp == kWarpIssue) tmem_dealloc<512>(tbase);
 }
@@ -725,12 +736,14 @@ int launch_dec_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_idx, 
                                     dP_out, dQpart, loss_part, TS)
 #define NADM_DEC_GO_WG(L, W, H)                                                                                        \
     do { if (wgs == 4) NADM_DEC_GO(L, W, 4, H); else NADM_DEC_GO(L, W, 3, H); } while (0)
+    // 3 slots always run 3 warpgroups: a fourth has no slot to work in, and a warpgroup's first mbarrier wait is only
+    // safe when the slot's previous phase is known to be over, i.e. WGS <= SLOTS (static_assert in the kernel).
     if (KH == 2) {
-        if (want_loss) NADM_DEC_GO_WG(true, 3, 2); else NADM_DEC_GO_WG(false, 3, 2);
+        if (want_loss) NADM_DEC_GO(true, 3, 3, 2); else NADM_DEC_GO(false, 3, 3, 2);
     } else if (slots == 4) {
         if (want_loss) NADM_DEC_GO_WG(true, 4, 1); else NADM_DEC_GO_WG(false, 4, 1);
     } else {
-        if (want_loss) NADM_DEC_GO_WG(true, 3, 1); else NADM_DEC_GO_WG(false, 3, 1);
+        if (want_loss) NADM_DEC_GO(true, 3, 3, 1); else NADM_DEC_GO(false, 3, 3, 1);
     }
 #undef NADM_DEC_GO_WG
 #undef NADM_DEC_GO

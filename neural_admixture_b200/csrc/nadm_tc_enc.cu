@@ -558,18 +558,20 @@ enc_fwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
 }
 
 // =================================================================================================================
-// forward, slab feed (the default): the same contraction as above, but the rows are streamed in 256-BYTE runs.
+// forward, slab feed (OPT-IN: NADM_ENC_FWD_SLAB=1; a measurement switch, not the default — see the end of this comment):
+// the same contraction as above, but the rows are streamed in 128- or 256-BYTE runs.
 //
-// Why: profiles/r2_gather_probe.txt.  Gathering B random sample rows out of HBM at 64 contiguous bytes per row and
-// request (one 256-SNP tile) reaches 2.1 TB/s whatever the depth, the tile order, the engine (cp.async, 1-D bulk copies,
-// TMA gather4) or an L2 prefetch hint; 128-byte runs reach 3.8 TB/s and 256-byte runs 4.5 TB/s (the same rows out of L2:
-// 5.2 TB/s).  The round-1 kernel's loads alone took 50 of its 64 us.  So a producer group now copies a SLAB = one row
-// block (128 rows) x 4 consecutive sub-tiles (1024 SNPs = 256 bytes per row) with one burst of cp.async instructions
-// whose lanes cover 2 rows x 256 contiguous bytes each, and then widens its four 256-SNP tiles out of it.
-// Tile order: slab column (4 sub-tiles) outer, row block, sub-tile inner; the accumulators of all row blocks stay in
-// tensor memory as before, four digit tiles (one slab column) are live and the next four are produced ahead.
+// Why it was built: profiles/r2_gather_probe.txt.  Gathering B random sample rows out of HBM at 64 contiguous bytes per
+// row and request (one 256-SNP tile) reaches 2.1 TB/s whatever the depth, the tile order, the engine (cp.async, 1-D bulk
+// copies, TMA gather4) or an L2 prefetch hint; 128-byte runs reach 3.8 TB/s and 256-byte runs 4.5 TB/s (the same rows out
+// of L2: 5.2 TB/s).  So a producer group copies a SLAB = one row block (128 rows) x kSlabSub consecutive sub-tiles with
+// one burst of cp.async instructions whose lanes cover contiguous runs of 64 kSlabSub bytes per row, and then widens its
+// 256-SNP tiles out of it.  Tile order: slab column outer, row block, sub-tile inner; the accumulators of all row blocks
+// stay in tensor memory as before, kSlabSub digit tiles (one slab column) are live and the next ones are produced ahead.
 // The genotype operand lives in tensor memory (TS form); widening leaves the 2-bit fields in place (4^j x code, j =
 // field index) and the digit operand of those K positions is built from V / 4^j, which removes the shifts.
+// What it measured (profiles/r2_encoder_slab_variants.txt): 59 vs 65 us alone, 0.4428 vs 0.4425 ms per step on the same
+// box, and -11 % on the forward-only Q pass (1024 instead of 2048 rows per launch) -> the round-1 kernel stays the default.
 // =================================================================================================================
 #ifndef NADM_SLAB_SUB
 #define NADM_SLAB_SUB 2
@@ -1122,8 +1124,9 @@ enc_bwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
 }
 
 // =================================================================================================================
-// backward, slab feed (the default): dV = X^T dZ + Adam with the rows streamed in 256-byte runs (see the forward slab
-// kernel for why).  The operand X^T must come from shared memory (SNPs on the M axis), so the widened stages stay
+// backward, slab feed (OPT-IN: NADM_ENC_BWD_SLAB=1; measured 82 vs 60 us for the kernel above — the half-tile stages
+// double the hand-overs —, kept as a measurement switch): dV = X^T dZ + Adam with the rows streamed in wide runs (see the
+// forward slab kernel for why).  The operand X^T must come from shared memory (SNPs on the M axis), so the widened stages stay
 // there — but as HALF tiles (128 rows x 128 SNPs, 16 KB) so that four 32 KB slabs fit beside them.  Order: slab column
 // (4 sub-tiles) outer, row block, sub-tile, half inner; the 4 x 2 accumulators (128 SNPs x 32 digit columns) of a
 // column are shared by both issuers (zero-initialised by the epilogue, every MMA accumulates: integer adds commute)

@@ -6,7 +6,7 @@ L.LIB_PATH = Path('/root/repo/neural_admixture_b200/csrc/' + (sys.argv[1] if len
 import torch
 from neural_admixture_b200 import ops
 dev = torch.device('cuda:0')
-N, M, k, B = 4000, 500000, 8, 800
+N, M, k, B = 4000, (int(sys.argv[2]) if len(sys.argv) > 2 else 500000), 8, 800
 gen = torch.Generator(device=dev).manual_seed(1)
 pg = ops.PackedGenotypes.empty(N, M, dev)
 for r0 in range(0, N, 500):
@@ -36,3 +36,6 @@ dec = (out[2][100:300] - out[1][100:300]).mean()
 wait = (out[1][100:300] - out[0][100:300]).mean()
 print(f"compute warpgroup: decode {dec:.0f} cycles/unit, wait for raw {wait:.0f} cycles/unit")
 print(f"issuer A: wait for G {(out[4][100:300] - out[3][100:300]).mean():.0f}, issue {(out[5][100:300] - out[4][100:300]).mean():.0f} cycles/unit")
+ph = out[0][500:506]
+print("phases (cycles): setup", int(ph[1] - ph[0]), " units of warpgroup 0", int(ph[2] - ph[1]), " wait for the last MMA2", int(ph[3] - ph[2]),
+      " dQ partial", int(ph[4] - ph[3]), " tail (last dP epilogue, sync)", int(ph[5] - ph[4]), " total", int(ph[5] - ph[0]))

@@ -6,7 +6,7 @@ L.LIB_PATH = Path('/root/repo/neural_admixture_b200/csrc') / (sys.argv[1] if len
 import torch
 from neural_admixture_b200 import ops
 dev = torch.device('cuda:0')
-N, M, C, B = 4000, 500000, 8, 800
+N, M, C, B = 4000, (int(sys.argv[2]) if len(sys.argv) > 2 else 500000), 8, 800
 gen = torch.Generator(device=dev).manual_seed(1)
 pg = ops.PackedGenotypes.empty(N, M, dev)
 for r0 in range(0, N, 500):
