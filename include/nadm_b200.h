@@ -196,6 +196,16 @@ int nadm_flip_packed(uint8_t* packed, int64_t pitch, int64_t N, int64_t M, void*
 int nadm_step_begin(const int64_t* order, int64_t order_len, int64_t* counters, int64_t stride, int32_t B,
                     int64_t* row_idx_out, const nadm_adam_t* hyper, void* coef_out, float* loss_accum, void* stream);
 int nadm_step_end(int64_t* counters, const float* loss, float* losses_out, void* stream);
+/* One bookkeeping kernel per replayed step instead of two.  counters: 4 x int64 (zero-initialised): [0], [1] as above,
+ * [2] = a step is pending, [3] = device address of the pending step's loss accumulator (0: its loss is not recorded).
+ * nadm_step_next: if a step is pending, finish it as nadm_step_end would (losses_out[counters[0]] = its loss when
+ *   recorded, both counters += 1); then begin the next one as nadm_step_begin would and leave it pending
+ *   (record_loss != 0: its loss accumulator is remembered for the following nadm_step_next / nadm_step_flush).
+ * nadm_step_flush: finish the pending step, if any (after the last replay of a run of steps). */
+int nadm_step_next(const int64_t* order, int64_t order_len, int64_t* counters, int64_t stride, int32_t B,
+                   int64_t* row_idx_out, const nadm_adam_t* hyper, void* coef_out, float* loss_accum,
+                   int32_t record_loss, float* losses_out, void* stream);
+int nadm_step_flush(int64_t* counters, float* losses_out, void* stream);
 
 /* ---- randomized-SVD products on the packed matrix ("next" row f2).  Replace multiply_A_omega / multiply_QT_A
  * (src/utils_c/rsvd.pyx:16-50, driven by src/svd.py:49-71): naive OpenMP triple loops over the N x M uint8 matrix.

@@ -72,6 +72,9 @@ SIGNATURES = {
     "nadm_step_begin": (C.c_int, [c_i64p, C.c_int64, c_i64p, C.c_int64, C.c_int32, c_i64p, C.POINTER(AdamHyper),
                                   C.c_void_p, c_f32p, C.c_void_p]),
     "nadm_step_end": (C.c_int, [c_i64p, c_f32p, c_f32p, C.c_void_p]),
+    "nadm_step_next": (C.c_int, [c_i64p, C.c_int64, c_i64p, C.c_int64, C.c_int32, c_i64p, C.POINTER(AdamHyper),
+                                 C.c_void_p, c_f32p, C.c_int32, c_f32p, C.c_void_p]),
+    "nadm_step_flush": (C.c_int, [c_i64p, c_f32p, C.c_void_p]),
     "nadm_geno_matmul": (C.c_int, [c_u8p, C.c_int64, C.c_int64, C.c_int64, c_f32p, C.c_int32, C.c_int32, c_f32p,
                                    C.c_void_p, C.c_size_t, C.c_void_p]),
     "nadm_geno_matmul_t": (C.c_int, [c_u8p, C.c_int64, C.c_int64, C.c_int64, c_f32p, C.c_int32, C.c_int32, c_f32p,

@@ -78,6 +78,70 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// ---- grid-wide barrier for the persistent kernels (one CTA per SM, grid <= SM count): OPT-IN, NADM_GRIDBAR=1 --------
+// The tensor-core kernels end with a sum over their CTAs' partial results, done by a separate small kernel.  The
+// experiment behind this switch: the CTAs meet at a barrier after writing their partials and each reduces its share of
+// the outputs out of L2, saving a launch.  MEASURED (profiles/r2_gridbar_ab.txt, clock64 phases of CTA 0): the barrier
+// costs 13-17 k cycles (the __threadfence() after 51 KB of partials + waiting for the slowest CTA), the share another
+// 8-13 k (three dependent round trips to L2 at ~1.3 us each) = 11-15 us against 5-6 us for the separate kernel, whose
+// 200 k threads do everything in one round trip: the step was 10 us SLOWER at both M = 500k and M = 62.5k.  Kept as a
+// switch so that the result can be reproduced.
+// Safe: the grid is launched with cudaLaunchAttributeCooperative (launch_coop below: the launch FAILS if the CTAs
+// cannot all be resident, it cannot deadlock), self-resetting (count returns to 0, the generation only grows: replayable
+// inside a CUDA graph without a memset node), bounded (a CTA that never arrives -> __trap() after ~seconds).  The two
+// words live in a __device__ global of the library (zero at module load, one copy per device); kernels that use the
+// same GridBar must not run concurrently on one device (stream order guarantees it for one caller per device, which
+// is the ABI's convention).
+struct GridBar { unsigned int count, gen; };
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu_u32(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// All threads of every CTA of the grid call this; global writes made by any thread before it are visible to every thread
+// after it (read them with ld.global.cg: L1 is not coherent).
+__device__ __forceinline__ void grid_barrier(GridBar* b, unsigned int nctas) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int gen0 = ld_acquire_gpu_u32(&b->gen);        // cannot advance before this CTA has arrived
+        __threadfence();
+        if (atomicAdd(&b->count, 1u) == nctas - 1u) {
+            atomicExch(&b->count, 0u);
+            __threadfence();
+            st_release_gpu_u32(&b->gen, gen0 + 1u);
+        } else {
+            unsigned int polls = 0;
+            while (ld_acquire_gpu_u32(&b->gen) == gen0) {
+                __nanosleep(64);
+                if (++polls > (1u << 25)) __trap();
+            }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+#endif
+// launch with the cooperative attribute (co-residency of the whole grid checked by the driver); never PDL
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_coop(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+bool gridbar_enabled();   // NADM_GRIDBAR=1: in-kernel reductions behind a grid barrier (A/B measurements; slower)
+
 // ---- tiling constants shared by kernels and the workspace query --------------------------------------------------
 constexpr int kMaxParts = 640;        // upper bound on per-CTA partial slabs (encoder slabs / decoder CTAs)
 constexpr int kStreamWarps = 8;       // warps per CTA in the lane<->byte streaming kernels

@@ -51,6 +51,15 @@ bool pdl_enabled() {   // opt-in (NADM_PDL=1): see nadm_common.cuh
     return v == 1;
 }
 
+bool gridbar_enabled() {   // opt-in (NADM_GRIDBAR=1): measured SLOWER than the separate reduction kernels, see nadm_common.cuh
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("NADM_GRIDBAR");
+        v = (e != nullptr && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
+
 bool use_generic_kernels() {
     static int cached = -1;
     if (cached < 0) {
@@ -166,62 +175,95 @@ static int make_xchg(const nadm_xchg_t* in, long long need_floats, int nctas, Xc
 // =================================================================================================================
 // forward
 // =================================================================================================================
+// Latency is what this kernel costs (10 us for 26 MFLOP): every phase used to start with a round trip to L2.  The
+// weights a thread needs first are therefore requested before anything that waits (the peer exchange, the RMSNorm), the
+// RMSNorm runs on 16 lanes per row, and a warp's logit column sits in registers (H = 1024: 32 values per lane).
 __global__ void __launch_bounds__(kMlpThreads)
 mlp_fwd_kernel(float* Z, int B, int C, int H, const float* __restrict__ w_rms,
                const float* __restrict__ W1, const float* __restrict__ b1, const float* __restrict__ W2,
                const float* __restrict__ b2, Heads hd, float* __restrict__ rinv_out, float* __restrict__ Hh,
                float* __restrict__ Q, Xchg xc) {
     pdl_prologue();
-    if (xc.world > 1) {   // sum the ranks' partial projections of this CTA's rows (in place)
-        const int r0 = blockIdx.x * kMlpRows;
-        xchg_allreduce_cta(xc, 0, Z, (long long)r0 * C, min(kMlpRows, B - r0) * C, nullptr, 0);
-    }
     extern __shared__ __align__(16) float sm[];
     float* Zn = sm;                         // kMlpRows x C
     float* Hs = Zn + kMlpRows * NADM_MAX_C;  // kMlpRows x H
     float* Ls = Hs + (size_t)kMlpRows * H;   // kMlpRows x sumK
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b0 = blockIdx.x * kMlpRows;
-
-    if (tid < kMlpRows) {
-        const int b = b0 + tid;
-        if (b < B) {
-            float ss = 0.f;
-            for (int c = 0; c < C; ++c) { float z = Z[(int64_t)b * C + c]; ss = fmaf(z, z, ss); }
-            const float r = 1.0f / sqrtf(ss / (float)C + 1e-8f);  // torch.nn.RMSNorm(C, eps=1e-8)
-            rinv_out[b] = r;
-            for (int c = 0; c < C; ++c) Zn[tid * NADM_MAX_C + c] = Z[(int64_t)b * C + c] * r * w_rms[c];
-        } else {
-            for (int c = 0; c < C; ++c) Zn[tid * NADM_MAX_C + c] = 0.f;
+    constexpr int kPre = 4;                  // hidden units per thread held in registers (H <= 1024)
+    const bool pre1 = (C == 8) && (H <= kPre * kMlpThreads);
+    const bool pre2 = (H == 32 * 32) && (warp < hd.sumK);
+    float4 wa[kPre], wb[kPre];
+    float bj[kPre], w2r[32];
+    if (pre1) {
+#pragma unroll
+        for (int i = 0; i < kPre; ++i) {
+            const int j = tid + i * kMlpThreads;
+            if (j < H) {
+                wa[i] = reinterpret_cast<const float4*>(W1 + (int64_t)j * 8)[0];
+                wb[i] = reinterpret_cast<const float4*>(W1 + (int64_t)j * 8)[1];
+                bj[i] = b1[j];
+            }
         }
     }
+    if (pre2) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) w2r[i] = W2[(int64_t)warp * H + lane + 32 * i];
+    }
+    if (xc.world > 1)   // sum the ranks' partial projections of this CTA's rows (in place)
+        xchg_allreduce_cta(xc, 0, Z, (long long)b0 * C, min(kMlpRows, B - b0) * C, nullptr, 0);
+
+    if (tid < kMlpRows * 16) {               // RMSNorm: 16 lanes per row (whole warps: full-mask shuffles)
+        const int r = tid >> 4, c = tid & 15, b = b0 + r;
+        const bool ok = (b < B) && (c < C);
+        const float z = ok ? Z[(int64_t)b * C + c] : 0.f;
+        float ss = z * z;
+#pragma unroll
+        for (int o = 8; o >= 1; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        const float rr = 1.0f / sqrtf(ss / (float)C + 1e-8f);  // torch.nn.RMSNorm(C, eps=1e-8)
+        if (c == 0 && b < B) rinv_out[b] = rr;
+        if (c < C) Zn[r * NADM_MAX_C + c] = ok ? z * rr * w_rms[c] : 0.f;
+    }
     __syncthreads();
+    if (pre1) {
+#pragma unroll
+        for (int i = 0; i < kPre; ++i) {
+            const int j = tid + i * kMlpThreads;
+            if (j < H) {
+                const float w[8] = {wa[i].x, wa[i].y, wa[i].z, wa[i].w, wb[i].x, wb[i].y, wb[i].z, wb[i].w};
+                float acc[kMlpRows];
+#pragma unroll
+                for (int r = 0; r < kMlpRows; ++r) acc[r] = bj[i];
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+#pragma unroll
+                    for (int r = 0; r < kMlpRows; ++r) acc[r] = fmaf(Zn[r * NADM_MAX_C + c], w[c], acc[r]);
+#pragma unroll
+                for (int r = 0; r < kMlpRows; ++r) {
+                    const float h = fmaxf(acc[r], 0.f);
+                    Hs[(size_t)r * H + j] = h;
+                    if (b0 + r < B) Hh[(int64_t)(b0 + r) * H + j] = h;
+                }
+            }
+        }
+    } else {
 #pragma unroll 4
-    for (int j = tid; j < H; j += blockDim.x) {
-        float acc[kMlpRows];
-        const float bj = b1[j];
+        for (int j = tid; j < H; j += blockDim.x) {
+            float acc[kMlpRows];
+            const float bjj = b1[j];
 #pragma unroll
-        for (int r = 0; r < kMlpRows; ++r) acc[r] = bj;
-        if (C == 8) {                                   // the default width: two 128-bit loads per hidden unit
-            const float4 wa = reinterpret_cast<const float4*>(W1 + (int64_t)j * 8)[0];
-            const float4 wb = reinterpret_cast<const float4*>(W1 + (int64_t)j * 8)[1];
-            const float w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-#pragma unroll
-            for (int c = 0; c < 8; ++c)
-#pragma unroll
-                for (int r = 0; r < kMlpRows; ++r) acc[r] = fmaf(Zn[r * NADM_MAX_C + c], w[c], acc[r]);
-        } else {
+            for (int r = 0; r < kMlpRows; ++r) acc[r] = bjj;
             for (int c = 0; c < C; ++c) {
                 const float w = W1[(int64_t)j * C + c];
 #pragma unroll
                 for (int r = 0; r < kMlpRows; ++r) acc[r] = fmaf(Zn[r * NADM_MAX_C + c], w, acc[r]);
             }
-        }
 #pragma unroll
-        for (int r = 0; r < kMlpRows; ++r) {
-            const float h = fmaxf(acc[r], 0.f);
-            Hs[(size_t)r * H + j] = h;
-            if (b0 + r < B) Hh[(int64_t)(b0 + r) * H + j] = h;
+            for (int r = 0; r < kMlpRows; ++r) {
+                const float h = fmaxf(acc[r], 0.f);
+                Hs[(size_t)r * H + j] = h;
+                if (b0 + r < B) Hh[(int64_t)(b0 + r) * H + j] = h;
+            }
         }
     }
     __syncthreads();
@@ -230,11 +272,18 @@ mlp_fwd_kernel(float* Z, int B, int C, int H, const float* __restrict__ w_rms,
         float acc[kMlpRows];
 #pragma unroll
         for (int r = 0; r < kMlpRows; ++r) acc[r] = 0.f;
-#pragma unroll 8
-        for (int j = lane; j < H; j += 32) {
-            const float w = W2[(int64_t)kk * H + j];
+        if (pre2 && kk == warp) {
 #pragma unroll
-            for (int r = 0; r < kMlpRows; ++r) acc[r] = fmaf(Hs[(size_t)r * H + j], w, acc[r]);
+            for (int i = 0; i < 32; ++i)
+#pragma unroll
+                for (int r = 0; r < kMlpRows; ++r) acc[r] = fmaf(Hs[(size_t)r * H + lane + 32 * i], w2r[i], acc[r]);
+        } else {
+#pragma unroll 8
+            for (int j = lane; j < H; j += 32) {
+                const float w = W2[(int64_t)kk * H + j];
+#pragma unroll
+                for (int r = 0; r < kMlpRows; ++r) acc[r] = fmaf(Hs[(size_t)r * H + j], w, acc[r]);
+            }
         }
 #pragma unroll
         for (int r = 0; r < kMlpRows; ++r) {
@@ -290,10 +339,23 @@ mlp_bwd_rows_kernel(float* dQ, const float* __restrict__ Q, const float* __restr
     float* Zn = dLs + (size_t)kBwdRows * hd.sumK;             // kBwdRows x MAX_C   (normalised inputs, recomputed)
     float* red = Zn + kBwdRows * CP;                  // nwarps x kBwdRows x MAX_C  (dZn partials per warp)
     float* sups = red + (kMlpThreads / 32) * kBwdRows * CP;   // kBwdRows
+    float* qs = sups + kBwdRows;                              // kBwdRows x sumK : the rows' Q
+    float* dqs = qs + (size_t)kBwdRows * hd.sumK;             // kBwdRows x sumK : the rows' dQ
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b0 = blockIdx.x * kBwdRows;
     const int sumK = hd.sumK;
     float* slab = part + (size_t)blockIdx.x * mlp_slab_floats(C, H, sumK);
+
+    // the rows' Q and dQ (one contiguous block each) into shared memory with ONE round of coalesced loads: the
+    // per-(row, head) threads below used to walk them with k dependent round trips to L2 each
+    {
+        const int nvalid = min(kBwdRows, B - b0) * sumK;
+        for (int i = tid; i < kBwdRows * sumK; i += blockDim.x) {
+            qs[i] = (i < nvalid) ? Q[(int64_t)b0 * sumK + i] : 0.f;
+            dqs[i] = (i < nvalid) ? dQ[(int64_t)b0 * sumK + i] : 0.f;
+        }
+    }
+    __syncthreads();
 
     // ---- softmax backward per (row, head); the supervised cross-entropy acts on head 0 only ----
     for (int i = tid; i < kBwdRows * hd.n; i += blockDim.x) {
@@ -306,8 +368,8 @@ mlp_bwd_rows_kernel(float* dQ, const float* __restrict__ Q, const float* __restr
             for (int kk = 0; kk < k; ++kk) out[kk] = 0.f;
             continue;
         }
-        const float* q = Q + (int64_t)b * sumK + off;
-        const float* dq = dQ + (int64_t)b * sumK + off;
+        const float* q = qs + r * sumK + off;
+        const float* dq = dqs + r * sumK + off;
         const bool sup = (labels != nullptr) && (h == 0);
         float mx = 0.f, lse = 0.f;
         int y = 0;
@@ -599,8 +661,19 @@ extern "C" int nadm_mlp_bwd(float* dQ, const float* Q, const float* Hh, const fl
     float* gpart = (float*)ws;
     cudaStream_t st = (cudaStream_t)stream;
     const int CP = C <= 8 ? 8 : 16;
-    const size_t smem = ((size_t)kBwdRows * hd.sumK + (size_t)kBwdRows * CP +
+    const size_t smem = ((size_t)3 * kBwdRows * hd.sumK + (size_t)kBwdRows * CP +
                          (size_t)(kMlpThreads / 32) * kBwdRows * CP + kBwdRows) * sizeof(float);
+    if (smem > 48 * 1024) {                          // very wide head sets only (sumK > ~480)
+        static PerDeviceOnce once_b;
+        bool* ab = once_b.slot();
+        if (ab == nullptr || !*ab) {
+            cudaError_t e = cudaFuncSetAttribute(mlp_bwd_rows_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+            if (e == cudaSuccess)
+                e = cudaFuncSetAttribute(mlp_bwd_rows_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(mlp_bwd_rows)");
+            if (ab) *ab = true;
+        }
+    }
     if (CP == 8)
         launch_pdl(mlp_bwd_rows_kernel<8>, dim3(nslab), dim3(kMlpThreads), smem, st, dQ, Q, Hh, Z, rinv, B, C, H, hd, labels,
                    sup_weight, p.w_rms, p.W1, p.W2, gpart, dZ, loss, xc);

@@ -570,7 +570,80 @@ __global__ void step_end_kernel(int64_t* __restrict__ counters, const float* __r
     counters[0] = s + 1;
     counters[1] += 1;
 }
+// nadm_step_next: finish the pending step (if any), then begin the next one and leave it pending: ONE bookkeeping kernel
+// per replayed step instead of two.  Single CTA (the counters are read, then written, by the same block).
+__device__ __forceinline__ void step_finish_pending(int64_t* counters, float* losses_out) {
+    if (counters[2] != 0) {
+        const float* lp = reinterpret_cast<const float*>(static_cast<uintptr_t>(counters[3]));
+        if (lp != nullptr && losses_out != nullptr) losses_out[counters[0]] = *lp;
+        counters[0] += 1;
+        counters[1] += 1;
+        counters[2] = 0;
+    }
+}
+__global__ void __launch_bounds__(256)
+step_next_kernel(const int64_t* __restrict__ order, int64_t order_len, int64_t* counters, int64_t stride, int B,
+                 int64_t* __restrict__ row_idx_out, float lr, float beta1, float beta2, float eps,
+                 float* __restrict__ coef_out, float* loss_accum, int record_loss, float* losses_out) {
+    pdl_prologue();
+    // every thread reads the counters BEFORE thread 0 rewrites them (one round trip instead of finish -> sync -> begin)
+    const int64_t c0 = counters[0], c1 = counters[1], pend = counters[2], lptr = counters[3];
+    __syncthreads();
+    const int64_t s = c0 + (pend != 0 ? 1 : 0), steps_done = c1 + (pend != 0 ? 1 : 0);
+    for (int i = threadIdx.x; i < B; i += blockDim.x) {
+        const int64_t j = s * stride + i;
+        row_idx_out[i] = (j < order_len) ? order[j] : 0;
+    }
+    if (threadIdx.x == 0) {
+        if (pend != 0) {                                                  // finish the pending step (= nadm_step_end)
+            const float* lp = reinterpret_cast<const float*>(static_cast<uintptr_t>(lptr));
+            if (lp != nullptr && losses_out != nullptr) losses_out[c0] = *lp;
+        }
+        if (loss_accum != nullptr) *loss_accum = 0.f;                     // (after the read above: it may be the same word)
+        counters[0] = s;
+        counters[1] = steps_done;
+        counters[2] = 1;
+        counters[3] = record_loss ? (int64_t)reinterpret_cast<uintptr_t>(loss_accum) : 0;
+    }
+    if (threadIdx.x == 32) {
+        const double t = (double)(steps_done + 1);
+        const double bc1 = 1.0 - pow((double)beta1, t), bc2 = 1.0 - pow((double)beta2, t);
+        coef_out[0] = beta1;
+        coef_out[1] = beta2;
+        coef_out[2] = 1.0f - beta1;
+        coef_out[3] = 1.0f - beta2;
+        coef_out[4] = (float)((double)lr / bc1);
+        coef_out[5] = (float)(1.0 / sqrt(bc2));
+        coef_out[6] = eps;
+        reinterpret_cast<int*>(coef_out)[7] = 1;
+    }
+}
+__global__ void step_flush_kernel(int64_t* counters, float* losses_out) {
+    pdl_prologue();
+    step_finish_pending(counters, losses_out);
+}
 }  // namespace nadm
+
+extern "C" int nadm_step_next(const int64_t* order, int64_t order_len, int64_t* counters, int64_t stride, int32_t B,
+                              int64_t* row_idx_out, const nadm_adam_t* hyper, void* coef_out, float* loss_accum,
+                              int32_t record_loss, float* losses_out, void* stream) {
+    NADM_REQUIRE(order && counters && row_idx_out && hyper && coef_out, "NULL pointer");
+    NADM_REQUIRE(B > 0 && stride >= B && order_len > 0, "bad minibatch geometry (B=%d, stride=%lld)", B, (long long)stride);
+    NADM_REQUIRE(((uintptr_t)coef_out & 15) == 0, "coef_out must be 16-byte aligned");
+    NADM_REQUIRE(!record_loss || loss_accum != nullptr, "record_loss needs a loss accumulator");
+    nadm::launch_pdl(nadm::step_next_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, order, order_len, counters, stride, B,
+                     row_idx_out, hyper->lr, hyper->beta1, hyper->beta2, hyper->eps, (float*)coef_out, loss_accum,
+                     (int)record_loss, losses_out);
+    NADM_CHECK_LAUNCH("step_next_kernel");
+    return NADM_OK;
+}
+
+extern "C" int nadm_step_flush(int64_t* counters, float* losses_out, void* stream) {
+    NADM_REQUIRE(counters, "NULL pointer");
+    nadm::launch_pdl(nadm::step_flush_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, counters, losses_out);
+    NADM_CHECK_LAUNCH("step_flush_kernel");
+    return NADM_OK;
+}
 
 extern "C" int nadm_step_begin(const int64_t* order, int64_t order_len, int64_t* counters, int64_t stride, int32_t B,
                                int64_t* row_idx_out, const nadm_adam_t* hyper, void* coef_out, float* loss_accum,

@@ -190,12 +190,17 @@ __device__ __forceinline__ void decode16_fast(const uint32_t (&v)[16], const flo
     }
 }
 
+__device__ GridBar g_bar_dec;
+
 template <bool kLoss, int SLOTS, int WGS, int KH>
 __global__ void __launch_bounds__(dec_threads(WGS), 1)
 dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* __restrict__ row_idx, int64_t row0, int B,
               int64_t M, const float* __restrict__ Q, int q_ld, int q_off, int k, float* __restrict__ P,
               float* __restrict__ Pm, float* __restrict__ Pv, AdamCoef adam_in, float* __restrict__ dP_out,
-              float* __restrict__ dQpart, float* __restrict__ loss_part, int TS) {
+              float* __restrict__ dQpart, float* __restrict__ loss_part, int TS, float* __restrict__ dQ_out,
+              float* __restrict__ loss_out) {
+    // dQ_out != NULL: the CTAs meet at a grid barrier after writing their partials and reduce them themselves
+    // (cooperative launch; loss_out += the summed loss); dQ_out == NULL: a separate reduce_parts_kernel follows.
     pdl_prologue();
     constexpr int kWGs = WGS, kWarpIssueA1 = 4 * WGS, kWarpIssueA2 = kWarpIssueA1 + 1, kWarpIssueB = kWarpIssueA1 + 2,
                   kWarpProd = kWarpIssueA1 + 3;
@@ -649,6 +654,55 @@ dec_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* 
         TL(0, 505);                                                     // every role done (incl. the last dP epilogue)
     }
     if (warp == kWarpIssue) tmem_dealloc<512>(tbase);
+    if (dQ_out != nullptr) {
+        // ---- fused reduction of the CTAs' dQ partials: this CTA sums outputs [n cta / nctas, n (cta + 1) / nctas) over all
+        // CTAs (deterministic) ----
+        grid_barrier(&g_bar_dec, gridDim.x);
+        if (tid == 0) TL(0, 506);
+        // Latency-bound: a work item = (output, one of 16 interleaved segments of the parts) holds all its loads in
+        // flight (<= 10 for 148 CTAs); segment sums are combined in a fixed order.
+        float* red = reinterpret_cast<float*>(GT);                      // (the G^T tiles are idle now)
+        const int nparts = (int)gridDim.x, colsp = 8 * KH, nthr = (int)blockDim.x;
+        const int64_t n = (int64_t)B * colsp;
+        const int o0 = (int)((n * blockIdx.x) / gridDim.x), o1 = (int)((n * (blockIdx.x + 1)) / gridDim.x);
+        for (int c0 = o0; c0 < o1; c0 += 128) {
+            const int cnt = min(128, o1 - c0);
+            for (int w = tid; w < cnt * 16; w += nthr) {
+                const int o = c0 + (w >> 4), seg = w & 15;
+                const float* src = dQpart + o;
+                float acc = 0.f;
+                if (nparts <= 160) {
+                    float v[10];
+#pragma unroll
+                    for (int i = 0; i < 10; ++i) {
+                        const int p = seg + 16 * i;
+                        v[i] = (p < nparts) ? __ldcg(src + (int64_t)p * n) : 0.f;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 10; ++i) acc += v[i];
+                } else {
+                    for (int p = seg; p < nparts; p += 16) acc += __ldcg(src + (int64_t)p * n);
+                }
+                red[w] = acc;
+            }
+            __syncthreads();
+            for (int w = tid; w < cnt; w += nthr) {
+                const int o = c0 + w, r = o / colsp, c = o - r * colsp;
+                float t = 0.f;
+#pragma unroll
+                for (int sg = 0; sg < 16; ++sg) t += red[16 * w + sg];
+                if (c < k) dQ_out[(int64_t)r * q_ld + q_off + c] = t;
+            }
+            __syncthreads();
+        }
+        if (kLoss && loss_out != nullptr && blockIdx.x == 0 && warp == 0) {
+            double acc2 = 0.0;
+            for (int q = lane; q < nparts; q += 32) acc2 += (double)__ldcg(loss_part + q);
+            acc2 = warp_sum_d(acc2);
+            if (lane == 0) *loss_out = (float)((double)*loss_out + acc2);
+        }
+        if (tid == 0) TL(0, 507);
+    }
 }
 
 // =================================================================================================================
@@ -673,7 +727,7 @@ template <bool kLoss, int SLOTS, int WGS, int KH>
 static int dec_launch_one(int ncta, size_t smem, cudaStream_t st, const uint8_t* packed, int64_t pitch,
                           const int64_t* row_idx, int64_t row0, int B, int64_t M, const float* Q, int q_ld, int q_off,
                           int k, float* P, float* Pm, float* Pv, const AdamCoef& adam, float* dP_out, float* dQpart,
-                          float* loss_part, int TS) {
+                          float* loss_part, int TS, float* dQ_out, float* loss_out) {
     static PerDeviceOnce once;                       // one per template instantiation
     bool* attr = once.slot();
     if (attr == nullptr || !*attr) {
@@ -682,8 +736,14 @@ static int dec_launch_one(int ncta, size_t smem, cudaStream_t st, const uint8_t*
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(dec_tc)");
         if (attr) *attr = true;
     }
-    launch_pdl(dec_tc_kernel<kLoss, SLOTS, WGS, KH>, dim3(ncta), dim3(dec_threads(WGS)), smem, st, packed, pitch, row_idx, row0, B, M, Q, q_ld,
-               q_off, k, P, Pm, Pv, adam, dP_out, dQpart, loss_part, TS);
+    cudaError_t le;
+    if (dQ_out != nullptr)   // fused reduction behind a grid barrier: cooperative launch
+        le = launch_coop(dec_tc_kernel<kLoss, SLOTS, WGS, KH>, dim3(ncta), dim3(dec_threads(WGS)), smem, st, packed, pitch, row_idx,
+                         row0, B, M, Q, q_ld, q_off, k, P, Pm, Pv, adam, dP_out, dQpart, loss_part, TS, dQ_out, loss_out);
+    else
+        le = launch_pdl(dec_tc_kernel<kLoss, SLOTS, WGS, KH>, dim3(ncta), dim3(dec_threads(WGS)), smem, st, packed, pitch, row_idx,
+                        row0, B, M, Q, q_ld, q_off, k, P, Pm, Pv, adam, dP_out, dQpart, loss_part, TS, dQ_out, loss_out);
+    if (le != cudaSuccess) return cuda_fail(le, "dec_tc_kernel");
     NADM_CHECK_LAUNCH("dec_tc_kernel");
     return NADM_OK;
 }
@@ -731,9 +791,10 @@ int launch_dec_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_idx, 
     const AdamCoef ac = make_adam(adam);
     int rc;
     const int wgs = dec_pick_wgs(want_loss);
+    const bool fused = gridbar_enabled();          // the CTAs sum their dQ partials themselves (opt-in, NADM_GRIDBAR=1)
 #define NADM_DEC_GO(L, W, G, H)                                                                                        \
     rc = dec_launch_one<L, W, G, H>(ncta, smem, st, packed, pitch, row_idx, row0, B, M, Q, q_ld, q_off, k, P, Pm, Pv, ac, \
-                                    dP_out, dQpart, loss_part, TS)
+                                    dP_out, dQpart, loss_part, TS, fused ? dQ : nullptr, fused ? loss : nullptr)
 #define NADM_DEC_GO_WG(L, W, H)                                                                                        \
     do { if (wgs == 4) NADM_DEC_GO(L, W, 4, H); else NADM_DEC_GO(L, W, 3, H); } while (0)
     // 3 slots always run 3 warpgroups: a fourth has no slot to work in, and a warpgroup's first mbarrier wait is only
@@ -747,7 +808,7 @@ int launch_dec_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_idx, 
     }
 #undef NADM_DEC_GO_WG
 #undef NADM_DEC_GO
-    if (rc != NADM_OK) return rc;
+    if (rc != NADM_OK || fused) return rc;
     return launch_reduce_parts(dQpart, ncta, B, 8 * KH, k, dQ, q_ld, q_off, 1.0f, want_loss ? loss_part : nullptr, loss, st);
 }
 

@@ -295,6 +295,59 @@ extern "C" int nadm_debug_enc_timeline(long long* host_out) {
 #define TLE(row, idx) do { } while (0)
 #endif
 
+constexpr int kZredOut = 64, kZredSeg = 16;   // outputs per chunk x part segments per output (1024 work items per chunk)
+__device__ GridBar g_bar_enc_fwd;
+
+// After the grid barrier: Z[b, c] = out_scale * sum over CTAs p of part_p[b, c] * 2^(e_p - 30).  Every CTA's partial is an
+// exact integer at the CTA's own power-of-two scale (exactly representable in double, as is the product); the CTAs are
+// summed in double in a fixed order (deterministic).  This CTA takes outputs [n cta / nctas, n (cta + 1) / nctas).
+// Latency-bound: a work item = (output, segment of the parts) holds all its loads in flight at once (<= 10 for 148
+// CTAs); with 4 segments of 37 dependent-looking loads the fused reduction was slower than the kernel it replaced.
+__device__ __forceinline__ void enc_fwd_reduce_share(const long long* __restrict__ part, const float* __restrict__ cta_vmax,
+                                                     int nparts, int B, int C, float* __restrict__ Z, double out_scale,
+                                                     double* back /* shared: nparts doubles */, double* zred /* shared */) {
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    for (int p = tid; p < nparts; p += nthr) back[p] = fix_scale(__ldcg(cta_vmax + p)).back;
+    __syncthreads();
+    const int64_t n = (int64_t)B * 8;
+    const int o0 = (int)((n * blockIdx.x) / gridDim.x), o1 = (int)((n * (blockIdx.x + 1)) / gridDim.x);
+    for (int c0 = o0; c0 < o1; c0 += kZredOut) {
+        const int cnt = min(kZredOut, o1 - c0);
+        for (int w = tid; w < cnt * kZredSeg; w += nthr) {
+            const int o = c0 + w / kZredSeg, seg = w % kZredSeg;
+            const long long* src = part + o;
+            if (nparts <= 10 * kZredSeg) {                              // (<= 160 CTAs: every load of the item in flight)
+                long long v[10];
+#pragma unroll
+                for (int i = 0; i < 10; ++i) {
+                    const int p = seg + i * kZredSeg;
+                    v[i] = (p < nparts) ? __ldcg(src + (int64_t)p * n) : 0ll;
+                }
+                double acc = 0.0;
+#pragma unroll
+                for (int i = 0; i < 10; ++i) {
+                    const int p = seg + i * kZredSeg;
+                    if (p < nparts) acc += (double)v[i] * back[p];
+                }
+                zred[w] = acc;
+            } else {
+                double acc = 0.0;
+                for (int p = seg; p < nparts; p += kZredSeg) acc += (double)__ldcg(src + (int64_t)p * n) * back[p];
+                zred[w] = acc;
+            }
+        }
+        __syncthreads();
+        for (int w = tid; w < cnt; w += nthr) {
+            const int o = c0 + w, b = o >> 3, c = o & 7;
+            double t = 0.0;
+#pragma unroll
+            for (int sg = 0; sg < kZredSeg; ++sg) t += zred[w * kZredSeg + sg];
+            if (c < C) Z[(int64_t)b * C + c] = (float)(t * out_scale);
+        }
+        __syncthreads();
+    }
+}
+
 struct EncSmem {
     uint64_t fullA[kAStages], emptyA[kAStages], fullV[2], emptyV[2], done, fdone;
     uint32_t tmem_base;
@@ -320,7 +373,9 @@ template <int NISS, bool RAW, bool TSA>   // NISS: MMA issuer warps in use (2, o
 __global__ void __launch_bounds__(kFwdThreads, 1)
 enc_fwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* __restrict__ row_idx, int64_t row0,
                   int B, int64_t M, const float* __restrict__ V, int C, float* __restrict__ cta_vmax,
-                  long long* __restrict__ part, int T, uint32_t mvx) {
+                  long long* __restrict__ part, int T, uint32_t mvx, float* __restrict__ Z, double out_scale) {
+    // Z != NULL: the CTAs meet at a grid barrier after writing their partials and reduce them themselves (cooperative
+    // launch); Z == NULL: a separate enc_fwd_reduce_kernel follows.
     pdl_prologue();
     extern __shared__ __align__(1024) uint8_t smem[];
     constexpr int kDepth = TSA ? kStDepthTS : kStDepth;
@@ -555,6 +610,14 @@ enc_fwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
     __syncthreads();
     if (tid == 0) TLE(2, 4);                                            // epilogue done
     if (warp == kFwdIssueWarp) tmem_dealloc<512>(tbase);
+    if (Z != nullptr) {
+        grid_barrier(&g_bar_enc_fwd, gridDim.x);
+        if (tid == 0) TLE(2, 5);                                        // every CTA's partial is visible
+        // (the staging ring is idle: all copies were consumed by the producers' loop)
+        enc_fwd_reduce_share(part, cta_vmax, (int)gridDim.x, B, C, Z, out_scale, reinterpret_cast<double*>(stage),
+                             reinterpret_cast<double*>(stage) + kMaxParts);
+        if (tid == 0) TLE(2, 6);
+    }
 }
 
 // =================================================================================================================
@@ -1536,21 +1599,31 @@ int launch_enc_fwd_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_i
     }
     const bool two = enc_issuers() == 2 && nblk_ >= 3 && nblk_ <= 8;   // two accumulator sets: 2 x 32 columns per row block
     const uint32_t mvx = raw_mv >= 0 ? (3u ^ (uint32_t)(raw_mv & 0xFF)) : 0u;
-#define NADM_FWD_GO(N_, R_)                                                                                            \
+    // the CTAs reduce their partials themselves behind a grid barrier (cooperative launch) only with NADM_GRIDBAR=1 (measured slower)
+    const bool fused = gridbar_enabled();
+    const double out_scale = raw_mv >= 0 ? 1.0 : 0.5;
+    float* Zk = fused ? Z : nullptr;
+    cudaError_t le = cudaSuccess;
+#define NADM_FWD_GO2(N_, R_, T_)                                                                                       \
     do {                                                                                                               \
-        if (tsa)                                                                                                       \
-            launch_pdl(enc_fwd_tc_kernel<N_, R_, true>, dim3(ncta), dim3(kFwdThreads), smem, st, packed, pitch, row_idx, \
-                       row0, B, M, V, C, vmax, part, T, mvx);                                                          \
+        if (fused)                                                                                                     \
+            le = launch_coop(enc_fwd_tc_kernel<N_, R_, T_>, dim3(ncta), dim3(kFwdThreads), smem, st, packed, pitch, row_idx, \
+                             row0, B, M, V, C, vmax, part, T, mvx, Zk, out_scale);                                     \
         else                                                                                                           \
-            launch_pdl(enc_fwd_tc_kernel<N_, R_, false>, dim3(ncta), dim3(kFwdThreads), smem, st, packed, pitch, row_idx, \
-                       row0, B, M, V, C, vmax, part, T, mvx);                                                          \
+            le = launch_pdl(enc_fwd_tc_kernel<N_, R_, T_>, dim3(ncta), dim3(kFwdThreads), smem, st, packed, pitch, row_idx, \
+                            row0, B, M, V, C, vmax, part, T, mvx, Zk, out_scale);                                      \
     } while (0)
+#define NADM_FWD_GO(N_, R_) do { if (tsa) NADM_FWD_GO2(N_, R_, true); else NADM_FWD_GO2(N_, R_, false); } while (0)
     if (raw_mv >= 0) { if (two) NADM_FWD_GO(2, true); else NADM_FWD_GO(1, true); }
     else { if (two) NADM_FWD_GO(2, false); else NADM_FWD_GO(1, false); }
 #undef NADM_FWD_GO
+#undef NADM_FWD_GO2
+    if (le != cudaSuccess) return cuda_fail(le, "enc_fwd_tc_kernel");
     NADM_CHECK_LAUNCH("enc_fwd_tc_kernel");
-    launch_pdl(enc_fwd_reduce_kernel, dim3(B), dim3(256), 0, st, part, ncta, B, C, vmax, Z, raw_mv >= 0 ? 1.0 : 0.5);
-    NADM_CHECK_LAUNCH("enc_fwd_reduce_kernel");
+    if (!fused) {
+        launch_pdl(enc_fwd_reduce_kernel, dim3(B), dim3(256), 0, st, part, ncta, B, C, vmax, Z, out_scale);
+        NADM_CHECK_LAUNCH("enc_fwd_reduce_kernel");
+    }
     return NADM_OK;
 }
 

@@ -387,7 +387,7 @@ class NeuralAdmixture:
         if gs is None or gs["order"].numel() < order_len:
             dev = self.device
             gs = {"order": torch.zeros(order_len, dtype=torch.int64, device=dev),
-                  "counters": torch.zeros(2, dtype=torch.int64, device=dev),
+                  "counters": torch.zeros(4, dtype=torch.int64, device=dev),
                   "coef": torch.zeros(8, dtype=torch.float32, device=dev),
                   "loss1": torch.zeros(1, dtype=torch.float32, device=dev),
                   "losses": torch.zeros(order_len, dtype=torch.float32, device=dev), "idx": {}, "graphs": {},
@@ -396,10 +396,11 @@ class NeuralAdmixture:
         return gs
 
     def _get_graph(self, gs: dict, Bs: int, want_loss: bool, sup: bool):
-        """The whole step for a minibatch of ``Bs`` rows as ONE replayable CUDA graph: ``nadm_step_begin`` (rows of the
-        minibatch out of the device-resident permutation + this step's Adam coefficients, both indexed by a device
-        counter), the five hot-path calls (and, sharded, their two all-reduces), ``nadm_step_end``.  Nothing in the
-        graph depends on host state, so an epoch is ``nsteps`` graph launches."""
+        """The whole step for a minibatch of ``Bs`` rows as ONE replayable CUDA graph: ``nadm_step_next`` (finishes the
+        previous step — its loss into the per-step array, the counters advanced — then the rows of this minibatch out of
+        the device-resident permutation + this step's Adam coefficients, both indexed by a device counter) and the
+        five hot-path calls (sharded: with their exchanges inside).  Nothing in the graph depends on host state, so an
+        epoch is ``nsteps`` graph launches + one ``nadm_step_flush`` for the last step."""
         key = (Bs, want_loss, sup, self.batch_size, self.raw_model.bind_epoch)
         g = gs["graphs"].get(key)
         if g is not None:
@@ -415,10 +416,10 @@ class NeuralAdmixture:
         g = torch.cuda.CUDAGraph()
         before, gen_before = ops.launch_count(), ops.generic_launch_count()
         with torch.cuda.graph(g):
-            ops.step_begin(gs["order"], gs["counters"], self.batch_size, Bs, idx, h_host, gs["coef"], loss_acc)
+            ops.step_next(gs["order"], gs["counters"], self.batch_size, Bs, idx, h_host, gs["coef"], loss_acc, want_loss,
+                          gs["losses"])
             labels = gs["pops"][idx] if sup else None
             self._train_step(idx, labels, loss_acc if want_loss else None, hyper=h_dev, managed_loss=True)
-            ops.step_end(gs["counters"], loss_acc if want_loss else None, gs["losses"] if want_loss else None)
         g.nadm_kernels = ops.launch_count() - before          # library kernels per replay (bench.py's gpu_launches)
         g.nadm_generic = ops.generic_launch_count() - gen_before
         self._warn_generic(g.nadm_generic)
@@ -452,7 +453,7 @@ class NeuralAdmixture:
                         gs["pops"] = torch.empty_like(pops)
                         gs["graphs"] = {k_: g_ for k_, g_ in gs["graphs"].items() if not k_[2]}
                     gs["pops"].copy_(pops)
-                gs["counters"].copy_(torch.tensor([first, o.step_count], dtype=torch.int64))
+                gs["counters"].copy_(torch.tensor([first, o.step_count, 0, 0], dtype=torch.int64))
                 graphs = [self._get_graph(gs, min(Bfull, n - (first + s) * Bfull), want_loss, pops is not None)
                           for s in range(nsteps)]
             except Exception as e:  # capture not possible (e.g. a collective that cannot be captured): eager steps
@@ -467,6 +468,7 @@ class NeuralAdmixture:
                     g.replay()
                     self.graph_kernel_launches += g.nadm_kernels
                     self.generic_kernel_launches += g.nadm_generic
+                ops.step_flush(gs["counters"], gs["losses"])          # the last step's loss, the counters' last advance
                 o.step_count += nsteps
                 return gs["losses"][first:first + nsteps] if want_loss else None
         losses = torch.zeros(nsteps, dtype=torch.float32, device=self.device) if want_loss else None
@@ -605,7 +607,7 @@ class NeuralAdmixture:
         if self.use_graph and uniform and labels is None:
             o = self.optimizer
             gs = self._graph_state(max(n, 1024))
-            gs["counters"].copy_(torch.tensor([0, o.step_count], dtype=torch.int64))
+            gs["counters"].copy_(torch.tensor([0, o.step_count, 0, 0], dtype=torch.int64))
             try:
                 graphs = [self._get_host_graph(gs, hs, s_) for s_ in range(min(2, n))]
             except Exception as e:

@@ -240,7 +240,7 @@ def step_begin(order: torch.Tensor, counters: torch.Tensor, stride: int, B: int,
     """Device-side start of a step: the minibatch's rows out of the device-resident permutation and the Adam
     coefficients of the step, both indexed by ``counters`` (2 x int64 on the device)."""
     _need_cuda(order, counters, row_idx_out, coef_out)
-    assert order.dtype == torch.int64 and counters.dtype == torch.int64 and counters.numel() == 2
+    assert order.dtype == torch.int64 and counters.dtype == torch.int64 and counters.numel() >= 2
     assert row_idx_out.dtype == torch.int64 and row_idx_out.numel() >= B and coef_out.numel() * coef_out.element_size() >= 32
     with _on(order): check(_lib.load().nadm_step_begin(_ptr(order), order.numel(), _ptr(counters), stride, B, _ptr(row_idx_out),
                                       C.byref(hyper), _ptr(coef_out), _ptr(loss_accum), _stream(order)))
@@ -248,6 +248,24 @@ def step_begin(order: torch.Tensor, counters: torch.Tensor, stride: int, B: int,
 
 def step_end(counters: torch.Tensor, loss: Optional[torch.Tensor], losses_out: Optional[torch.Tensor]) -> None:
     with _on(counters): check(_lib.load().nadm_step_end(_ptr(counters), _ptr(loss), _ptr(losses_out), _stream(counters)))
+
+
+def step_next(order: torch.Tensor, counters: torch.Tensor, stride: int, B: int, row_idx_out: torch.Tensor,
+              hyper: AdamHyper, coef_out: torch.Tensor, loss_accum: Optional[torch.Tensor], record_loss: bool,
+              losses_out: Optional[torch.Tensor]) -> None:
+    """``step_end`` of the pending step (if any) + ``step_begin`` of the next in ONE kernel; ``counters``: 4 x int64
+    (see nadm_step_next).  The last step of a run is finished by ``step_flush``."""
+    _need_cuda(order, counters, row_idx_out, coef_out)
+    assert order.dtype == torch.int64 and counters.dtype == torch.int64 and counters.numel() == 4
+    assert row_idx_out.dtype == torch.int64 and row_idx_out.numel() >= B and coef_out.numel() * coef_out.element_size() >= 32
+    with _on(order): check(_lib.load().nadm_step_next(_ptr(order), order.numel(), _ptr(counters), stride, B, _ptr(row_idx_out),
+                                     C.byref(hyper), _ptr(coef_out), _ptr(loss_accum), 1 if record_loss else 0,
+                                     _ptr(losses_out), _stream(order)))
+
+
+def step_flush(counters: torch.Tensor, losses_out: Optional[torch.Tensor]) -> None:
+    assert counters.dtype == torch.int64 and counters.numel() == 4
+    with _on(counters): check(_lib.load().nadm_step_flush(_ptr(counters), _ptr(losses_out), _stream(counters)))
 
 
 def geno_matmul(pg: PackedGenotypes, Omega: torch.Tensor, ws: torch.Tensor, missing_value: int = 3) -> torch.Tensor:

@@ -39,3 +39,5 @@ print(f"issuer A: wait for G {(out[4][100:300] - out[3][100:300]).mean():.0f}, i
 ph = out[0][500:506]
 print("phases (cycles): setup", int(ph[1] - ph[0]), " units of warpgroup 0", int(ph[2] - ph[1]), " wait for the last MMA2", int(ph[3] - ph[2]),
       " dQ partial", int(ph[4] - ph[3]), " tail (last dP epilogue, sync)", int(ph[5] - ph[4]), " total", int(ph[5] - ph[0]))
+ph2 = out[0][505:508]
+print("fused reduction (cycles): grid barrier", int(ph2[1] - ph2[0]), " reduce share", int(ph2[2] - ph2[1]))

@@ -33,3 +33,4 @@ t = out[2]
 print("phases (cycles): setup", int(t[1] - t[0]), " first tile start after setup", int(out[0][0] - t[1]),
       " producers' loop", int(t[2] - out[0][0]), " drain MMAs", int(t[3] - t[2]), " epilogue", int(t[4] - t[3]),
       " total", int(t[4] - t[0]))
+print("fused reduction (cycles): grid barrier", int(t[5] - t[4]), " reduce share", int(t[6] - t[5]))
