@@ -87,6 +87,13 @@ size_t nadm_workspace_bytes(int32_t B, int64_t M, int32_t C, int32_t H, int32_t 
  * (inference.py:71-77, neural_admixture.py:369-383).   Z: B x C. */
 int nadm_encoder_fwd(const uint8_t* packed, int64_t pitch, const int64_t* row_idx, int64_t row0, int32_t B,
                      int64_t M, const float* V, int32_t C, float* Z, void* ws, size_t ws_bytes, void* stream);
+/* Same call, but the sum over the kernel's per-CTA partial results MAY be left pending: the next nadm_mlp_fwd of this
+ * host thread that is given the same Z completes it inside its own kernel (each CTA sums the partials of its rows: one
+ * kernel boundary and one round trip through L2 fewer per step).  Contract: nothing reads Z and nothing writes `ws`
+ * before that nadm_mlp_fwd call.  Whether the reduction was deferred is the library's decision (tensor-core path, one
+ * launch); otherwise this is nadm_encoder_fwd. */
+int nadm_encoder_fwd_deferred(const uint8_t* packed, int64_t pitch, const int64_t* row_idx, int64_t row0, int32_t B,
+                              int64_t M, const float* V, int32_t C, float* Z, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- SNP-sharded runs: the exchange of the two small per-step messages, fused into the kernels that consume them.
  * Rank r owns a contiguous slice of the SNP axis; the B x C partial projection (after nadm_encoder_fwd) and the
@@ -94,7 +101,8 @@ int nadm_encoder_fwd(const uint8_t* packed, int64_t pitch, const int64_t* row_id
  * gradient all-reduce in the reference (model/neural_admixture.py:315-319), 25.6 KB instead of 32-96 MB.  Instead of
  * two NCCL all-reduce kernels per step, nadm_mlp_fwd / nadm_mlp_bwd do the exchange themselves when given a
  * nadm_xchg_t: every CTA stores its rows' partial values into all peers' exchange areas over NVLink (peer-mapped device
- * memory), publishes a sequence number, waits for the peers' numbers for the same rows, and sums the slots in rank
+ * memory) as 8-byte {value, exchange number} pairs (one atomic store each: no fence, no separate flag), spins on the
+ * pairs the peers store into its own area until they carry the same exchange number, and sums the values in rank
  * order (so every rank obtains bit-identical sums).  One area per rank, allocated with nadm_ipc_alloc and opened by the
  * peers with nadm_ipc_open (CUDA IPC: one process per GPU on one node).  `seq` is LOCAL device memory of
  * NADM_XCHG_SEQ_WORDS uint32, zero-initialised, private to the rank.  xchg == NULL: no exchange (single GPU, or the
@@ -137,6 +145,14 @@ int nadm_decoder_step(const uint8_t* packed, int64_t pitch, const int64_t* row_i
                       int64_t M, const float* Q, float* dQ, int32_t q_ld, int32_t q_off, int32_t k,
                       float* P, float* Pm, float* Pv, const nadm_adam_t* adam /*[host], NULL = no update*/,
                       float* dP_out, float* loss, void* ws, size_t ws_bytes, void* stream);
+/* Same call, but the sum over the kernel's per-CTA partials of dQ[:, q_off:q_off+k] (and of the head's loss) MAY be left
+ * pending: the next nadm_mlp_bwd of this host thread that is given the same dQ (and the same ws) completes it inside its
+ * own kernel; a later nadm_decoder_step(_deferred) on the same dQ completes it first.  Contract: nothing reads those
+ * columns of dQ or *loss, and nothing else writes `ws`, before that call.  Use it for the last head of a step. */
+int nadm_decoder_step_deferred(const uint8_t* packed, int64_t pitch, const int64_t* row_idx, int64_t row0, int32_t B,
+                               int64_t M, const float* Q, float* dQ, int32_t q_ld, int32_t q_off, int32_t k,
+                               float* P, float* Pm, float* Pv, const nadm_adam_t* adam, float* dP_out, float* loss,
+                               void* ws, size_t ws_bytes, void* stream);
 
 /* ---- backward of the small network + Adam on its parameters.  dQ: B x sumK (sum of the decoder's and, when
  * labels != NULL, of supervised_loss_weight * CrossEntropyLoss(sum)(Q_0, labels) — neural_admixture.py:293,:473 —

@@ -47,9 +47,14 @@ SIGNATURES = {
     "nadm_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32]),
     "nadm_encoder_fwd": (C.c_int, [c_u8p, C.c_int64, c_i64p, C.c_int64, C.c_int32, C.c_int64, c_f32p, C.c_int32,
                                    c_f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "nadm_encoder_fwd_deferred": (C.c_int, [c_u8p, C.c_int64, c_i64p, C.c_int64, C.c_int32, C.c_int64, c_f32p, C.c_int32,
+                                   c_f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "nadm_mlp_fwd": (C.c_int, [c_f32p, C.c_int32, C.c_int32, C.c_int32, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p,
                                C.POINTER(C.c_int32), C.c_int32, c_f32p, c_f32p, c_f32p, C.POINTER(Xchg), C.c_void_p]),
     "nadm_decoder_step": (C.c_int, [c_u8p, C.c_int64, c_i64p, C.c_int64, C.c_int32, C.c_int64, c_f32p, c_f32p,
+                                    C.c_int32, C.c_int32, C.c_int32, c_f32p, c_f32p, c_f32p, C.POINTER(AdamHyper),
+                                    c_f32p, c_f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "nadm_decoder_step_deferred": (C.c_int, [c_u8p, C.c_int64, c_i64p, C.c_int64, C.c_int32, C.c_int64, c_f32p, c_f32p,
                                     C.c_int32, C.c_int32, C.c_int32, c_f32p, c_f32p, c_f32p, C.POINTER(AdamHyper),
                                     c_f32p, c_f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "nadm_mlp_bwd": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int32, C.c_int32, C.c_int32,

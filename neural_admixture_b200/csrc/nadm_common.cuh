@@ -176,9 +176,31 @@ inline AdamCoef make_adam(const nadm_adam_t* a) {
     return c;
 }
 
+// ---- deferred reductions: nadm_encoder_fwd_deferred / nadm_decoder_step_deferred leave the sum over their CTAs'
+// partials to the kernel that consumes the result (nadm_mlp_fwd / nadm_mlp_bwd), which saves a kernel boundary and a round
+// trip through L2 per reduction.  The hand-over is a host-side record per host thread (one host thread per device is the
+// ABI's convention), keyed by the destination pointer (Z, resp. dQ): the consumer looks its argument up.
+struct DeferredZ {
+    const float* Z;             // destination the record belongs to (NULL: nothing pending)
+    const long long* part;      // nparts x B x 8 exact integer partial sums
+    const float* vmax;          // nparts per-CTA |max| (-> the CTA's power-of-two scale)
+    int nparts, B;
+};
+struct DeferredDQ {
+    const float* dQ;            // destination (NULL: nothing pending)
+    const float* part;          // nparts x B x cols_p
+    const float* loss_part;     // nparts partial losses, or NULL (gradients only)
+    float* loss;                // where the summed loss is added
+    int nparts, B, cols_p, k, q_ld, q_off;
+    size_t bytes;               // extent of the partials inside the workspace (the consumer's own scratch goes behind)
+};
+DeferredZ& deferred_z();
+DeferredDQ& deferred_dq();
+
 // tensor-core (tcgen05) encoder kernels, nadm_tc_enc.cu
 int launch_enc_fwd_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_idx, int64_t row0, int B, int64_t M,
-                      const float* V, int C, float* Z, void* ws, size_t ws_bytes, cudaStream_t st, int raw_mv = -1);
+                      const float* V, int C, float* Z, void* ws, size_t ws_bytes, cudaStream_t st, int raw_mv = -1,
+                      bool defer = false);
 int launch_enc_bwd_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_idx, int64_t row0, int B, int64_t M,
                       const float* dZ, int C, float* V, float* Vm, float* Vv, const nadm_adam_t* adam, float* dV_out,
                       cudaStream_t st, int raw_mv = -1, int accumulate = 0);
@@ -191,13 +213,34 @@ bool enc_bwd_slab_supported(int B);   // the slab-fed backward kernel (256-byte 
 bool dec_tc_supported(int B, int k);
 int launch_dec_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_idx, int64_t row0, int B, int64_t M,
                   const float* Q, float* dQ, int q_ld, int q_off, int k, float* P, float* Pm, float* Pv,
-                  const nadm_adam_t* adam, float* dP_out, float* loss, float* ws, size_t ws_bytes, cudaStream_t st);
+                  const nadm_adam_t* adam, float* dP_out, float* loss, float* ws, size_t ws_bytes, cudaStream_t st,
+                  bool defer = false);
 // deterministic sum of per-CTA partials (nadm_stream.cu)
 int launch_reduce_parts(const float* part, int nparts, int rows, int cols_p, int cols_out, float* out, int out_ld,
                         int out_off, float scale, const float* loss_part, float* loss, cudaStream_t st);
 bool use_generic_kernels();   // NADM_GENERIC=1: force the CUDA-core formulation (A/B testing only)
 
 #ifdef __CUDACC__
+// power-of-two fixed-point scale for values with absolute maximum `mx`: q = rint(v * inv) fits in [-2^30, 2^30]
+struct FixScale {
+    float inv;      // 2^(30 - e)
+    double back;    // 2^(e - 30)
+};
+__device__ __forceinline__ FixScale fix_scale(float mx) {
+    FixScale s;
+    const int E = (int)((__float_as_uint(mx) >> 23) & 0xFF);       // biased exponent: mx < 2^(E - 126)
+    if (E == 255) {   // Inf or NaN among the values: the result is NaN, as a floating-point matmul would give
+        s.inv = 0.f;
+        s.back = __longlong_as_double(0x7FF8000000000000ll);
+        return s;
+    }
+    if (mx == 0.f || E == 0) { s.inv = 0.f; s.back = 0.0; return s; }
+    const int e = max(E - 126, -96);                                // keep 2^(30-e) a finite float
+    s.inv = __uint_as_float((uint32_t)(127 + 30 - e) << 23);
+    s.back = __longlong_as_double((long long)(1023 + e - 30) << 52);
+    return s;
+}
+
 // torch.optim.Adam (no weight decay / amsgrad), same operation order as torch's fused kernel:
 //   m = lerp(m, g, 1-b1); v = b2*v + (1-b2)*g*g; p -= step_size * m / (sqrt(v)/sqrt(bc2) + eps)
 // kernels call this once on their by-value copy: coefficients written on the device by nadm_step_begin win

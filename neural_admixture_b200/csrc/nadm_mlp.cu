@@ -8,6 +8,7 @@
 // B x H x (C + sumK) is ~26 MFLOP at the default sizes: these kernels are latency-, not bandwidth-bound; they are
 // written for few launches and deterministic reductions (no atomics), not for tensor cores.
 #include "nadm_common.cuh"
+#include <algorithm>
 
 #include <mutex>
 #include <string.h>
@@ -83,71 +84,76 @@ struct Heads {
 // =================================================================================================================
 // fused peer exchange (SNP-sharded runs): see nadm_xchg_t in nadm_b200.h
 // =================================================================================================================
-// Layout of one rank's exchange area: flags [2 phases][NADM_XCHG_MAX_CTAS][NADM_MAX_RANKS] uint32, then slots
-// [2 phases][2 parities][NADM_MAX_RANKS][slot_floats] float.  Phase 0 = partial projection Z (nadm_mlp_fwd), phase 1 =
-// partial dQ | loss (nadm_mlp_bwd).  A CTA's exchange number `seq` counts the exchanges that CTA index has done in that
-// phase; slots are double-buffered by its parity: a peer can be at most one exchange ahead (it cannot finish exchange
-// seq + 1 without this rank's contribution to it, which this rank sends only after it has consumed exchange seq).
+// LL protocol (the low-latency protocol of NCCL, restated): every float travels as an 8-byte {value, sequence number}
+// pair written with ONE 8-byte store, which is atomic — over NVLink too —, so the value needs no flag behind a fence: the
+// receiver spins on the pair itself until it carries the number of the exchange it is waiting for.  The earlier form of
+// this exchange (values, __threadfence_system(), st.release.sys flag, ld.acquire.sys poll, then read the values)
+// cost two fenced NVLink round trips per exchange: 0.1479 ms per step at 8 GPUs against 0.112 ms for a rank's kernels
+// alone (profiles/r2_scaling_8gpu_flag_exchange.txt).
+// Layout of one rank's exchange area: slots [2 phases][2 parities][NADM_MAX_RANKS][slot_floats] of uint2.  Phase 0 =
+// partial projection Z (nadm_mlp_fwd), phase 1 = partial dQ | loss (nadm_mlp_bwd).  A CTA's exchange number `seq`
+// counts the exchanges that CTA index has done in that phase (from 1: zeroed memory never matches); slots are
+// double-buffered by its parity: a peer can be at most one exchange ahead (it cannot finish exchange seq + 1 without
+// this rank's contribution to it, which this rank sends only after it has consumed exchange seq).
 struct Xchg {
     int world, rank;
     uint8_t* area[NADM_MAX_RANKS];
     uint32_t* seq;
     long long slot_floats;
 };
-constexpr size_t kXchgFlagBytes = (size_t)2 * NADM_XCHG_MAX_CTAS * NADM_MAX_RANKS * sizeof(uint32_t);
 __host__ __device__ inline size_t xchg_area_bytes(long long slot_floats) {
-    return kXchgFlagBytes + (size_t)2 * 2 * NADM_MAX_RANKS * (size_t)slot_floats * sizeof(float);
+    return (size_t)2 * 2 * NADM_MAX_RANKS * (size_t)slot_floats * sizeof(uint2);
 }
-__device__ __forceinline__ uint32_t* xchg_flag(uint8_t* area, int phase, int cta, int src) {
-    return reinterpret_cast<uint32_t*>(area) + ((size_t)phase * NADM_XCHG_MAX_CTAS + cta) * NADM_MAX_RANKS + src;
+__device__ __forceinline__ uint2* xchg_slot(uint8_t* area, long long slot_floats, int phase, int parity, int src) {
+    return reinterpret_cast<uint2*>(area) + ((size_t)(phase * 2 + parity) * NADM_MAX_RANKS + src) * (size_t)slot_floats;
 }
-__device__ __forceinline__ float* xchg_slot(uint8_t* area, long long slot_floats, int phase, int parity, int src) {
-    return reinterpret_cast<float*>(area + kXchgFlagBytes) + ((size_t)(phase * 2 + parity) * NADM_MAX_RANKS + src) * (size_t)slot_floats;
+__device__ __forceinline__ void st_ll(uint2* p, float v, uint32_t flag) {
+    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(flag) : "memory");
 }
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ float ld_ll_wait(const uint2* p, uint32_t flag) {
+    uint32_t v, f, polls = 0;
+    for (;;) {
+        asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(f) : "l"(p) : "memory");
+        if (f == flag) break;
+        if (++polls > (1u << 24)) __trap();          // a peer never arrived: fail the launch instead of hanging
+    }
+    return __uint_as_float(v);
 }
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-// All threads of the CTA call this.  vals[off .. off + n) are this CTA's floats of the rank's partial result (global
-// memory, written by an earlier kernel); on return they hold the sum over the ranks, visible to the whole CTA.
-// `extra` (CTA 0 only, may be NULL): one more scalar exchanged through slot element extra_off (the partial loss).
-__device__ void xchg_allreduce_cta(const Xchg& x, int phase, float* vals, long long off, int n, float* extra,
+// All threads of the CTA call this.  vals (SHARED memory, n floats): this CTA's values of the rank's partial result on
+// entry, the sum over the ranks (in rank order: bit-identical on every rank) on return.  `off`: position of vals[0] in
+// the slot.  tmp: shared scratch of world * n floats.  `extra` (CTA 0 only, may be NULL): one more scalar in global
+// memory exchanged through slot element extra_off (the partial loss).
+__device__ void xchg_allreduce_cta(const Xchg& x, int phase, float* vals, long long off, int n, float* tmp, float* extra,
                                    long long extra_off) {
-    const int tid = threadIdx.x, cta = blockIdx.x;
+    const int tid = threadIdx.x, cta = blockIdx.x, nthr = blockDim.x;
     const uint32_t seq = x.seq[phase * NADM_XCHG_MAX_CTAS + cta] + 1u;
     const int parity = (int)(seq & 1u);
-    // push: my values into slot [rank] of every rank's area (own included)
-    for (int idx = tid; idx < x.world * n; idx += blockDim.x) {
+    const float mine_extra = (extra != nullptr) ? *extra : 0.f;
+    // push: my values into slot [rank] of every peer's area
+    for (int idx = tid; idx < x.world * n; idx += nthr) {
         const int r = idx / n, i = idx - r * n;
-        xchg_slot(x.area[r], x.slot_floats, phase, parity, x.rank)[off + i] = vals[off + i];
+        if (r != x.rank) st_ll(xchg_slot(x.area[r], x.slot_floats, phase, parity, x.rank) + off + i, vals[i], seq);
     }
-    if (extra != nullptr && tid < x.world) xchg_slot(x.area[tid], x.slot_floats, phase, parity, x.rank)[extra_off] = *extra;
-    __threadfence_system();
-    __syncthreads();
-    if (tid < x.world) {
-        st_release_sys(xchg_flag(x.area[tid], phase, cta, x.rank), seq);
-        // pull: wait until rank `tid` has published this exchange of this CTA index into MY area
-        const uint32_t* f = xchg_flag(x.area[x.rank], phase, cta, tid);
-        uint32_t polls = 0;
-        while ((int32_t)(ld_acquire_sys(f) - seq) < 0) {
-            __nanosleep(32);
-            if (++polls > (1u << 25)) __trap();      // a peer never arrived: fail the launch instead of hanging
-        }
-    }
-    __syncthreads();
-    for (int i = tid; i < n; i += blockDim.x) {
-        float acc = 0.f;
-        for (int r = 0; r < x.world; ++r) acc += __ldcg(xchg_slot(x.area[x.rank], x.slot_floats, phase, parity, r) + off + i);
-        vals[off + i] = acc;
+    if (extra != nullptr && tid < x.world && tid != x.rank)
+        st_ll(xchg_slot(x.area[tid], x.slot_floats, phase, parity, x.rank) + extra_off, mine_extra, seq);
+    // pull: every peer's values for the same positions out of MY area, as they arrive
+    for (int idx = tid; idx < x.world * n; idx += nthr) {
+        const int r = idx / n, i = idx - r * n;
+        tmp[idx] = (r == x.rank) ? vals[i]
+                                 : ld_ll_wait(xchg_slot(x.area[x.rank], x.slot_floats, phase, parity, r) + off + i, seq);
     }
     if (extra != nullptr && tid == 0) {
         float acc = 0.f;
-        for (int r = 0; r < x.world; ++r) acc += __ldcg(xchg_slot(x.area[x.rank], x.slot_floats, phase, parity, r) + extra_off);
+        for (int r = 0; r < x.world; ++r)
+            acc += (r == x.rank) ? mine_extra
+                                 : ld_ll_wait(xchg_slot(x.area[x.rank], x.slot_floats, phase, parity, r) + extra_off, seq);
         *extra = acc;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += nthr) {
+        float acc = 0.f;
+        for (int r = 0; r < x.world; ++r) acc += tmp[r * n + i];
+        vals[i] = acc;
     }
     if (tid == 0) x.seq[phase * NADM_XCHG_MAX_CTAS + cta] = seq;
     __syncthreads();
@@ -178,18 +184,30 @@ static int make_xchg(const nadm_xchg_t* in, long long need_floats, int nctas, Xc
 // Latency is what this kernel costs (10 us for 26 MFLOP): every phase used to start with a round trip to L2.  The
 // weights a thread needs first are therefore requested before anything that waits (the peer exchange, the RMSNorm), the
 // RMSNorm runs on 16 lanes per row, and a warp's logit column sits in registers (H = 1024: 32 values per lane).
-__global__ void __launch_bounds__(kMlpThreads)
+// deferred reduction of the encoder's per-CTA partials (see DeferredZ): nparts == 0 -> Z is complete in global memory
+struct ZParts {
+    const long long* part;
+    const float* vmax;
+    int nparts;
+};
+constexpr int kZSegs = kMlpThreads / (kMlpRows * 8);   // 8 part segments per (row, component) output
+constexpr int kZMaxIter = 19;                          // loads in flight per thread: nparts <= 152
+
+__global__ void __launch_bounds__(kMlpThreads, 2)   // 200 CTAs for B = 800: two per SM, one wave
 mlp_fwd_kernel(float* Z, int B, int C, int H, const float* __restrict__ w_rms,
                const float* __restrict__ W1, const float* __restrict__ b1, const float* __restrict__ W2,
                const float* __restrict__ b2, Heads hd, float* __restrict__ rinv_out, float* __restrict__ Hh,
-               float* __restrict__ Q, Xchg xc) {
+               float* __restrict__ Q, ZParts zp, Xchg xc) {
     pdl_prologue();
     extern __shared__ __align__(16) float sm[];
-    float* Zn = sm;                         // kMlpRows x C
-    float* Hs = Zn + kMlpRows * NADM_MAX_C;  // kMlpRows x H
-    float* Ls = Hs + (size_t)kMlpRows * H;   // kMlpRows x sumK
+    float* Zn = sm;                              // kMlpRows x MAX_C
+    float* Zs = Zn + kMlpRows * NADM_MAX_C;      // kMlpRows x C, compact: this rank's / the summed projection of the rows
+    float* xt = Zs + kMlpRows * NADM_MAX_C;      // exchange scratch: MAX_RANKS x kMlpRows x MAX_C (also the segment sums)
+    float* Hs = xt + NADM_MAX_RANKS * kMlpRows * NADM_MAX_C;   // kMlpRows x H
+    float* Ls = Hs + (size_t)kMlpRows * H;       // kMlpRows x sumK
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b0 = blockIdx.x * kMlpRows;
+    const int nrows = min(kMlpRows, B - b0);
     constexpr int kPre = 4;                  // hidden units per thread held in registers (H <= 1024)
     const bool pre1 = (C == 8) && (H <= kPre * kMlpThreads);
     const bool pre2 = (H == 32 * 32) && (warp < hd.sumK);
@@ -210,13 +228,48 @@ mlp_fwd_kernel(float* Z, int B, int C, int H, const float* __restrict__ w_rms,
 #pragma unroll
         for (int i = 0; i < 32; ++i) w2r[i] = W2[(int64_t)warp * H + lane + 32 * i];
     }
-    if (xc.world > 1)   // sum the ranks' partial projections of this CTA's rows (in place)
-        xchg_allreduce_cta(xc, 0, Z, (long long)b0 * C, min(kMlpRows, B - b0) * C, nullptr, 0);
+    // ---- this rank's projection of the CTA's rows -> Zs ----
+    if (zp.nparts > 0) {
+        // sum the encoder's per-CTA partials for these rows here (no reduction kernel, no round trip of Z through L2):
+        // thread = (output o = row x 8 + component, segment of the parts), every load of the thread in flight at once.
+        // Each partial is an exact integer times its CTA's power-of-two scale, stored as a double; summed in a fixed order.
+        const int o = tid / kZSegs, seg = tid % kZSegs, r = o >> 3;
+        double acc = 0.0;
+        if (r < nrows) {
+            const long long* src = zp.part + (int64_t)b0 * 8 + o;
+            const int64_t n = (int64_t)B * 8;
+            long long v[kZMaxIter];
+#pragma unroll
+            for (int i = 0; i < kZMaxIter; ++i) {
+                const int p = seg + kZSegs * i;
+                v[i] = (p < zp.nparts) ? __ldcg(src + (int64_t)p * n) : 0ll;
+            }
+#pragma unroll
+            for (int i = 0; i < kZMaxIter; ++i) acc += __longlong_as_double(v[i]);   // (0 bits = +0.0 past the end)
+        }
+        double* zred = reinterpret_cast<double*>(xt);               // 256 doubles = 2 KB <= the exchange scratch (2 KB)
+        zred[tid] = acc;
+        __syncthreads();
+        if (tid < kMlpRows * 8) {
+            const int rr = tid >> 3, c = tid & 7;
+            double t = 0.0;
+#pragma unroll
+            for (int sg = 0; sg < kZSegs; ++sg) t += zred[tid * kZSegs + sg];
+            if (rr < nrows && c < C) Zs[rr * C + c] = (float)(t * 0.5);   // x = code / 2
+        }
+    } else if (tid < kMlpRows * NADM_MAX_C) {
+        const int rr = tid / NADM_MAX_C, c = tid % NADM_MAX_C;
+        if (rr < nrows && c < C) Zs[rr * C + c] = Z[(int64_t)(b0 + rr) * C + c];
+    }
+    __syncthreads();
+    if (xc.world > 1)   // sum the ranks' partial projections of this CTA's rows
+        xchg_allreduce_cta(xc, 0, Zs, (long long)b0 * C, nrows * C, xt, nullptr, 0);
+    if ((zp.nparts > 0 || xc.world > 1) && tid < nrows * C) Z[(int64_t)b0 * C + tid] = Zs[tid];   // (kept for the backward)
 
     if (tid < kMlpRows * 16) {               // RMSNorm: 16 lanes per row (whole warps: full-mask shuffles)
         const int r = tid >> 4, c = tid & 15, b = b0 + r;
         const bool ok = (b < B) && (c < C);
-        const float z = ok ? Z[(int64_t)b * C + c] : 0.f;
+        const float z = ok ? Zs[r * C + c] : 0.f;
         float ss = z * z;
 #pragma unroll
         for (int o = 8; o >= 1; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
@@ -321,41 +374,94 @@ __host__ __device__ inline size_t mlp_slab_floats(int C, int H, int sumK) {
     return (size_t)(C + 1) * H + (size_t)sumK * H + (size_t)sumK + (size_t)C + 1;
 }
 
+// deferred reduction of the decoder's per-CTA dQ partials of ONE head (see DeferredDQ): nparts == 0 -> dQ is complete
+struct DQParts {
+    const float* part;
+    const float* loss_part;
+    int nparts, cols_p, k, q_off;
+};
+constexpr int kDqMaxIter = 19;
+
 template <int CP>   // components padded to 8 or 16
 __global__ void __launch_bounds__(kMlpThreads)
 mlp_bwd_rows_kernel(float* dQ, const float* __restrict__ Q, const float* __restrict__ Hh,
                     const float* __restrict__ Z, const float* __restrict__ rinv, int B, int C, int H, Heads hd,
                     const int64_t* __restrict__ labels, float sup_weight, const float* __restrict__ w_rms,
                     const float* __restrict__ W1, const float* __restrict__ W2, float* __restrict__ part,
-                    float* __restrict__ dZ, float* loss, Xchg xc) {
+                    float* __restrict__ dZ, float* loss, DQParts dp, Xchg xc) {
     pdl_prologue();
-    if (xc.world > 1) {   // sum the ranks' partial dQ of this CTA's rows (in place); CTA 0 also sums the partial losses
-        const int r0 = blockIdx.x * kBwdRows;
-        xchg_allreduce_cta(xc, 1, dQ, (long long)r0 * hd.sumK, min(kBwdRows, B - r0) * hd.sumK,
-                           blockIdx.x == 0 ? loss : nullptr, (long long)B * hd.sumK);
-    }
     extern __shared__ __align__(16) float sm[];
     float* dLs = sm;                                         // kBwdRows x sumK
     float* Zn = dLs + (size_t)kBwdRows * hd.sumK;             // kBwdRows x MAX_C   (normalised inputs, recomputed)
     float* red = Zn + kBwdRows * CP;                  // nwarps x kBwdRows x MAX_C  (dZn partials per warp)
     float* sups = red + (kMlpThreads / 32) * kBwdRows * CP;   // kBwdRows
     float* qs = sups + kBwdRows;                              // kBwdRows x sumK : the rows' Q
-    float* dqs = qs + (size_t)kBwdRows * hd.sumK;             // kBwdRows x sumK : the rows' dQ
+    float* dqs = qs + (size_t)kBwdRows * hd.sumK;             // kBwdRows x sumK : the rows' dQ (summed over CTAs / ranks)
+    float* xt = dqs + (size_t)kBwdRows * hd.sumK;             // scratch: max(256, world x kBwdRows x sumK) floats
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b0 = blockIdx.x * kBwdRows;
     const int sumK = hd.sumK;
+    const int nrows = min(kBwdRows, B - b0);
     float* slab = part + (size_t)blockIdx.x * mlp_slab_floats(C, H, sumK);
 
-    // the rows' Q and dQ (one contiguous block each) into shared memory with ONE round of coalesced loads: the
-    // per-(row, head) threads below used to walk them with k dependent round trips to L2 each
+    // ---- everything the rows need from global memory is requested in ONE round: Q, dQ (or the decoder's per-CTA
+    // partials of it), the normalised inputs.  (The per-(row, head) threads below used to walk Q / dQ with k dependent
+    // round trips to L2 each.) ----
     {
-        const int nvalid = min(kBwdRows, B - b0) * sumK;
+        const int nvalid = nrows * sumK;
         for (int i = tid; i < kBwdRows * sumK; i += blockDim.x) {
             qs[i] = (i < nvalid) ? Q[(int64_t)b0 * sumK + i] : 0.f;
-            dqs[i] = (i < nvalid) ? dQ[(int64_t)b0 * sumK + i] : 0.f;
+            const int c = i % sumK;
+            const bool from_parts = dp.nparts > 0 && c >= dp.q_off && c < dp.q_off + dp.k;
+            dqs[i] = (i < nvalid && !from_parts) ? dQ[(int64_t)b0 * sumK + i] : 0.f;
+        }
+        for (int i = tid; i < kBwdRows * CP; i += blockDim.x) {
+            const int r = i / CP, c = i % CP, b = b0 + r;
+            Zn[i] = (b < B && c < C) ? Z[(int64_t)b * C + c] * rinv[b] * w_rms[c] : 0.f;
+        }
+    }
+    if (dp.nparts > 0) {
+        // sum the decoder's per-CTA partials of these rows' dQ here (no reduction kernel): thread = (output o = row x
+        // cols_p + column, segment of the parts); the rows' partials are contiguous, so a warp's loads are coalesced.
+        const int nout = kBwdRows * dp.cols_p, segs = kMlpThreads / nout;      // 64 x 4 or 128 x 2
+        const int o = tid % nout, seg = tid / nout;
+        const int64_t n = (int64_t)B * dp.cols_p;
+        float acc = 0.f;
+        if (o < nrows * dp.cols_p) {
+            const float* src = dp.part + (int64_t)b0 * dp.cols_p + o;
+            for (int p0 = seg; p0 < dp.nparts; p0 += segs * kDqMaxIter) {
+                float v[kDqMaxIter];
+#pragma unroll
+                for (int i = 0; i < kDqMaxIter; ++i) {
+                    const int p = p0 + segs * i;
+                    v[i] = (p < dp.nparts) ? __ldcg(src + (int64_t)p * n) : 0.f;
+                }
+#pragma unroll
+                for (int i = 0; i < kDqMaxIter; ++i) acc += v[i];
+            }
+        }
+        __syncthreads();                                                       // (xt is not in use yet; keeps the order simple)
+        xt[tid] = acc;
+        __syncthreads();
+        if (tid < nout) {
+            float t = 0.f;
+            for (int sg = 0; sg < segs; ++sg) t += xt[sg * nout + tid];
+            const int r = tid / dp.cols_p, c = tid % dp.cols_p;
+            if (r < nrows && c < dp.k) dqs[r * sumK + dp.q_off + c] = t;
+        }
+        if (blockIdx.x == 0 && warp == 7 && dp.loss_part != nullptr) {       // the head's loss: partials of all CTAs
+            double acc2 = 0.0;
+            for (int q = lane; q < dp.nparts; q += 32) acc2 += (double)__ldcg(dp.loss_part + q);
+            acc2 = warp_sum_d(acc2);
+            if (lane == 0) *loss = (float)((double)*loss + acc2);
         }
     }
     __syncthreads();
+    if (xc.world > 1)   // sum the ranks' partial dQ of this CTA's rows; CTA 0 also sums the partial losses
+        xchg_allreduce_cta(xc, 1, dqs, (long long)b0 * sumK, nrows * sumK, xt, blockIdx.x == 0 ? loss : nullptr,
+                           (long long)B * sumK);
+    if (dp.nparts > 0 || xc.world > 1)            // (the complete dQ of these rows, for whoever looks at it afterwards)
+        for (int i = tid; i < nrows * sumK; i += blockDim.x) dQ[(int64_t)b0 * sumK + i] = dqs[i];
 
     // ---- softmax backward per (row, head); the supervised cross-entropy acts on head 0 only ----
     for (int i = tid; i < kBwdRows * hd.n; i += blockDim.x) {
@@ -391,11 +497,6 @@ mlp_bwd_rows_kernel(float* dQ, const float* __restrict__ Q, const float* __restr
             dot = fmaf(gk, q[kk], dot);
         }
         for (int kk = 0; kk < k; ++kk) out[kk] = q[kk] * (g[kk] - dot);
-    }
-    // ---- Zn[r][c] = Z[b][c] * rinv[b] * w_rms[c] ----
-    for (int i = tid; i < kBwdRows * CP; i += blockDim.x) {
-        const int r = i / CP, c = i % CP, b = b0 + r;
-        Zn[i] = (b < B && c < C) ? Z[(int64_t)b * C + c] * rinv[b] * w_rms[c] : 0.f;
     }
     __syncthreads();
 
@@ -624,8 +725,20 @@ extern "C" int nadm_mlp_fwd(float* Z, int32_t B, int32_t C, int32_t H, const flo
     NADM_REQUIRE(B > 0 && H > 0, "empty batch or hidden layer");
     NADM_REQUIRE(C >= 1 && C <= NADM_MAX_C, "n_components C=%d unsupported (1..%d)", C, NADM_MAX_C);
     NADM_REQUIRE(Z && w_rms && W1 && b1 && W2 && b2 && rinv && Hh && Q, "NULL pointer");
-    const size_t smem = ((size_t)kMlpRows * NADM_MAX_C + (size_t)kMlpRows * H + (size_t)kMlpRows * hd.sumK) * sizeof(float);
+    const size_t smem = ((size_t)(2 + NADM_MAX_RANKS) * kMlpRows * NADM_MAX_C + (size_t)kMlpRows * H +
+                         (size_t)kMlpRows * hd.sumK) * sizeof(float);
     NADM_REQUIRE(smem <= 200 * 1024, "hidden_size H=%d too large", H);
+    // a reduction that nadm_encoder_fwd_deferred left pending for this Z is completed by the kernel itself
+    ZParts zp{nullptr, nullptr, 0};
+    {
+        DeferredZ& d = deferred_z();
+        if (d.Z == Z && d.Z != nullptr) {
+            NADM_REQUIRE(d.B == B && C <= 8, "deferred projection: batch %d / C=%d do not match the pending reduction (batch %d)",
+                         B, C, d.B);
+            zp.part = d.part; zp.vmax = d.vmax; zp.nparts = d.nparts;
+            d.Z = nullptr;
+        }
+    }
     static PerDeviceOnce once;
     bool* attr = once.slot();
     if (attr == nullptr || !*attr) {
@@ -634,7 +747,7 @@ extern "C" int nadm_mlp_fwd(float* Z, int32_t B, int32_t C, int32_t H, const flo
         if (attr) *attr = true;
     }
     launch_pdl(mlp_fwd_kernel, dim3((B + kMlpRows - 1) / kMlpRows), dim3(kMlpThreads), smem, (cudaStream_t)stream, Z, B, C, H,
-               w_rms, W1, b1, W2, b2, hd, rinv, Hh, Q, xc);
+               w_rms, W1, b1, W2, b2, hd, rinv, Hh, Q, zp, xc);
     NADM_CHECK_LAUNCH("mlp_fwd_kernel");
     return NADM_OK;
 }
@@ -660,9 +773,32 @@ extern "C" int nadm_mlp_bwd(float* dQ, const float* Q, const float* Hh, const fl
     NADM_REQUIRE(need <= ws_bytes, "workspace too small for mlp_bwd (%zu > %zu)", need, ws_bytes);
     float* gpart = (float*)ws;
     cudaStream_t st = (cudaStream_t)stream;
+    // a reduction that nadm_decoder_step_deferred left pending for this dQ is completed by the kernel itself; its
+    // partials live in the workspace, so the slabs go behind them (or, if they do not fit, the reduction runs now)
+    DQParts dp{nullptr, nullptr, 0, 8, 0, 0};
+    {
+        DeferredDQ& d = deferred_dq();
+        if (d.dQ == dQ && d.dQ != nullptr) {
+            const DeferredDQ r = d;
+            d.dQ = nullptr;
+            uint8_t* behind = (uint8_t*)r.part + ((r.bytes + 255) & ~(size_t)255);
+            const bool fits = r.B == B && r.q_ld == hd.sumK && (uint8_t*)r.part >= (uint8_t*)ws &&
+                              behind + need <= (uint8_t*)ws + ws_bytes;
+            if (fits) {
+                gpart = (float*)behind;
+                dp.part = r.part; dp.loss_part = r.loss_part; dp.nparts = r.nparts; dp.cols_p = r.cols_p; dp.k = r.k;
+                dp.q_off = r.q_off;
+                NADM_REQUIRE(r.loss_part == nullptr || r.loss == loss, "deferred dQ: the loss accumulator changed");
+            } else if (int rc = launch_reduce_parts(r.part, r.nparts, r.B, r.cols_p, r.k, dQ, r.q_ld, r.q_off, 1.0f, r.loss_part,
+                                                    r.loss, st)) {
+                return rc;
+            }
+        }
+    }
     const int CP = C <= 8 ? 8 : 16;
+    const size_t xt_floats = std::max<size_t>(kMlpThreads, xc.world > 1 ? (size_t)xc.world * kBwdRows * hd.sumK : 0);
     const size_t smem = ((size_t)3 * kBwdRows * hd.sumK + (size_t)kBwdRows * CP +
-                         (size_t)(kMlpThreads / 32) * kBwdRows * CP + kBwdRows) * sizeof(float);
+                         (size_t)(kMlpThreads / 32) * kBwdRows * CP + kBwdRows + xt_floats) * sizeof(float);
     if (smem > 48 * 1024) {                          // very wide head sets only (sumK > ~480)
         static PerDeviceOnce once_b;
         bool* ab = once_b.slot();
@@ -676,10 +812,10 @@ extern "C" int nadm_mlp_bwd(float* dQ, const float* Q, const float* Hh, const fl
     }
     if (CP == 8)
         launch_pdl(mlp_bwd_rows_kernel<8>, dim3(nslab), dim3(kMlpThreads), smem, st, dQ, Q, Hh, Z, rinv, B, C, H, hd, labels,
-                   sup_weight, p.w_rms, p.W1, p.W2, gpart, dZ, loss, xc);
+                   sup_weight, p.w_rms, p.W1, p.W2, gpart, dZ, loss, dp, xc);
     else
         launch_pdl(mlp_bwd_rows_kernel<16>, dim3(nslab), dim3(kMlpThreads), smem, st, dQ, Q, Hh, Z, rinv, B, C, H, hd, labels,
-                   sup_weight, p.w_rms, p.W1, p.W2, gpart, dZ, loss, xc);
+                   sup_weight, p.w_rms, p.W1, p.W2, gpart, dZ, loss, dp, xc);
     NADM_CHECK_LAUNCH("mlp_bwd_rows_kernel");
     const AdamCoef ac = make_adam(adam);
     const size_t nparam = mlp_slab_floats(C, H, hd.sumK);

@@ -675,8 +675,8 @@ extern "C" size_t nadm_workspace_bytes(int32_t B, int64_t M, int32_t C, int32_t 
     size_t ll = (size_t)kMaxParts * sizeof(double) * 2;
     size_t enc_tc = enc_tc_workspace_bytes(B);
     enc = enc > enc_tc ? enc : enc_tc;
-    size_t m = enc > dec ? enc : dec;
-    m = m > mlp ? m : mlp;
+    size_t m = enc > dec + mlp ? enc : dec + mlp;   // (a deferred dQ reduction keeps the decoder's partials alive next to
+                                                    //  the MLP backward's slabs)
     m = m > ll ? m : ll;
     return m + 256;
 }
@@ -708,9 +708,25 @@ static int launch_enc_fwd(const uint8_t* packed, int64_t pitch, const int64_t* r
     return NADM_OK;
 }
 
-extern "C" int nadm_encoder_fwd(const uint8_t* packed, int64_t pitch, const int64_t* row_idx, int64_t row0, int32_t B,
-                                int64_t M, const float* V, int32_t C, float* Z, void* ws, size_t ws_bytes,
-                                void* stream) {
+namespace nadm {
+DeferredZ& deferred_z() { static thread_local DeferredZ d{}; return d; }
+DeferredDQ& deferred_dq() { static thread_local DeferredDQ d{}; return d; }
+}
+// a reduction left pending for this dQ by an earlier nadm_decoder_step_deferred (another head of the same step) is
+// completed before the workspace is reused
+static int flush_deferred_dq(const float* dQ, cudaStream_t st) {
+    DeferredDQ& r = deferred_dq();
+    if (r.dQ == nullptr || r.dQ != dQ) return NADM_OK;
+    const DeferredDQ d = r;
+    r.dQ = nullptr;
+    return launch_reduce_parts(d.part, d.nparts, d.B, d.cols_p, d.k, const_cast<float*>(d.dQ), d.q_ld, d.q_off, 1.0f,
+                               d.loss_part, d.loss, st);
+}
+
+static int encoder_fwd_impl(const uint8_t* packed, int64_t pitch, const int64_t* row_idx, int64_t row0, int32_t B,
+                            int64_t M, const float* V, int32_t C, float* Z, void* ws, size_t ws_bytes, void* stream,
+                            bool defer) {
+    if (deferred_z().Z == Z) deferred_z().Z = nullptr;               // (a pending record for this Z is superseded)
     if (int rc = check_packed(packed, pitch, M)) return rc;
     NADM_REQUIRE(B > 0 && M > 0, "empty batch or no SNPs (B=%d, M=%lld)", B, (long long)M);
     NADM_REQUIRE(C >= 1 && C <= NADM_MAX_C, "n_components C=%d unsupported (1..%d)", C, NADM_MAX_C);
@@ -722,7 +738,8 @@ extern "C" int nadm_encoder_fwd(const uint8_t* packed, int64_t pitch, const int6
         for (int r0 = 0; r0 < B; r0 += chunk) {
             const int nb = std::min(chunk, B - r0);
             if (int rc = launch_enc_fwd_tc(packed, pitch, row_idx ? row_idx + r0 : nullptr, row0 + r0, nb, M, V, C,
-                                           Z + (int64_t)r0 * C, ws, ws_bytes, (cudaStream_t)stream))
+                                           Z + (int64_t)r0 * C, ws, ws_bytes, (cudaStream_t)stream, -1,
+                                           defer && B <= chunk && !enc_fwd_slab()))
                 return rc;
         }
         return NADM_OK;
@@ -730,6 +747,16 @@ extern "C" int nadm_encoder_fwd(const uint8_t* packed, int64_t pitch, const int6
     if (pad_c(C) == 8)
         return launch_enc_fwd<8>(packed, pitch, row_idx, row0, B, M, V, C, Z, (float*)ws, ws_bytes, (cudaStream_t)stream);
     return launch_enc_fwd<16>(packed, pitch, row_idx, row0, B, M, V, C, Z, (float*)ws, ws_bytes, (cudaStream_t)stream);
+}
+extern "C" int nadm_encoder_fwd(const uint8_t* packed, int64_t pitch, const int64_t* row_idx, int64_t row0, int32_t B,
+                                int64_t M, const float* V, int32_t C, float* Z, void* ws, size_t ws_bytes,
+                                void* stream) {
+    return encoder_fwd_impl(packed, pitch, row_idx, row0, B, M, V, C, Z, ws, ws_bytes, stream, false);
+}
+extern "C" int nadm_encoder_fwd_deferred(const uint8_t* packed, int64_t pitch, const int64_t* row_idx, int64_t row0,
+                                         int32_t B, int64_t M, const float* V, int32_t C, float* Z, void* ws,
+                                         size_t ws_bytes, void* stream) {
+    return encoder_fwd_impl(packed, pitch, row_idx, row0, B, M, V, C, Z, ws, ws_bytes, stream, true);
 }
 
 template <int KP>
@@ -762,10 +789,11 @@ static int launch_dec(const uint8_t* packed, int64_t pitch, const int64_t* row_i
     return NADM_OK;
 }
 
-extern "C" int nadm_decoder_step(const uint8_t* packed, int64_t pitch, const int64_t* row_idx, int64_t row0, int32_t B,
-                                 int64_t M, const float* Q, float* dQ, int32_t q_ld, int32_t q_off, int32_t k, float* P,
-                                 float* Pm, float* Pv, const nadm_adam_t* adam, float* dP_out, float* loss, void* ws,
-                                 size_t ws_bytes, void* stream) {
+static int decoder_step_impl(const uint8_t* packed, int64_t pitch, const int64_t* row_idx, int64_t row0, int32_t B,
+                             int64_t M, const float* Q, float* dQ, int32_t q_ld, int32_t q_off, int32_t k, float* P,
+                             float* Pm, float* Pv, const nadm_adam_t* adam, float* dP_out, float* loss, void* ws,
+                             size_t ws_bytes, void* stream, bool defer) {
+    if (int rc = flush_deferred_dq(dQ, (cudaStream_t)stream)) return rc;
     if (int rc = check_packed(packed, pitch, M)) return rc;
     NADM_REQUIRE(B > 0 && M > 0, "empty batch or no SNPs (B=%d, M=%lld)", B, (long long)M);
     NADM_REQUIRE(k >= 1 && k <= NADM_MAX_K, "k=%d unsupported (1..%d)", k, NADM_MAX_K);
@@ -779,12 +807,26 @@ extern "C" int nadm_decoder_step(const uint8_t* packed, int64_t pitch, const int
         (Pv == nullptr || (reinterpret_cast<uintptr_t>(Pv) & 15) == 0) &&
         (dP_out == nullptr || (reinterpret_cast<uintptr_t>(dP_out) & 15) == 0))
         return launch_dec_tc(packed, pitch, row_idx, row0, B, M, Q, dQ, q_ld, q_off, k, P, Pm, Pv, adam, dP_out, loss, w,
-                             ws_bytes, st);
+                             ws_bytes, st, defer);
     switch (pad_k(k)) {
         case 4: return launch_dec<4>(packed, pitch, row_idx, row0, B, M, Q, dQ, q_ld, q_off, k, P, Pm, Pv, adam, dP_out, loss, w, ws_bytes, st);
         case 8: return launch_dec<8>(packed, pitch, row_idx, row0, B, M, Q, dQ, q_ld, q_off, k, P, Pm, Pv, adam, dP_out, loss, w, ws_bytes, st);
         default: return launch_dec<16>(packed, pitch, row_idx, row0, B, M, Q, dQ, q_ld, q_off, k, P, Pm, Pv, adam, dP_out, loss, w, ws_bytes, st);
     }
+}
+extern "C" int nadm_decoder_step(const uint8_t* packed, int64_t pitch, const int64_t* row_idx, int64_t row0, int32_t B,
+                                 int64_t M, const float* Q, float* dQ, int32_t q_ld, int32_t q_off, int32_t k, float* P,
+                                 float* Pm, float* Pv, const nadm_adam_t* adam, float* dP_out, float* loss, void* ws,
+                                 size_t ws_bytes, void* stream) {
+    return decoder_step_impl(packed, pitch, row_idx, row0, B, M, Q, dQ, q_ld, q_off, k, P, Pm, Pv, adam, dP_out, loss, ws,
+                             ws_bytes, stream, false);
+}
+extern "C" int nadm_decoder_step_deferred(const uint8_t* packed, int64_t pitch, const int64_t* row_idx, int64_t row0,
+                                          int32_t B, int64_t M, const float* Q, float* dQ, int32_t q_ld, int32_t q_off,
+                                          int32_t k, float* P, float* Pm, float* Pv, const nadm_adam_t* adam,
+                                          float* dP_out, float* loss, void* ws, size_t ws_bytes, void* stream) {
+    return decoder_step_impl(packed, pitch, row_idx, row0, B, M, Q, dQ, q_ld, q_off, k, P, Pm, Pv, adam, dP_out, loss, ws,
+                             ws_bytes, stream, true);
 }
 
 template <int CP>

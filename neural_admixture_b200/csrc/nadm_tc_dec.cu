@@ -776,7 +776,8 @@ static int dec_pick_wgs(bool want_loss) {
 
 int launch_dec_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_idx, int64_t row0, int B, int64_t M,
                   const float* Q, float* dQ, int q_ld, int q_off, int k, float* P, float* Pm, float* Pv,
-                  const nadm_adam_t* adam, float* dP_out, float* loss, float* ws, size_t ws_bytes, cudaStream_t st) {
+                  const nadm_adam_t* adam, float* dP_out, float* loss, float* ws, size_t ws_bytes, cudaStream_t st,
+                  bool defer) {
     const bool want_loss = loss != nullptr;
     const int nblk = (B + 127) / 128;
     const int TS = (int)((M + kMS - 1) / kMS);
@@ -809,6 +810,14 @@ int launch_dec_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_idx, 
 #undef NADM_DEC_GO_WG
 #undef NADM_DEC_GO
     if (rc != NADM_OK || fused) return rc;
+    if (defer && ncta <= 152) {
+        // the consumer (nadm_mlp_bwd on this dQ) sums the partials of its own rows: no reduction kernel
+        DeferredDQ& d = deferred_dq();
+        d.dQ = dQ; d.part = dQpart; d.loss_part = want_loss ? loss_part : nullptr; d.loss = loss;
+        d.nparts = ncta; d.B = B; d.cols_p = 8 * KH; d.k = k; d.q_ld = q_ld; d.q_off = q_off;
+        d.bytes = (size_t)ncta * ((size_t)B * 8 * KH + 1) * sizeof(float);
+        return NADM_OK;
+    }
     return launch_reduce_parts(dQpart, ncta, B, 8 * KH, k, dQ, q_ld, q_off, 1.0f, want_loss ? loss_part : nullptr, loss, st);
 }
 

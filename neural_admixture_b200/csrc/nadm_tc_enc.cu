@@ -114,25 +114,6 @@ __device__ __forceinline__ void widen_regs(uint32_t w, uint32_t mvx, uint32_t* o
     }
 }
 
-// power-of-two fixed-point scale for values with absolute maximum `mx`: q = rint(v * inv) fits in [-2^30, 2^30]
-struct FixScale {
-    float inv;      // 2^(30 - e)
-    double back;    // 2^(e - 30)
-};
-__device__ __forceinline__ FixScale fix_scale(float mx) {
-    FixScale s;
-    const int E = (int)((__float_as_uint(mx) >> 23) & 0xFF);       // biased exponent: mx < 2^(E - 126)
-    if (E == 255) {   // Inf or NaN among the values: the result is NaN, as a floating-point matmul would give
-        s.inv = 0.f;
-        s.back = __longlong_as_double(0x7FF8000000000000ll);
-        return s;
-    }
-    if (mx == 0.f || E == 0) { s.inv = 0.f; s.back = 0.0; return s; }
-    const int e = max(E - 126, -96);                                // keep 2^(30-e) a finite float
-    s.inv = __uint_as_float((uint32_t)(127 + 30 - e) << 23);
-    s.back = __longlong_as_double((long long)(1023 + e - 30) << 52);
-    return s;
-}
 // |max| over floats as the maximum of their sign-cleared BIT PATTERNS: same order as the values for finite numbers, and
 // Inf / NaN (which fmaxf would drop) come out on top, so that fix_scale sees them
 __device__ __forceinline__ uint32_t absbits(float x) { return __float_as_uint(x) & 0x7FFFFFFFu; }
@@ -307,7 +288,8 @@ __device__ __forceinline__ void enc_fwd_reduce_share(const long long* __restrict
                                                      int nparts, int B, int C, float* __restrict__ Z, double out_scale,
                                                      double* back /* shared: nparts doubles */, double* zred /* shared */) {
     const int tid = threadIdx.x, nthr = blockDim.x;
-    for (int p = tid; p < nparts; p += nthr) back[p] = fix_scale(__ldcg(cta_vmax + p)).back;
+    (void)cta_vmax;                                                     // (the partials are pre-scaled doubles)
+    for (int p = tid; p < nparts; p += nthr) back[p] = 1.0;
     __syncthreads();
     const int64_t n = (int64_t)B * 8;
     const int o0 = (int)((n * blockIdx.x) / gridDim.x), o1 = (int)((n * (blockIdx.x + 1)) / gridDim.x);
@@ -327,12 +309,12 @@ __device__ __forceinline__ void enc_fwd_reduce_share(const long long* __restrict
 #pragma unroll
                 for (int i = 0; i < 10; ++i) {
                     const int p = seg + i * kZredSeg;
-                    if (p < nparts) acc += (double)v[i] * back[p];
+                    if (p < nparts) acc += __longlong_as_double(v[i]) * back[p];
                 }
                 zred[w] = acc;
             } else {
                 double acc = 0.0;
-                for (int p = seg; p < nparts; p += kZredSeg) acc += (double)__ldcg(src + (int64_t)p * n) * back[p];
+                for (int p = seg; p < nparts; p += kZredSeg) acc += __longlong_as_double(__ldcg(src + (int64_t)p * n)) * back[p];
                 zred[w] = acc;
             }
         }
@@ -507,12 +489,15 @@ enc_fwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
             }
             const int b = blk * 128 + q * 32 + lane;
             if (b < B) {
+                // the CTA's exact integer sums, times its power-of-two scale: exact in double (|sum| < 2^45), so the
+                // consumers just add doubles
                 long long* out = part + ((int64_t)blockIdx.x * B + b) * 8;
+                const double back = fix_scale(vmax).back;
 #pragma unroll
                 for (int c = 0; c < 8; c += 2) {
                     longlong2 z;
-                    z.x = combine4(v, c);
-                    z.y = combine4(v, c + 1);
+                    z.x = __double_as_longlong((double)combine4(v, c) * back);
+                    z.y = __double_as_longlong((double)combine4(v, c + 1) * back);
                     *reinterpret_cast<longlong2*>(out + c) = z;
                 }
             }
@@ -949,13 +934,19 @@ enc_fwd_reduce_kernel(const long long* __restrict__ part, int nparts, int B, int
     pdl_prologue();
     __shared__ double red[32][8];
     __shared__ double back[kMaxParts];
-    for (int p = threadIdx.x; p < nparts; p += blockDim.x) back[p] = fix_scale(cta_vmax[p]).back;
-    __syncthreads();
+    const bool scaled = (cta_vmax == nullptr);          // partials already multiplied by their CTA's scale (doubles)
+    if (!scaled) {
+        for (int p = threadIdx.x; p < nparts; p += blockDim.x) back[p] = fix_scale(cta_vmax[p]).back;
+        __syncthreads();
+    }
     const int c = threadIdx.x & 7, seg = threadIdx.x >> 3;
     const int b = blockIdx.x;
     const int64_t i = (int64_t)b * 8 + c;
     double acc = 0.0;
-    for (int p = seg; p < nparts; p += 32) acc += (double)part[(int64_t)p * B * 8 + i] * back[p];
+    if (scaled)
+        for (int p = seg; p < nparts; p += 32) acc += __longlong_as_double(part[(int64_t)p * B * 8 + i]);
+    else
+        for (int p = seg; p < nparts; p += 32) acc += (double)part[(int64_t)p * B * 8 + i] * back[p];
     red[seg][c] = acc;
     __syncthreads();
     if (threadIdx.x < 8 && c < C) {
@@ -1539,7 +1530,7 @@ size_t enc_tc_workspace_bytes(int B) { return (size_t)sm_count() * (size_t)B * 8
 
 // raw_mv < 0: training semantics (x = code / 2, missing -> 0).  raw_mv >= 0: raw uint8 values, code 3 -> raw_mv.
 int launch_enc_fwd_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_idx, int64_t row0, int B, int64_t M,
-                      const float* V, int C, float* Z, void* ws, size_t ws_bytes, cudaStream_t st, int raw_mv) {
+                      const float* V, int C, float* Z, void* ws, size_t ws_bytes, cudaStream_t st, int raw_mv, bool defer) {
     const int T = (int)((M + kSub - 1) / kSub);
     const int ncta = std::min(T, sm_count());
     const size_t need = (size_t)ncta * B * 8 * sizeof(long long) + kEncWsHeader;
@@ -1620,8 +1611,12 @@ int launch_enc_fwd_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_i
 #undef NADM_FWD_GO2
     if (le != cudaSuccess) return cuda_fail(le, "enc_fwd_tc_kernel");
     NADM_CHECK_LAUNCH("enc_fwd_tc_kernel");
-    if (!fused) {
-        launch_pdl(enc_fwd_reduce_kernel, dim3(B), dim3(256), 0, st, part, ncta, B, C, vmax, Z, out_scale);
+    if (!fused && defer && raw_mv < 0 && ncta <= 152) {
+        // the consumer (nadm_mlp_fwd on this Z) sums the partials of its own rows: no reduction kernel
+        DeferredZ& d = deferred_z();
+        d.Z = Z; d.part = part; d.vmax = nullptr; d.nparts = ncta; d.B = B;
+    } else if (!fused) {
+        launch_pdl(enc_fwd_reduce_kernel, dim3(B), dim3(256), 0, st, part, ncta, B, C, (const float*)nullptr, Z, out_scale);
         NADM_CHECK_LAUNCH("enc_fwd_reduce_kernel");
     }
     return NADM_OK;

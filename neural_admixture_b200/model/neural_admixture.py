@@ -154,8 +154,10 @@ class Q_P(torch.nn.Module):
         self.bind()
         B = row_idx.numel() if row_idx is not None else B
         buf = self._fwd_buffers(B)
-        ops.encoder_fwd(pg, self.V.data, buf["Z"], buf["ws"], row_idx=row_idx, row0=row0, B=B)
-        if allreduce is not None and xchg is None:
+        # the sum over the encoder's CTAs is left to the MLP kernel unless something (NCCL) must read Z in between
+        via_nccl = allreduce is not None and xchg is None
+        ops.encoder_fwd(pg, self.V.data, buf["Z"], buf["ws"], row_idx=row_idx, row0=row0, B=B, deferred=not via_nccl)
+        if via_nccl:
             allreduce(buf["Z"])
         ks = self.multihead_encoder.ks
         ops.mlp_fwd(buf["Z"], self.batch_norm.weight.data, self.common_encoder[0].weight.data,
@@ -363,9 +365,13 @@ class NeuralAdmixture:
             o.step_count += 1
             hyper = o.hyper()
         off = 0
-        for i, k in enumerate(m.multihead_encoder.ks):
+        ks = m.multihead_encoder.ks
+        via_nccl = self.sharded and xc is None
+        for i, k in enumerate(ks):
+            # the last head's sum over the decoder's CTAs is left to the MLP backward kernel (unless NCCL reads dQ first)
             ops.decoder_step(pg, fb["Q"], sb["dQ"], off, k, m.decoders.decoders[i].weight.data, o.m["P"][i], o.v["P"][i],
-                             hyper, sb["loss"] if loss_out is not None else None, fb["ws"], row_idx=row_idx)
+                             hyper, sb["loss"] if loss_out is not None else None, fb["ws"], row_idx=row_idx,
+                             deferred=(i == len(ks) - 1) and not via_nccl)
             off += k
         if self.sharded and xc is None:
             self._allreduce(sb["dq_loss"])

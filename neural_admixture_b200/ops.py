@@ -3,6 +3,7 @@ every computation below is a call into libnadm_b200.so on the current CUDA strea
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Sequence
 
 import torch
@@ -150,15 +151,22 @@ class PackedGenotypes:
         return out
 
 
+_DEFER = os.environ.get("NADM_NO_DEFER", "0") != "1"   # A/B switch: keep the separate reduction kernels
+
+
 def encoder_fwd(pg: PackedGenotypes, V: torch.Tensor, Z: torch.Tensor, ws: torch.Tensor, *,
-                row_idx: Optional[torch.Tensor] = None, row0: int = 0, B: Optional[int] = None) -> None:
+                row_idx: Optional[torch.Tensor] = None, row0: int = 0, B: Optional[int] = None,
+                deferred: bool = False) -> None:
+    """``deferred``: the sum over the kernel's CTAs may be left to the ``mlp_fwd`` call that follows ON THE SAME Z (and the
+    same ``ws``, untouched in between): nothing may read Z before that call."""
     _need_cuda(V, Z, ws, row_idx)
     B = (row_idx.numel() if row_idx is not None else B)
     assert V.dtype == torch.float32 and V.is_contiguous() and V.shape[0] == pg.M
     assert Z.dtype == torch.float32 and Z.is_contiguous() and Z.shape == (B, V.shape[1])
     assert row_idx is None or (row_idx.dtype == torch.int64 and row_idx.is_contiguous())
-    with _on(pg.storage): check(_lib.load().nadm_encoder_fwd(_ptr(pg.storage), pg.pitch, _ptr(row_idx), row0, B, pg.M, _ptr(V), V.shape[1],
-                                       _ptr(Z), _ptr(ws), ws.numel() * ws.element_size(), _stream(pg.storage)))
+    fn = _lib.load().nadm_encoder_fwd_deferred if (deferred and _DEFER) else _lib.load().nadm_encoder_fwd
+    with _on(pg.storage): check(fn(_ptr(pg.storage), pg.pitch, _ptr(row_idx), row0, B, pg.M, _ptr(V), V.shape[1],
+                                   _ptr(Z), _ptr(ws), ws.numel() * ws.element_size(), _stream(pg.storage)))
 
 
 def mlp_fwd(Z, w_rms, W1, b1, W2, b2, ks, rinv, Hh, Q, xchg: Optional[Xchg] = None) -> None:
@@ -174,16 +182,19 @@ def mlp_fwd(Z, w_rms, W1, b1, W2, b2, ks, rinv, Hh, Q, xchg: Optional[Xchg] = No
 
 
 def decoder_step(pg: PackedGenotypes, Q, dQ, q_off: int, k: int, P, Pm, Pv, adam: Optional[AdamHyper], loss, ws, *,
-                 row_idx=None, row0: int = 0, dP_out=None) -> None:
+                 row_idx=None, row0: int = 0, dP_out=None, deferred: bool = False) -> None:
+    """``deferred``: the sum over the kernel's CTAs (this head's columns of dQ, the head's loss) may be left to the
+    ``mlp_bwd`` call that follows ON THE SAME dQ and ``ws``; a later ``decoder_step`` on the same dQ completes it too."""
     _need_cuda(Q, dQ, P, Pm, Pv, loss, ws, row_idx, dP_out)   # loss may be None: gradients only
     B, q_ld = Q.shape
     assert P.shape == (pg.M, k) and P.is_contiguous() and P.dtype == torch.float32
     assert Q.is_contiguous() and dQ.is_contiguous() and dQ.shape == Q.shape
     assert row_idx is None or (row_idx.dtype == torch.int64 and row_idx.is_contiguous() and row_idx.numel() == B)
-    with _on(pg.storage): check(_lib.load().nadm_decoder_step(_ptr(pg.storage), pg.pitch, _ptr(row_idx), row0, B, pg.M, _ptr(Q), _ptr(dQ),
-                                        q_ld, q_off, k, _ptr(P), _ptr(Pm), _ptr(Pv),
-                                        None if adam is None else C.byref(adam), _ptr(dP_out), _ptr(loss), _ptr(ws),
-                                        ws.numel() * ws.element_size(), _stream(pg.storage)))
+    fn = _lib.load().nadm_decoder_step_deferred if (deferred and _DEFER) else _lib.load().nadm_decoder_step
+    with _on(pg.storage): check(fn(_ptr(pg.storage), pg.pitch, _ptr(row_idx), row0, B, pg.M, _ptr(Q), _ptr(dQ),
+                                   q_ld, q_off, k, _ptr(P), _ptr(Pm), _ptr(Pv),
+                                   None if adam is None else C.byref(adam), _ptr(dP_out), _ptr(loss), _ptr(ws),
+                                   ws.numel() * ws.element_size(), _stream(pg.storage)))
 
 
 def mlp_bwd(dQ, Q, Hh, Z, rinv, ks, params: MlpParams, adam: Optional[AdamHyper], dZ, loss, ws, *, labels=None,

@@ -173,6 +173,52 @@ def test_mlp_fwd_bwd(ops, dev, ks, H, B):
         assert abs(loss.item() - sup_loss) < 1e-5 * abs(sup_loss)
 
 
+@pytest.mark.parametrize("ks,B,M", [([8], 800, 40000), ([5], 130, 3000), ([3, 12, 6], 300, 9001), ([8], 2048, 20000)])
+def test_deferred_reductions_match_separate_kernels(ops, dev, ks, B, M):
+    """encoder_fwd(deferred) + mlp_fwd and decoder_step(deferred) + mlp_bwd (the sums over the producers' CTAs are
+    completed inside the consuming MLP kernels) against the same calls with their separate reduction kernels: the
+    forward sums exact integers in double (same value up to the final rounding), dQ is a re-ordered fp32 sum."""
+    from neural_admixture_b200._lib import MlpParams
+    rng = np.random.default_rng(B + M)
+    N, C, H, sumK = B + 50, 8, 256, sum(ks)
+    G = rand_genotypes(rng, N, M)
+    pg = packed_from(ops, G, dev)
+    idx = t(rng.permutation(N)[:B], dev, torch.int64)
+    V = t((rng.standard_normal((M, C)) / np.sqrt(M)), dev)
+    prm = {"w_rms": t(1 + 0.1 * rng.standard_normal(C), dev), "W1": t(rng.standard_normal((H, C)) / np.sqrt(C), dev),
+           "b1": t(0.1 * rng.standard_normal(H), dev), "W2": t(rng.standard_normal((sumK, H)) / np.sqrt(H), dev),
+           "b2": t(0.1 * rng.standard_normal(sumK), dev)}
+    Ps = [t(rng.uniform(0.02, 0.98, size=(M, k)), dev) for k in ks]
+    ws = ws_for(ops, B, M, C, H, sumK, dev)
+    outs = []
+    for deferred in (False, True):
+        Z = torch.empty((B, C), device=dev)
+        rinv, Hh, Q = torch.empty(B, device=dev), torch.empty((B, H), device=dev), torch.empty((B, sumK), device=dev)
+        ops.encoder_fwd(pg, V, Z, ws, row_idx=idx, deferred=deferred)
+        ops.mlp_fwd(Z, prm["w_rms"], prm["W1"], prm["b1"], prm["W2"], prm["b2"], ks, rinv, Hh, Q)
+        dQ = torch.zeros((B, sumK), device=dev)
+        loss = torch.zeros(1, device=dev)
+        off = 0
+        for i, k in enumerate(ks):       # every head deferred: a pending reduction is completed by the next head's call
+            ops.decoder_step(pg, Q, dQ, off, k, Ps[i], None, None, None, loss, ws, row_idx=idx, deferred=deferred)
+            off += k
+        g = {n: torch.zeros_like(prm[n]) for n in prm}
+        p = MlpParams()
+        for n in prm:
+            setattr(p, n, prm[n].data_ptr())
+            setattr(p, "g_" + n, g[n].data_ptr())
+        dZ = torch.empty((B, C), device=dev)
+        ops.mlp_bwd(dQ, Q, Hh, Z, rinv, ks, p, None, dZ, loss, ws)
+        outs.append({"Z": Z, "Q": Q, "Hh": Hh, "dQ": dQ, "dZ": dZ, "loss": loss, **{"g_" + n: g[n] for n in g}})
+    a, b = outs
+    assert torch.equal(a["Z"], b["Z"]) or relF(b["Z"].cpu().numpy(), a["Z"].cpu().numpy()) < 1e-7
+    for n in ("Q", "Hh"):
+        assert relF(b[n].cpu().numpy(), a[n].cpu().numpy()) < 1e-6, n
+    for n in ("dQ", "dZ", "g_W1", "g_W2", "g_b1", "g_b2", "g_w_rms"):
+        assert relF(b[n].cpu().numpy(), a[n].cpu().numpy()) < 2e-6, n
+    assert abs(a["loss"].item() - b["loss"].item()) <= 2e-7 * abs(a["loss"].item())
+
+
 @pytest.mark.parametrize("N,M,k,B,edge", [(64, 203, 5, 48, True), (300, 4099, 8, 300, False), (1000, 20000, 8, 800, True),
                                           (40, 1024, 3, 40, True), (90, 515, 12, 77, False), (20, 9, 2, 20, True),
                                           (900, 9001, 16, 800, True), (300, 2050, 9, 300, True)])
