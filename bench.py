@@ -554,8 +554,8 @@ def main():
 
     step_launch = "cuda-graph replay (one graph launch per step)" if na.use_graph else "eager launches"
     exchange = None if world == 1 else (
-        "fused into the MLP kernels: stores over NVLink into peer-mapped exchange areas + sequence flags (no NCCL kernel "
-        "in the step)" if na.exchange is not None else "2 NCCL all-reduces per step (inside the replayed graph)")
+        "fused into the MLP kernels: 8-byte {value, exchange number} stores over NVLink into peer-mapped exchange areas, "
+        "no fence, no flag, no NCCL kernel in the step" if na.exchange is not None else "2 NCCL all-reduces per step (inside the replayed graph)")
     generic = int(na.generic_kernel_launches)
     fallback = na.graph_fallback
     cpu = None
