@@ -300,7 +300,7 @@ def cuda_reference(wl, ks, M, B, steps, warmup):
 def ncu_digest(M_loc, B, ks):
     """(dram bytes per launch, warp instructions per launch) of dec_tc_kernel from profiles/*ncu_summary.json whose
     recorded config equals this run's (M_loc, B, heads); (None, None) otherwise — never a number from another shape."""
-    for name in ("r2_ncu_summary.json",):
+    for name in ("r2_final_ncu_summary.json", "r2_ncu_summary.json"):
         f = ROOT / "profiles" / name
         if not f.exists():
             continue
@@ -473,7 +473,7 @@ def main():
                 "frac": dec_bytes / (dec_t * 1e-3) / 1e9 / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": dec_bytes, "ms_per_launch": dec_t,
                 "traffic_source": ("dram__bytes_read.sum + dram__bytes_write.sum of one launch at this configuration, "
-                                   "profiles/r2_ncu_summary.json") if traffic else
+                                   "profiles/r2_final_ncu_summary.json") if traffic else
                                   "null: no ncu --set full capture committed for this (M_loc, B, heads)",
                 "issue_floor_ms": issue_floor_ms,
                 "issue_floor_what": "warp instructions of one launch (ncu capture, this configuration) / (148 SMs x 4 "
