@@ -330,6 +330,9 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=25.0, help="seconds of CPU work for the cpu_baseline leg")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--breakdown", action="store_true",
+                    help="add `calls_us`: in-pipeline CUDA-event time of every library call of a step (eager launches "
+                         "after the timed region), on rank 0 and as the max over ranks: how a rank's step is apportioned")
     args = ap.parse_args()
     assert args.warmup >= 0 and args.steps >= 1
 
@@ -552,6 +555,40 @@ def main():
                        "pinned host memory (double-buffered side stream), the fused step runs, loss read back"}
         assert all(math.isfinite(x) for x in hl)
 
+    # ---- optional: how the step is apportioned (eager launches with an event pair around every library call) --------
+    calls_us = None
+    if args.breakdown:
+        from collections import defaultdict
+        names = ["encoder_fwd", "mlp_fwd", "decoder_step", "mlp_bwd", "encoder_bwd"]
+        orig = {n_: getattr(ops, n_) for n_ in names}
+        rec = defaultdict(list)
+
+        def wrap(n_):
+            f = orig[n_]
+
+            def g(*a, **kw):
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record()
+                f(*a, **kw)
+                ev1.record()
+                rec[n_].append((ev0, ev1))
+            return g
+
+        for n_ in names:
+            setattr(ops, n_, wrap(n_))
+        lb = torch.zeros(1, device=dev)
+        for s_ in range(24):
+            na._train_step(order[s_ * B:(s_ + 1) * B], None, lb)
+        sync_all()
+        for n_ in names:
+            setattr(ops, n_, orig[n_])
+        mine = {n_: sum(a.elapsed_time(b) for a, b in v[4:]) * 1e3 / max(1, len(v) - 4) for n_, v in rec.items()}
+        calls_us = {"rank0": {k_: round(mine[k_], 1) for k_ in names},
+                    "max_over_ranks": {k_: round(max_over_ranks(mine[k_]), 1) for k_ in names},
+                    "what": "eager launches, CUDA events around each library call on the step's stream (20 steps); "
+                            "mlp_fwd / mlp_bwd include the wait for the peers inside the fused exchange; the graph-"
+                            "replayed step (ms_per_step) has none of the host launch gaps these calls see"}
+
     step_launch = "cuda-graph replay (one graph launch per step)" if na.use_graph else "eager launches"
     exchange = None if world == 1 else (
         "fused into the MLP kernels: 8-byte {value, exchange number} stores over NVLink into peer-mapped exchange areas, "
@@ -582,7 +619,7 @@ def main():
                 "clocks": clocks, "loss": {"first_timed_step": loss_first, "last_timed_step": loss_last,
                                            "schedule": "evaluated on every timed step, as the reference does"},
                 "step_launch": step_launch, "graph_fallback": fallback, "generic_kernel_launches": generic,
-                "exchange": exchange,
+                "exchange": exchange, "calls_us": calls_us,
                 "infer": infer, "late_training": late,
                 "grad_only": {"value": B * n_go / (ms_go * 1e-3), "unit": UNIT, "steps": n_go,
                               "ms_per_step": ms_go / n_go,

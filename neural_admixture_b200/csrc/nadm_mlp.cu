@@ -72,6 +72,10 @@ bool use_generic_kernels() {
 
 constexpr int kMlpRows = 4;       // batch rows per CTA in the per-row kernels
 constexpr int kMlpThreads = 256;
+#ifndef NADM_BWD_THREADS
+#define NADM_BWD_THREADS 256
+#endif
+constexpr int kBwdThreads = NADM_BWD_THREADS;   // threads of the backward rows kernel
 constexpr int kMaxSumK = NADM_MAX_K * NADM_MAX_HEADS;
 
 struct Heads {
@@ -383,7 +387,7 @@ struct DQParts {
 constexpr int kDqMaxIter = 19;
 
 template <int CP>   // components padded to 8 or 16
-__global__ void __launch_bounds__(kMlpThreads)
+__global__ void __launch_bounds__(kBwdThreads)
 mlp_bwd_rows_kernel(float* dQ, const float* __restrict__ Q, const float* __restrict__ Hh,
                     const float* __restrict__ Z, const float* __restrict__ rinv, int B, int C, int H, Heads hd,
                     const int64_t* __restrict__ labels, float sup_weight, const float* __restrict__ w_rms,
@@ -394,7 +398,7 @@ mlp_bwd_rows_kernel(float* dQ, const float* __restrict__ Q, const float* __restr
     float* dLs = sm;                                         // kBwdRows x sumK
     float* Zn = dLs + (size_t)kBwdRows * hd.sumK;             // kBwdRows x MAX_C   (normalised inputs, recomputed)
     float* red = Zn + kBwdRows * CP;                  // nwarps x kBwdRows x MAX_C  (dZn partials per warp)
-    float* sups = red + (kMlpThreads / 32) * kBwdRows * CP;   // kBwdRows
+    float* sups = red + (kBwdThreads / 32) * kBwdRows * CP;   // kBwdRows
     float* qs = sups + kBwdRows;                              // kBwdRows x sumK : the rows' Q
     float* dqs = qs + (size_t)kBwdRows * hd.sumK;             // kBwdRows x sumK : the rows' dQ (summed over CTAs / ranks)
     float* xt = dqs + (size_t)kBwdRows * hd.sumK;             // scratch: max(256, world x kBwdRows x sumK) floats
@@ -423,7 +427,7 @@ mlp_bwd_rows_kernel(float* dQ, const float* __restrict__ Q, const float* __restr
     if (dp.nparts > 0) {
         // sum the decoder's per-CTA partials of these rows' dQ here (no reduction kernel): thread = (output o = row x
         // cols_p + column, segment of the parts); the rows' partials are contiguous, so a warp's loads are coalesced.
-        const int nout = kBwdRows * dp.cols_p, segs = kMlpThreads / nout;      // 64 x 4 or 128 x 2
+        const int nout = kBwdRows * dp.cols_p, segs = kBwdThreads / nout;      // 64 x 4 or 128 x 2
         const int o = tid % nout, seg = tid / nout;
         const int64_t n = (int64_t)B * dp.cols_p;
         float acc = 0.f;
@@ -570,7 +574,7 @@ mlp_bwd_rows_kernel(float* dQ, const float* __restrict__ Q, const float* __restr
         const int r = tid / CP, c = tid % CP, b = b0 + r;
         float d = 0.f;
 #pragma unroll
-        for (int w = 0; w < kMlpThreads / 32; ++w) d += red[(w * kBwdRows + r) * CP + c];
+        for (int w = 0; w < kBwdThreads / 32; ++w) d += red[(w * kBwdRows + r) * CP + c];
         const bool ok = (b < B) && (c < C);
         const float z = ok ? Z[(int64_t)b * C + c] : 0.f;
         const float wr = ok ? w_rms[c] : 0.f;
@@ -796,9 +800,9 @@ extern "C" int nadm_mlp_bwd(float* dQ, const float* Q, const float* Hh, const fl
         }
     }
     const int CP = C <= 8 ? 8 : 16;
-    const size_t xt_floats = std::max<size_t>(kMlpThreads, xc.world > 1 ? (size_t)xc.world * kBwdRows * hd.sumK : 0);
+    const size_t xt_floats = std::max<size_t>(kBwdThreads, xc.world > 1 ? (size_t)xc.world * kBwdRows * hd.sumK : 0);
     const size_t smem = ((size_t)3 * kBwdRows * hd.sumK + (size_t)kBwdRows * CP +
-                         (size_t)(kMlpThreads / 32) * kBwdRows * CP + kBwdRows + xt_floats) * sizeof(float);
+                         (size_t)(kBwdThreads / 32) * kBwdRows * CP + kBwdRows + xt_floats) * sizeof(float);
     if (smem > 48 * 1024) {                          // very wide head sets only (sumK > ~480)
         static PerDeviceOnce once_b;
         bool* ab = once_b.slot();
@@ -811,10 +815,10 @@ extern "C" int nadm_mlp_bwd(float* dQ, const float* Q, const float* Hh, const fl
         }
     }
     if (CP == 8)
-        launch_pdl(mlp_bwd_rows_kernel<8>, dim3(nslab), dim3(kMlpThreads), smem, st, dQ, Q, Hh, Z, rinv, B, C, H, hd, labels,
+        launch_pdl(mlp_bwd_rows_kernel<8>, dim3(nslab), dim3(kBwdThreads), smem, st, dQ, Q, Hh, Z, rinv, B, C, H, hd, labels,
                    sup_weight, p.w_rms, p.W1, p.W2, gpart, dZ, loss, dp, xc);
     else
-        launch_pdl(mlp_bwd_rows_kernel<16>, dim3(nslab), dim3(kMlpThreads), smem, st, dQ, Q, Hh, Z, rinv, B, C, H, hd, labels,
+        launch_pdl(mlp_bwd_rows_kernel<16>, dim3(nslab), dim3(kBwdThreads), smem, st, dQ, Q, Hh, Z, rinv, B, C, H, hd, labels,
                    sup_weight, p.w_rms, p.W1, p.W2, gpart, dZ, loss, dp, xc);
     NADM_CHECK_LAUNCH("mlp_bwd_rows_kernel");
     const AdamCoef ac = make_adam(adam);
