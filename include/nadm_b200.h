@@ -172,6 +172,15 @@ int nadm_mlp_bwd(float* dQ, const float* Q, const float* Hh, const float* Z, con
                  const nadm_mlp_params_t* params /*[host]*/, const nadm_adam_t* adam /*[host]*/,
                  float* dZ, float* loss, void* ws, size_t ws_bytes, const nadm_xchg_t* xchg /*[host], may be NULL*/,
                  void* stream);
+/* Same call, but the parameter update (sum of the per-CTA gradient slabs in `ws` + Adam on W1, b1, W2, b2, w_rms + the
+ * supervised loss term) is left pending: the nadm_encoder_bwd of this host thread that follows on the same dZ runs it on
+ * its epilogue warps, inside the same kernel (the update depends on nothing that kernel computes; bit-identical to the
+ * separate kernel).  Any other call of this library that reads the network's parameters or finishes a step runs the
+ * pending update first, as its own kernel.  Contract: nothing else reads the parameters, *loss or writes `ws` in between. */
+int nadm_mlp_bwd_deferred(float* dQ, const float* Q, const float* Hh, const float* Z, const float* rinv,
+                          int32_t B, int32_t C, int32_t H, const int32_t* ks, int32_t nheads, const int64_t* labels,
+                          float sup_weight, const nadm_mlp_params_t* params, const nadm_adam_t* adam, float* dZ,
+                          float* loss, void* ws, size_t ws_bytes, const nadm_xchg_t* xchg, void* stream);
 
 /* ---- encoder backward: dV = X^T dZ, then Adam on V.  Replaces the autograd of `X @ self.V`
  * (neural_admixture.py:172,:410) and the V part of optimizer.step() (:411).  dV_out optional. */

@@ -61,6 +61,10 @@ SIGNATURES = {
                                C.POINTER(C.c_int32), C.c_int32, c_i64p, C.c_float, C.POINTER(MlpParams),
                                C.POINTER(AdamHyper), c_f32p, c_f32p, C.c_void_p, C.c_size_t, C.POINTER(Xchg),
                                C.c_void_p]),
+    "nadm_mlp_bwd_deferred": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int32, C.c_int32, C.c_int32,
+                               C.POINTER(C.c_int32), C.c_int32, c_i64p, C.c_float, C.POINTER(MlpParams),
+                               C.POINTER(AdamHyper), c_f32p, c_f32p, C.c_void_p, C.c_size_t, C.POINTER(Xchg),
+                               C.c_void_p]),
     "nadm_xchg_area_bytes": (C.c_size_t, [C.c_int64]),
     "nadm_ipc_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p), C.c_void_p]),
     "nadm_ipc_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),

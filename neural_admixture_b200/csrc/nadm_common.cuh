@@ -196,6 +196,32 @@ struct DeferredDQ {
 };
 DeferredZ& deferred_z();
 DeferredDQ& deferred_dq();
+// ---- deferred parameter update of the small network: nadm_mlp_bwd_deferred leaves "sum the CTAs' gradient slabs +
+// Adam on W1, b1, W2, b2, w_rms" pending; the nadm_encoder_bwd call that follows on the same dZ runs it on its epilogue
+// warps while its producers fill the first tiles (the update depends on nothing that kernel computes), instead of a
+// kernel of its own between the two.  Any other library call that reads the network's parameters or the loss first
+// runs the pending update as the separate kernel (flush_deferred_apply).
+#ifdef __CUDACC__
+#define NADM_HD __host__ __device__
+#else
+#define NADM_HD
+#endif
+NADM_HD inline size_t mlp_slab_floats(int C, int H, int sumK) {
+    return (size_t)(C + 1) * H + (size_t)sumK * H + (size_t)sumK + (size_t)C + 1;
+}
+struct ApplyJob {
+    const float* part;          // nslab slabs of mlp_slab_floats(C, H, sumK) partial gradients (NULL / nslab 0: no job)
+    int nslab, C, H, sumK, has_sup;
+    nadm_mlp_params_t prm;
+    AdamCoef adam;
+    float* loss;
+};
+struct DeferredApply {
+    const float* dZ;            // key: the dZ the pending update belongs to (NULL: nothing pending)
+    ApplyJob job;
+};
+DeferredApply& deferred_apply();
+int flush_deferred_apply(cudaStream_t st);   // nadm_mlp.cu
 
 // tensor-core (tcgen05) encoder kernels, nadm_tc_enc.cu
 int launch_enc_fwd_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_idx, int64_t row0, int B, int64_t M,
@@ -203,7 +229,8 @@ int launch_enc_fwd_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_i
                       bool defer = false);
 int launch_enc_bwd_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_idx, int64_t row0, int B, int64_t M,
                       const float* dZ, int C, float* V, float* Vm, float* Vv, const nadm_adam_t* adam, float* dV_out,
-                      cudaStream_t st, int raw_mv = -1, int accumulate = 0);
+                      cudaStream_t st, int raw_mv = -1, int accumulate = 0, const struct ApplyJob* job = nullptr);
+bool enc_bwd_runs_apply(int B);   // the default backward kernel can take a pending parameter update along (not the slab variant)
 size_t enc_tc_workspace_bytes(int B);
 size_t mlp_bwd_workspace_bytes(int B, int C, int H, int sumK);   // nadm_mlp.cu
 bool enc_bwd_tc_supported(int B);
@@ -258,6 +285,85 @@ __device__ __forceinline__ float adam_apply(float p, float g, float& m, float& v
     v = c.beta2 * v + c.one_minus_beta2 * g * g;
     float denom = sqrtf(v) * c.inv_bc2_sqrt + c.eps;
     return p - c.step_size * (m / denom);
+}
+__device__ __forceinline__ void adam_store(float* p, float* m, float* v, float* gout, int64_t i, float g,
+                                           const AdamCoef& c) {
+    if (gout != nullptr) gout[i] = g;
+    if (c.enabled) {
+        float mm = m[i], vv = v[i];
+        p[i] = adam_apply(p[i], g, mm, vv, c);
+        m[i] = mm;
+        v[i] = vv;
+    }
+}
+// element i of the network's flat gradient (slab layout: [(C+1) x H | sumK x H | sumK | C | 1]) -> its parameter
+__device__ __forceinline__ void mlp_apply_param(size_t i, float g, const ApplyJob& jb, const AdamCoef& adam) {
+    const int C = jb.C, H = jb.H, sumK = jb.sumK;
+    const nadm_mlp_params_t& prm = jb.prm;
+    const size_t n1 = (size_t)(C + 1) * H, n2 = n1 + (size_t)sumK * H;
+    if (i < n1) {
+        const int c = (int)(i / H), jj = (int)(i % H);
+        if (c < C) adam_store(prm.W1, prm.m_W1, prm.v_W1, prm.g_W1, (int64_t)jj * C + c, g, adam);
+        else adam_store(prm.b1, prm.m_b1, prm.v_b1, prm.g_b1, jj, g, adam);
+    } else if (i < n2) {
+        adam_store(prm.W2, prm.m_W2, prm.v_W2, prm.g_W2, (int64_t)(i - n1), g, adam);
+    } else if (i < n2 + sumK) {
+        adam_store(prm.b2, prm.m_b2, prm.v_b2, prm.g_b2, (int64_t)(i - n2), g, adam);
+    } else if (i < n2 + sumK + C) {
+        adam_store(prm.w_rms, prm.m_w_rms, prm.v_w_rms, prm.g_w_rms, (int64_t)(i - n2 - sumK), g, adam);
+    } else if (jb.has_sup) {
+        *jb.loss += g;
+    }
+}
+// Sum over the slabs in EXACTLY the association of mlp_bwd_apply_kernel (8 interleaved groups of two chains each, the
+// groups' sums added pairwise in order): the two forms of the update are bit-identical.  Group q of element i:
+__device__ __forceinline__ float mlp_apply_group_sum(const float* __restrict__ part, size_t n, size_t i, int nslab, int q) {
+    float g0 = 0.f, g1 = 0.f;
+    if (nslab <= 13 * 8) {
+        // every slab of the group in flight at once (this runs on warps that have better things to wait for); adding the
+        // +0 of an absent slab changes nothing, so the association is the loop's below
+        float v[13];
+#pragma unroll
+        for (int k = 0; k < 13; ++k) {
+            const int z = q + 8 * k;
+            v[k] = (z < nslab) ? __ldcg(part + (size_t)z * n + i) : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 13; k += 2) g0 += v[k];
+#pragma unroll
+        for (int k = 1; k < 13; k += 2) g1 += v[k];
+        return g0 + g1;
+    }
+    int z = q;
+    for (; z + 8 < nslab; z += 16) {
+        g0 += __ldcg(part + (size_t)z * n + i);
+        g1 += __ldcg(part + (size_t)(z + 8) * n + i);
+    }
+    if (z < nslab) g0 += __ldcg(part + (size_t)z * n + i);
+    return g0 + g1;
+}
+// The share of CTA `cta` of `nctas` of a pending update, run by `nthr` threads (whole warps, t = 0 .. nthr - 1): lane
+// pairs (2 p, 2 p + 1) take one parameter, four groups each, and meet through two shuffles.
+__device__ __forceinline__ void mlp_apply_share(const ApplyJob& jb, int cta, int nctas, int t, int nthr) {
+    const AdamCoef adam = adam_resolve(jb.adam);
+    const size_t n = mlp_slab_floats(jb.C, jb.H, jb.sumK);
+    const size_t i0 = n * (size_t)cta / (size_t)nctas, i1 = n * (size_t)(cta + 1) / (size_t)nctas;
+    const int half = t & 1;
+    const size_t cnt = i1 - i0, cnt_pad = (cnt + 15) & ~(size_t)15;     // whole warps stay in the loop (shuffles)
+    for (size_t pi = (size_t)(t >> 1); pi < cnt_pad; pi += (size_t)(nthr >> 1)) {
+        const bool ok = pi < cnt;
+        const size_t i = i0 + (ok ? pi : 0);
+        float r[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) r[q] = ok ? mlp_apply_group_sum(jb.part, n, i, jb.nslab, 4 * half + q) : 0.f;
+        const float a = r[0] + r[1], b = r[2] + r[3];                  // (red[q] + red[q + 1]) of this half
+        const float a1 = __shfl_xor_sync(0xffffffffu, a, 1), b1 = __shfl_xor_sync(0xffffffffu, b, 1);
+        if (ok && half == 0) {
+            float g = 0.f;
+            g += a; g += b; g += a1; g += b1;                           // 0 + (r0+r1) + (r2+r3) + (r4+r5) + (r6+r7)
+            mlp_apply_param(i, g, jb, adam);
+        }
+    }
 }
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {

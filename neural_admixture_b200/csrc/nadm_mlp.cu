@@ -374,9 +374,6 @@ mlp_fwd_kernel(float* Z, int B, int C, int H, const float* __restrict__ w_rms,
 // =================================================================================================================
 constexpr int kBwdRows = 8;
 
-__host__ __device__ inline size_t mlp_slab_floats(int C, int H, int sumK) {
-    return (size_t)(C + 1) * H + (size_t)sumK * H + (size_t)sumK + (size_t)C + 1;
-}
 
 // deferred reduction of the decoder's per-CTA dQ partials of ONE head (see DeferredDQ): nparts == 0 -> dQ is complete
 struct DQParts {
@@ -604,17 +601,6 @@ mlp_bwd_rows_kernel(float* dQ, const float* __restrict__ Q, const float* __restr
 // backward, phase 2: sum the slabs in a fixed order (deterministic) and apply Adam to W1, b1, W2, b2, w_rms; the
 // supervised loss term is added to *loss.
 // =================================================================================================================
-__device__ __forceinline__ void adam_store(float* p, float* m, float* v, float* gout, int64_t i, float g,
-                                           const AdamCoef& c) {
-    if (gout != nullptr) gout[i] = g;
-    if (c.enabled) {
-        float mm = m[i], vv = v[i];
-        p[i] = adam_apply(p[i], g, mm, vv, c);
-        m[i] = mm;
-        v[i] = vv;
-    }
-}
-
 constexpr int kApplyParams = 64, kApplyGroups = 8;   // a block sums 64 parameters' slabs in 8 interleaved groups
 
 __global__ void __launch_bounds__(kApplyParams * kApplyGroups)
@@ -642,20 +628,26 @@ mlp_bwd_apply_kernel(const float* __restrict__ part, int nslab, int C, int H, in
     float g = 0.f;
 #pragma unroll
     for (int q = 0; q < kApplyGroups; q += 2) g += red[q][j] + red[q + 1][j];      // fixed order
-    const size_t n1 = (size_t)(C + 1) * H, n2 = n1 + (size_t)sumK * H;
-    if (i < n1) {
-        const int c = (int)(i / H), jj = (int)(i % H);
-        if (c < C) adam_store(prm.W1, prm.m_W1, prm.v_W1, prm.g_W1, (int64_t)jj * C + c, g, adam);
-        else adam_store(prm.b1, prm.m_b1, prm.v_b1, prm.g_b1, jj, g, adam);
-    } else if (i < n2) {
-        adam_store(prm.W2, prm.m_W2, prm.v_W2, prm.g_W2, (int64_t)(i - n1), g, adam);
-    } else if (i < n2 + sumK) {
-        adam_store(prm.b2, prm.m_b2, prm.v_b2, prm.g_b2, (int64_t)(i - n2), g, adam);
-    } else if (i < n2 + sumK + C) {
-        adam_store(prm.w_rms, prm.m_w_rms, prm.v_w_rms, prm.g_w_rms, (int64_t)(i - n2 - sumK), g, adam);
-    } else if (has_sup) {
-        *loss += g;
-    }
+    ApplyJob jb{part, nslab, C, H, sumK, has_sup, prm, adam, loss};
+    mlp_apply_param(i, g, jb, adam);
+}
+
+DeferredApply& deferred_apply() { static thread_local DeferredApply d{}; return d; }
+
+static int launch_apply(const ApplyJob& jb, cudaStream_t st) {
+    const size_t nparam = mlp_slab_floats(jb.C, jb.H, jb.sumK);
+    launch_pdl(mlp_bwd_apply_kernel, dim3((unsigned)((nparam + kApplyParams - 1) / kApplyParams)), dim3(kApplyParams * kApplyGroups),
+               0, st, jb.part, jb.nslab, jb.C, jb.H, jb.sumK, jb.has_sup, jb.prm, jb.adam, jb.loss);
+    NADM_CHECK_LAUNCH("mlp_bwd_apply_kernel");
+    return NADM_OK;
+}
+// a pending update (nadm_mlp_bwd_deferred not followed by the nadm_encoder_bwd that would have run it) as its own kernel
+int flush_deferred_apply(cudaStream_t st) {
+    DeferredApply& d = deferred_apply();
+    if (d.dZ == nullptr) return NADM_OK;
+    const ApplyJob jb = d.job;
+    d.dZ = nullptr;
+    return launch_apply(jb, st);
 }
 
 size_t mlp_bwd_workspace_bytes(int B, int C, int H, int sumK) {
@@ -722,6 +714,7 @@ extern "C" int nadm_ipc_free(void* dev_ptr) {
 extern "C" int nadm_mlp_fwd(float* Z, int32_t B, int32_t C, int32_t H, const float* w_rms, const float* W1,
                             const float* b1, const float* W2, const float* b2, const int32_t* ks, int32_t nheads,
                             float* rinv, float* Hh, float* Q, const nadm_xchg_t* xchg, void* stream) {
+    if (int rc = flush_deferred_apply((cudaStream_t)stream)) return rc;   // (this kernel reads the network's parameters)
     Heads hd;
     if (int rc = make_heads(ks, nheads, &hd)) return rc;
     Xchg xc;
@@ -756,10 +749,11 @@ extern "C" int nadm_mlp_fwd(float* Z, int32_t B, int32_t C, int32_t H, const flo
     return NADM_OK;
 }
 
-extern "C" int nadm_mlp_bwd(float* dQ, const float* Q, const float* Hh, const float* Z, const float* rinv,
-                            int32_t B, int32_t C, int32_t H, const int32_t* ks, int32_t nheads, const int64_t* labels,
-                            float sup_weight, const nadm_mlp_params_t* params, const nadm_adam_t* adam, float* dZ,
-                            float* loss, void* ws, size_t ws_bytes, const nadm_xchg_t* xchg, void* stream) {
+static int mlp_bwd_impl(float* dQ, const float* Q, const float* Hh, const float* Z, const float* rinv,
+                        int32_t B, int32_t C, int32_t H, const int32_t* ks, int32_t nheads, const int64_t* labels,
+                        float sup_weight, const nadm_mlp_params_t* params, const nadm_adam_t* adam, float* dZ,
+                        float* loss, void* ws, size_t ws_bytes, const nadm_xchg_t* xchg, void* stream, bool defer_apply) {
+    if (int rc = flush_deferred_apply((cudaStream_t)stream)) return rc;
     Heads hd;
     if (int rc = make_heads(ks, nheads, &hd)) return rc;
     Xchg xc;
@@ -821,10 +815,27 @@ extern "C" int nadm_mlp_bwd(float* dQ, const float* Q, const float* Hh, const fl
         launch_pdl(mlp_bwd_rows_kernel<16>, dim3(nslab), dim3(kBwdThreads), smem, st, dQ, Q, Hh, Z, rinv, B, C, H, hd, labels,
                    sup_weight, p.w_rms, p.W1, p.W2, gpart, dZ, loss, dp, xc);
     NADM_CHECK_LAUNCH("mlp_bwd_rows_kernel");
-    const AdamCoef ac = make_adam(adam);
-    const size_t nparam = mlp_slab_floats(C, H, hd.sumK);
-    launch_pdl(mlp_bwd_apply_kernel, dim3((unsigned)((nparam + kApplyParams - 1) / kApplyParams)), dim3(kApplyParams * kApplyGroups),
-               0, st, gpart, nslab, C, H, hd.sumK, (int)(labels != nullptr), p, ac, loss);
-    NADM_CHECK_LAUNCH("mlp_bwd_apply_kernel");
-    return NADM_OK;
+    const ApplyJob jb{gpart, nslab, C, H, hd.sumK, (int)(labels != nullptr), p, make_adam(adam), loss};
+    if (defer_apply) {       // the nadm_encoder_bwd that follows on this dZ runs the update on its epilogue warps
+        DeferredApply& d = deferred_apply();
+        d.dZ = dZ;
+        d.job = jb;
+        return NADM_OK;
+    }
+    return launch_apply(jb, st);
+}
+extern "C" int nadm_mlp_bwd(float* dQ, const float* Q, const float* Hh, const float* Z, const float* rinv,
+                            int32_t B, int32_t C, int32_t H, const int32_t* ks, int32_t nheads, const int64_t* labels,
+                            float sup_weight, const nadm_mlp_params_t* params, const nadm_adam_t* adam, float* dZ,
+                            float* loss, void* ws, size_t ws_bytes, const nadm_xchg_t* xchg, void* stream) {
+    return mlp_bwd_impl(dQ, Q, Hh, Z, rinv, B, C, H, ks, nheads, labels, sup_weight, params, adam, dZ, loss, ws, ws_bytes,
+                        xchg, stream, false);
+}
+extern "C" int nadm_mlp_bwd_deferred(float* dQ, const float* Q, const float* Hh, const float* Z, const float* rinv,
+                                     int32_t B, int32_t C, int32_t H, const int32_t* ks, int32_t nheads,
+                                     const int64_t* labels, float sup_weight, const nadm_mlp_params_t* params,
+                                     const nadm_adam_t* adam, float* dZ, float* loss, void* ws, size_t ws_bytes,
+                                     const nadm_xchg_t* xchg, void* stream) {
+    return mlp_bwd_impl(dQ, Q, Hh, Z, rinv, B, C, H, ks, nheads, labels, sup_weight, params, adam, dZ, loss, ws, ws_bytes,
+                        xchg, stream, true);
 }

@@ -627,6 +627,7 @@ __global__ void step_flush_kernel(int64_t* counters, float* losses_out) {
 extern "C" int nadm_step_next(const int64_t* order, int64_t order_len, int64_t* counters, int64_t stride, int32_t B,
                               int64_t* row_idx_out, const nadm_adam_t* hyper, void* coef_out, float* loss_accum,
                               int32_t record_loss, float* losses_out, void* stream) {
+    if (int rc0 = nadm::flush_deferred_apply((cudaStream_t)stream)) return rc0;   // (a pending update adds the supervised loss term)
     NADM_REQUIRE(order && counters && row_idx_out && hyper && coef_out, "NULL pointer");
     NADM_REQUIRE(B > 0 && stride >= B && order_len > 0, "bad minibatch geometry (B=%d, stride=%lld)", B, (long long)stride);
     NADM_REQUIRE(((uintptr_t)coef_out & 15) == 0, "coef_out must be 16-byte aligned");
@@ -639,6 +640,7 @@ extern "C" int nadm_step_next(const int64_t* order, int64_t order_len, int64_t* 
 }
 
 extern "C" int nadm_step_flush(int64_t* counters, float* losses_out, void* stream) {
+    if (int rc0 = nadm::flush_deferred_apply((cudaStream_t)stream)) return rc0;   // (a pending update adds the supervised loss term)
     NADM_REQUIRE(counters, "NULL pointer");
     nadm::launch_pdl(nadm::step_flush_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, counters, losses_out);
     NADM_CHECK_LAUNCH("step_flush_kernel");
@@ -648,6 +650,7 @@ extern "C" int nadm_step_flush(int64_t* counters, float* losses_out, void* strea
 extern "C" int nadm_step_begin(const int64_t* order, int64_t order_len, int64_t* counters, int64_t stride, int32_t B,
                                int64_t* row_idx_out, const nadm_adam_t* hyper, void* coef_out, float* loss_accum,
                                void* stream) {
+    if (int rc0 = nadm::flush_deferred_apply((cudaStream_t)stream)) return rc0;   // (a pending update adds the supervised loss term)
     NADM_REQUIRE(order && counters && row_idx_out && hyper && coef_out, "NULL pointer");
     NADM_REQUIRE(B > 0 && stride >= B && order_len > 0, "bad minibatch geometry (B=%d, stride=%lld)", B, (long long)stride);
     NADM_REQUIRE(((uintptr_t)coef_out & 15) == 0, "coef_out must be 16-byte aligned");
@@ -659,6 +662,7 @@ extern "C" int nadm_step_begin(const int64_t* order, int64_t order_len, int64_t*
 }
 
 extern "C" int nadm_step_end(int64_t* counters, const float* loss, float* losses_out, void* stream) {
+    if (int rc0 = nadm::flush_deferred_apply((cudaStream_t)stream)) return rc0;   // (a pending update adds the supervised loss term)
     NADM_REQUIRE(counters, "NULL pointer");
     nadm::launch_pdl(nadm::step_end_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, counters, loss, losses_out);
     NADM_CHECK_LAUNCH("step_end_kernel");
@@ -863,8 +867,17 @@ extern "C" int nadm_encoder_bwd(const uint8_t* packed, int64_t pitch, const int6
     NADM_REQUIRE(adam == nullptr || (Vm && Vv), "Adam moments are NULL");
     NADM_REQUIRE(adam != nullptr || dV_out != nullptr, "nothing to do: neither Adam nor dV_out requested");
     NADM_REQUIRE(row0 >= 0 && row0 + B <= (1ll << 32), "row numbers must fit 32 bits (row0=%lld)", (long long)row0);
-    if (C <= 8 && enc_bwd_tc_supported(B) && !use_generic_kernels() && (reinterpret_cast<uintptr_t>(V) & 15) == 0 &&
-        (dV_out == nullptr || (reinterpret_cast<uintptr_t>(dV_out) & 15) == 0))
+    const bool tc = C <= 8 && enc_bwd_tc_supported(B) && !use_generic_kernels() && (reinterpret_cast<uintptr_t>(V) & 15) == 0 &&
+                    (dV_out == nullptr || (reinterpret_cast<uintptr_t>(dV_out) & 15) == 0);
+    // a parameter update of the network left pending for this dZ (nadm_mlp_bwd_deferred) rides along on the kernel's
+    // epilogue warps; in every other case it runs now, as its own kernel
+    if (tc && enc_bwd_runs_apply(B) && deferred_apply().dZ == dZ && dZ != nullptr) {
+        const ApplyJob job = deferred_apply().job;
+        deferred_apply().dZ = nullptr;
+        return launch_enc_bwd_tc(packed, pitch, row_idx, row0, B, M, dZ, C, V, Vm, Vv, adam, dV_out, (cudaStream_t)stream, -1, 0, &job);
+    }
+    if (int rc = flush_deferred_apply((cudaStream_t)stream)) return rc;
+    if (tc)
         return launch_enc_bwd_tc(packed, pitch, row_idx, row0, B, M, dZ, C, V, Vm, Vv, adam, dV_out, (cudaStream_t)stream);
     if (pad_c(C) == 8)
         return launch_enc_bwd<8>(packed, pitch, row_idx, row0, B, M, dZ, C, V, Vm, Vv, adam, dV_out, (cudaStream_t)stream);

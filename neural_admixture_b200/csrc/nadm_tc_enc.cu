@@ -975,7 +975,9 @@ __global__ void __launch_bounds__(bwd_threads(EPW), 1)
 enc_bwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64_t* __restrict__ row_idx, int64_t row0,
                   int B, int64_t M, const float* __restrict__ dZ, int C, float* __restrict__ V, float* __restrict__ Vm,
                   float* __restrict__ Vv, AdamCoef adam_in, float* __restrict__ dV_out, int T, uint32_t mvx,
-                  double out_scale, int accumulate) {
+                  double out_scale, int accumulate, ApplyJob job) {
+    // job.nslab > 0: the pending parameter update of the small network (see DeferredApply) runs on this kernel's epilogue
+    // warps before their first accumulators arrive
     pdl_prologue();
     const AdamCoef adam = adam_resolve(adam_in);
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -1093,6 +1095,8 @@ enc_bwd_tc_kernel(const uint8_t* __restrict__ packed, int64_t pitch, const int64
         const int q = warp & 3;             // tensor-memory lane quadrant this warp may access (warp id % 4)
         constexpr int kHalves = (EPW == 8) ? 1 : 2;                   // 128-SNP halves of a sub-tile per thread
         const int hsel = (EPW == 8) ? ((warp - (kProdWarps + 2)) >> 2) : 0;
+        if (job.nslab > 0)      // this CTA's share of the network's parameter update: nothing here depends on it
+            mlp_apply_share(job, (int)blockIdx.x, (int)gridDim.x, tid - (kProdWarps + 2) * 32, EPW * 32);
         for (int tt = 0; tt < t1 - t0; ++tt) {
             const int buf = tt & 1;
             // (measured and kept out, profiles/r2_*: with Adam this kernel takes 85 us against 60 without.  Requesting the
@@ -1511,6 +1515,7 @@ static bool enc_bwd_slab() {
     }
     return v == 1;
 }
+bool enc_bwd_runs_apply(int B) { return !(enc_bwd_slab() && enc_bwd_slab_supported(B)); }
 static int enc_issuers() {
     static int n = 0;
     if (n == 0) {
@@ -1624,7 +1629,8 @@ int launch_enc_fwd_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_i
 
 int launch_enc_bwd_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_idx, int64_t row0, int B, int64_t M,
                       const float* dZ, int C, float* V, float* Vm, float* Vv, const nadm_adam_t* adam, float* dV_out,
-                      cudaStream_t st, int raw_mv, int accumulate) {
+                      cudaStream_t st, int raw_mv, int accumulate, const ApplyJob* job) {
+    const ApplyJob jb = (job != nullptr) ? *job : ApplyJob{};
     const int T = (int)((M + kSub - 1) / kSub);
     const int ncta = std::min(T, sm_count());
     const int nblk = (B + 127) / 128;
@@ -1685,7 +1691,7 @@ int launch_enc_bwd_tc(const uint8_t* packed, int64_t pitch, const int64_t* row_i
     }
 #define NADM_BWD_GO(N_, R_, E_)                                                                                        \
     launch_pdl(enc_bwd_tc_kernel<N_, R_, E_>, dim3(ncta), dim3(bwd_threads(E_)), smem, st, packed, pitch, row_idx, row0, B, M, \
-               dZ, C, V, Vm, Vv, make_adam(adam), dV_out, T, mvx, scale, accumulate)
+               dZ, C, V, Vm, Vv, make_adam(adam), dV_out, T, mvx, scale, accumulate, jb)
 #define NADM_BWD_GO_E(N_, R_) do { if (epw == 8) NADM_BWD_GO(N_, R_, 8); else NADM_BWD_GO(N_, R_, 4); } while (0)
     if (raw_mv >= 0) { if (two) NADM_BWD_GO_E(2, true); else NADM_BWD_GO_E(1, true); }
     else { if (two) NADM_BWD_GO_E(2, false); else NADM_BWD_GO_E(1, false); }

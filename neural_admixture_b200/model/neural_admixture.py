@@ -377,7 +377,8 @@ class NeuralAdmixture:
             self._allreduce(sb["dq_loss"])
         ops.mlp_bwd(sb["dQ"], fb["Q"], fb["Hh"], fb["Z"], fb["rinv"], m.multihead_encoder.ks, self._mlp_params(), hyper,
                     sb["dZ"], sb["loss"], fb["ws"], labels=labels,
-                    sup_weight=float(self.supervised_loss_weight) if labels is not None else 0.0, xchg=xc)
+                    sup_weight=float(self.supervised_loss_weight) if labels is not None else 0.0, xchg=xc,
+                    deferred_apply=True)         # (the update rides along on the encoder backward below)
         ops.encoder_bwd(pg, sb["dZ"], m.V.data, o.m["V"], o.v["V"], hyper, fb["ws"], row_idx=row_idx)
         if loss_out is not None and not managed_loss:
             loss_out.copy_(sb["loss"])

@@ -198,12 +198,15 @@ def decoder_step(pg: PackedGenotypes, Q, dQ, q_off: int, k: int, P, Pm, Pv, adam
 
 
 def mlp_bwd(dQ, Q, Hh, Z, rinv, ks, params: MlpParams, adam: Optional[AdamHyper], dZ, loss, ws, *, labels=None,
-            sup_weight: float = 0.0, xchg: Optional[Xchg] = None) -> None:
+            sup_weight: float = 0.0, xchg: Optional[Xchg] = None, deferred_apply: bool = False) -> None:
+    """``deferred_apply``: the parameter update is left to the ``encoder_bwd`` call that follows ON THE SAME dZ (it runs on
+    that kernel's epilogue warps); any other library call that needs the parameters runs it first."""
     _need_cuda(dQ, Q, Hh, Z, rinv, dZ, loss, ws, labels)
     B, C_ = Z.shape
     H = Hh.shape[1]
     assert labels is None or (labels.dtype == torch.int64 and labels.is_contiguous() and labels.numel() == B)
-    with _on(dQ): check(_lib.load().nadm_mlp_bwd(_ptr(dQ), _ptr(Q), _ptr(Hh), _ptr(Z), _ptr(rinv), B, C_, H, _ks_array(ks), len(ks),
+    fn = _lib.load().nadm_mlp_bwd_deferred if (deferred_apply and _DEFER) else _lib.load().nadm_mlp_bwd
+    with _on(dQ): check(fn(_ptr(dQ), _ptr(Q), _ptr(Hh), _ptr(Z), _ptr(rinv), B, C_, H, _ks_array(ks), len(ks),
                                    _ptr(labels), float(sup_weight), C.byref(params),
                                    None if adam is None else C.byref(adam), _ptr(dZ), _ptr(loss), _ptr(ws),
                                    ws.numel() * ws.element_size(), None if xchg is None else C.byref(xchg), _stream(dQ)))

@@ -219,6 +219,56 @@ def test_deferred_reductions_match_separate_kernels(ops, dev, ks, B, M):
     assert abs(a["loss"].item() - b["loss"].item()) <= 2e-7 * abs(a["loss"].item())
 
 
+@pytest.mark.parametrize("ks,B,M,adam", [([8], 800, 30000, True), ([4, 12], 130, 2000, False)])
+def test_deferred_parameter_update_is_bit_identical(ops, dev, ks, B, M, adam):
+    """mlp_bwd(deferred_apply) + encoder_bwd (the network's parameter update runs on the encoder backward's epilogue
+    warps) against mlp_bwd with its own update kernel: same association of the slab sums -> bit-identical parameters,
+    moments, raw gradients and loss; and a pending update that no encoder_bwd picks up is run by the next call that
+    needs the parameters (here mlp_fwd)."""
+    from neural_admixture_b200._lib import MlpParams
+    rng = np.random.default_rng(B)
+    N, C, H, sumK = B + 20, 8, 1024, sum(ks)
+    G = rand_genotypes(rng, N, M)
+    pg = packed_from(ops, G, dev)
+    idx = t(rng.permutation(N)[:B], dev, torch.int64)
+    Z = t(rng.standard_normal((B, C)) * 0.3, dev)
+    dQ0 = t(rng.standard_normal((B, sumK)) * 10, dev)
+    labels = t(rng.integers(0, ks[0], size=B), dev, torch.int64)
+    init = {"w_rms": 1 + 0.1 * rng.standard_normal(C), "W1": rng.standard_normal((H, C)) / np.sqrt(C),
+            "b1": 0.1 * rng.standard_normal(H), "W2": rng.standard_normal((sumK, H)) / np.sqrt(H),
+            "b2": 0.1 * rng.standard_normal(sumK)}
+    V0 = rng.standard_normal((M, C)) / np.sqrt(M)
+    ws = ws_for(ops, B, M, C, H, sumK, dev)
+    results = []
+    for mode in ("separate", "rides_along", "flushed"):
+        prm = {n: t(v, dev) for n, v in init.items()}
+        mom = {n: (torch.zeros_like(prm[n]), torch.zeros_like(prm[n])) for n in prm}
+        grd = {n: torch.zeros_like(prm[n]) for n in prm}
+        p = MlpParams()
+        for n in prm:
+            setattr(p, n, prm[n].data_ptr())
+            setattr(p, "m_" + n, mom[n][0].data_ptr())
+            setattr(p, "v_" + n, mom[n][1].data_ptr())
+            setattr(p, "g_" + n, grd[n].data_ptr())
+        rinv, Hh, Q = torch.empty(B, device=dev), torch.empty((B, H), device=dev), torch.empty((B, sumK), device=dev)
+        Zc = Z.clone()
+        ops.mlp_fwd(Zc, prm["w_rms"], prm["W1"], prm["b1"], prm["W2"], prm["b2"], ks, rinv, Hh, Q)
+        dQ, dZ, loss = dQ0.clone(), torch.empty((B, C), device=dev), torch.zeros(1, device=dev)
+        V, Vm, Vv = t(V0, dev), torch.zeros((M, C), device=dev), torch.zeros((M, C), device=dev)
+        hyper = ops.adam_hyper(2e-3, 3) if adam else None
+        ops.mlp_bwd(dQ, Q, Hh, Zc, rinv, ks, p, hyper, dZ, loss, ws, labels=labels, sup_weight=100.0,
+                    deferred_apply=(mode != "separate"))
+        if mode == "flushed":          # nobody picks the update up: the next reader of the parameters runs it
+            ops.mlp_fwd(Zc, prm["w_rms"], prm["W1"], prm["b1"], prm["W2"], prm["b2"], ks, rinv, Hh, Q)
+        ops.encoder_bwd(pg, dZ, V, Vm, Vv, ops.adam_hyper(2e-3, 3), ws, row_idx=idx)
+        results.append({**{n: prm[n].clone() for n in prm}, **{"m_" + n: mom[n][0].clone() for n in prm},
+                        **{"g_" + n: grd[n].clone() for n in prm}, "loss": loss.clone(), "V": V.clone(), "dZ": dZ.clone()})
+    for other in results[1:]:
+        for n, a in results[0].items():
+            assert torch.equal(a, other[n]), n
+    assert results[0]["loss"].item() > 0 and float(results[0]["g_W1"].abs().max()) > 0
+
+
 @pytest.mark.parametrize("N,M,k,B,edge", [(64, 203, 5, 48, True), (300, 4099, 8, 300, False), (1000, 20000, 8, 800, True),
                                           (40, 1024, 3, 40, True), (90, 515, 12, 77, False), (20, 9, 2, 20, True),
                                           (900, 9001, 16, 800, True), (300, 2050, 9, 300, True)])
