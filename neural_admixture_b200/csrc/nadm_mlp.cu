@@ -119,7 +119,9 @@ __device__ __forceinline__ float ld_ll_wait(const uint2* p, uint32_t flag) {
     for (;;) {
         asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(f) : "l"(p) : "memory");
         if (f == flag) break;
-        if (++polls > (1u << 24)) __trap();          // a peer never arrived: fail the launch instead of hanging
+        // a peer that never arrives fails the launch instead of hanging it; the bound (about a minute of polling) leaves
+        // room for a peer that is merely late (its first launch of a kernel, a graph instantiation, a slower host)
+        if (++polls > (1u << 27)) __trap();
     }
     return __uint_as_float(v);
 }
