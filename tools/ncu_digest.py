@@ -37,7 +37,7 @@ def num(x):
 
 out = {"_config": {"M_loc": int(sys.argv[2]), "B": int(sys.argv[3]), "ks": [int(sys.argv[4])]},
        "_source": "ncu --set full --clock-control none --import-source on; bench.py --rows 20000 --steps 3 --warmup 3 "
-                  "--no-cpu --no-e2e (tools/r2_call17.sh); units as ncu prints them (Mbyte = 1e6 bytes)"}
+                  "--no-cpu --no-e2e (tools/gpu_calls/r2_call17.sh); units as ncu prints them (Mbyte = 1e6 bytes)"}
 for path in sys.argv[5:]:
     rows = list(csv.reader(open(path)))
     h = rows[0]
