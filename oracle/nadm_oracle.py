@@ -16,8 +16,10 @@ The oracle is therefore pinned against outputs of the reference itself, imported
 /root/reference by ``tests/golden/make_golden.py`` (fixtures committed under ``tests/golden/``; checked by
 ``tests/test_oracle_golden.py``), and against the demo's shipped ``demo_run.7.{Q,P}.expected`` files at the
 ~1e-3 level the reference itself reproduces them to.  The 2-bit pack/unpack layout (pack2bit.cu) is CUDA-only in
-the reference and cannot be executed in the build container: for that row parity is pinned by restatement only
-("parity unpinned" for pack2bit; it is a pure bit layout, exercised through round trips).
+the reference and cannot be executed in the build container, but it compiles there: ``oracle/build_ref.py`` builds the
+reference's file unmodified into ``oracle/_ref/pack2bit_ref.so``, and on the GPU box
+``tests/test_gpu_parity.py::test_pack_unpack_against_the_compiled_reference_kernels`` pins this file's ``pack2bit`` /
+``unpack2bit`` and the library's kernels to the reference's own, bit for bit.
 
 All citations are ``path:line`` under /root/reference/neural_admixture/.
 """

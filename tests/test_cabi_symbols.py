@@ -67,3 +67,21 @@ def test_no_cpu_path():
     m = Q_P(16, 8, torch.zeros(12, 8), torch.zeros(3, 12), [3])
     with pytest.raises(NadmError):
         m.bind()
+
+
+def test_compiled_reference_checker_loads_and_exports_the_reference_surface():
+    """oracle/_ref/pack2bit_ref.so (the reference's pack2bit.cu compiled unmodified by oracle/build_ref.py): present in the
+    build container, loads without a GPU and exports the two functions of the reference's pybind module
+    (pack2bit.cu:144-147).  Calling them needs a device: that is tests/test_gpu_parity.py."""
+    import importlib.util
+    from pathlib import Path
+
+    import pytest
+    so = Path(__file__).resolve().parent.parent / "oracle" / "_ref" / "pack2bit_ref.so"
+    if not so.exists():
+        pytest.skip("oracle/_ref not built here (python oracle/build_ref.py needs /root/reference)")
+    import torch  # noqa: F401  (its libraries must be loaded first)
+    spec = importlib.util.spec_from_file_location("pack2bit_ref", so)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert callable(mod.pack2bit_cpu_to_gpu) and callable(mod.unpack2bit_gpu_to_gpu)

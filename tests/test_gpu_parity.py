@@ -6,6 +6,8 @@ Tolerances (floating point; fp32 kernels vs the fp64 oracle):
   STEP_TOL   = 5e-5   parameters after one/two full optimisation steps (Adam normalises gradients: |dp| = lr)
   QP_TOL     = 1e-4   north-star bar: ||Q - Q_ref||_F / ||Q_ref||_F (and P) after short trainings
 Integer work (pack / unpack) is bit-exact."""
+from pathlib import Path
+
 import numpy as np
 import pytest
 import torch
@@ -79,6 +81,46 @@ def test_pack_unpack_bit_exact(ops, dev, N, M):
     pg = packed_from(ops, G & 3, dev)
     st = pg.storage.cpu().numpy()
     assert np.array_equal(st[:, :pc], orc.pack2bit(G)) and not st[:, pc:].any()
+
+
+def _reference_pack2bit_module():
+    """oracle/_ref/pack2bit_ref.so: the reference's own pack2bit.cu compiled unmodified by oracle/build_ref.py (in the
+    build container, where /root/reference exists; it travels to the GPU box with the snapshot)."""
+    import importlib.util
+    so = Path(__file__).resolve().parent.parent / "oracle" / "_ref" / "pack2bit_ref.so"
+    if not so.exists():
+        pytest.skip("oracle/_ref/pack2bit_ref.so was not built (python oracle/build_ref.py needs /root/reference)")
+    try:
+        spec = importlib.util.spec_from_file_location("pack2bit_ref", so)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    except Exception as e:        # e.g. a torch build on the box other than the one it was compiled against
+        pytest.skip(f"the compiled reference module does not load here: {type(e).__name__}: {e}")
+    return mod
+
+
+@pytest.mark.parametrize("N,M", [(3, 4), (5, 7), (16, 203), (1100, 1025), (33, 4099)])
+def test_pack_unpack_against_the_compiled_reference_kernels(ops, dev, N, M):
+    """The 2-bit layout pinned to the reference ITSELF: its pack2bit_cpu_to_gpu / unpack2bit_gpu_to_gpu (pack2bit.cu:10-63,
+    compiled from /root/reference by oracle/build_ref.py) against nadm_pack2bit / nadm_unpack2bit, bit for bit, both
+    directions and crosswise (each side unpacks what the other packed)."""
+    ref = _reference_pack2bit_module()
+    rng = np.random.default_rng(N * 131 + M)
+    G = rng.integers(0, 256, size=(N, M), dtype=np.uint8)          # high bits must be dropped by both
+    pc = (M + 3) // 4
+    theirs = torch.full((N, pc), 0x55, dtype=torch.uint8, device=dev)
+    ref.pack2bit_cpu_to_gpu(torch.as_tensor(G), theirs)
+    mine = torch.full((N, pc), 0xAA, dtype=torch.uint8, device=dev)
+    ops.pack2bit(torch.as_tensor(G, device=dev), mine)
+    torch.cuda.synchronize()
+    assert torch.equal(mine, theirs)
+    assert np.array_equal(theirs.cpu().numpy(), orc.pack2bit(G))    # and the oracle's restatement of it
+    a = torch.full((N, M), 9, dtype=torch.uint8, device=dev)
+    b = torch.full((N, M), 7, dtype=torch.uint8, device=dev)
+    ref.unpack2bit_gpu_to_gpu(mine, a)                              # the reference unpacks what this library packed
+    ops.unpack2bit(theirs, b)                                       # and the other way round
+    torch.cuda.synchronize()
+    assert torch.equal(a, b) and np.array_equal(a.cpu().numpy(), G & 3)
 
 
 def test_reference_pack2bit_module_surface(ops, dev):
